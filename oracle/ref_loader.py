@@ -1,0 +1,78 @@
+"""TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference (ExTrack 1.6.3) in-process.
+
+Only ``tests/``, ``tests/golden/make_golden.py`` and ad-hoc validation scripts may import
+this module.  It works only where ``/root/reference`` exists (the build container); the
+GPU box has no reference tree, so nothing on the ``-m gpu`` / ``smoke()`` / ``bench.py``
+paths may depend on it (they use the committed fixtures under ``tests/golden``).
+
+The reference imports ``lmfit`` at module import (``extrack/tracking.py:31``) and lmfit is
+absent from this image, so the repo's stand-in (``extrack_b200._lmfit_compat``) is
+installed under the name ``lmfit`` first.  Only ``Parameters`` / ``.value`` are touched
+by the likelihood path.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("EXTRACK_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "extrack", "tracking.py"))
+
+
+def _install_lmfit_stub():
+    if "lmfit" in sys.modules:
+        return
+    try:
+        import lmfit  # noqa: F401
+
+        return
+    except Exception:
+        pass
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from extrack_b200 import _lmfit_compat as compat
+
+    stub = types.ModuleType("lmfit")
+    stub.Parameters = compat.Parameters
+    stub.Parameter = compat.Parameter
+    stub.minimize = compat.minimize
+    sys.modules["lmfit"] = stub
+
+
+def _load(name: str, relpath: str):
+    modname = "_extrack_reference_" + name
+    if modname in sys.modules:
+        return sys.modules[modname]
+    _install_lmfit_stub()
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    spec = importlib.util.spec_from_file_location(modname, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_tracking():
+    """The reference's ``extrack/tracking.py`` as a module object (unmodified)."""
+    return _load("tracking", "extrack/tracking.py")
+
+
+def load_simulate():
+    return _load("simulate_tracks", "extrack/simulate_tracks.py")
+
+
+def load_readers():
+    # readers.py imports xmltodict at module import; only the csv reader is used here
+    if "xmltodict" not in sys.modules:
+        try:
+            import xmltodict  # noqa: F401
+        except Exception:
+            sys.modules["xmltodict"] = types.ModuleType("xmltodict")
+    return _load("readers", "extrack/readers.py")
