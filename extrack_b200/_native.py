@@ -1,0 +1,230 @@
+"""ctypes binding of ``libxtrack_b200.so`` (C ABI declared in ``include/xtrack.h``).
+
+There is no CPU fallback: importing this module raises if the shared library has not been
+built (``python -c 'import __graft_entry__ as g; g.build()'`` or ``python -m extrack_b200.build``),
+and creating an :class:`Engine` raises if no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+XT_MAX_HEADS = 128
+XT_MAX_STATES = 8
+XT_MAX_DIMS = 3
+XT_FLAG_INT8_WRAP = 1
+
+XT_ERR_CUDA, XT_ERR_ARG, XT_ERR_GROUPING, XT_ERR_CAPACITY, XT_ERR_STATE = -1, -2, -3, -4, -5
+
+LIB_NAME = "libxtrack_b200.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+
+class XtParams(C.Structure):
+    _fields_ = [
+        ("nS", C.c_int32),
+        ("nsub", C.c_int32),
+        ("d", C.c_int32),
+        ("n_loc", C.c_int32),
+        ("frame_len", C.c_int32),
+        ("min_len", C.c_int32),
+        ("max_nb_states", C.c_int32),
+        ("flags", C.c_uint32),
+        ("threshold", C.c_double),
+        ("l2", C.c_double * XT_MAX_DIMS),
+        ("dd", C.c_double * XT_MAX_HEADS),
+        ("LT", C.c_double * XT_MAX_HEADS),
+        ("LF", C.c_double * XT_MAX_HEADS),
+        ("Lp_stay", C.c_double * XT_MAX_HEADS),
+        ("L_leave", C.c_double * XT_MAX_HEADS),
+    ]
+
+
+class XtStats(C.Structure):
+    _fields_ = [
+        ("n_tracks", C.c_int64),
+        ("track_steps", C.c_int64),
+        ("seq_updates", C.c_int64),
+        ("seq_groups", C.c_int64),
+        ("max_nB_in", C.c_int32),
+        ("n_chunks", C.c_int32),
+        ("k1_launches", C.c_int32),
+        ("k2_launches", C.c_int32),
+        ("ms_plan", C.c_float),
+        ("ms_replay", C.c_float),
+    ]
+
+
+# every symbol include/xtrack.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "xt_create",
+    "xt_destroy",
+    "xt_last_error",
+    "xt_upload",
+    "xt_sum_logp",
+    "xt_sum_logp_async",
+    "xt_chunk_logp",
+    "xt_plan_dump",
+    "xt_predict",
+    "xt_get_stats",
+    "xt_fp64_peak_tflops",
+    "xt_host_alloc",
+    "xt_host_free",
+)
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA engine; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_NAME} not found at {LIB_PATH}: the CUDA engine is not built. "
+            "Run `python -m extrack_b200.build` (needs nvcc). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    P = C.POINTER
+    lib.xt_create.argtypes = [C.c_int, P(vp)]
+    lib.xt_destroy.argtypes = [vp]
+    lib.xt_destroy.restype = None
+    lib.xt_last_error.argtypes = [vp]
+    lib.xt_last_error.restype = C.c_char_p
+    lib.xt_upload.argtypes = [vp, i32, P(i32), P(i64), P(i32), P(vp), i32, i32]
+    lib.xt_sum_logp.argtypes = [vp, P(XtParams), P(dbl)]
+    lib.xt_sum_logp_async.argtypes = [vp, P(XtParams), vp, vp]
+    lib.xt_chunk_logp.argtypes = [vp, i32, P(XtParams), P(dbl)]
+    lib.xt_plan_dump.argtypes = [vp, i32, i32, P(i32), P(i32), P(i32), i32, P(dbl)]
+    lib.xt_predict.argtypes = [vp, P(XtParams), P(vp)]
+    lib.xt_get_stats.argtypes = [vp, P(XtStats)]
+    lib.xt_fp64_peak_tflops.argtypes = [vp, P(dbl)]
+    lib.xt_host_alloc.argtypes = [P(vp), C.c_uint64]
+    lib.xt_host_free.argtypes = [vp]
+    for name in EXPORTS:
+        if name not in ("xt_destroy", "xt_last_error"):
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"xtrack error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def _raise(code: int, msg: str):
+    # error conventions of the reference: malformed input / grouping -> ValueError
+    if code in (XT_ERR_ARG, XT_ERR_GROUPING, XT_ERR_CAPACITY):
+        raise ValueError(msg)
+    raise EngineError(code, msg)
+
+
+class Engine:
+    """One context = one GPU.  Owns all device memory; freed on ``close()`` / garbage collection."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.xt_create(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.xt_last_error(None).decode()
+            self._h = None
+            raise EngineError(rc, f"cannot create a CUDA context on device {device}: {msg} (no CPU fallback)")
+        self.device = int(device)
+        self.segments = []  # (L, n) per uploaded segment
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.xt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            _raise(rc, self._lib.xt_last_error(self._h).decode())
+
+    # -- data ----------------------------------------------------------------------------
+    def upload(self, segments: Sequence[np.ndarray], isBL: Sequence[int], chunk_size: int):
+        """segments: float64 arrays [n, L, d] (made C-contiguous here if they are not)."""
+        segs = [np.ascontiguousarray(s, dtype=np.float64) for s in segments]
+        if len(segs) == 0:
+            raise ValueError("No track could be detected. The loaded tracks seem empty.")
+        d = segs[0].shape[2]
+        for s in segs:
+            if s.ndim != 3 or s.shape[2] != d:
+                raise ValueError("all track arrays must have shape [n, L, d] with the same d")
+        n = len(segs)
+        Ls = (C.c_int32 * n)(*[s.shape[1] for s in segs])
+        ns = (C.c_int64 * n)(*[s.shape[0] for s in segs])
+        bl = (C.c_int32 * n)(*[int(b) for b in isBL])
+        ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in segs])
+        self._check(self._lib.xt_upload(self._h, n, Ls, ns, bl, ptrs, d, int(chunk_size)))
+        self.segments = [(s.shape[1], s.shape[0]) for s in segs]
+        self.chunk_size = int(chunk_size)
+        self.d = d
+
+    # -- evaluation ----------------------------------------------------------------------
+    def sum_logp(self, p: XtParams) -> float:
+        out = C.c_double()
+        self._check(self._lib.xt_sum_logp(self._h, C.byref(p), C.byref(out)))
+        return out.value
+
+    def sum_logp_async(self, p: XtParams, d_out_ptr: int, stream_ptr: Optional[int] = None):
+        self._check(self._lib.xt_sum_logp_async(self._h, C.byref(p), C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or 0)))
+
+    def chunk_logp(self, chunk: int, nT: int, p: XtParams) -> np.ndarray:
+        out = np.empty(nT, dtype=np.float64)
+        self._check(self._lib.xt_chunk_logp(self._h, int(chunk), C.byref(p), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def plan_dump(self, chunk: int, step: int, cap: int = 4096):
+        nB, nG, th = C.c_int32(), C.c_int32(), C.c_double()
+        gid = np.empty(cap, dtype=np.int32)
+        self._check(
+            self._lib.xt_plan_dump(
+                self._h, int(chunk), int(step), C.byref(nB), C.byref(nG), gid.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(th)
+            )
+        )
+        return nB.value, nG.value, gid[: nB.value].copy(), th.value
+
+    def predict(self, p: XtParams, nS: int) -> List[np.ndarray]:
+        outs = [np.empty((n, L, nS), dtype=np.float64) for (L, n) in self.segments]
+        ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+        self._check(self._lib.xt_predict(self._h, C.byref(p), ptrs))
+        return outs
+
+    def stats(self) -> dict:
+        st = XtStats()
+        self._check(self._lib.xt_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in XtStats._fields_}
+
+    def fp64_peak_tflops(self) -> float:
+        out = C.c_double()
+        self._check(self._lib.xt_fp64_peak_tflops(self._h, C.byref(out)))
+        return out.value
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by pinned host memory (for end-to-end timing with host buffers)."""
+    lib = load_library()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    if lib.xt_host_alloc(C.byref(p), max(nbytes, 8)) != 0:
+        raise EngineError(XT_ERR_CUDA, "cudaMallocHost failed")
+    buf = (C.c_char * max(nbytes, 8)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr

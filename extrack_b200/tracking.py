@@ -1,0 +1,499 @@
+"""Drop-in mirror of ``extrack.tracking``'s fit / predict API on top of the sm_100a CUDA engine.
+
+Same names, argument meaning and error behaviour as the reference (ExTrack 1.6.3,
+``extrack/tracking.py``): ``param_fitting`` (:1299), ``cum_Proba_Cs`` (:991), ``Proba_Cs`` (:769),
+``predict_Bs`` (:792), ``extract_params`` (:913), ``generate_params`` (:1214), ``get_params``
+(:1090) and the legacy ``get_2DSPT_params`` (``old_tracking.py:585``).  Host code stays
+Python: parameter extraction, the parameter guard and the tiny per-evaluation tables
+(incl. ``scipy.stats.norm.cdf`` for the field-of-view term) are computed here exactly as the
+reference does; everything per track runs in hand-written CUDA kernels reached through the C
+ABI in ``include/xtrack.h``.  There is no CPU fallback.
+
+Tracks are packed and uploaded once per ``param_fitting`` / ``predict_Bs`` call (or once per
+distinct list of arrays handed to ``cum_Proba_Cs``) and stay resident on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from ._lmfit_compat import Parameters, minimize
+
+MAX_TRACKS_PER_CHUNK = 2000  # tracking.py:991 max_number_of_tracks_per_matrix
+
+
+# --------------------------------------------------------------------------------------
+# parameters -> model quantities (host; tracking.py:913-986)
+# --------------------------------------------------------------------------------------
+def extract_params(params, dt, nb_states, nb_substeps, input_LocErr=None, Matrix_type=1):
+    """lmfit ``Parameters`` -> ``(LocErr, ds, Fs, TrMat, pBL)`` with the reference's conventions.
+
+    ``LocErr`` is ``[array(1,1,k)]``; ``ds = sqrt(2 D dt)``; ``TrMat`` holds per-sub-step
+    transition probabilities.  Peak-wise ``input_LocErr`` and per-track ``dt`` are not
+    supported by the CUDA path yet and raise ``NotImplementedError``.
+    """
+    if input_LocErr is not None:
+        raise NotImplementedError("peak-wise input_LocErr is not supported by the CUDA engine yet (SURVEY.md §8f N1)")
+    if isinstance(dt, (list, dict)):
+        raise NotImplementedError("per-track dt is not supported by the CUDA engine yet (SURVEY.md §8f N1)")
+    names = sorted(params.keys())
+    loc = [params[n].value for n in names if n.startswith("LocErr")]
+    LocErr = [np.array(loc, dtype=float)[None, None]]
+    Ds = np.array([params[n].value for n in names if n.startswith("D") and len(n) < 3], dtype=float)
+    Fs = np.array([params[n].value for n in names if n.startswith("F")], dtype=float)
+    nS = len(Ds)
+    TrMat = np.zeros((nS, nS))
+    pBL = None
+    for n in params:
+        if n == "pBL":
+            pBL = params[n].value
+        elif n.startswith("p"):
+            TrMat[int(n[1]), int(n[2])] = params[n].value
+    TrMat = TrMat / nb_substeps
+    diag = np.arange(nS)
+    if Matrix_type == 0:
+        TrMat[diag, diag] = 1 - np.sum(TrMat, 1)
+    if Matrix_type == 1:
+        TrMat = 1 - np.exp(-TrMat)
+        TrMat[diag, diag] = 1 - np.sum(TrMat, 1)
+    elif Matrix_type in (2, 3, 4):
+        from scipy import linalg
+
+        if Matrix_type == 2:
+            TrMat[diag, diag] = -np.sum(TrMat, 1)
+            TrMat = linalg.expm(TrMat)
+        else:
+            TrMat[diag, diag] = 0
+            G = np.copy(TrMat)
+            TrMat[diag, diag] = 1 - np.sum(TrMat, 1)
+            G[diag, diag] = -np.sum(G, 1)
+            TrMatG = linalg.expm(G)
+            TrMat = np.mean([TrMat, TrMatG], axis=0) if Matrix_type == 3 else (TrMat * TrMatG) ** 0.5
+    ds = np.sqrt(2 * Ds * dt)
+    return LocErr, ds, Fs, TrMat, pBL
+
+
+def _p_stay(ds, nS, nsub, cell_dims):
+    """P(stay in the field of view) per sub-step state tuple (tracking.py:508-523)."""
+    import scipy.stats
+
+    K = nS**nsub
+    tup = np.arange(K)[:, None] // nS ** np.arange(nsub)[None, :] % nS
+    sub_ds = np.mean(ds[tup] ** 2, axis=1) ** 0.5
+    p_stay = np.ones(K)
+    for cell_len in cell_dims:
+        xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
+        cur = np.mean(
+            scipy.stats.norm.cdf((cell_len - xs[:, None]) / (sub_ds + 1e-200))
+            - scipy.stats.norm.cdf(-xs[:, None] / (sub_ds + 1e-200)),
+            0,
+        )
+        p_stay = p_stay * cur
+    return p_stay
+
+
+def build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold,
+                 max_nb_states, nb_dims, int8_wrap=True) -> _native.XtParams:
+    """Model quantities -> the engine's per-evaluation POD (``xt_params`` in include/xtrack.h).
+
+    Restates the table-building half of ``P_Cs_inter_bound_stats_th`` (tracking.py:474-524,
+    549-555, 630-631) once per evaluation instead of once per chunk.
+    """
+    ds = np.asarray(ds, dtype=float)
+    Fs = np.asarray(Fs, dtype=float)
+    TrMat = np.asarray(TrMat, dtype=float)
+    nS, nsub = len(ds), int(nb_substeps)
+    loc = np.asarray(LocErr, dtype=float).reshape(-1)
+    if len(loc) not in (1, nb_dims):
+        raise ValueError(
+            "Localization error is not specified correctly, in case of unique localization error specify a float "
+            "number in estimated_vals['LocErr'].\n If one localization error per dimension, specify a list or 1D "
+            "array of elements the localization error for each dimension."
+        )
+    K = nS**nsub
+    nH = K * nS
+    if nH > _native.XT_MAX_HEADS or nS > _native.XT_MAX_STATES:
+        raise ValueError(f"nb_states**(nb_substeps+1) = {nH} exceeds the engine limit {_native.XT_MAX_HEADS}")
+    p = _native.XtParams()
+    p.nS, p.nsub, p.d, p.n_loc = nS, nsub, int(nb_dims), len(loc)
+    p.frame_len, p.min_len, p.max_nb_states = int(frame_len), int(min_len), int(min(max_nb_states, 2**31 - 1))
+    p.flags = _native.XT_FLAG_INT8_WRAP if int8_wrap else 0
+    p.threshold = float(threshold)
+    for k, v in enumerate(loc**2):
+        p.l2[k] = v
+    # head h: digit k (base nS) = state k sub-steps ago, digit nsub = newest state of the parent
+    dig = np.arange(nH)[:, None] // nS ** np.arange(nsub + 1)[None, :] % nS
+    d2 = ds[dig] ** 2
+    dd = np.mean((d2[:, 1:] + d2[:, :-1]) / 2, axis=1)
+    Tt = TrMat.T
+    LT = np.zeros(nH)
+    for k in range(nsub):
+        LT += np.log(Tt[dig[:, k], dig[:, k + 1]])
+    p_stay = _p_stay(ds, nS, nsub, cell_dims)
+    Lp_stay = np.log(p_stay * (1 - pBL))
+    e = p_stay[dig[:, 0]]  # indexed by the newest *state value* (reference quirk, tracking.py:630)
+    L_leave = np.log(pBL + (1 - e) - pBL * (1 - e)) + LT
+    LF = np.log(Fs[dig[:, nsub]])
+    for h in range(nH):
+        p.dd[h], p.LT[h], p.LF[h], p.L_leave[h] = dd[h], LT[h], LF[h], L_leave[h]
+    for r in range(K):
+        p.Lp_stay[r] = Lp_stay[r]
+    return p
+
+
+# --------------------------------------------------------------------------------------
+# resident data set
+# --------------------------------------------------------------------------------------
+def _sorted_buckets(all_tracks: Dict[str, np.ndarray]):
+    """Numerically sorted, non-empty length buckets (tracking.py:1346-1359, :822-833)."""
+    keys = np.sort(np.array(list(all_tracks.keys())).astype(int)).astype(str)
+    return [all_tracks[k] for k in keys if len(all_tracks[k]) > 0], [k for k in keys]
+
+
+def chunk_table(sorted_tracks: Sequence[np.ndarray], chunk: int, reverse: bool = True):
+    """Reference chunk list: ``(bucket, start, stop, isBL)`` (tracking.py:1024-1044)."""
+    max_len = sorted_tracks[-1].shape[1]
+    out = []
+    for b, arr in enumerate(sorted_tracks):
+        for n in range(int(np.ceil(len(arr) / chunk))):
+            out.append((b, n * chunk, min((n + 1) * chunk, len(arr)), 0 if arr.shape[1] == max_len else 1))
+    if reverse:
+        out.reverse()
+    return out
+
+
+def shard_chunks(chunks, sorted_tracks, world_size: int) -> List[List[int]]:
+    """Longest-processing-time-first assignment of chunks to ranks; cost = nT*(L-1).
+
+    Chunks are the atomic unit (the grouping plan is decided per chunk, tracking.py:677-691),
+    so shards are sets of whole chunks and the result is independent of ``world_size``.
+    """
+    cost = [(z - a) * (sorted_tracks[b].shape[1] - 1) for (b, a, z, _) in chunks]
+    order = sorted(range(len(chunks)), key=lambda i: (-cost[i], i))
+    load = [0] * world_size
+    owner: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        owner[r].append(i)
+        load[r] += cost[i]
+    for r in range(world_size):
+        owner[r].sort()
+    return owner
+
+
+class TrackSet:
+    """Tracks of one fit, packed and resident on this process's GPU.
+
+    With ``torch.distributed`` initialised (one process per GPU) each rank uploads only its
+    shard of the chunk list and ``sum_logp`` all-reduces the partial sums (one 8-byte
+    all-reduce per objective call, NCCL over NVLink).
+    """
+
+    def __init__(self, sorted_tracks: Sequence[np.ndarray], chunk: int = MAX_TRACKS_PER_CHUNK, device: Optional[int] = None,
+                 rank: Optional[int] = None, world_size: Optional[int] = None, reverse: bool = True):
+        if len(sorted_tracks) < 1:
+            raise ValueError("No track could be detected. The loaded tracks seem empty. Errors often come from wrong input paths.")
+        for a in sorted_tracks:
+            if a.shape[1] < 2:
+                raise ValueError("minimal track length = 2, here track length = %s" % a.shape[1])
+        self.sorted_tracks = list(sorted_tracks)
+        self.min_len = sorted_tracks[0].shape[1]
+        self.max_len = sorted_tracks[-1].shape[1]
+        self.nb_dims = sorted_tracks[0].shape[2]
+        self.chunk = int(chunk)
+        self.rank, self.world_size = _dist_info(rank, world_size)
+        self.chunks = chunk_table(sorted_tracks, self.chunk, reverse)
+        mine = shard_chunks(self.chunks, sorted_tracks, self.world_size)[self.rank] if self.world_size > 1 else list(range(len(self.chunks)))
+        self.my_chunks = mine
+        if device is None:
+            device = _default_device()
+        self.engine = _native.Engine(device)
+        self.device = device
+        segs = [self.sorted_tracks[b][a:z] for (b, a, z, _) in (self.chunks[i] for i in mine)]
+        bl = [self.chunks[i][3] for i in mine]
+        self.n_local_chunks = len(segs)
+        if segs:
+            self.engine.upload(segs, bl, self.chunk)
+        self._dist_buf = None
+
+    # local chunk index of global chunk i (or None when another rank owns it)
+    def local_index(self, i: int) -> Optional[int]:
+        try:
+            return self.my_chunks.index(i)
+        except ValueError:
+            return None
+
+    def sum_logp(self, p: _native.XtParams) -> float:
+        if self.world_size == 1:
+            return self.engine.sum_logp(p)
+        import torch
+        import torch.distributed as dist
+
+        if self._dist_buf is None:
+            dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            self._dist_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+        buf = self._dist_buf
+        if buf.is_cuda and self.n_local_chunks:
+            # result stays on the device; the all-reduce is chained on torch's current stream
+            self.engine.sum_logp_async(p, buf.data_ptr(), torch.cuda.current_stream(buf.device).cuda_stream)
+        else:
+            buf[0] = self.engine.sum_logp(p) if self.n_local_chunks else 0.0
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        return float(buf.item())
+
+    def close(self):
+        self.engine.close()
+
+
+def _dist_info(rank, world_size):
+    if rank is not None and world_size is not None:
+        return int(rank), int(world_size)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def _default_device() -> int:
+    import os
+
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+_TRACKSET_CACHE: List = []  # [(key, refs, TrackSet)] most recent first
+
+
+def _trackset_for(all_tracks: Sequence[np.ndarray], chunk: int) -> TrackSet:
+    """Resident data for a list of arrays handed to ``cum_Proba_Cs`` (upload once per fit)."""
+    key = tuple((id(a), a.shape, a.__array_interface__["data"][0]) for a in all_tracks) + (chunk,)
+    for k, refs, ts in _TRACKSET_CACHE:
+        if k == key:
+            return ts
+    ts = TrackSet(all_tracks, chunk)
+    _TRACKSET_CACHE.insert(0, (key, list(all_tracks), ts))
+    while len(_TRACKSET_CACHE) > 2:
+        _, _, old = _TRACKSET_CACHE.pop()
+        old.close()
+    return ts
+
+
+# --------------------------------------------------------------------------------------
+# objective (tracking.py:991-1088)
+# --------------------------------------------------------------------------------------
+def cum_Proba_Cs(params, all_tracks, dt, cell_dims, input_LocErr, nb_states, nb_substeps, frame_len, verbose=1,
+                 workers=1, Matrix_type=1, threshold=0.2, max_nb_states=120, max_number_of_tracks_per_matrix=2000,
+                 _trackset: Optional[TrackSet] = None):
+    """-sum log L over all tracks for ``params`` (``np.inf`` for invalid parameters).
+
+    ``all_tracks`` is the sorted list of ``[n, L, d]`` arrays (as ``param_fitting`` builds it);
+    ``workers`` is accepted and ignored (the GPU replaces the process pool).
+    """
+    LocErr, ds, Fs, TrMat, pBL = extract_params(params, dt, nb_states, nb_substeps, input_LocErr, Matrix_type)
+    ts = _trackset if _trackset is not None else _trackset_for(all_tracks, max_number_of_tracks_per_matrix)
+    quiet = ts.rank != 0
+    if np.all(TrMat > 0) and np.all(Fs > 0) and np.all(ds[1:] - ds[:-1] >= 0):
+        p = build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, ts.min_len, threshold,
+                         max_nb_states, ts.nb_dims)
+        Cum_P = ts.sum_logp(p)
+        if not quiet:
+            if verbose == 1:
+                q = [param + " = " + str(np.round(params[param].value, 6)) for param in params]
+                print(Cum_P, q)
+            else:
+                print(".", end="")
+        out = -Cum_P
+    else:
+        out = np.inf
+        if not quiet:
+            print("x", end="")
+            if verbose == 1:
+                q = [param + " = " + str(np.round(params[param].value, 4)) for param in params]
+                print(q)
+    if np.isnan(out):
+        out = np.inf
+        if not quiet:
+            print("input parameters give nans, you may want to pick more suitable parameter initial values")
+    return out
+
+
+def Proba_Cs(Cs, LocErr, ds, Fs, TrMat, pBL, isBL, cell_dims, nb_substeps, frame_len, min_len, threshold, max_nb_states):
+    """log P(track) for every track of one chunk (tracking.py:769-787). Test / parity seam."""
+    Cs = np.asarray(Cs, dtype=np.float64)
+    if Cs.shape[1] < 2:
+        raise ValueError("minimal track length = 2, here track length = %s" % Cs.shape[1])
+    p = build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold, max_nb_states,
+                     Cs.shape[2])
+    eng = _native.Engine(_default_device())
+    try:
+        eng.upload([Cs], [isBL], max(len(Cs), 1))
+        return eng.chunk_logp(0, len(Cs), p)
+    finally:
+        eng.close()
+
+
+# --------------------------------------------------------------------------------------
+# state annotation (tracking.py:792-906)
+# --------------------------------------------------------------------------------------
+def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, max_nb_states=200, threshold=0.1,
+               workers=1, input_LocErr=None, verbose=0, nb_max=1):
+    """Per-localisation state posteriors, ``{str(L): float64[n, L, nb_states]}``."""
+    sorted_tracks, l_list = _sorted_buckets(all_tracks)
+    nb_substeps = 1  # substeps should not impact the step labelling (tracking.py:839)
+    if not isinstance(params, Parameters):
+        raise TypeError("params must be either of the class 'lmfit.parameter.Parameters' or a dictionary of the relevant parameters")
+    LocErr, ds, Fs, TrMat, pBL = extract_params(params, dt, nb_states, nb_substeps, input_LocErr)
+    if len(ds) != nb_states:
+        raise ValueError("nb_states (%d) must equal the number of D parameters (%d)" % (nb_states, len(ds)))
+    out = {l: np.empty((0, int(l), nb_states)) for l in l_list}
+    if not sorted_tracks:
+        return out
+    min_len, max_len = int(l_list[0]), int(l_list[-1])
+    p = build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold, max_nb_states,
+                     sorted_tracks[0].shape[2])
+    eng = _native.Engine(_default_device())
+    try:
+        eng.upload(sorted_tracks, [0 if a.shape[1] == max_len else 1 for a in sorted_tracks], int(nb_max))
+        preds = eng.predict(p, nb_states)
+    finally:
+        eng.close()
+    for a, pr in zip(sorted_tracks, preds):
+        out[str(a.shape[1])] = pr
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# parameter builders (host only; tracking.py:1090-1290) and the fit driver (:1299-1386)
+# --------------------------------------------------------------------------------------
+def generate_params(nb_states=3, LocErr_type=1, nb_dims=3, LocErr_bounds=[0.005, 0.1], D_max=10,
+                    Fractions_bounds=[0.001, 0.99], estimated_LocErr=None, estimated_Ds=None, estimated_Fs=None,
+                    estimated_transition_rates=0.1, slope_offsets_estimates=None):
+    """lmfit ``Parameters`` for an ``nb_states`` model (same names / bounds / exprs as tracking.py:1214-1290)."""
+    params = Parameters()
+    for s in range(nb_states):
+        v = 0.5 * s**2 * D_max / (nb_states - 1) ** 2 if estimated_Ds is None else estimated_Ds[s]
+        params.add("D" + str(s), value=v, min=0, max=D_max, vary=True)
+    geo = (LocErr_bounds[0] * LocErr_bounds[1]) ** 0.5
+    lo, hi = LocErr_bounds
+    if LocErr_type == 1:
+        params.add("LocErr", value=geo if estimated_LocErr is None else estimated_LocErr[0], min=lo, max=hi, vary=True)
+    elif LocErr_type == 2:
+        for d in range(nb_dims):
+            params.add("LocErr" + str(d), value=geo if estimated_LocErr is None else estimated_LocErr[d], min=lo, max=hi, vary=True)
+    elif LocErr_type == 3:
+        params.add("LocErr0", value=geo if estimated_LocErr is None else estimated_LocErr[0], min=lo, max=hi, vary=True)
+        params.add("LocErr1", expr="LocErr0")
+        params.add("LocErr2", value=geo if estimated_LocErr is None else estimated_LocErr[-1], min=lo, max=hi, vary=True)
+    if LocErr_type == 4:
+        params.add("slope_LocErr", value=slope_offsets_estimates[0], min=-1, max=20, vary=True)
+        params.add("offset_LocErr", value=slope_offsets_estimates[1], min=-1, max=1, vary=True)
+    F_expr = "1"
+    for s in range(nb_states - 1):
+        v = 1 / nb_states if estimated_Fs is None else estimated_Fs[s]
+        params.add("F" + str(s), value=v, min=Fractions_bounds[0], max=Fractions_bounds[1], vary=True)
+        F_expr += " - F" + str(s)
+    params.add("F" + str(nb_states - 1), expr=F_expr)
+    if not isinstance(estimated_transition_rates, (np.ndarray, list)):
+        estimated_transition_rates = [estimated_transition_rates] * (nb_states * (nb_states - 1))
+    idx = 0
+    for i in range(nb_states):
+        for j in range(nb_states):
+            if i != j:
+                params.add("p" + str(i) + str(j), value=estimated_transition_rates[idx], min=0.0001, max=1, vary=True)
+                idx += 1
+    params.add("pBL", value=0.1, min=0.0001, max=1, vary=True)
+    return params
+
+
+def get_params(nb_states=2, steady_state=False,
+               vary_params={"LocErr": True, "D0": True, "D1": True, "F0": True, "p01": True, "p10": True, "pBL": True},
+               estimated_vals={"LocErr": 0.025, "D0": 1e-20, "D1": 0.05, "F0": 0.45, "p01": 0.05, "p10": 0.05, "pBL": 0.1},
+               min_values={"LocErr": 0.007, "D0": 1e-12, "D1": 0.00001, "F0": 0.001, "p01": 0.01, "p10": 0.01, "pBL": 0.01},
+               max_values={"LocErr": 0.6, "D0": 1, "D1": 10, "F0": 0.999, "p01": 1.0, "p10": 1.0, "pBL": 0.99}):
+    """lmfit ``Parameters`` from dictionaries (generic live branch of tracking.py:1164-1212).
+
+    ``nb_states`` and ``steady_state`` are accepted and ignored, as in the reference.
+    """
+    params = Parameters()
+    keys = list(estimated_vals.keys())
+    if "slope_LocErr" in keys:
+        for n in ("slope_LocErr", "offset_LocErr"):
+            params.add(n, value=estimated_vals[n], min=min_values[n], max=max_values[n], vary=vary_params[n])
+    if "LocErr" in keys:
+        LocErr = estimated_vals["LocErr"]
+        if type(LocErr) == float:
+            params.add("LocErr", value=LocErr, min=min_values["LocErr"], max=max_values["LocErr"], vary=vary_params["LocErr"])
+        elif isinstance(LocErr, (np.ndarray, list)):
+            for s in range(len(LocErr)):
+                params.add("LocErr" + str(s), value=LocErr[s], min=min_values["LocErr"][s], max=max_values["LocErr"][s],
+                           vary=vary_params["LocErr"][s])
+    Dn = [k for k in vary_params if k.startswith("D")]
+    Fn = [k for k in vary_params if k.startswith("F")]
+    params.add("D0", value=estimated_vals["D0"], min=min_values["D0"], max=0.3, brute_step=0.04, vary=vary_params["D0"])
+    last_D, sum_Ds, expr = "D0", estimated_vals["D0"], "D0"
+    for D in Dn[1:]:
+        nm = D + "_minus_" + last_D
+        params.add(nm, value=estimated_vals[D] - sum_Ds, min=0, max=max_values[D], vary=vary_params[D])
+        expr = expr + "+" + nm
+        params.add(D, expr=expr)
+        last_D = D
+        sum_Ds += estimated_vals[D]
+    params.add("F0", value=estimated_vals["F0"], min=min_values["F0"], max=max_values["F0"], brute_step=0.04, vary=vary_params["F0"])
+    expr = "1-F0"
+    for F in Fn[1 : len(Dn) - 1]:
+        params.add(F, value=estimated_vals[F], min=0.001, max=0.99, vary=vary_params[F])
+        expr = expr + "-" + F
+    params.add("F" + str(len(Dn) - 1), expr=expr)
+    for k in vary_params:
+        if k.startswith("p"):
+            params.add(k, value=estimated_vals[k], min=min_values[k], max=max_values[k], vary=vary_params[k])
+    return params
+
+
+def param_fitting(all_tracks, dt, params=None, nb_states=2, nb_substeps=1, frame_len=6, verbose=1, workers=1,
+                  Matrix_type=1, method="bfgs", steady_state=False, cell_dims=[1], input_LocErr=None, threshold=0.2,
+                  max_nb_states=120):
+    """Maximum-likelihood fit of the model parameters; returns the lmfit result (tracking.py:1299-1386).
+
+    The tracks are packed and uploaded to the GPU once; every objective evaluation then runs
+    the plan / replay kernels on the resident data.
+    """
+    if params is None:
+        params = generate_params(nb_states=nb_states, LocErr_type=1, LocErr_bounds=[0.005, 0.1], D_max=3,
+                                 Fractions_bounds=[0.001, 0.99], estimated_transition_rates=0.1)
+    if input_LocErr is not None or isinstance(dt, dict):
+        extract_params(params, [] if isinstance(dt, dict) else dt, nb_states, nb_substeps, input_LocErr)  # raises
+    sorted_tracks, _ = _sorted_buckets(all_tracks)
+    if len(sorted_tracks) < 1:
+        raise ValueError("No track could be detected. The loaded tracks seem empty. Errors often come from wrong input paths.")
+    print("cell_dims", cell_dims)
+    ts = TrackSet(sorted_tracks, MAX_TRACKS_PER_CHUNK)
+    try:
+        fit = minimize(cum_Proba_Cs, params,
+                       args=(sorted_tracks, dt, cell_dims, input_LocErr, nb_states, nb_substeps, frame_len, verbose, workers,
+                             Matrix_type, threshold, max_nb_states),
+                       kws={"_trackset": ts}, method=method, nan_policy="propagate")
+    finally:
+        ts.close()
+    if verbose == 0:
+        print("")
+    return fit
+
+
+def get_2DSPT_params(all_tracks, dt, nb_substeps=1, nb_states=2, frame_len=8, verbose=1, workers=1, method="powell",
+                     steady_state=False, cell_dims=[1],
+                     vary_params={"LocErr": True, "D0": True, "D1": True, "F0": True, "p01": True, "p10": True, "pBL": True},
+                     estimated_vals={"LocErr": 0.025, "D0": 1e-20, "D1": 0.05, "F0": 0.45, "p01": 0.05, "p10": 0.05, "pBL": 0.1},
+                     min_values={"LocErr": 0.007, "D0": 1e-12, "D1": 0.00001, "F0": 0.001, "p01": 0.01, "p10": 0.01, "pBL": 0.01},
+                     max_values={"LocErr": 0.6, "D0": 1, "D1": 10, "F0": 0.999, "p01": 1.0, "p10": 1.0, "pBL": 0.99}):
+    """Legacy entry point (``old_tracking.py:585-674``) kept as a wrapper: builds the parameters
+    with ``get_params`` and runs ``param_fitting`` on the current likelihood engine."""
+    params = get_params(nb_states, steady_state, vary_params, estimated_vals, min_values, max_values)
+    return param_fitting(all_tracks, dt, params=params, nb_states=nb_states, nb_substeps=nb_substeps, frame_len=frame_len,
+                         verbose=verbose, workers=workers, method=method, steady_state=steady_state, cell_dims=cell_dims)

@@ -1,0 +1,142 @@
+/*
+ * xtrack.h — C ABI of the B200-native ExTrack track-likelihood engine (libxtrack_b200.so).
+ *
+ * The reference (ExTrack 1.6.3, pure Python) has no FFI layer; its "operator API" for this
+ * path is a set of Python call signatures in extrack/tracking.py.  Each entry point below
+ * names the reference interface it stands in for (file:line relative to the reference
+ * tree).  Plain pointers and sizes only; no torch / numpy types.  All functions return 0 on
+ * success or a negative XT_ERR_* code; xt_last_error() gives the message.
+ *
+ * Threading: one caller thread per context (the reference objective is called from one
+ * Python thread by lmfit, tracking.py:1371).  One context drives one GPU; multi-GPU runs
+ * use one process (and one context) per GPU, each holding a subset of the chunks.
+ */
+#ifndef XTRACK_H
+#define XTRACK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XT_MAX_HEADS 128 /* nS^(nb_substeps+1) */
+#define XT_MAX_STATES 8
+#define XT_MAX_DIMS 3
+
+#define XT_OK 0
+#define XT_ERR_CUDA (-1)      /* CUDA runtime failure */
+#define XT_ERR_ARG (-2)       /* malformed argument (maps to ValueError / TypeError in Python) */
+#define XT_ERR_GROUPING (-3)  /* a sequence ended ungrouped: tracking.py:700-701 ValueError */
+#define XT_ERR_CAPACITY (-4)  /* more live sequences than the engine's hard cap */
+#define XT_ERR_STATE (-5)     /* call order (e.g. evaluate before upload) */
+
+#define XT_FLAG_INT8_WRAP 1u /* reproduce the int8 wrap of history labels, tracking.py:543,619 */
+
+typedef struct xt_ctx xt_ctx;
+
+/*
+ * Per-evaluation model tables.  Built on the host exactly as the reference builds them
+ * (extract_params tracking.py:913-986; setup part of P_Cs_inter_bound_stats_th :474-524),
+ * including p_stay via scipy.stats.norm.cdf, so that erf parity is exact.
+ *
+ * head id h = r + K*parent_state with K = nS^nsub and r = child index mod K; digit k of r
+ * (base nS) is the state k sub-steps ago (digit 0 = newest), parent_state = newest state of
+ * the sequence before the expansion.
+ */
+typedef struct xt_params {
+  int32_t nS;            /* number of diffusive states (len(Ds), tracking.py:933-943) */
+  int32_t nsub;          /* nb_substeps */
+  int32_t d;             /* spatial dimensions of the uploaded tracks */
+  int32_t n_loc;         /* 1: one LocErr for all dims; d: one per dim (tracking.py:920-925) */
+  int32_t frame_len;     /* window length, tracking.py:679-681,714-715 */
+  int32_t min_len;       /* shortest bucket length: gates the stay term, tracking.py:565-568 */
+  int32_t max_nb_states; /* threshold escalation trigger, tracking.py:581-582 */
+  uint32_t flags;        /* XT_FLAG_* */
+  double threshold;      /* fusion threshold, tracking.py:689-691 */
+  double l2[XT_MAX_DIMS];          /* LocErr^2 per dim (first n_loc entries used), :457 */
+  double dd[XT_MAX_HEADS];         /* mean mid-sub-step displacement variance per head, :549-553 */
+  double LT[XT_MAX_HEADS];         /* sum of log transition probabilities per head, :555,:759-767 */
+  double LF[XT_MAX_HEADS];         /* log initial fraction of the oldest state of the head, :488 */
+  double Lp_stay[XT_MAX_HEADS];    /* log(p_stay*(1-pBL)) per r (first K entries), :524 */
+  double L_leave[XT_MAX_HEADS];    /* end-of-track leave term + LT per head, :630-631 */
+} xt_params;
+
+/* Work counters of the last evaluation (for seq-updates/s and the algorithmic flop count,
+ * SURVEY.md §8(d)). */
+typedef struct xt_stats {
+  int64_t n_tracks;
+  int64_t track_steps;   /* sum over tracks of (L-1) */
+  int64_t seq_updates;   /* sum over (chunk, step) of nT * nB_in */
+  int64_t seq_groups;    /* sum over (chunk, fused step) of nT * nG */
+  int32_t max_nB_in;     /* largest number of live sequences after an expansion */
+  int32_t n_chunks;
+  int32_t k1_launches;   /* kernels launched by the last evaluation */
+  int32_t k2_launches;
+  float ms_plan;         /* CUDA-event time of the plan kernel(s) */
+  float ms_replay;       /* CUDA-event time of the replay kernel(s) incl. the reduction */
+} xt_stats;
+
+/* Lifetime.  `device` is the CUDA ordinal this context drives. */
+int xt_create(int device, xt_ctx** out);
+void xt_destroy(xt_ctx* ctx);
+const char* xt_last_error(xt_ctx* ctx); /* ctx may be NULL: last creation error */
+
+/*
+ * Upload the tracks this context owns — replaces the per-call pickling of every chunk to the
+ * worker pool (tracking.py:1046-1063) with one upload per fit.  A *segment* s is `n[s]` tracks
+ * of `L[s]` localisations in `d` dims: xyz[s] points at a C-order double[n][L][d] host buffer (a
+ * whole length bucket, or a chunk-aligned slice of one when buckets are sharded over GPUs).
+ * The engine cuts each segment into chunks of `chunk_size` tracks exactly like
+ * `Css[n*nb_max:(n+1)*nb_max]` (tracking.py:1030-1036; 2000 for the fit, nb_max for
+ * predict_Bs :866-867); chunks are numbered in upload order.  isBL[s] = 0 for segments of the
+ * longest bucket (tracking.py:1037-1040).  Data are repacked on the device into a time-major
+ * struct-of-arrays layout [L][d][nT_pad] per chunk.  Host buffers are not retained.
+ */
+int xt_upload(xt_ctx* ctx, int32_t n_segments, const int32_t* L, const int64_t* n, const int32_t* isBL,
+              const double* const* xyz, int32_t d, int32_t chunk_size);
+
+/*
+ * Objective — replaces the body of cum_Proba_Cs (tracking.py:1058-1070): plan kernel, replay
+ * kernel, deterministic device reduction.  *out = sum over this context's tracks of log P
+ * (the caller negates / all-reduces; parameter guards :1017 stay on the host).
+ */
+int xt_sum_logp(xt_ctx* ctx, const xt_params* p, double* out);
+
+/* Same, but the result stays on the device: d_out is a device pointer to one double and the
+ * work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream) so a
+ * collective can be chained without a host round trip.  No synchronisation on return. */
+int xt_sum_logp_async(xt_ctx* ctx, const xt_params* p, double* d_out, void* cuda_stream);
+
+/* Test seam = Proba_Cs (tracking.py:769-787): log P per track of chunk `chunk` after the last
+ * xt_sum_logp call's parameters `p`.  out has nT[chunk] entries. */
+int xt_chunk_logp(xt_ctx* ctx, int32_t chunk, const xt_params* p, double* out);
+
+/* Test seam = instrumented fuse_tracks_th (tracking.py:652-701): grouping of fusion step
+ * `step` (2 <= step <= L-2, the reference's current_step) of chunk `chunk` from the last
+ * evaluation.  gid[c] = group of incoming sequence c.  Returns XT_ERR_ARG if cap < nB_in. */
+int xt_plan_dump(xt_ctx* ctx, int32_t chunk, int32_t step, int32_t* nB_in, int32_t* nG, int32_t* gid,
+                 int32_t cap, double* threshold_used);
+
+/*
+ * State annotation — replaces the chunk loop of predict_Bs (tracking.py:860-896) for the
+ * uploaded tracks (upload them with the caller's nb_max as chunk_size; default 1 track).
+ * out[s] receives double[n[s]][L[s]][nS] posteriors of segment s in forward time
+ * (tracking.py:641-649).
+ */
+int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out);
+
+int xt_get_stats(xt_ctx* ctx, xt_stats* out);
+
+/* Measured FP64 FMA throughput of this GPU in TFLOP/s (2 flops per DFMA), used as the
+ * compute-roofline denominator by bench.py. */
+int xt_fp64_peak_tflops(xt_ctx* ctx, double* out);
+
+/* Pinned host memory helpers for end-to-end timing with host buffers. */
+int xt_host_alloc(void** out, uint64_t bytes);
+int xt_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XTRACK_H */

@@ -1,0 +1,75 @@
+"""Ad-hoc GPU bring-up script (not a pytest): engine vs oracle on a handful of chunks, with timing.
+
+    python tests/gpu_quick.py
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from extrack_b200 import _native  # noqa: E402
+from helpers import engine_params, gid_from_groups, make_model, random_walk_tracks  # noqa: E402
+from oracle import extrack_oracle as orc  # noqa: E402
+
+
+def one(nS, nsub, d, fl, L, nT, isBL, seed=0, **kw):
+    rng = np.random.default_rng(seed)
+    model = make_model(nS=nS, nsub=nsub, frame_len=fl, **kw)
+    C = random_walk_tracks(nT, L, d, rng, Ds=(model.ds**2 / (2 * 0.02)))
+    plan = []
+    t = time.time()
+    ref = orc.chunk_logp(C, model, isBL, plan_out=plan)
+    t_or = time.time() - t
+    p = engine_params(model, d)
+    eng = _native.Engine(0)
+    eng.upload([C], [isBL], max(nT, 1))
+    t = time.time()
+    got = eng.chunk_logp(0, nT, p)
+    t_en = time.time() - t
+    err = np.max(np.abs(got - ref) / np.abs(ref))
+    mism = 0
+    for rec in plan:
+        nB, nG, gid, th = eng.plan_dump(0, rec["step"])
+        want = gid_from_groups(rec["groups"], rec["nB_in"])
+        if nB != rec["nB_in"] or nG != len(rec["groups"]) or not np.array_equal(gid, want):
+            mism += 1
+    st = eng.stats()
+    print(f"nS={nS} nsub={nsub} d={d} fl={fl} L={L} nT={nT} isBL={isBL} kw={kw}: relerr={err:.2e} sum_rel={abs(got.sum()-ref.sum())/abs(ref.sum()):.2e} "
+          f"plan_mismatch={mism}/{len(plan)} maxnB={st['max_nB_in']} oracle={t_or:.3f}s engine={t_en*1e3:.2f}ms (plan {st['ms_plan']:.3f} replay {st['ms_replay']:.3f})")
+    eng.close()
+    return err, mism
+
+
+if __name__ == "__main__":
+    bad = 0
+    for cfg in [
+        dict(nS=2, nsub=1, d=2, fl=8, L=20, nT=300, isBL=1),
+        dict(nS=2, nsub=1, d=2, fl=8, L=12, nT=25, isBL=0),
+        dict(nS=2, nsub=1, d=2, fl=4, L=3, nT=50, isBL=1),
+        dict(nS=2, nsub=1, d=2, fl=4, L=2, nT=50, isBL=1),
+        dict(nS=2, nsub=1, d=2, fl=4, L=4, nT=1, isBL=0),
+        dict(nS=2, nsub=1, d=2, fl=6, L=30, nT=2000, isBL=1),
+        dict(nS=3, nsub=2, d=2, fl=6, L=15, nT=100, isBL=1, max_nb_states=500),
+        dict(nS=3, nsub=1, d=3, fl=6, L=14, nT=100, isBL=0, max_nb_states=60),
+        dict(nS=3, nsub=1, d=3, fl=5, L=14, nT=100, isBL=1, loc_err=(0.02, 0.02, 0.03)),
+        dict(nS=2, nsub=1, d=2, fl=6, L=14, nT=100, isBL=1, min_len=10),
+        dict(nS=2, nsub=2, d=2, fl=6, L=14, nT=64, isBL=1),
+        dict(nS=4, nsub=1, d=2, fl=5, L=12, nT=64, isBL=1, max_nb_states=200),
+    ]:
+        try:
+            err, mism = one(**cfg)
+            if not (err < 1e-9) or mism:
+                bad += 1
+        except Exception as e:  # keep going: show every failure in one GPU call
+            import traceback
+
+            traceback.print_exc()
+            bad += 1
+    eng = _native.Engine(0)
+    print("fp64 peak TFLOP/s:", eng.fp64_peak_tflops())
+    print("FAILED" if bad else "ALL OK", bad)
+    sys.exit(1 if bad else 0)
