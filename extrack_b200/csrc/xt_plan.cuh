@@ -33,29 +33,61 @@ __device__ __forceinline__ int xt_label(int x, int nS, bool wrap) {
 // halving above) applied to f(k), k in [lo, lo+n).  Used where the reference reduces over a
 // contiguous axis (sum of weights, and the s2 merge when s2 has one component).
 template <typename F>
-__device__ double xt_pairwise(F f, int lo, int n) {
+__device__ __forceinline__ double xt_pairwise_block(F f, int lo, int n) {  // n <= 128
   if (n < 8) {
     double res = 0.0;
     for (int k = 0; k < n; ++k) res = __dadd_rn(res, f(lo + k));
     return res;
   }
-  if (n <= 128) {
-    double r[8];
+  double r[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = f(lo + k);
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
+  for (int k = 0; k < 8; ++k) r[k] = f(lo + k);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], f(lo + i + k));
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __dadd_rn(res, f(lo + i));
-    return res;
+    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], f(lo + i + k));
   }
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  return __dadd_rn(xt_pairwise(f, lo, n2), xt_pairwise(f, lo + n2, n - n2));
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, f(lo + i));
+  return res;
+}
+
+// The recursion "n > 128: split at n/2 rounded down to a multiple of 8" is unrolled into an
+// explicit post-order walk with a small value stack (depth <= log2(XT_HARD_CAP/128)+1), so no
+// device call stack is needed.
+template <typename F>
+__device__ double xt_pairwise(F f, int lo, int n) {
+  if (n <= 128) return xt_pairwise_block(f, lo, n);
+  int s_lo[8], s_n[8], s_state[8];
+  double s_val[8];
+  int sp = 0;
+  s_lo[0] = lo; s_n[0] = n; s_state[0] = 0;
+  double ret = 0.0;
+  while (sp >= 0) {
+    const int clo = s_lo[sp], cn = s_n[sp];
+    if (cn <= 128) {
+      ret = xt_pairwise_block(f, clo, cn);
+      --sp;
+      continue;
+    }
+    int n2 = cn / 2;
+    n2 -= n2 % 8;
+    if (s_state[sp] == 0) {          // descend into the left half
+      s_state[sp] = 1;
+      ++sp;
+      s_lo[sp] = clo; s_n[sp] = n2; s_state[sp] = 0;
+    } else if (s_state[sp] == 1) {   // left done -> keep it, descend into the right half
+      s_val[sp] = ret;
+      s_state[sp] = 2;
+      ++sp;
+      s_lo[sp] = clo + n2; s_n[sp] = cn - n2; s_state[sp] = 0;
+    } else {                         // both done
+      ret = __dadd_rn(s_val[sp], ret);
+      --sp;
+    }
+  }
+  return ret;
 }
 
 template <int D, int KS>

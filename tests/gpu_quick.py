@@ -71,5 +71,35 @@ if __name__ == "__main__":
             bad += 1
     eng = _native.Engine(0)
     print("fp64 peak TFLOP/s:", eng.fp64_peak_tflops())
+    eng.close()
+    # multi-bucket data set: objective vs oracle + repeated timing
+    from extrack_b200 import tracking as xt
+    from extrack_b200.simulate import sim_tracks
+
+    n_tracks = int(os.environ.get("QUICK_TRACKS", "100000"))
+    t = time.time()
+    tracks = sim_tracks(n_tracks, seed=0, device="cuda", max_track_len=30, min_track_len=10, LocErr=0.02, Ds=[0, 0.25],
+                        nb_dims=2, initial_fractions=[0.6, 0.4], TrMat=[[0.9, 0.1], [0.1, 0.9]], dt=0.02, pBL=0.05,
+                        cell_dims=[1, None, None])
+    print("generated", sum(len(v) for v in tracks.values()), "tracks in", round(time.time() - t, 2), "s")
+    sorted_tracks, _ = xt._sorted_buckets(tracks)
+    model = make_model(nS=2, nsub=1, frame_len=8, min_len=sorted_tracks[0].shape[1], Ds=[1e-5, 0.25], Fs=[0.6, 0.4])
+    p = engine_params(model, 2)
+    t = time.time()
+    ts = xt.TrackSet(sorted_tracks)
+    print("upload", round(time.time() - t, 3), "s; chunks", len(ts.chunks))
+    for it in range(5):
+        t = time.time()
+        v = ts.sum_logp(p)
+        dtm = time.time() - t
+        st = ts.engine.stats()
+        print(f"eval {it}: sum_logp={v!r} wall={dtm*1e3:.3f}ms plan={st['ms_plan']:.3f}ms replay={st['ms_replay']:.3f}ms "
+              f"track_steps={st['track_steps']} -> {st['track_steps']/dtm/1e9:.3f} G track-steps/s; seq_updates={st['seq_updates']} maxnB={st['max_nB_in']}")
+    if n_tracks <= 200000:
+        t = time.time()
+        ref = -orc.neg_log_likelihood(sorted_tracks, model, workers=8)
+        print("oracle", ref, "in", round(time.time() - t, 2), "s; rel err", abs(ref - v) / abs(ref))
+        if not abs(ref - v) / abs(ref) < 1e-9:
+            bad += 1
     print("FAILED" if bad else "ALL OK", bad)
     sys.exit(1 if bad else 0)
