@@ -3,8 +3,16 @@
 // (explicit round-to-nearest intrinsics, no FMA contraction) so that the discontinuous
 // `value < threshold` / `count/30 > 0.8` decisions see the same numbers as numpy does.
 //
-// One CTA per chunk.  lane = leader track, warps stride over sequences.  Leader-track state
-// lives in a per-chunk global scratch block that stays L1/L2 resident.
+// One CTA per chunk, several CTAs resident per SM (the kernel is latency-bound: the steps of a
+// chunk are strictly sequential).  lane = leader track; warps stride over parents / sequences /
+// candidate leaders.  Leader-track state lives in a per-chunk global scratch block that stays
+// L1/L2 resident.
+//
+// Grouping, two modes with identical results:
+//  * nC <= 64  : every warp evaluates the full row of one *candidate* leader (the next not yet
+//                grouped / not yet visited sequences in ascending order); one thread then resolves
+//                the candidates greedily in order on 64-bit masks and emits the CSR lists.
+//  * nC  > 64  : leaders are visited one at a time and the row is split over all warps.
 #pragma once
 #include "xt_common.cuh"
 
@@ -29,69 +37,9 @@ __device__ __forceinline__ int xt_label(int x, int nS, bool wrap) {
   return x % nS;
 }
 
-// numpy's pairwise summation (n < 8: plain loop; blocks of 8 accumulators up to 128; recursive
-// halving above) applied to f(k), k in [lo, lo+n).  Used where the reference reduces over a
-// contiguous axis (sum of weights, and the s2 merge when s2 has one component).
-template <typename F>
-__device__ __forceinline__ double xt_pairwise_block(F f, int lo, int n) {  // n <= 128
-  if (n < 8) {
-    double res = 0.0;
-    for (int k = 0; k < n; ++k) res = __dadd_rn(res, f(lo + k));
-    return res;
-  }
-  double r[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) r[k] = f(lo + k);
-  int i = 8;
-  for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], f(lo + i + k));
-  }
-  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __dadd_rn(res, f(lo + i));
-  return res;
-}
-
-// The recursion "n > 128: split at n/2 rounded down to a multiple of 8" is unrolled into an
-// explicit post-order walk with a small value stack (depth <= log2(XT_HARD_CAP/128)+1), so no
-// device call stack is needed.
-template <typename F>
-__device__ double xt_pairwise(F f, int lo, int n) {
-  if (n <= 128) return xt_pairwise_block(f, lo, n);
-  int s_lo[8], s_n[8], s_state[8];
-  double s_val[8];
-  int sp = 0;
-  s_lo[0] = lo; s_n[0] = n; s_state[0] = 0;
-  double ret = 0.0;
-  while (sp >= 0) {
-    const int clo = s_lo[sp], cn = s_n[sp];
-    if (cn <= 128) {
-      ret = xt_pairwise_block(f, clo, cn);
-      --sp;
-      continue;
-    }
-    int n2 = cn / 2;
-    n2 -= n2 % 8;
-    if (s_state[sp] == 0) {          // descend into the left half
-      s_state[sp] = 1;
-      ++sp;
-      s_lo[sp] = clo; s_n[sp] = n2; s_state[sp] = 0;
-    } else if (s_state[sp] == 1) {   // left done -> keep it, descend into the right half
-      s_val[sp] = ret;
-      s_state[sp] = 2;
-      ++sp;
-      s_lo[sp] = clo + n2; s_n[sp] = cn - n2; s_state[sp] = 0;
-    } else {                         // both done
-      ret = __dadd_rn(s_val[sp], ret);
-      --sp;
-    }
-  }
-  return ret;
-}
-
 template <int D, int KS>
-__global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
+__global__ void __launch_bounds__(XT_K1_THREADS, XT_K1_MIN_CTAS)
+k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
   constexpr int W = XT_K1_THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
@@ -109,7 +57,9 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
   int* grank = gid + cap;
   int* gcnt = grank + cap;            // [cap+1]: group sizes -> offsets
   unsigned char* curP = (unsigned char*)(gcnt + cap + 1);
-  __shared__ int s_flag;
+  __shared__ int s_flag, s_nG, s_off;
+  __shared__ unsigned long long s_grouped, s_visited, s_row[W];
+  __shared__ int s_cand[W];
 
   XtChunkSummary* sm = &a.summ[blockIdx.x];
   const int nP0 = K * nS;
@@ -141,6 +91,13 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
   const int t = act ? lane : 0;
   const double* Cp = a.soa + ck.xyz_off + t;
   const size_t npad = (size_t)ck.nTpad;
+  // smallest count with (double)count / (Kt*KS) > 0.8  (np.mean(bool) > 0.8, tracking.py:689-691)
+  int min_cnt = Kt * KS + 1;
+  {
+    const double denom = (double)(Kt * KS);
+    for (int c = Kt * KS; c >= 0; --c)
+      if (__ddiv_rn((double)c, denom) > 0.8) min_cnt = c;
+  }
 
   double* bufP = a.state + (size_t)blockIdx.x * 2 * cap * CO * 32;
   double* bufC = bufP + (size_t)cap * CO * 32;
@@ -199,17 +156,19 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
     const int rows_cmp = LhC < P.frame_len ? LhC : P.frame_len;  // rows kept in the window code
     const bool use_window = LhC > P.frame_len;
     const unsigned long long cmask = (bits * rows_cmp >= 64) ? ~0ull : ((1ull << (bits * rows_cmp)) - 1ull);
+    uint16_t* goff = a.plan.goff + (size_t)rec * (a.plan.cap + 1);
+    uint32_t* ent = a.plan.ent + (size_t)rec * a.plan.cap;
+    uint16_t* pgid = a.plan.gid + (size_t)rec * a.plan.cap;
 
-    // ---- expansion + Gaussian update on the leader tracks (tracking.py:540-570, :87-98) ----
+    // ---- expansion + Gaussian update on the leader tracks (tracking.py:540-570, :87-98);
+    //      one warp per parent, its K children share q, the new mean and the log term ----
     double cl[D];
 #pragma unroll
     for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((step - 1) * D + dim) * npad];
-    for (int c = warp; c < nC; c += W) {
-      const int p = c / K, r = c - p * K;
-      const int head = r + K * (int)curP[p];
-      const double dd = P.dd[head];
+    const bool stay = step >= P.min_len;
+    for (int p = warp; p < nP; p += W) {
       const double LPp = ST(bufP, p, D + 2 * KS);
-      double mm[D], s2[KS], q[KS];
+      double mm[D], s2[KS], q[KS], nm[D];
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) mm[dim] = ST(bufP, p, dim);
 #pragma unroll
@@ -224,9 +183,7 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
         const double df = __dsub_rn(cl[dim], mm[dim]);
         const double term = __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, q[k]));
         quad = (dim == 0) ? term : __dadd_rn(quad, term);
-        const double nm = __ddiv_rn(__dadd_rn(__dmul_rn(mm[dim], l2[k]), __dmul_rn(cl[dim], s2[k])),
-                                    __dadd_rn(l2[k], s2[k]));
-        ST(bufC, c, dim) = nm;
+        nm[dim] = __ddiv_rn(__dadd_rn(__dmul_rn(mm[dim], l2[k]), __dmul_rn(cl[dim], s2[k])), __dadd_rn(l2[k], s2[k]));
       }
       if (KS == 1) {
         logs = __dmul_rn((double)D * -0.5, log(__dmul_rn(XT_TWO_PI, q[0])));
@@ -237,17 +194,24 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
           logs = (k == 0) ? lg : __dadd_rn(logs, lg);
         }
       }
-#pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const double ns2 = __ddiv_rn(
-            __dadd_rn(__dadd_rn(__dmul_rn(dd, l2[k]), __dmul_rn(dd, s2[k])), __dmul_rn(l2[k], s2[k])), q[k]);
-        ST(bufC, c, D + k) = ns2;
-        ST(bufC, c, D + KS + k) = __dsqrt_rn(ns2);
-      }
       const double LC = __dsub_rn(logs, quad);
-      double add = __dadd_rn(P.LT[head], LC);
-      if (step >= P.min_len) add = __dadd_rn(add, P.Lp_stay[r]);
-      ST(bufC, c, D + 2 * KS) = __dadd_rn(LPp, add);
+      const int hbase = K * (int)curP[p];
+      for (int r = 0; r < K; ++r) {
+        const int c = p * K + r, head = r + hbase;
+        const double dd = P.dd[head];
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) ST(bufC, c, dim) = nm[dim];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const double ns2 = __ddiv_rn(
+              __dadd_rn(__dadd_rn(__dmul_rn(dd, l2[k]), __dmul_rn(dd, s2[k])), __dmul_rn(l2[k], s2[k])), q[k]);
+          ST(bufC, c, D + k) = ns2;
+          ST(bufC, c, D + KS + k) = __dsqrt_rn(ns2);
+        }
+        double add = __dadd_rn(P.LT[head], LC);
+        if (stay) add = __dadd_rn(add, P.Lp_stay[r]);
+        ST(bufC, c, D + 2 * KS) = __dadd_rn(LPp, add);
+      }
     }
     // window codes of the children: nsub new labels in front of the parent's rows
     for (int c = tid; c < nC; c += XT_K1_THREADS) {
@@ -261,95 +225,172 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
       codeC[c] = code & cmask;
       gid[c] = -1;
     }
+    if (tid == 0) {
+      s_grouped = 0ull;
+      s_visited = 0ull;
+      s_nG = 0;
+      s_off = 0;
+    }
     if (nC > P.max_nb_states) th = __dmul_rn(th, 1.2);  // sticky escalation, tracking.py:581-582
     __syncthreads();
 
-    // ---- greedy grouping (tracking.py:667-698) ----
-    int nG = 0;
-    const double denom = (double)(Kt * KS);
-    for (int i = 0; i < nC; ++i) {
-      if (gid[i] >= 0) continue;  // uniform
-      double mi[D], si[KS];
+    // predicate "leader i captures sequence j" (all lanes of the warp must call it together)
+    auto pair_ok = [&](const double (&mi)[D], const double (&si)[KS], unsigned long long ci, int j) -> bool {
+      const unsigned long long cj = codeC[j];
+      if (use_window && cj == ci) return true;             // state_mask, tracking.py:679-681
+      if ((cj & rowmask) != (ci & rowmask)) return false;  // cur_state_mask, :673-674
+      double am = 0.0, as = 0.0;
 #pragma unroll
-      for (int dim = 0; dim < D; ++dim) mi[dim] = ST(bufC, i, dim);
-#pragma unroll
-      for (int k = 0; k < KS; ++k) si[k] = ST(bufC, i, D + KS + k);
-      const unsigned long long ci = codeC[i];
-      for (int j = warp; j < nC; j += W) {
-        if (gid[j] >= 0) continue;  // warp-uniform
-        const unsigned long long cj = codeC[j];
-        double am = 0.0, as = 0.0;
-#pragma unroll
-        for (int dim = 0; dim < D; ++dim) {
-          const double v = fabs(__dsub_rn(ST(bufC, j, dim), mi[dim]));
-          am = (dim == 0) ? v : __dadd_rn(am, v);
-        }
-        am = __ddiv_rn(am, (double)D);
-        double sj[KS];
-#pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          sj[k] = ST(bufC, j, D + KS + k);
-          const double v = fabs(__dsub_rn(sj[k], si[k]));
-          as = (k == 0) ? v : __dadd_rn(as, v);
-        }
-        as = __ddiv_rn(as, (double)KS);
-        int cnt_m = 0, cnt_s = 0;
-#pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          cnt_m += __popc(__ballot_sync(0xffffffffu, act && (__ddiv_rn(am, sj[k]) < th)));
-          cnt_s += __popc(__ballot_sync(0xffffffffu, act && (__ddiv_rn(as, sj[k]) < th)));
-        }
-        const bool m_ok = __ddiv_rn((double)cnt_m, denom) > 0.8;
-        const bool s_ok = __ddiv_rn((double)cnt_s, denom) > 0.8;
-        const bool same_state = (cj & rowmask) == (ci & rowmask);
-        const bool same_win = use_window && (cj == ci);
-        if (((m_ok && s_ok && same_state) || same_win) && lane == 0) gid[j] = nG;
+      for (int dim = 0; dim < D; ++dim) {
+        const double v = fabs(__dsub_rn(ST(bufC, j, dim), mi[dim]));
+        am = (dim == 0) ? v : __dadd_rn(am, v);
       }
-      ++nG;
+      am = (D == 2) ? __dmul_rn(am, 0.5) : ((D == 1) ? am : __ddiv_rn(am, (double)D));
+      double sj[KS];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        sj[k] = ST(bufC, j, D + KS + k);
+        const double v = fabs(__dsub_rn(sj[k], si[k]));
+        as = (k == 0) ? v : __dadd_rn(as, v);
+      }
+      as = (KS == 2) ? __dmul_rn(as, 0.5) : ((KS == 1) ? as : __ddiv_rn(as, (double)KS));
+      int cnt_m = 0, cnt_s = 0;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        cnt_m += __popc(__ballot_sync(0xffffffffu, act && (__ddiv_rn(am, sj[k]) < th)));
+        cnt_s += __popc(__ballot_sync(0xffffffffu, act && (__ddiv_rn(as, sj[k]) < th)));
+      }
+      return cnt_m >= min_cnt && cnt_s >= min_cnt;
+    };
+
+    int nG = 0;
+    if (nC <= 64) {
+      // ---- batch mode ----
+      const unsigned long long full = (nC == 64) ? ~0ull : ((1ull << nC) - 1ull);
+      for (;;) {
+        const unsigned long long grouped = s_grouped;
+        unsigned long long candset = full & ~grouped & ~s_visited;
+        if (candset == 0ull) break;  // uniform
+        unsigned long long r = candset;
+        for (int k = 0; k < warp; ++k) r &= r - 1ull;
+        const int cand = r ? (__ffsll((long long)r) - 1) : -1;
+        unsigned long long row = 0ull;
+        if (cand >= 0) {
+          double mi[D], si[KS];
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) mi[dim] = ST(bufC, cand, dim);
+#pragma unroll
+          for (int k = 0; k < KS; ++k) si[k] = ST(bufC, cand, D + KS + k);
+          const unsigned long long ci = codeC[cand];
+          unsigned long long todo = full & ~grouped;
+          while (todo) {
+            const int j = __ffsll((long long)todo) - 1;
+            todo &= todo - 1ull;
+            if (pair_ok(mi, si, ci, j)) row |= 1ull << j;
+          }
+        }
+        if (lane == 0) {
+          s_row[warp] = row;
+          s_cand[warp] = cand;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          unsigned long long g = s_grouped, vis = s_visited;
+          int ng = s_nG, off = s_off;
+          for (int w = 0; w < W; ++w) {
+            const int c = s_cand[w];
+            if (c < 0) break;
+            if ((g >> c) & 1ull) continue;  // captured by an earlier leader of this batch
+            vis |= 1ull << c;
+            unsigned long long mem = s_row[w] & ~g;
+            if (mem == 0ull) {  // empty group: the reference fails on the zero-size max (:725)
+              s_flag = 1;
+              continue;
+            }
+            g |= mem;
+            gcnt[ng] = off;
+            while (mem) {
+              const int j = __ffsll((long long)mem) - 1;
+              mem &= mem - 1ull;
+              gid[j] = ng;
+              const int p = j / K, rr = j - p * K;
+              ent[off++] = xt_pack_ent(p, rr + K * (int)curP[p], rr);
+            }
+            ++ng;
+          }
+          gcnt[ng] = off;
+          s_grouped = g;
+          s_visited = vis;
+          s_nG = ng;
+          s_off = off;
+        }
+        __syncthreads();
+      }
+      nG = s_nG;
+      if (tid == 0 && s_grouped != full) s_flag = 1;  // tracking.py:700-701
+      for (int c = tid; c < nC; c += XT_K1_THREADS) pgid[c] = (uint16_t)gid[c];
+      for (int g = tid; g <= nG; g += XT_K1_THREADS) goff[g] = (uint16_t)gcnt[g];
       __syncthreads();
-    }
-    // every sequence must have been grouped (tracking.py:700-701)
-    for (int c = tid; c < nC; c += XT_K1_THREADS)
-      if (gid[c] < 0) s_flag = 1;
-    for (int g = tid; g <= nC; g += XT_K1_THREADS) gcnt[g] = 0;
-    __syncthreads();
-    if (s_flag) {
-      if (tid == 0) sm->err = 1;
-      return;
-    }
-    // ---- CSR member lists: rank inside the group (ascending child id), sizes, offsets ----
-    for (int c = tid; c < nC; c += XT_K1_THREADS) {
-      const int g = gid[c];
-      int rk = 0;
-      for (int c2 = 0; c2 < c; ++c2) rk += (gid[c2] == g);
-      grank[c] = rk;
-      atomicAdd(&gcnt[g + 1], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int g = 0; g < nG; ++g) gcnt[g + 1] += gcnt[g];
-    }
-    __syncthreads();
-    {
-      uint16_t* goff = a.plan.goff + (size_t)rec * (a.plan.cap + 1);
-      uint32_t* ent = a.plan.ent + (size_t)rec * a.plan.cap;
-      uint16_t* pg = a.plan.gid + (size_t)rec * a.plan.cap;
+      if (s_flag) {
+        if (tid == 0) sm->err = 1;
+        return;
+      }
+    } else {
+      // ---- split mode ----
+      for (int i = 0; i < nC; ++i) {
+        if (gid[i] >= 0) continue;  // uniform
+        double mi[D], si[KS];
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) mi[dim] = ST(bufC, i, dim);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) si[k] = ST(bufC, i, D + KS + k);
+        const unsigned long long ci = codeC[i];
+        for (int j = warp; j < nC; j += W) {
+          if (gid[j] >= 0) continue;  // warp-uniform
+          if (pair_ok(mi, si, ci, j) && lane == 0) gid[j] = nG;
+        }
+        ++nG;
+        __syncthreads();
+      }
+      // every sequence must have been grouped (tracking.py:700-701)
+      for (int c = tid; c < nC; c += XT_K1_THREADS)
+        if (gid[c] < 0) s_flag = 1;
+      for (int g = tid; g <= nC; g += XT_K1_THREADS) gcnt[g] = 0;
+      __syncthreads();
+      if (s_flag) {
+        if (tid == 0) sm->err = 1;
+        return;
+      }
+      // CSR member lists: rank inside the group (ascending child id), sizes, offsets
+      for (int c = tid; c < nC; c += XT_K1_THREADS) {
+        const int g = gid[c];
+        int rk = 0;
+        for (int c2 = 0; c2 < c; ++c2) rk += (gid[c2] == g);
+        grank[c] = rk;
+        atomicAdd(&gcnt[g + 1], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int g = 0; g < nG; ++g) gcnt[g + 1] += gcnt[g];
+      }
+      __syncthreads();
       for (int g = tid; g <= nG; g += XT_K1_THREADS) goff[g] = (uint16_t)gcnt[g];
       for (int c = tid; c < nC; c += XT_K1_THREADS) {
         const int p = c / K, r = c - p * K;
         ent[gcnt[gid[c]] + grank[c]] = xt_pack_ent(p, r + K * (int)curP[p], r);
-        pg[c] = (uint16_t)gid[c];
+        pgid[c] = (uint16_t)gid[c];
       }
-      if (tid == 0) {
-        a.plan.hdr[rec].nC = nC;
-        a.plan.hdr[rec].nG = nG;
-        a.plan.hdr[rec].th = th;
-      }
+      __syncthreads();  // ent visible to the CTA (read back below through global memory)
     }
-    __syncthreads();  // ent visible to the CTA (read back below through global memory)
-    const uint32_t* ent = a.plan.ent + (size_t)rec * a.plan.cap;
+    if (tid == 0) {
+      a.plan.hdr[rec].nC = nC;
+      a.plan.hdr[rec].nG = nG;
+      a.plan.hdr[rec].th = th;
+    }
 
-    // ---- merge on the leader tracks (tracking.py:723-741), reference summation orders ----
+    // ---- merge on the leader tracks (tracking.py:723-741) ----
+    // `LP[:, subgroup]` is an F-ordered fancy-index copy in numpy, so every reduction over the
+    // members runs sequentially in ascending member order (checked against numpy 2.3).
     for (int g = warp; g < nG; g += W) {
       const int o = gcnt[g], n = gcnt[g + 1] - o;
       if (n == 1) {
@@ -361,41 +402,30 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
       auto child = [&](int k) { return (int)(ent[o + k] & 0xFFFF) * K + (int)(ent[o + k] >> 24); };
       double mx = ST(bufC, child(0), D + 2 * KS);
       for (int k = 1; k < n; ++k) mx = fmax(mx, ST(bufC, child(k), D + 2 * KS));
-      auto wfun = [&](int k) { return exp(__dsub_rn(ST(bufC, child(k), D + 2 * KS), mx)); };
-      const double sw = xt_pairwise(wfun, 0, n);
-      double am[D];
+      double sw = 0.0, am[D], as2[KS];
+      for (int k = 0; k < n; ++k) {
+        const int c = child(k);
+        const double w = exp(__dsub_rn(ST(bufC, c, D + 2 * KS), mx));
+        sw = (k == 0) ? w : __dadd_rn(sw, w);
 #pragma unroll
-      for (int dim = 0; dim < D; ++dim) {
-        if (D == 1) {
-          am[dim] = xt_pairwise([&](int k) { return __dmul_rn(wfun(k), ST(bufC, child(k), dim)); }, 0, n);
-        } else {
-          double acc = 0.0;
-          for (int k = 0; k < n; ++k) {
-            const double v = __dmul_rn(wfun(k), ST(bufC, child(k), dim));
-            acc = (k == 0) ? v : __dadd_rn(acc, v);
-          }
-          am[dim] = acc;
+        for (int dim = 0; dim < D; ++dim) {
+          const double v = __dmul_rn(w, ST(bufC, c, dim));
+          am[dim] = (k == 0) ? v : __dadd_rn(am[dim], v);
         }
-        ST(bufP, g, dim) = __ddiv_rn(am[dim], sw);
+#pragma unroll
+        for (int k2 = 0; k2 < KS; ++k2) {
+          const double v = __dmul_rn(w, ST(bufC, c, D + k2));
+          as2[k2] = (k == 0) ? v : __dadd_rn(as2[k2], v);
+        }
       }
 #pragma unroll
-      for (int k2 = 0; k2 < KS; ++k2) {
-        double acc;
-        if (KS == 1) {
-          acc = xt_pairwise([&](int k) { return __dmul_rn(wfun(k), ST(bufC, child(k), D + k2)); }, 0, n);
-        } else {
-          acc = 0.0;
-          for (int k = 0; k < n; ++k) {
-            const double v = __dmul_rn(wfun(k), ST(bufC, child(k), D + k2));
-            acc = (k == 0) ? v : __dadd_rn(acc, v);
-          }
-        }
-        ST(bufP, g, D + k2) = __ddiv_rn(acc, sw);
-      }
+      for (int dim = 0; dim < D; ++dim) ST(bufP, g, dim) = __ddiv_rn(am[dim], sw);
+#pragma unroll
+      for (int k2 = 0; k2 < KS; ++k2) ST(bufP, g, D + k2) = __ddiv_rn(as2[k2], sw);
       ST(bufP, g, D + 2 * KS) = __dadd_rn(log(sw), mx);
     }
     // ---- history rows of the groups (fit mode: mean one-hot over members and leader tracks,
-    //      tracking.py:714-715,735-737), accumulated in numpy's (track, member) order ----
+    //      tracking.py:714-715,735-737), accumulated in numpy's (member, track) order ----
     const int rows_out = rows_cmp;  // truncated to frame_len
     const int Kh = hist_dim0_is_nT ? Kt : 1;
     for (int idx = tid; idx < nG * rows_out * nS; idx += XT_K1_THREADS) {
@@ -417,11 +447,13 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
       } else {
         double acc = 0.0;
         bool first = true;
-        for (int tt = 0; tt < Kh; ++tt)
-          for (int k = 0; k < n; ++k) {
-            acc = first ? val(k) : __dadd_rn(acc, val(k));
+        for (int k = 0; k < n; ++k) {  // numpy order for the fancy-indexed copy: member outer, track inner
+          const double v = val(k);
+          for (int tt = 0; tt < Kh; ++tt) {
+            acc = first ? v : __dadd_rn(acc, v);
             first = false;
           }
+        }
         out = __ddiv_rn(acc, (double)(Kh * n));
       }
       histN[((size_t)g * a.RH + row) * nS + s] = out;
@@ -444,9 +476,9 @@ __global__ void __launch_bounds__(XT_K1_THREADS) k1_plan(const K1Args a, const _
           }
           code |= (unsigned long long)best << (bits * row);
         }
-        // publish after all reads of curP/codeP of this step are done (next barrier)
+        // published after all reads of curP/codeP of this step are done (next barrier)
         grank[g] = (int)cs;
-        ((unsigned long long*)codeC)[g] = code;  // codeC is dead until the next expansion
+        codeC[g] = code;  // codeC is dead until the next expansion
         pcur[g] = cs;
       }
     }

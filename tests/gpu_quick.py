@@ -46,7 +46,7 @@ def one(nS, nsub, d, fl, L, nT, isBL, seed=0, **kw):
 
 if __name__ == "__main__":
     bad = 0
-    for cfg in [
+    cfgs = [] if os.environ.get("QUICK_SKIP") else [
         dict(nS=2, nsub=1, d=2, fl=8, L=20, nT=300, isBL=1),
         dict(nS=2, nsub=1, d=2, fl=8, L=12, nT=25, isBL=0),
         dict(nS=2, nsub=1, d=2, fl=4, L=3, nT=50, isBL=1),
@@ -59,7 +59,10 @@ if __name__ == "__main__":
         dict(nS=2, nsub=1, d=2, fl=6, L=14, nT=100, isBL=1, min_len=10),
         dict(nS=2, nsub=2, d=2, fl=6, L=14, nT=64, isBL=1),
         dict(nS=4, nsub=1, d=2, fl=5, L=12, nT=64, isBL=1, max_nb_states=200),
-    ]:
+        dict(nS=3, nsub=2, d=2, fl=6, L=15, nT=100, isBL=1, max_nb_states=500, int8_wrap=False),
+        dict(nS=3, nsub=2, d=3, fl=4, L=12, nT=40, isBL=0, max_nb_states=120),
+    ]
+    for cfg in cfgs:
         try:
             err, mism = one(**cfg)
             if not (err < 1e-9) or mism:
