@@ -70,6 +70,7 @@ EXPORTS = (
     "xt_plan_dump",
     "xt_predict",
     "xt_get_stats",
+    "xt_set_option",
     "xt_fp64_peak_tflops",
     "xt_host_alloc",
     "xt_host_free",
@@ -103,6 +104,7 @@ def load_library() -> C.CDLL:
     lib.xt_plan_dump.argtypes = [vp, i32, i32, P(i32), P(i32), P(i32), i32, P(dbl)]
     lib.xt_predict.argtypes = [vp, P(XtParams), P(vp)]
     lib.xt_get_stats.argtypes = [vp, P(XtStats)]
+    lib.xt_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     lib.xt_fp64_peak_tflops.argtypes = [vp, P(dbl)]
     lib.xt_host_alloc.argtypes = [P(vp), C.c_uint64]
     lib.xt_host_free.argtypes = [vp]
@@ -211,6 +213,9 @@ class Engine:
         st = XtStats()
         self._check(self._lib.xt_get_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in XtStats._fields_}
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.xt_set_option(self._h, name.encode(), int(value)))
 
     def fp64_peak_tflops(self) -> float:
         out = C.c_double()

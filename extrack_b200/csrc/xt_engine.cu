@@ -10,6 +10,7 @@
 #include "xt_common.cuh"
 #include "xt_plan.cuh"
 #include "xt_replay.cuh"
+#include "xt_replay_lin.cuh"
 #include "xt_predict.cuh"
 
 struct xt_ctx {
@@ -43,6 +44,7 @@ struct xt_ctx {
   size_t gstate_bytes = 0;
   int smem_optin = 0, n_sm = 0;
   bool have_eval = false;
+  bool force_global = false;  // test hook: run the log-domain global-memory replay variant
   xt_params last_p{};
   xt_stats stats{};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -295,13 +297,16 @@ static cudaError_t launch_k1(xt_ctx* ctx, const K1Args& a, const xt_params& p, s
   return cudaGetLastError();
 }
 
+#define XT_K2_WPC 4  // warps cooperating on one 32-track tile in the fast replay kernel
+
 template <int D, int KS>
-static cudaError_t launch_k2(xt_ctx* ctx, const K2Args& a, const xt_params& p, size_t smem, bool use_smem, int grid) {
+static cudaError_t launch_k2(xt_ctx* ctx, const K2Args& a, const xt_params& p, const K2Lin& lin, size_t smem,
+                             bool use_smem, int grid) {
   if (use_smem) {
-    auto kern = k2_replay<D, KS, true>;
+    auto kern = k2_replay_lin<D, KS, XT_K2_WPC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 32, smem, ctx->stream>>>(a, p);
+    kern<<<grid, 32 * XT_K2_WPC, smem, ctx->stream>>>(a, p, lin);
   } else {
     k2_replay<D, KS, false><<<grid, 32, 0, ctx->stream>>>(a, p);
   }
@@ -415,12 +420,21 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
     for (int r = 0; r < K; ++r) acc += std::exp(p->L_leave[r + K * s] - mx);
     a.Lsum[s] = std::log(acc) + mx;
   }
-  const size_t smem = (size_t)2 * Pmax * CO * 32 * sizeof(double);
-  const bool use_smem = smem <= (size_t)ctx->smem_optin;
+  // linear-domain tables of the fast replay kernel
+  K2Lin lin{};
+  for (int h = 0; h < K * p->nS; ++h) {
+    lin.winit[h] = std::exp(p->LT[h] + p->LF[h]);
+    lin.tau0[h] = std::exp(p->LT[h]);
+    lin.tau1[h] = std::exp(p->LT[h] + p->Lp_stay[h % K]);
+  }
+  for (int s = 0; s < p->nS; ++s) lin.leave[s] = std::exp(a.Lsum[s]);
+  const size_t state_bytes = (size_t)2 * Pmax * CO * 32 * sizeof(double);
+  const size_t smem = state_bytes + (size_t)2 * XT_K2_WPC * 32 * sizeof(double);
+  const bool use_smem = smem <= (size_t)ctx->smem_optin && !ctx->force_global;
   int grid = a.n_work;
   if (!use_smem) {
     grid = std::min(a.n_work, ctx->n_sm * 16);
-    const size_t need = (size_t)grid * smem;
+    const size_t need = (size_t)grid * state_bytes;
     if (need > ctx->gstate_bytes) {
       cudaFree(ctx->d_gstate);
       ctx->d_gstate = nullptr;
@@ -431,7 +445,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
     a.gstate = ctx->d_gstate;
   }
   cudaError_t e = cudaSuccess;
-#define CALL_K2(D_, KS_) e = launch_k2<D_, KS_>(ctx, a, *p, smem, use_smem, grid)
+#define CALL_K2(D_, KS_) e = launch_k2<D_, KS_>(ctx, a, *p, lin, smem, use_smem, grid)
   XT_DISPATCH(p->d, p->n_loc, CALL_K2);
 #undef CALL_K2
   XT_CUDA_OK(e);
@@ -466,6 +480,17 @@ extern "C" int xt_sum_logp_async(xt_ctx* ctx, const xt_params* p, double* d_out,
   if (rc) return rc;
   if (cuda_stream) XT_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->ev[2], 0));
   return XT_OK;
+}
+
+extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return XT_ERR_ARG;
+  if (std::strcmp(name, "force_global_replay") == 0) {
+    ctx->force_global = value != 0;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  set_error(ctx, std::string("xt_set_option: unknown option ") + name);
+  return XT_ERR_ARG;
 }
 
 extern "C" int xt_get_stats(xt_ctx* ctx, xt_stats* out) {

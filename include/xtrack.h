@@ -128,6 +128,11 @@ int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out);
 
 int xt_get_stats(xt_ctx* ctx, xt_stats* out);
 
+/* Engine options (tests / diagnostics).  "force_global_replay" = 1 runs the log-domain replay
+ * kernel with its state in global memory (the path taken when the live sequences of a track do
+ * not fit in shared memory) instead of the shared-memory linear-domain kernel. */
+int xt_set_option(xt_ctx* ctx, const char* name, int value);
+
 /* Measured FP64 FMA throughput of this GPU in TFLOP/s (2 flops per DFMA), used as the
  * compute-roofline denominator by bench.py. */
 int xt_fp64_peak_tflops(xt_ctx* ctx, double* out);

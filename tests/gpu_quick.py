@@ -31,6 +31,11 @@ def one(nS, nsub, d, fl, L, nT, isBL, seed=0, **kw):
     got = eng.chunk_logp(0, nT, p)
     t_en = time.time() - t
     err = np.max(np.abs(got - ref) / np.abs(ref))
+    eng.set_option("force_global_replay", 1)
+    got2 = eng.chunk_logp(0, nT, p)
+    err = max(err, np.max(np.abs(got2 - ref) / np.abs(ref)))
+    eng.set_option("force_global_replay", 0)
+    eng.chunk_logp(0, nT, p)
     mism = 0
     for rec in plan:
         nB, nG, gid, th = eng.plan_dump(0, rec["step"])
