@@ -53,6 +53,7 @@ struct XtPlanPtrs {
   uint32_t* ent;     // [nrec_total][cap]   members sorted by group, ascending child id inside a group
   uint8_t* curG;     // [nrec_total][cap]   newest true state of each group's representative
   uint16_t* gid;     // [nrec_total][cap]   group of each incoming child (dump / tests)
+  unsigned long long* grec;  // [nrec_total][cap] per group: p0:16|head0:8|n:8 | (p1:16|head1:8)<<32, n capped at 255
   int32_t cap;
 };
 

@@ -84,7 +84,7 @@ __global__ void k_fp64_peak(double* out, int iters) {
 
 static void free_plan(xt_ctx* ctx) {
   cudaFree(ctx->plan.hdr); cudaFree(ctx->plan.goff); cudaFree(ctx->plan.ent);
-  cudaFree(ctx->plan.curG); cudaFree(ctx->plan.gid);
+  cudaFree(ctx->plan.curG); cudaFree(ctx->plan.gid); cudaFree(ctx->plan.grec);
   cudaFree(ctx->d_state1); cudaFree(ctx->d_hist1);
   ctx->plan = XtPlanPtrs{};
   ctx->d_state1 = ctx->d_hist1 = nullptr;
@@ -278,6 +278,7 @@ static int ensure_plan(xt_ctx* ctx, const xt_params* p, int cap) {
   XT_CUDA_OK(cudaMalloc(&ctx->plan.ent, sizeof(uint32_t) * nrec * cap));
   XT_CUDA_OK(cudaMalloc(&ctx->plan.curG, sizeof(uint8_t) * nrec * cap));
   XT_CUDA_OK(cudaMalloc(&ctx->plan.gid, sizeof(uint16_t) * nrec * cap));
+  XT_CUDA_OK(cudaMalloc(&ctx->plan.grec, sizeof(unsigned long long) * nrec * cap));
   ctx->plan.cap = cap;
   XT_CUDA_OK(cudaMalloc(&ctx->d_state1, sizeof(double) * nch * 2 * cap * CO1 * 32));
   XT_CUDA_OK(cudaMalloc(&ctx->d_hist1, sizeof(double) * nch * 2 * cap * RH * p->nS));

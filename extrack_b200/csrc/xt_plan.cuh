@@ -57,9 +57,9 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   int* grank = gid + cap;
   int* gcnt = grank + cap;            // [cap+1]: group sizes -> offsets
   unsigned char* curP = (unsigned char*)(gcnt + cap + 1);
-  __shared__ int s_flag, s_nG, s_off;
-  __shared__ unsigned long long s_grouped, s_visited, s_row[W];
-  __shared__ int s_cand[W];
+  __shared__ int s_flag;
+  __shared__ unsigned long long s_row[2 * W];
+  __shared__ int s_cand[2 * W];
 
   XtChunkSummary* sm = &a.summ[blockIdx.x];
   const int nP0 = K * nS;
@@ -225,15 +225,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       codeC[c] = code & cmask;
       gid[c] = -1;
     }
-    if (tid == 0) {
-      s_grouped = 0ull;
-      s_visited = 0ull;
-      s_nG = 0;
-      s_off = 0;
-    }
     if (nC > P.max_nb_states) th = __dmul_rn(th, 1.2);  // sticky escalation, tracking.py:581-582
     __syncthreads();
 
+    const double th_lo = __dmul_rn(th, 1.0 - 1e-14), th_hi = __dmul_rn(th, 1.0 + 1e-14);
     // predicate "leader i captures sequence j" (all lanes of the warp must call it together)
     auto pair_ok = [&](const double (&mi)[D], const double (&si)[KS], unsigned long long ci, int j) -> bool {
       const unsigned long long cj = codeC[j];
@@ -257,8 +252,13 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       int cnt_m = 0, cnt_s = 0;
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
-        cnt_m += __popc(__ballot_sync(0xffffffffu, act && (__ddiv_rn(am, sj[k]) < th)));
-        cnt_s += __popc(__ballot_sync(0xffffffffu, act && (__ddiv_rn(as, sj[k]) < th)));
+        // fl(x / s) < th decided without a division unless x is within 1e-14 (relative) of th*s
+        const double lo = __dmul_rn(th_lo, sj[k]), hi = __dmul_rn(th_hi, sj[k]);
+        bool pm = am < lo, ps = as < lo;
+        if (!pm && !(am > hi)) pm = __ddiv_rn(am, sj[k]) < th;
+        if (!ps && !(as > hi)) ps = __ddiv_rn(as, sj[k]) < th;
+        cnt_m += __popc(__ballot_sync(0xffffffffu, act && pm));
+        cnt_s += __popc(__ballot_sync(0xffffffffu, act && ps));
       }
       return cnt_m >= min_cnt && cnt_s >= min_cnt;
     };
@@ -266,10 +266,14 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     int nG = 0;
     if (nC <= 64) {
       // ---- batch mode ----
+      // grouped / visited / nG / CSR offset are kept redundantly in registers by every thread
+      // (the resolution below is deterministic), so a batch needs a single barrier.
       const unsigned long long full = (nC == 64) ? ~0ull : ((1ull << nC) - 1ull);
-      for (;;) {
-        const unsigned long long grouped = s_grouped;
-        unsigned long long candset = full & ~grouped & ~s_visited;
+      unsigned long long grouped = 0ull, visited = 0ull;
+      int off = 0, batch = 0;
+      bool bad = false;
+      for (;; ++batch) {
+        const unsigned long long candset = full & ~grouped & ~visited;
         if (candset == 0ull) break;  // uniform
         unsigned long long r = candset;
         for (int k = 0; k < warp; ++k) r &= r - 1ull;
@@ -283,54 +287,55 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
           for (int k = 0; k < KS; ++k) si[k] = ST(bufC, cand, D + KS + k);
           const unsigned long long ci = codeC[cand];
           unsigned long long todo = full & ~grouped;
+          // sequences below the candidate are already grouped unless an earlier leader failed
+          if ((visited & ~grouped) == 0ull) todo &= ~((1ull << cand) - 1ull);
           while (todo) {
             const int j = __ffsll((long long)todo) - 1;
             todo &= todo - 1ull;
             if (pair_ok(mi, si, ci, j)) row |= 1ull << j;
           }
         }
+        unsigned long long* b_row = s_row + (batch & 1) * W;
+        int* b_cand = s_cand + (batch & 1) * W;
         if (lane == 0) {
-          s_row[warp] = row;
-          s_cand[warp] = cand;
+          b_row[warp] = row;
+          b_cand[warp] = cand;
         }
         __syncthreads();
-        if (tid == 0) {
-          unsigned long long g = s_grouped, vis = s_visited;
-          int ng = s_nG, off = s_off;
-          for (int w = 0; w < W; ++w) {
-            const int c = s_cand[w];
-            if (c < 0) break;
-            if ((g >> c) & 1ull) continue;  // captured by an earlier leader of this batch
-            vis |= 1ull << c;
-            unsigned long long mem = s_row[w] & ~g;
-            if (mem == 0ull) {  // empty group: the reference fails on the zero-size max (:725)
-              s_flag = 1;
-              continue;
-            }
-            g |= mem;
-            gcnt[ng] = off;
+        // greedy resolution of the candidates in ascending order (tracking.py:667-698)
+#pragma unroll
+        for (int wq = 0; wq < W; ++wq) {
+          const int c = b_cand[wq];
+          if (c < 0) break;
+          if ((grouped >> c) & 1ull) continue;  // captured by an earlier leader of this batch
+          visited |= 1ull << c;
+          unsigned long long mem = b_row[wq] & ~grouped;
+          if (mem == 0ull) {  // empty group: the reference fails on the zero-size max (:725)
+            bad = true;
+            continue;
+          }
+          const int nmem = __popcll(mem);
+          grouped |= mem;
+          if (tid == wq) {  // one thread per accepted leader writes its member list
+            gcnt[nG] = off;
+            int o = off;
             while (mem) {
               const int j = __ffsll((long long)mem) - 1;
               mem &= mem - 1ull;
-              gid[j] = ng;
+              gid[j] = nG;
               const int p = j / K, rr = j - p * K;
-              ent[off++] = xt_pack_ent(p, rr + K * (int)curP[p], rr);
+              ent[o++] = xt_pack_ent(p, rr + K * (int)curP[p], rr);
             }
-            ++ng;
           }
-          gcnt[ng] = off;
-          s_grouped = g;
-          s_visited = vis;
-          s_nG = ng;
-          s_off = off;
+          off += nmem;
+          ++nG;
         }
-        __syncthreads();
       }
-      nG = s_nG;
-      if (tid == 0 && s_grouped != full) s_flag = 1;  // tracking.py:700-701
+      if (tid == 0) gcnt[nG] = off;
+      if (bad || grouped != full) s_flag = 1;  // tracking.py:700-701
+      __syncthreads();
       for (int c = tid; c < nC; c += XT_K1_THREADS) pgid[c] = (uint16_t)gid[c];
       for (int g = tid; g <= nG; g += XT_K1_THREADS) goff[g] = (uint16_t)gcnt[g];
-      __syncthreads();
       if (s_flag) {
         if (tid == 0) sm->err = 1;
         return;
@@ -386,6 +391,14 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       a.plan.hdr[rec].nC = nC;
       a.plan.hdr[rec].nG = nG;
       a.plan.hdr[rec].th = th;
+    }
+    {  // inline group records for the replay kernel: first two members + size in one 64-bit word
+      unsigned long long* grec = a.plan.grec + (size_t)rec * a.plan.cap;
+      for (int g = tid; g < nG; g += XT_K1_THREADS) {
+        const int o = gcnt[g], n = gcnt[g + 1] - o;
+        const unsigned long long e0 = ent[o], e1 = (n > 1) ? ent[o + 1] : 0u;
+        grec[g] = (e0 & 0xFFFFFFull) | ((unsigned long long)(n > 255 ? 255 : n) << 24) | ((e1 & 0xFFFFFFull) << 32);
+      }
     }
 
     // ---- merge on the leader tracks (tracking.py:723-741) ----
