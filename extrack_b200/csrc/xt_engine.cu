@@ -45,6 +45,7 @@ struct xt_ctx {
   int smem_optin = 0, n_sm = 0;
   bool have_eval = false;
   bool force_global = false;  // test hook: run the log-domain global-memory replay variant
+  int k2_wpc = 4;             // warps cooperating on one 32-track tile in the fast replay kernel
   xt_params last_p{};
   xt_stats stats{};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -298,19 +299,24 @@ static cudaError_t launch_k1(xt_ctx* ctx, const K1Args& a, const xt_params& p, s
   return cudaGetLastError();
 }
 
-#define XT_K2_WPC 4  // warps cooperating on one 32-track tile in the fast replay kernel
+template <int D, int KS, int WPC>
+static cudaError_t launch_k2_lin(xt_ctx* ctx, const K2Args& a, const xt_params& p, const K2Lin& lin, size_t smem, int grid) {
+  auto kern = k2_replay_lin<D, KS, WPC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32 * WPC, smem, ctx->stream>>>(a, p, lin);
+  return cudaGetLastError();
+}
 
 template <int D, int KS>
 static cudaError_t launch_k2(xt_ctx* ctx, const K2Args& a, const xt_params& p, const K2Lin& lin, size_t smem,
-                             bool use_smem, int grid) {
+                             bool use_smem, int grid, int wpc) {
   if (use_smem) {
-    auto kern = k2_replay_lin<D, KS, XT_K2_WPC>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, 32 * XT_K2_WPC, smem, ctx->stream>>>(a, p, lin);
-  } else {
-    k2_replay<D, KS, false><<<grid, 32, 0, ctx->stream>>>(a, p);
+    if (wpc == 8) return launch_k2_lin<D, KS, 8>(ctx, a, p, lin, smem, grid);
+    if (wpc == 2) return launch_k2_lin<D, KS, 2>(ctx, a, p, lin, smem, grid);
+    return launch_k2_lin<D, KS, 4>(ctx, a, p, lin, smem, grid);
   }
+  k2_replay<D, KS, false><<<grid, 32, 0, ctx->stream>>>(a, p);
   return cudaGetLastError();
 }
 
@@ -430,7 +436,8 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
   }
   for (int s = 0; s < p->nS; ++s) lin.leave[s] = std::exp(a.Lsum[s]);
   const size_t state_bytes = (size_t)2 * Pmax * CO * 32 * sizeof(double);
-  const size_t smem = state_bytes + (size_t)2 * XT_K2_WPC * 32 * sizeof(double);
+  const int wpc = ctx->k2_wpc;
+  const size_t smem = state_bytes + (size_t)2 * wpc * 32 * sizeof(double);
   const bool use_smem = smem <= (size_t)ctx->smem_optin && !ctx->force_global;
   int grid = a.n_work;
   if (!use_smem) {
@@ -446,7 +453,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
     a.gstate = ctx->d_gstate;
   }
   cudaError_t e = cudaSuccess;
-#define CALL_K2(D_, KS_) e = launch_k2<D_, KS_>(ctx, a, *p, lin, smem, use_smem, grid)
+#define CALL_K2(D_, KS_) e = launch_k2<D_, KS_>(ctx, a, *p, lin, smem, use_smem, grid, wpc)
   XT_DISPATCH(p->d, p->n_loc, CALL_K2);
 #undef CALL_K2
   XT_CUDA_OK(e);
@@ -487,6 +494,15 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return XT_ERR_ARG;
   if (std::strcmp(name, "force_global_replay") == 0) {
     ctx->force_global = value != 0;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k2_wpc") == 0) {
+    if (value != 2 && value != 4 && value != 8) {
+      set_error(ctx, "xt_set_option: k2_wpc must be 2, 4 or 8");
+      return XT_ERR_ARG;
+    }
+    ctx->k2_wpc = value;
     ctx->have_eval = false;
     return XT_OK;
   }

@@ -147,54 +147,110 @@ __global__ void __launch_bounds__(32 * WPC) k2_replay_lin(const K2Args a, const 
   double lnscale = 0.0;
   const int xoff0 = w * SL;
 
+  constexpr int R = 4;  // parents per warp kept in registers across the scale exchange
+  double cn[D];         // localisation of the next step, loaded one step ahead (hides DRAM latency)
+  Cs += cstride;
+#pragma unroll
+  for (int dim = 0; dim < D; ++dim) cn[dim] = Cs[(size_t)dim * npad];  // C[1] (exists: L >= 2)
+
   for (int step = 2; step <= L - 1; ++step) {
-    Cs += cstride;
     double cl[D];
 #pragma unroll
-    for (int dim = 0; dim < D; ++dim) cl[dim] = Cs[(size_t)dim * npad];
-    // ---- update, pass 1: m', u, exponent e and prefactor f per parent ----
-    double kmax = -INFINITY;
-    {
-      double* x = X + xoff0;
-      double* y = Y + xoff0;
-      for (int p = w; p < nP; p += WPC, x += WPC * SL, y += WPC * SL) {
-        double rq[KS], s2[KS];
+    for (int dim = 0; dim < D; ++dim) cl[dim] = cn[dim];
+    Cs += cstride;  // step + 1 <= L  =>  C[step] exists
 #pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          s2[k] = x[(D + k) * 32];
-          rq[k] = xt_rcp(l2[k] + s2[k]);
-        }
-        double quad = 0.0;
-#pragma unroll
-        for (int dim = 0; dim < D; ++dim) {
-          const int k = (KS == 1) ? 0 : dim;
-          const double mm = x[dim * 32];
-          const double df = cl[dim] - mm;
-          quad += df * df * rq[k];
-          y[dim * 32] = (mm * l2[k] + cl[dim] * s2[k]) * rq[k];
-        }
-#pragma unroll
-        for (int k = 0; k < KS; ++k) y[(D + k) * 32] = l2[k] * s2[k] * rq[k];
-        const double e = -0.5 * quad;
-        const double f = x[IW] * xt_normfac<D, KS>(rq);
-        kmax = fmax(kmax, e + xt_expo_ln2(f));
-        y[IW] = e;
-        x[IW] = f;
-      }
-    }
+    for (int dim = 0; dim < D; ++dim) cn[dim] = Cs[(size_t)dim * npad];
     double* rd = red + (step & 1) * WPC * 32;
-    rd[w * 32] = kmax;
-    __syncthreads();
-    double E = rd[0];
+    if (nP <= R * WPC) {
+      // ---- update, register path: this warp's <= R parents stay in registers between the
+      //      two passes (no smem round trip for e and f, R independent dependency chains) ----
+      double e[R], f[R];
+      double kmax = -INFINITY;
 #pragma unroll
-    for (int k = 1; k < WPC; ++k) E = fmax(E, rd[k * 32]);
-    E = fmax(E, -1e300);
-    lnscale += E;
-    // ---- update, pass 2: W' = f * exp(e - E) ----
-    {
-      double* x = X + xoff0;
-      double* y = Y + xoff0;
-      for (int p = w; p < nP; p += WPC, x += WPC * SL, y += WPC * SL) y[IW] = x[IW] * xt_exp(y[IW] - E);
+      for (int i = 0; i < R; ++i) {
+        const int p = w + i * WPC;
+        e[i] = -INFINITY;
+        f[i] = 0.0;
+        if (p < nP) {
+          double* x = X + p * SL;
+          double* y = Y + p * SL;
+          double rq[KS], s2[KS];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            s2[k] = x[(D + k) * 32];
+            rq[k] = xt_rcp(l2[k] + s2[k]);
+          }
+          double quad = 0.0;
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) {
+            const int k = (KS == 1) ? 0 : dim;
+            const double mm = x[dim * 32];
+            const double df = cl[dim] - mm;
+            quad += df * df * rq[k];
+            y[dim * 32] = (mm * l2[k] + cl[dim] * s2[k]) * rq[k];
+          }
+#pragma unroll
+          for (int k = 0; k < KS; ++k) y[(D + k) * 32] = l2[k] * s2[k] * rq[k];
+          e[i] = -0.5 * quad;
+          f[i] = x[IW] * xt_normfac<D, KS>(rq);
+          kmax = fmax(kmax, e[i] + xt_expo_ln2(f[i]));
+        }
+      }
+      rd[w * 32] = kmax;
+      __syncthreads();
+      double E = rd[0];
+#pragma unroll
+      for (int k = 1; k < WPC; ++k) E = fmax(E, rd[k * 32]);
+      E = fmax(E, -1e300);
+      lnscale += E;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int p = w + i * WPC;
+        if (p < nP) Y[p * SL + IW] = f[i] * xt_exp(e[i] - E);
+      }
+    } else {
+      // ---- update, generic path (any number of parents): e and f go through shared memory ----
+      double kmax = -INFINITY;
+      {
+        double* x = X + xoff0;
+        double* y = Y + xoff0;
+        for (int p = w; p < nP; p += WPC, x += WPC * SL, y += WPC * SL) {
+          double rq[KS], s2[KS];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            s2[k] = x[(D + k) * 32];
+            rq[k] = xt_rcp(l2[k] + s2[k]);
+          }
+          double quad = 0.0;
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) {
+            const int k = (KS == 1) ? 0 : dim;
+            const double mm = x[dim * 32];
+            const double df = cl[dim] - mm;
+            quad += df * df * rq[k];
+            y[dim * 32] = (mm * l2[k] + cl[dim] * s2[k]) * rq[k];
+          }
+#pragma unroll
+          for (int k = 0; k < KS; ++k) y[(D + k) * 32] = l2[k] * s2[k] * rq[k];
+          const double e = -0.5 * quad;
+          const double f = x[IW] * xt_normfac<D, KS>(rq);
+          kmax = fmax(kmax, e + xt_expo_ln2(f));
+          y[IW] = e;
+          x[IW] = f;
+        }
+      }
+      rd[w * 32] = kmax;
+      __syncthreads();
+      double E = rd[0];
+#pragma unroll
+      for (int k = 1; k < WPC; ++k) E = fmax(E, rd[k * 32]);
+      E = fmax(E, -1e300);
+      lnscale += E;
+      {
+        double* x = X + xoff0;
+        double* y = Y + xoff0;
+        for (int p = w; p < nP; p += WPC, x += WPC * SL, y += WPC * SL) y[IW] = x[IW] * xt_exp(y[IW] - E);
+      }
     }
     __syncthreads();
     if (step <= L - 2) {
@@ -267,10 +323,9 @@ __global__ void __launch_bounds__(32 * WPC) k2_replay_lin(const K2Args a, const 
   }
 
   // ---- end of track (tracking.py:613-639, :781-786) ----
-  Cs += cstride;  // last localisation C[L-1]
-  double cl[D];
+  double cl[D];  // last localisation C[L-1] (prefetched)
 #pragma unroll
-  for (int dim = 0; dim < D; ++dim) cl[dim] = Cs[(size_t)dim * npad];
+  for (int dim = 0; dim < D; ++dim) cl[dim] = cn[dim];
   const double* tau = ((L - 1) >= P.min_len) ? T.tau1 : T.tau0;
   const double* src = implicit ? Y : X;
   const int Kc = implicit ? K : 1;

@@ -96,7 +96,10 @@ if __name__ == "__main__":
     t = time.time()
     ts = xt.TrackSet(sorted_tracks)
     print("upload", round(time.time() - t, 3), "s; chunks", len(ts.chunks))
-    for it in range(5):
+    for it in range(9):
+        if it >= 3:
+            ts.engine.set_option("k2_wpc", [2, 2, 8, 8, 4, 4][it - 3])
+            print("k2_wpc", [2, 2, 8, 8, 4, 4][it - 3])
         t = time.time()
         v = ts.sum_logp(p)
         dtm = time.time() - t
