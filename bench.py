@@ -1,0 +1,342 @@
+#!/usr/bin/env python3
+"""Benchmark of the track-likelihood hot path (BASELINE.json metric: track-steps/s of one -log L
+evaluation, 2-state 2-D, frame_len = 8, sim_FOV synthetic tracks of length 10-30).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--tracks T] [--impl ours|reference]
+
+A *step* is one objective evaluation over the resident data set (plan kernel, replay kernel,
+device reduction; plus one 8-byte all-reduce when N > 1).  N = 1 workload: BASELINE.json configs[1]
+(10^6 tracks on one B200).  For N > 1 every rank holds its own 10^6-track field of view
+(weak scaling); ranks evaluate their chunks independently and the partial log-likelihoods are
+summed with one NCCL all-reduce per step.  Prints ONE JSON line (rank 0).
+
+--impl reference times the CPU path instead: the numpy oracle port of the reference algorithm
+(the reference is pure Python and does not travel to the GPU box) on all host cores, on a bounded
+sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SIM_KW = dict(max_track_len=30, min_track_len=10, LocErr=0.02, Ds=[0, 0.25], nb_dims=2, initial_fractions=[0.6, 0.4],
+              TrMat=[[0.9, 0.1], [0.1, 0.9]], dt=0.02, pBL=0.05, cell_dims=[1, None, None])
+EVAL = dict(D0=1e-5, D1=0.25, LocErr=0.02, F0=0.6, p01=0.1, p10=0.1, pBL=0.05)
+FRAME_LEN, THRESHOLD, MAX_NB_STATES, DT, CELL = 8, 0.2, 120, 0.02, [1]
+METRIC = "track-steps/sec of -logL eval (2-state, frame_len=8)"
+UNIT = "track-steps/s"
+
+
+def eval_params():
+    from extrack_b200._lmfit_compat import Parameters
+
+    p = Parameters()
+    for k, v in EVAL.items():
+        p.add(k, value=v)
+    p.add("F1", expr="1-F0")
+    return p
+
+
+def oracle_model(min_len):
+    import numpy as np
+
+    from extrack_b200 import tracking as xt
+    from oracle import extrack_oracle as orc
+
+    LocErr, ds, Fs, TrMat, pBL = xt.extract_params(eval_params(), DT, 2, 1)
+    return orc.Model(np.asarray(LocErr[0]).reshape(-1), ds, Fs, TrMat, pBL, CELL, 1, FRAME_LEN, min_len, THRESHOLD, MAX_NB_STATES)
+
+
+def cpu_leg(npz_path):
+    """Runs in a fresh, CUDA-free subprocess (the oracle forks a worker pool): evaluate the sample
+    stored in `npz_path` with the numpy oracle port on all host cores; print one JSON line."""
+    import numpy as np
+
+    from oracle import extrack_oracle as orc
+
+    z = np.load(npz_path)
+    st = [z[k] for k in sorted(z.files, key=int)]
+    cores = len(os.sched_getaffinity(0))
+    model = oracle_model(st[0].shape[1])
+    orc.neg_log_likelihood(st[:1], model, workers=1)  # warm-up: lazy scipy.stats import
+    t = time.perf_counter()
+    val = orc.neg_log_likelihood(st, model, workers=cores)
+    secs = time.perf_counter() - t
+    print(json.dumps({"value": orc.track_steps(st) / secs, "neglogl": val, "secs": secs, "cores": cores,
+                      "tracks": int(sum(len(a) for a in st))}))
+
+
+def cpu_baseline(st):
+    """cpu_baseline leg: the oracle port on a bounded sample, in a subprocess."""
+    import tempfile
+
+    import numpy as np
+
+    path = os.path.join(tempfile.mkdtemp(), "sample.npz")
+    np.savez(path, **{str(a.shape[1]): a for a in st})
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-leg", path], capture_output=True, text=True, timeout=1200)
+    os.remove(path)
+    if out.returncode != 0:
+        raise RuntimeError("cpu_baseline leg failed: " + out.stderr[-2000:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        import statistics
+
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    n = args.ref_tracks
+    # build the sample once, then time K steps (each step = one objective evaluation of the sample)
+    from extrack_b200 import tracking as xt
+    from extrack_b200.simulate import sim_tracks
+    from oracle import extrack_oracle as orc
+
+    tracks = sim_tracks(n, seed=10_000, device="cpu", **SIM_KW)
+    st, _ = xt._sorted_buckets(tracks)
+    model = oracle_model(st[0].shape[1])
+    steps_per_eval = orc.track_steps(st)
+    for _ in range(args.warmup):
+        orc.neg_log_likelihood(st, model, workers=cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        val = orc.neg_log_likelihood(st, model, workers=cores)
+    dt = time.perf_counter() - t
+    v = steps_per_eval * args.steps / dt
+    sample = f"{n} sim_FOV tracks ({steps_per_eval} track-steps, whole 2000-track chunks) per step, numpy oracle port, fork pool"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: sim_FOV synthetic 2-state 2D, tracks length 10-30, frame_len=8 (bounded sample)",
+                   "tracks_per_step": n, "neglogl": val},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--tracks", type=int, default=1_000_000, help="tracks per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-tracks", type=int, default=100_000)
+    ap.add_argument("--cpu-tracks", type=int, default=200_000, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--cpu-leg", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.cpu_leg:
+        return cpu_leg(args.cpu_leg)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import numpy as np
+    import torch
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from extrack_b200 import _native
+    from extrack_b200 import tracking as xt
+    from extrack_b200.simulate import sim_tracks
+
+    # ---- synthetic data: generated on this rank's GPU (seed differs per rank), config 2 ----
+    t0 = time.perf_counter()
+    tracks = sim_tracks(args.tracks, seed=1000 * rank, device=f"cuda:{local}", **SIM_KW)
+    st, _ = xt._sorted_buckets(tracks)
+    gen_s = time.perf_counter() - t0
+    torch.cuda.empty_cache()
+    params = eval_params()
+    LocErr, ds, Fs, TrMat, pBL = xt.extract_params(params, DT, 2, 1)
+    p = xt.build_tables(LocErr, ds, Fs, TrMat, pBL, CELL, 1, FRAME_LEN, st[0].shape[1], THRESHOLD, MAX_NB_STATES, 2)
+
+    ts = xt.TrackSet(st, rank=0, world_size=1, device=local)  # every rank owns its whole field of view
+    eng = ts.engine
+    buf = torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        eng.sum_logp_async(p, buf.data_ptr(), stream)
+        if world > 1:
+            dist.all_reduce(buf)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_plan = ms_replay = 0.0
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+        # per-kernel device times of this step (CUDA events recorded by the engine on its own stream)
+        s = eng.stats()
+        ms_plan += s["ms_plan"]
+        ms_replay += s["ms_replay"]
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    sampler.stop_flag = True
+    total = float(buf.item())
+    stats = eng.stats()
+    tms = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    tsteps = torch.tensor([float(stats["track_steps"])], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsteps)
+    ms = float(tms.item())
+    all_steps = float(tsteps.item())
+    value = all_steps * args.steps / (ms * 1e-3)
+
+    # ---- e2e: public API with HOST buffers: upload (pinned H2D + device repack) + evaluate + read back ----
+    h2d = int(sum(a.nbytes for a in st))
+    pinned = []
+    for a in st:
+        b = _native.pinned_empty(a.shape)
+        b[...] = a
+        pinned.append(b)
+    bl = [0 if a.shape[1] == st[-1].shape[1] else 1 for a in st]
+    e2e_eng = _native.Engine(local)
+    e2e_eng.upload(pinned, bl, xt.MAX_TRACKS_PER_CHUNK)
+    e2e_eng.sum_logp(p)
+    barrier()
+    t = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_eng.upload(pinned, bl, xt.MAX_TRACKS_PER_CHUNK)
+        e2e_val = e2e_eng.sum_logp(p)
+        if world > 1:
+            b2 = torch.tensor([e2e_val], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(b2)
+            e2e_val = float(b2.item())
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t) / args.e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = all_steps / float(te.item())
+    e2e_eng.close()
+
+    if rank == 0:
+        peak = eng.fp64_peak_tflops()
+        # algorithmic flops of the replay kernel: F = nB_in*(25+9d) + nG*(3+d) per track-step
+        d = 2
+        flops = stats["seq_updates"] * (25 + 9 * d) + stats["seq_groups"] * (3 + d)
+        replay_ms = ms_replay / args.steps
+        achieved = flops / (replay_ms * 1e-3) / 1e12
+        alg_bytes = sum(a.size for a in st) * 8 + stats["n_tracks"] * 8
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        # ---- cpu_baseline: oracle port on a bounded sample of the same generator, in a CUDA-free
+        #      subprocess; the engine is evaluated on the same sample as a parity check ----
+        cpu, parity = None, None
+        if world == 1 and not args.no_cpu:
+            sample = sim_tracks(args.cpu_tracks, seed=777_000, device=f"cuda:{local}", **SIM_KW)
+            st_c, _ = xt._sorted_buckets(sample)
+            r = cpu_baseline(st_c)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                   "sample": f"{r['tracks']} sim_FOV tracks of the same generator/config (seed 777000), one evaluation = "
+                             f"{r['secs']:.1f} s on {r['cores']} processes (numpy oracle port of the reference algorithm, fork pool)"}
+            tsc = xt.TrackSet(st_c, rank=0, world_size=1, device=local)
+            pc = xt.build_tables(LocErr, ds, Fs, TrMat, pBL, CELL, 1, FRAME_LEN, st_c[0].shape[1], THRESHOLD, MAX_NB_STATES, 2)
+            parity = abs(-tsc.sum_logp(pc) - r["neglogl"]) / abs(r["neglogl"])
+            tsc.close()
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
+            if int(tj.get("tracks", -1)) == int(stats["n_tracks"]):
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: sim_FOV synthetic 2-state 2D, 10^6 tracks length 10-30, frame_len=8, one -logL evaluation",
+                       "tracks_per_gpu": int(stats["n_tracks"]), "track_steps_per_gpu": int(stats["track_steps"]),
+                       "chunks_per_gpu": int(stats["n_chunks"]), "max_live_sequences": int(stats["max_nB_in"]),
+                       "l2_policy": f"inputs larger than L2 ({alg_bytes/1e6:.0f} MB of localisations per GPU vs 126 MB L2)",
+                       "sum_logp": total, "generator_seconds": round(gen_s, 1)},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "what": "xt_upload (pinned host -> device + repack) + xt_sum_logp per step"},
+            "gpu_launches": int(args.steps * (stats["k1_launches"] + stats["k2_launches"])),
+            "kernel_ms": {"plan": ms_plan / args.steps, "replay_and_reduce": replay_ms},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k2_replay_lin",
+                         "peak_source": "FP64 FMA microbenchmark measured live on this GPU (xt_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 figure",
+                         "algorithmic_flops_per_launch": flops,
+                         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (replay_ms * 1e-3) / 1e9,
+                                 "peak_gbs": peaks.get("hbm_gbs")}},
+            "cpu_baseline": cpu,
+            "parity_rel_err_vs_oracle_on_cpu_sample": parity,
+        }
+        print(json.dumps(line))
+    ts.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,92 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Each case stores the inputs (tracks, model quantities exactly as `extract_params` produced them,
+configuration) and the reference outputs of `Proba_Cs` (per-track log P) and, for nb_substeps=1,
+of `P_Cs_inter_bound_stats_th(do_preds=1)` (state posteriors).  One multi-bucket case stores the
+value of `cum_Proba_Cs`.  Seeds are fixed; numpy/scipy versions are recorded.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
+
+from helpers import make_model, random_walk_tracks  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+CASES = [
+    dict(name="s2_fl8_L20", nS=2, nsub=1, d=2, fl=8, L=20, nT=120, isBL=1, seed=1),
+    dict(name="s2_fl6_L30_noBL", nS=2, nsub=1, d=2, fl=6, L=30, nT=64, isBL=0, seed=2),
+    dict(name="s2_fl4_L3", nS=2, nsub=1, d=2, fl=4, L=3, nT=40, isBL=1, seed=3),
+    dict(name="s2_fl4_L2", nS=2, nsub=1, d=2, fl=4, L=2, nT=40, isBL=1, seed=4),
+    dict(name="s2_single_track", nS=2, nsub=1, d=2, fl=5, L=9, nT=1, isBL=1, seed=5),
+    dict(name="s3_nsub2_wrap", nS=3, nsub=2, d=2, fl=6, L=13, nT=48, isBL=1, seed=6, max_nb_states=500),
+    dict(name="s3_3d", nS=3, nsub=1, d=3, fl=6, L=14, nT=64, isBL=0, seed=7, max_nb_states=60),
+    dict(name="s3_3d_locerr_per_dim", nS=3, nsub=1, d=3, fl=5, L=12, nT=48, isBL=1, seed=8, loc_err=(0.02, 0.02, 0.03)),
+    dict(name="s2_minlen10", nS=2, nsub=1, d=2, fl=6, L=14, nT=64, isBL=1, seed=9, min_len=10),
+    dict(name="s2_nsub2", nS=2, nsub=2, d=2, fl=6, L=12, nT=48, isBL=1, seed=10),
+    dict(name="s4", nS=4, nsub=1, d=2, fl=5, L=11, nT=48, isBL=1, seed=11, max_nb_states=200),
+    dict(name="s2_escalate", nS=2, nsub=1, d=2, fl=10, L=16, nT=48, isBL=1, seed=12, max_nb_states=12, threshold=0.05),
+]
+
+
+def main():
+    trk = ref_loader.load_tracking()
+    import scipy
+
+    meta = dict(numpy=np.__version__, scipy=scipy.__version__)
+    for c in CASES:
+        kw = {k: c[k] for k in ("loc_err", "min_len", "max_nb_states", "threshold") if k in c}
+        model = make_model(nS=c["nS"], nsub=c["nsub"], frame_len=c["fl"], **kw)
+        rng = np.random.default_rng(c["seed"])
+        C = random_walk_tracks(c["nT"], c["L"], c["d"], rng, Ds=model.ds**2 / (2 * 0.02))
+        LocErr = np.asarray(model.loc_err)[None, None]
+        with contextlib.redirect_stdout(io.StringIO()):
+            logp = trk.Proba_Cs(C, LocErr, model.ds, model.Fs, model.TrMat, model.pBL, c["isBL"], model.cell_dims,
+                                model.nb_substeps, model.frame_len, model.min_len, model.threshold, model.max_nb_states)
+            preds = np.zeros(0)
+            if c["nsub"] == 1:  # predict_Bs forces nb_substeps = 1; default nb_max = 1 => one track per call
+                preds = np.concatenate([
+                    trk.P_Cs_inter_bound_stats_th(C[i : i + 1], LocErr, model.ds, model.Fs, model.TrMat, model.pBL, c["isBL"],
+                                                  model.cell_dims, 1, model.frame_len, 1, model.min_len, 0.1, 200)[2]
+                    for i in range(min(len(C), 24))
+                ])
+        np.savez_compressed(
+            os.path.join(HERE, c["name"] + ".npz"), C=C, loc_err=model.loc_err, ds=model.ds, Fs=model.Fs, TrMat=model.TrMat,
+            pBL=model.pBL, cell_dims=np.asarray(model.cell_dims), nsub=model.nb_substeps, frame_len=model.frame_len,
+            min_len=model.min_len, threshold=model.threshold, max_nb_states=model.max_nb_states, isBL=c["isBL"],
+            ref_logp=logp, ref_preds=preds, meta=str(meta))
+        print(c["name"], float(np.sum(logp)))
+
+    # multi-bucket objective through the reference's own parameter path (lmfit-style Parameters)
+    from lmfit import Parameters
+
+    rng = np.random.default_rng(100)
+    buckets = {str(L): random_walk_tracks(n, L, 2, rng) for L, n in ((5, 30), (8, 70), (12, 2100), (17, 45))}
+    p = Parameters()
+    for k, v in dict(D0=1e-5, D1=0.25, LocErr=0.02, F0=0.6, p01=0.1, p10=0.12, pBL=0.05).items():
+        p.add(k, value=v)
+    p.add("F1", expr="1-F0")
+    keys = sorted(buckets, key=int)
+    st = [buckets[k] for k in keys]
+    vals = {}
+    for fl in (4, 7):
+        with contextlib.redirect_stdout(io.StringIO()):
+            vals[fl] = float(trk.cum_Proba_Cs(p, st, 0.02, [1], None, 2, 1, fl, 0, 1, 1, 0.2, 120))
+    np.savez_compressed(os.path.join(HERE, "objective_multibucket.npz"), keys=np.array(keys), fl=np.array(list(vals)),
+                        neglogl=np.array(list(vals.values())), meta=str(meta), **{"C" + k: buckets[k] for k in keys})
+    print("objective", vals)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+"""Host-side logic and the C-ABI surface (CPU only; no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from extrack_b200 import _native
+from extrack_b200 import tracking as xt
+from extrack_b200._lmfit_compat import Parameters, minimize
+from helpers import make_model, random_walk_tracks
+from oracle import extrack_oracle as orc
+from oracle import ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def two_state_params():
+    p = Parameters()
+    for k, v in dict(D0=1e-5, D1=0.25, LocErr=0.02, F0=0.6, p01=0.1, p10=0.12, pBL=0.05).items():
+        p.add(k, value=v, min=0, max=10)
+    p.add("F1", expr="1-F0")
+    return p
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "xtrack.h")).read()
+    declared = set(re.findall(r"\b(xt_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTS)
+    lib = _native.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_params_struct_layout_matches_header():
+    assert ctypes.sizeof(_native.XtParams) == 8 * 4 + 8 + 8 * 3 + 5 * 8 * _native.XT_MAX_HEADS
+    assert ctypes.sizeof(_native.XtStats) == 4 * 8 + 4 * 4 + 2 * 4
+
+
+def test_engine_fails_loudly_without_gpu(gpu_available):
+    if gpu_available:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_native.EngineError, match="no CPU fallback"):
+        _native.Engine(0)
+    with pytest.raises(_native.EngineError):
+        xt.Proba_Cs(np.zeros((2, 4, 2)), np.array([[[0.02]]]), np.array([0.01, 0.1]), np.array([0.5, 0.5]),
+                    np.array([[0.9, 0.1], [0.1, 0.9]]), 0.1, 1, [1], 1, 4, 3, 0.2, 120)
+
+
+def test_extract_params_conventions():
+    LocErr, ds, Fs, TrMat, pBL = xt.extract_params(two_state_params(), 0.02, 2, 1)
+    assert LocErr[0].shape == (1, 1, 1) and LocErr[0][0, 0, 0] == 0.02
+    np.testing.assert_allclose(ds, np.sqrt(2 * np.array([1e-5, 0.25]) * 0.02))
+    np.testing.assert_allclose(Fs, [0.6, 0.4])
+    assert pBL == 0.05
+    np.testing.assert_allclose(TrMat, [[np.exp(-0.1), 1 - np.exp(-0.1)], [1 - np.exp(-0.12), np.exp(-0.12)]])
+    _, _, _, T2, _ = xt.extract_params(two_state_params(), 0.02, 2, 2)
+    np.testing.assert_allclose(T2[0, 1], 1 - np.exp(-0.05))
+    _, _, _, T0, _ = xt.extract_params(two_state_params(), 0.02, 2, 1, Matrix_type=0)
+    np.testing.assert_allclose(T0, [[0.9, 0.1], [0.12, 0.88]])
+    for mt in (2, 3, 4):
+        _, _, _, Tm, _ = xt.extract_params(two_state_params(), 0.02, 2, 1, Matrix_type=mt)
+        np.testing.assert_allclose(Tm.sum(1), 1.0, atol=1e-3)
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("nsub,mt", [(1, 1), (2, 1), (1, 0), (1, 2), (1, 3), (1, 4)])
+def test_extract_params_equals_reference(nsub, mt):
+    trk = ref_loader.load_tracking()
+    from lmfit import Parameters as RP
+
+    rp = RP()
+    for k, v in dict(D0=1e-5, D1=0.04, D2=0.3, LocErr=0.02, F0=0.3, F1=0.3, p01=0.1, p02=0.03, p10=0.12, p12=0.05, p20=0.02,
+                     p21=0.07, pBL=0.05).items():
+        rp.add(k, value=v)
+    rp.add("F2", expr="1-F0-F1")
+    a = trk.extract_params(rp, 0.02, 3, nsub, None, mt)
+    b = xt.extract_params(rp, 0.02, 3, nsub, None, mt)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(np.asarray(x[0] if isinstance(x, list) else x), np.asarray(y[0] if isinstance(y, list) else y))
+
+
+def test_per_dim_locerr_param_names():
+    p = xt.generate_params(nb_states=2, LocErr_type=2, nb_dims=3)
+    LocErr, *_ = xt.extract_params(p, 0.02, 2, 1)
+    assert LocErr[0].shape == (1, 1, 3)
+    p3 = xt.generate_params(nb_states=2, LocErr_type=3)
+    assert p3["LocErr1"].value == p3["LocErr0"].value
+
+
+def test_unsupported_inputs_raise():
+    with pytest.raises(NotImplementedError):
+        xt.extract_params(two_state_params(), 0.02, 2, 1, input_LocErr=[np.zeros((2, 3, 2))])
+    with pytest.raises(NotImplementedError):
+        xt.extract_params(two_state_params(), [np.zeros((2, 3))], 2, 1)
+
+
+@pytest.mark.parametrize("kw", [dict(nS=2, nsub=1), dict(nS=3, nsub=2), dict(nS=3, nsub=1, loc_err=(0.02, 0.02, 0.03)), dict(nS=4, nsub=1)])
+def test_build_tables_match_oracle_tables(kw):
+    m = make_model(**kw)
+    d = len(m.loc_err) if len(m.loc_err) > 1 else 2
+    p = xt.build_tables(m.loc_err, m.ds, m.Fs, m.TrMat, m.pBL, m.cell_dims, m.nb_substeps, m.frame_len, m.min_len, m.threshold,
+                        m.max_nb_states, d)
+    tb = orc.HeadTables(m)
+    nH = tb.K * m.nS
+    for name in ("dd", "LT", "LF", "L_leave"):
+        np.testing.assert_array_equal(np.array(getattr(p, name)[:nH]), getattr(tb, name))
+    np.testing.assert_array_equal(np.array(p.Lp_stay[: tb.K]), tb.Lp_stay)
+    assert (p.nS, p.nsub, p.d, p.n_loc) == (m.nS, m.nb_substeps, d, len(m.loc_err))
+    assert p.flags & _native.XT_FLAG_INT8_WRAP
+
+
+def test_build_tables_rejects_bad_locerr_shape():
+    m = make_model()
+    with pytest.raises(ValueError, match="Localization error"):
+        xt.build_tables(np.array([0.02, 0.03]), m.ds, m.Fs, m.TrMat, m.pBL, m.cell_dims, 1, 6, 3, 0.2, 120, 3)
+
+
+def test_chunk_table_matches_reference_order():
+    rng = np.random.default_rng(0)
+    st = [np.zeros((n, L, 2)) for L, n in ((5, 10), (7, 4100), (9, 2000))]
+    ch = xt.chunk_table(st, 2000)
+    assert ch == orc.make_chunks(st, 2000)
+    assert ch[0] == (2, 0, 2000, 0) and ch[-1] == (0, 0, 10, 1)
+    assert [c[3] for c in ch] == [0, 1, 1, 1, 1]
+
+
+def test_shard_chunks_is_balanced_partition():
+    st = [np.zeros((n, L, 2)) for L, n in ((10, 6000), (20, 9000), (30, 15000))]
+    ch = xt.chunk_table(st, 2000)
+    for ws in (1, 2, 3, 8):
+        own = xt.shard_chunks(ch, st, ws)
+        flat = sorted(i for o in own for i in o)
+        assert flat == list(range(len(ch)))
+        cost = [sum((ch[i][2] - ch[i][1]) * (st[ch[i][0]].shape[1] - 1) for i in o) for o in own]
+        assert max(cost) - min(cost) <= 2000 * 29
+
+
+def test_sorted_buckets_numeric_order_and_empty_dropped():
+    d = {"10": np.zeros((1, 10, 2)), "9": np.zeros((2, 9, 2)), "100": np.zeros((3, 100, 2)), "11": np.zeros((0, 11, 2))}
+    st, keys = xt._sorted_buckets(d)
+    assert [a.shape[1] for a in st] == [9, 10, 100]
+    assert keys == ["9", "10", "11", "100"]
+
+
+def test_generate_params_names_and_exprs():
+    p = xt.generate_params(nb_states=3, LocErr_type=1)
+    names = list(p.keys())
+    assert names[:3] == ["D0", "D1", "D2"] and "LocErr" in names and names[-1] == "pBL"
+    assert {"p01", "p02", "p10", "p12", "p20", "p21"} <= set(names)
+    assert abs(p["F2"].value - (1 - p["F0"].value - p["F1"].value)) < 1e-15
+    p["F0"].value = 0.5
+    assert abs(p["F2"].value - (0.5 - p["F1"].value)) < 1e-15
+
+
+def test_get_params_generic_branch():
+    p = xt.get_params()
+    assert list(p.keys()) == ["LocErr", "D0", "D1_minus_D0", "D1", "F0", "F1", "p01", "p10", "pBL"]
+    assert abs(p["D1"].value - 0.05) < 1e-11 and abs(p["F1"].value - 0.55) < 1e-15  # D0 is clipped to its lower bound
+
+
+def test_lmfit_standin_bounds_and_bfgs():
+    p = Parameters()
+    p.add("a", value=0.5, min=0, max=2)
+    p.add("b", value=3.0, min=1)
+    p.add("c", expr="a + b")
+
+    def f(pp):
+        return (pp["a"].value - 1.25) ** 2 + (pp["b"].value - 2.0) ** 2 + 0 * pp["c"].value
+
+    res = minimize(f, p, method="bfgs", nan_policy="propagate")
+    assert abs(res.params["a"].value - 1.25) < 1e-5 and abs(res.params["b"].value - 2.0) < 1e-5
+    assert abs(res.params["c"].value - 3.25) < 1e-4
+    assert res.residual.shape == (1,) and res.residual[0] < 1e-9
+    res2 = minimize(f, p, method="powell")
+    assert abs(res2.params["a"].value - 1.25) < 1e-4
+
+
+def test_simulator_statistics():
+    from extrack_b200.simulate import sim_FOV, sim_tracks
+
+    tr, st = sim_FOV(nb_tracks=3000, max_track_len=20, min_track_len=5, LocErr=0.02, Ds=[0, 0.25], nb_dims=2,
+                     initial_fractions=[0.6, 0.4], TrMat=[[0.9, 0.1], [0.1, 0.9]], dt=0.02, pBL=0.05, cell_dims=[1, None, None],
+                     seed=3, return_states=True)
+    assert all(v.shape[1] == int(k) and v.shape[2] == 2 for k, v in tr.items())
+    assert set(tr) <= {str(i) for i in range(5, 21)} and len(tr["20"]) > len(tr["19"])
+    d = np.concatenate([(v[:, 1:] - v[:, :-1]).reshape(-1, 2) for v in tr.values()])
+    s = np.concatenate([v[:, :-1].reshape(-1) for v in st.values()])
+    assert 8e-4 < np.mean(d[s == 0] ** 2) < 1.6e-3  # immobile at frame start: 2 sigma^2 (+ switches inside the frame)
+    assert 0.006 < np.mean(d[s == 1] ** 2) < 0.012  # 2 D dt + 2 sigma^2 ~ 0.0108 (minus state switching)
+    same = sim_FOV(nb_tracks=200, max_track_len=12, min_track_len=5, seed=5)[0]
+    again = sim_FOV(nb_tracks=200, max_track_len=12, min_track_len=5, seed=5)[0]
+    assert all(np.array_equal(same[k], again[k]) for k in same)
+    many = sim_tracks(5000, block=3000, seed=1, max_track_len=12, min_track_len=5)
+    assert sum(len(v) for v in many.values()) == 5000
