@@ -19,6 +19,7 @@ struct XtChunk {
   int32_t isBL;      // 0 for the longest bucket
   int64_t xyz_off;   // offset (doubles) of the chunk's SoA block [L][d][nTpad]
   int64_t trk_off;   // offset of the chunk's first track in per-track outputs
+  int64_t loc_off;   // offset of the chunk's first localisation in per-localisation outputs
   int32_t rec0;      // first plan record of the chunk (records for steps 2..L-2)
   int32_t nrec;      // max(0, L-3)
   int32_t seg;       // uploaded segment the chunk came from

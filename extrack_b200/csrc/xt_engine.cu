@@ -19,7 +19,10 @@ struct xt_ctx {
   std::string err;
   // data
   int d = 0;
-  int64_t n_tracks = 0, track_steps = 0;
+  int64_t n_tracks = 0, track_steps = 0, n_locs = 0;
+  std::vector<int> seg_chunk0;
+  std::vector<int64_t> seg_n;
+  std::vector<int> seg_L;
   std::vector<XtChunk> chunks;
   std::vector<XtWork> work;
   int nrec_total = 0;
@@ -161,6 +164,7 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
   free_data(ctx);
   ctx->d = d;
   ctx->n_tracks = 0;
+  ctx->n_locs = 0;
   ctx->track_steps = 0;
   ctx->maxL = 0;
   int64_t soa_elems = 0, max_seg_elems = 0;
@@ -186,6 +190,7 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
       ck.isBL = isBL[s];
       ck.xyz_off = soa_elems;
       ck.trk_off = ctx->n_tracks;
+      ck.loc_off = ctx->n_locs;
       ck.rec0 = rec;
       ck.nrec = std::max(0, ck.L - 3);
       ck.seg = s;
@@ -193,12 +198,16 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
       rec += ck.nrec;
       soa_elems += (int64_t)ck.L * d * ck.nTpad;
       ctx->n_tracks += ck.nT;
+      ctx->n_locs += (int64_t)ck.nT * ck.L;
       ctx->track_steps += (int64_t)ck.nT * (ck.L - 1);
       for (int t0 = 0; t0 < ck.nT; t0 += 32) ctx->work.push_back(XtWork{(int)ctx->chunks.size(), t0});
       ctx->chunks.push_back(ck);
     }
   }
   ctx->nrec_total = rec;
+  ctx->seg_chunk0 = seg_chunk0;
+  ctx->seg_n.assign(n, n + n_seg);
+  ctx->seg_L.assign(L, L + n_seg);
   const size_t nch = ctx->chunks.size();
   XT_CUDA_OK(cudaMalloc(&ctx->d_soa, sizeof(double) * (size_t)soa_elems));
   XT_CUDA_OK(cudaMemsetAsync(ctx->d_soa, 0, sizeof(double) * (size_t)soa_elems, ctx->stream));

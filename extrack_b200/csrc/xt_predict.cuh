@@ -1,3 +1,427 @@
-// K3 — state annotation kernel (predict_Bs).  Placeholder until the fit path is parity-green.
+// K3 — state annotation kernel (predict_Bs, tracking.py:792-906 with the default nb_max = 1:
+// every track is its own chunk, so the grouping plan is decided per track from that track alone).
+//
+// One warp per track, lanes stride over state sequences.  Forward pass = the recursion of
+// P_Cs_inter_bound_stats_th(do_preds=1) in the reference's operation order (same faithful
+// arithmetic as the plan kernel, because here every track's own numbers drive the discontinuous
+// grouping decisions).  The reference carries, for every sequence, the posterior of *all* past
+// states (cur_Bs_cat[nT, nB, L, nS], rewritten at every step: O(L^2) traffic).  Only the newest
+// frame_len rows ever influence a decision (tracking.py:679-681), so the forward pass keeps that
+// window, records the normalised merge weights of every fusion, and a backward sweep over the
+// recorded lattice produces the same posteriors in O(L):
+//     a_final[c]  = softmax_c(LP_c)                                   (:641-648)
+//     pred[s][label_s(c)] += a_child[c];  a_parent[p] = sum_r a_child[pK + r]
+//     a_child(step s-1)[c'] = a_parent(step s)[gid[c']] * w[c'] / sum_group w
+// The history labels keep the reference's int8 wrap (:543).  nb_substeps is 1 (:839).
 #pragma once
 #include "xt_common.cuh"
+#include "xt_plan.cuh"
+
+#define XT_K3_WARPS 8
+
+struct K3Args {
+  const XtChunk* chunks;
+  const XtWork* work;
+  const double* soa;
+  double* scratch;     // per resident warp
+  double* pred;        // [sum over tracks of L][nS], forward time
+  int32_t* err;        // [n_work]  0 ok, 1 grouping failure, 2 capacity overflow (need in err_need)
+  int32_t* err_need;
+  int32_t n_work;
+  int32_t cap;         // children capacity
+  int32_t maxL;
+  int32_t bits;
+  double Lsum[XT_MAX_STATES];
+  size_t warp_scratch; // 8-byte units per warp (k3_layout(...).total)
+};
+
+// per-warp scratch layout, in 8-byte units
+struct K3Layout {
+  size_t bufP, bufC, histP, histN, codeP, codeC, recW, aC, aP, gid, order, goff, curP, recN, recGid, total;
+};
+__host__ __device__ inline K3Layout k3_layout(int cap, int CO, int fl, int nS, int maxL) {
+  K3Layout l;
+  size_t o = 0;
+  l.bufP = o;   o += (size_t)cap * CO;
+  l.bufC = o;   o += (size_t)cap * CO;
+  l.histP = o;  o += (size_t)cap * fl * nS;
+  l.histN = o;  o += (size_t)cap * fl * nS;
+  l.codeP = o;  o += cap;
+  l.codeC = o;  o += cap;
+  l.recW = o;   o += (size_t)maxL * cap;
+  l.aC = o;     o += cap;
+  l.aP = o;     o += cap;
+  l.gid = o;    o += (cap + 1) / 2;        // int32[cap]
+  l.order = o;  o += (cap + 1) / 2;
+  l.goff = o;   o += (cap + 2) / 2;        // int32[cap+1]
+  l.curP = o;   o += (cap + 1) / 2;
+  l.recN = o;   o += (maxL + 2) / 2;       // int32[maxL+1]
+  l.recGid = o; o += ((size_t)maxL * cap + 3) / 4;  // uint16[maxL][cap]
+  l.total = o + 4;
+  return l;
+}
+
+template <int D, int KS>
+__global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, const __grid_constant__ xt_params P) {
+  constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nS = P.nS, K = P.nS, cap = a.cap, fl = P.frame_len, bits = a.bits;
+  const bool wrap = (P.flags & XT_FLAG_INT8_WRAP) != 0;
+  const unsigned long long rowmask = (1ull << bits) - 1ull;
+
+  // ---- per-warp scratch carve-up ----
+  const K3Layout lay = k3_layout(cap, CO, fl, nS, a.maxL);
+  double* base = a.scratch + (size_t)(blockIdx.x * XT_K3_WARPS + warp) * a.warp_scratch;
+  double* bufP = base + lay.bufP;            // [CO][cap]
+  double* bufC = base + lay.bufC;
+  double* histP = base + lay.histP;          // [cap][fl][nS]
+  double* histN = base + lay.histN;
+  unsigned long long* codeP = (unsigned long long*)(base + lay.codeP);
+  unsigned long long* codeC = (unsigned long long*)(base + lay.codeC);
+  double* recW = base + lay.recW;            // [maxL][cap]
+  double* aC = base + lay.aC;
+  double* aP = base + lay.aP;
+  int* gid = (int*)(base + lay.gid);
+  int* order = (int*)(base + lay.order);
+  int* goff = (int*)(base + lay.goff);       // [cap+1]
+  int* curP = (int*)(base + lay.curP);
+  int* recN = (int*)(base + lay.recN);       // children per fused step
+  uint16_t* recGid = (uint16_t*)(base + lay.recGid);
+
+#define BP(slot, comp) bufP[(size_t)(comp) * cap + (slot)]
+#define BC(slot, comp) bufC[(size_t)(comp) * cap + (slot)]
+
+  double l2[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) l2[k] = P.l2[k];
+
+  for (int wi = blockIdx.x; wi < a.n_work; wi += gridDim.x) {
+    const XtWork wk = a.work[wi];
+    const XtChunk ck = a.chunks[wk.chunk];
+    const int L = ck.L;
+    for (int tsub = warp; tsub < 32; tsub += XT_K3_WARPS) {
+      const int t = wk.t0 + tsub;
+      if (t >= ck.nT) break;  // warp-uniform
+      const double* Cp = a.soa + ck.xyz_off + t;
+      const size_t npad = (size_t)ck.nTpad;
+      double* out = a.pred + ((size_t)ck.loc_off + (size_t)t * L) * nS;
+      int errc = 0;
+
+      // ---- first localisation (tracking.py:478-529) ----
+      int nP = nS * nS;
+      for (int c = lane; c < nP; c += 32) {
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) BP(c, dim) = Cp[(size_t)dim * npad];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) BP(c, D + k) = __dadd_rn(l2[k], P.dd[c]);
+        BP(c, D + 2 * KS) = __dadd_rn(P.LT[c], P.LF[c]);
+        curP[c] = c % nS;
+        const int d0 = c % nS, d1 = c / nS;
+        codeP[c] = (unsigned long long)d0 | ((unsigned long long)d1 << bits);
+        for (int s = 0; s < nS; ++s) {
+          histP[((size_t)c * fl + 0) * nS + s] = (d0 == s) ? 1.0 : 0.0;
+          if (fl > 1) histP[((size_t)c * fl + 1) * nS + s] = (d1 == s) ? 1.0 : 0.0;
+        }
+      }
+      int LhP = 2;       // full history length (never truncated in predict mode)
+      double th = P.threshold;
+      __syncwarp();
+
+      for (int step = 2; step <= L - 1; ++step) {
+        const int nC = nP * K;
+        if (nC > cap) {
+          errc = 2;
+          if (lane == 0) atomicMax(&a.err_need[wi], nC);
+          break;
+        }
+        const int LhC = LhP + 1;
+        const int rows_cmp = LhC < fl ? LhC : fl;    // rows stored / compared for the children
+        const bool use_window = LhC > fl;
+        const unsigned long long cmask = (bits * rows_cmp >= 64) ? ~0ull : ((1ull << (bits * rows_cmp)) - 1ull);
+        double cl[D];
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((step - 1) * D + dim) * npad];
+        const bool stay = step >= P.min_len;
+        // ---- expansion + Gaussian update (tracking.py:540-570, :87-98), lane = child ----
+        for (int c = lane; c < nC; c += 32) {
+          const int p = c / K, r = c - p * K;
+          const int head = r + K * curP[p];
+          const double dd = P.dd[head];
+          double s2[KS], q[KS];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            s2[k] = BP(p, D + k);
+            q[k] = __dadd_rn(l2[k], s2[k]);
+          }
+          double quad = 0.0, logs = 0.0;
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) {
+            const int k = (KS == 1) ? 0 : dim;
+            const double mm = BP(p, dim);
+            const double df = __dsub_rn(cl[dim], mm);
+            const double term = __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, q[k]));
+            quad = (dim == 0) ? term : __dadd_rn(quad, term);
+            BC(c, dim) = __ddiv_rn(__dadd_rn(__dmul_rn(mm, l2[k]), __dmul_rn(cl[dim], s2[k])), __dadd_rn(l2[k], s2[k]));
+          }
+          if (KS == 1) {
+            logs = __dmul_rn((double)D * -0.5, log(__dmul_rn(XT_TWO_PI, q[0])));
+          } else {
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+              const double lg = __dmul_rn(-0.5, log(__dmul_rn(XT_TWO_PI, q[k])));
+              logs = (k == 0) ? lg : __dadd_rn(logs, lg);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            const double ns2 = __ddiv_rn(
+                __dadd_rn(__dadd_rn(__dmul_rn(dd, l2[k]), __dmul_rn(dd, s2[k])), __dmul_rn(l2[k], s2[k])), q[k]);
+            BC(c, D + k) = ns2;
+            BC(c, D + KS + k) = __dsqrt_rn(ns2);
+          }
+          double add = __dadd_rn(P.LT[head], __dsub_rn(logs, quad));
+          if (stay) add = __dadd_rn(add, P.Lp_stay[r]);
+          BC(c, D + 2 * KS) = __dadd_rn(BP(p, D + 2 * KS), add);
+          codeC[c] = ((codeP[p] << bits) | (unsigned long long)xt_label(c, nS, wrap)) & cmask;
+          gid[c] = -1;
+        }
+        if (nC > P.max_nb_states) th = __dmul_rn(th, 1.2);
+        __syncwarp();
+        if (step == L - 1) {  // last step: no fusion (tracking.py:591)
+          nP = nC;
+          LhP = LhC;
+          break;
+        }
+
+        // ---- greedy grouping from this track alone (tracking.py:667-698 with one leader track) ----
+        int nG = 0, off = 0;
+        for (int i = 0; i < nC; ++i) {
+          if (gid[i] >= 0) continue;  // warp-uniform (memory made visible by __syncwarp)
+          double mi[D], si[KS];
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) mi[dim] = BC(i, dim);
+#pragma unroll
+          for (int k = 0; k < KS; ++k) si[k] = BC(i, D + KS + k);
+          const unsigned long long ci = codeC[i];
+          goff[nG] = off;
+          for (int j0 = 0; j0 < nC; j0 += 32) {
+            const int j = j0 + lane;
+            bool ok = false;
+            if (j < nC && gid[j] < 0) {
+              const unsigned long long cj = codeC[j];
+              if (use_window && cj == ci) {
+                ok = true;
+              } else if ((cj & rowmask) == (ci & rowmask)) {
+                double am = 0.0, as = 0.0;
+#pragma unroll
+                for (int dim = 0; dim < D; ++dim) {
+                  const double v = fabs(__dsub_rn(BC(j, dim), mi[dim]));
+                  am = (dim == 0) ? v : __dadd_rn(am, v);
+                }
+                am = (D == 2) ? __dmul_rn(am, 0.5) : ((D == 1) ? am : __ddiv_rn(am, (double)D));
+                double sj[KS];
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                  sj[k] = BC(j, D + KS + k);
+                  const double v = fabs(__dsub_rn(sj[k], si[k]));
+                  as = (k == 0) ? v : __dadd_rn(as, v);
+                }
+                as = (KS == 2) ? __dmul_rn(as, 0.5) : ((KS == 1) ? as : __ddiv_rn(as, (double)KS));
+                // one leader track: mean(bool over KS comps) > 0.8  <=>  every component passes
+                ok = true;
+#pragma unroll
+                for (int k = 0; k < KS; ++k)
+                  ok = ok && (__ddiv_rn(am, sj[k]) < th) && (__ddiv_rn(as, sj[k]) < th);
+              }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+              gid[j] = nG;
+              order[off + __popc(m & ((1u << lane) - 1u))] = j;
+            }
+            off += __popc(m);
+          }
+          if (off == goff[nG]) errc = 1;  // leader failed its own test and captured nobody (:725)
+          ++nG;
+          __syncwarp();
+        }
+        if (lane == 0) goff[nG] = off;
+        for (int c = lane; c < nC; c += 32)
+          if (gid[c] < 0) errc = 1;  // tracking.py:700-701
+        errc = __reduce_max_sync(0xffffffffu, errc);
+        __syncwarp();
+        if (errc) break;
+
+        // ---- merge, lane = group (tracking.py:723-741); record normalised weights ----
+        if (lane == 0) recN[step] = nC;
+        const int rows_out = rows_cmp;  // window rows kept (older rows never influence a decision)
+        for (int g = lane; g < nG; g += 32) {
+          const int o = goff[g], n = goff[g + 1] - o;
+          const int c0 = order[o];
+          if (n == 1) {
+#pragma unroll
+            for (int q = 0; q < CO; ++q) BP(g, q) = BC(c0, q);
+            recW[(size_t)step * cap + c0] = 1.0;
+            recGid[(size_t)step * cap + c0] = (uint16_t)g;
+            for (int row = 0; row < rows_out; ++row)
+              for (int s = 0; s < nS; ++s)
+                histN[((size_t)g * fl + row) * nS + s] =
+                    (row == 0) ? ((xt_label(c0, nS, wrap) == s) ? 1.0 : 0.0) : histP[((size_t)(c0 / K) * fl + row - 1) * nS + s];
+          } else {
+            double mx = BC(c0, D + 2 * KS);
+            for (int k = 1; k < n; ++k) mx = fmax(mx, BC(order[o + k], D + 2 * KS));
+            double sw = 0.0, am[D], as2[KS];
+            for (int k = 0; k < n; ++k) {
+              const int c = order[o + k];
+              const double w = exp(__dsub_rn(BC(c, D + 2 * KS), mx));
+              recW[(size_t)step * cap + c] = w;
+              recGid[(size_t)step * cap + c] = (uint16_t)g;
+              sw = (k == 0) ? w : __dadd_rn(sw, w);
+#pragma unroll
+              for (int dim = 0; dim < D; ++dim) {
+                const double v = __dmul_rn(w, BC(c, dim));
+                am[dim] = (k == 0) ? v : __dadd_rn(am[dim], v);
+              }
+#pragma unroll
+              for (int k2 = 0; k2 < KS; ++k2) {
+                const double v = __dmul_rn(w, BC(c, D + k2));
+                as2[k2] = (k == 0) ? v : __dadd_rn(as2[k2], v);
+              }
+            }
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) BP(g, dim) = __ddiv_rn(am[dim], sw);
+#pragma unroll
+            for (int k2 = 0; k2 < KS; ++k2) BP(g, D + k2) = __ddiv_rn(as2[k2], sw);
+            BP(g, D + 2 * KS) = __dadd_rn(log(sw), mx);
+            for (int k = 0; k < n; ++k) {  // normalise the recorded weights
+              const int c = order[o + k];
+              recW[(size_t)step * cap + c] = __ddiv_rn(recW[(size_t)step * cap + c], sw);
+            }
+            // weighted mean of the members' window rows (tracking.py:733), member order
+            for (int row = 0; row < rows_out; ++row)
+              for (int s = 0; s < nS; ++s) {
+                double acc = 0.0;
+                for (int k = 0; k < n; ++k) {
+                  const int c = order[o + k];
+                  const double hv = (row == 0) ? ((xt_label(c, nS, wrap) == s) ? 1.0 : 0.0)
+                                               : histP[((size_t)(c / K) * fl + row - 1) * nS + s];
+                  const double v = __dmul_rn(exp(__dsub_rn(BC(c, D + 2 * KS), mx)), hv);
+                  acc = (k == 0) ? v : __dadd_rn(acc, v);
+                }
+                histN[((size_t)g * fl + row) * nS + s] = __ddiv_rn(acc, sw);
+              }
+          }
+          // window code of the merged history (argmax per row, ties -> lowest state)
+          unsigned long long code = 0;
+          for (int row = 0; row < rows_out; ++row) {
+            int best = 0;
+            double bv = histN[((size_t)g * fl + row) * nS];
+            for (int s = 1; s < nS; ++s) {
+              const double v = histN[((size_t)g * fl + row) * nS + s];
+              if (v > bv) { bv = v; best = s; }
+            }
+            code |= (unsigned long long)best << (bits * row);
+          }
+          codeC[g] = code;                 // staged: codeP/curP are still read by other lanes' merges? (no: only codeC/BC/histP)
+          gid[g] = c0 % nS;                // staged newest true state (gid is dead after the CSR build)
+        }
+        __syncwarp();
+        for (int g = lane; g < nG; g += 32) {
+          codeP[g] = codeC[g];
+          curP[g] = gid[g];
+        }
+        {
+          double* tmp = histP;
+          histP = histN;
+          histN = tmp;
+        }
+        nP = nG;
+        LhP = LhC;
+        __syncwarp();
+      }
+      if (errc) {
+        if (lane == 0) atomicMax(&a.err[wi], errc);
+        continue;
+      }
+
+      // ---- end of track: last-localisation term, optional leave expansion (tracking.py:613-639) ----
+      const bool have_children = L > 2;  // final sequences live in bufC (children of the last step) or bufP (L == 2)
+      double* FB = have_children ? bufC : bufP;
+      double clast[D];
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) clast[dim] = Cp[(size_t)((L - 1) * D + dim) * npad];
+      double vmax = -INFINITY;
+      for (int c = lane; c < nP; c += 32) {
+        double term = 0.0;
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) {
+          const int k = (KS == 1) ? 0 : dim;
+          const double q = __dadd_rn(FB[(size_t)(D + k) * cap + c], l2[k]);
+          const double df = __dsub_rn(clast[dim], FB[(size_t)dim * cap + c]);
+          const double tt = __dsub_rn(__dmul_rn(-0.5, log(__dmul_rn(XT_TWO_PI, q))), __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, q)));
+          term = (dim == 0) ? tt : __dadd_rn(term, tt);
+        }
+        double v = FB[(size_t)(D + 2 * KS) * cap + c] + term;
+        if (ck.isBL) v += a.Lsum[c % nS];
+        aC[c] = v;
+        vmax = fmax(vmax, v);
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o2));
+      double ssum = 0.0;
+      for (int c = lane; c < nP; c += 32) {
+        const double e = exp(aC[c] - vmax);
+        aC[c] = e;
+        ssum += e;
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o2);
+      const double inv = 1.0 / ssum;
+      for (int c = lane; c < nP; c += 32) aC[c] *= inv;
+      __syncwarp();
+
+      // ---- backward sweep over the recorded lattice (deterministic warp reductions) ----
+      // aC holds the posterior of the sequences *after* the expansion of `step`.
+      auto emit_row = [&](int row, const double* av, int n, int mode) {
+        // mode 0: label = int8-wrapped child index; 1: j % nS; 2: j / nS
+        for (int s = 0; s < nS; ++s) {
+          double acc = 0.0;
+          for (int c = lane; c < n; c += 32) {
+            const int lab = (mode == 0) ? xt_label(c, nS, wrap) : ((mode == 1) ? (c % nS) : (c / nS));
+            if (lab == s) acc += av[c];
+          }
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+          if (lane == 0) out[(size_t)row * nS + s] = acc;
+        }
+      };
+      int nC = nP;
+      const double* init_src = aC;  // L == 2: the final sequences are the initial ones
+      for (int step = L - 1; step >= 2; --step) {
+        emit_row(step, aC, nC, 0);  // newest row of this level: forward-time index = step
+        const int nPar = nC / K;
+        for (int p = lane; p < nPar; p += 32) {
+          double sacc = 0.0;
+          for (int r = 0; r < K; ++r) sacc += aC[p * K + r];
+          aP[p] = sacc;
+        }
+        __syncwarp();
+        if (step > 2) {  // the parents of `step` are the groups of step-1
+          const int nCprev = recN[step - 1];
+          for (int c = lane; c < nCprev; c += 32)
+            aC[c] = aP[recGid[(size_t)(step - 1) * cap + c]] * recW[(size_t)(step - 1) * cap + c];
+          nC = nCprev;
+        } else {
+          init_src = aP;
+        }
+        __syncwarp();
+      }
+      // initial sequences j = h0 + nS*h1: row 1 = h0 (newest of the two), row 0 = h1 (oldest)
+      emit_row(1, init_src, nS * nS, 1);
+      emit_row(0, init_src, nS * nS, 2);
+      __syncwarp();
+    }
+  }
+#undef BP
+#undef BC
+}

@@ -1,5 +1,114 @@
+// Host driver of the state-annotation kernel (included by xt_engine.cu).
+template <int D, int KS>
+static cudaError_t launch_k3(xt_ctx* ctx, const K3Args& a, const xt_params& p, int grid) {
+  k3_predict<D, KS><<<grid, 32 * XT_K3_WARPS, 0, ctx->stream>>>(a, p);
+  return cudaGetLastError();
+}
+
 extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
-  (void)p; (void)out;
-  set_error(ctx, "xt_predict: not implemented yet");
-  return XT_ERR_STATE;
+  if (!ctx) return XT_ERR_ARG;
+  if (ctx->chunks.empty()) {
+    set_error(ctx, "no tracks uploaded");
+    return XT_ERR_STATE;
+  }
+  int bits = 0;
+  int rc = check_params(ctx, p, &bits);
+  if (rc) return rc;
+  if (p->nsub != 1) {
+    set_error(ctx, "xt_predict: nb_substeps must be 1 (predict_Bs forces it, tracking.py:839)");
+    return XT_ERR_ARG;
+  }
+  XT_CUDA_OK(cudaSetDevice(ctx->device));
+  const int nS = p->nS, KS = p->n_loc, CO = p->d + 2 * KS + 1;
+  const int n_work = (int)ctx->work.size();
+  const int grid = std::min(n_work, ctx->n_sm * 4);
+  double* d_pred = nullptr;
+  int32_t* d_err = nullptr;
+  double* d_scratch = nullptr;
+  XT_CUDA_OK(cudaMalloc(&d_pred, sizeof(double) * (size_t)ctx->n_locs * nS));
+  XT_CUDA_OK(cudaMalloc(&d_err, sizeof(int32_t) * 2 * (size_t)n_work));
+  std::vector<int32_t> h_err(2 * (size_t)n_work);
+  int cap = std::max(64, nS * nS * nS);
+  int result = XT_OK;
+  for (;;) {
+    if (cap > XT_HARD_CAP) {
+      set_error(ctx, "more than " + std::to_string(XT_HARD_CAP) + " live state sequences; lower frame_len or raise threshold");
+      result = XT_ERR_CAPACITY;
+      break;
+    }
+    const K3Layout lay = k3_layout(cap, CO, p->frame_len, nS, ctx->maxL + 1);
+    const size_t bytes = sizeof(double) * lay.total * (size_t)grid * XT_K3_WARPS;
+    cudaFree(d_scratch);
+    d_scratch = nullptr;
+    if (cudaMalloc(&d_scratch, bytes) != cudaSuccess) {
+      set_error(ctx, "xt_predict: cannot allocate scratch");
+      result = XT_ERR_CUDA;
+      break;
+    }
+    cudaMemsetAsync(d_err, 0, sizeof(int32_t) * 2 * (size_t)n_work, ctx->stream);
+    K3Args a{};
+    a.chunks = ctx->d_chunks;
+    a.work = ctx->d_work;
+    a.soa = ctx->d_soa;
+    a.scratch = d_scratch;
+    a.pred = d_pred;
+    a.err = d_err;
+    a.err_need = d_err + n_work;
+    a.n_work = n_work;
+    a.cap = cap;
+    a.maxL = ctx->maxL + 1;
+    a.bits = bits;
+    a.warp_scratch = lay.total;
+    for (int s = 0; s < nS; ++s) {  // nsub == 1: K = nS
+      double mx = -INFINITY;
+      for (int r = 0; r < nS; ++r) mx = std::max(mx, p->L_leave[r + nS * s]);
+      double acc = 0;
+      for (int r = 0; r < nS; ++r) acc += std::exp(p->L_leave[r + nS * s] - mx);
+      a.Lsum[s] = std::log(acc) + mx;
+    }
+    cudaError_t e = cudaSuccess;
+#define CALL_K3(D_, KS_) e = launch_k3<D_, KS_>(ctx, a, *p, grid)
+    XT_DISPATCH(p->d, p->n_loc, CALL_K3);
+#undef CALL_K3
+    if (e != cudaSuccess || cudaMemcpyAsync(h_err.data(), d_err, sizeof(int32_t) * 2 * (size_t)n_work, cudaMemcpyDeviceToHost,
+                                            ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      set_error(ctx, std::string("xt_predict: ") + cudaGetErrorString(cudaGetLastError()));
+      result = XT_ERR_CUDA;
+      break;
+    }
+    int need = 0;
+    bool grouping = false;
+    for (int i = 0; i < n_work; ++i) {
+      if (h_err[i] == 1) grouping = true;
+      need = std::max(need, h_err[n_work + i]);
+    }
+    if (grouping) {
+      set_error(ctx, "problem with grouping: a state sequence ended ungrouped (threshold must be > 0 and the model finite)");
+      result = XT_ERR_GROUPING;
+      break;
+    }
+    if (!need) break;
+    while (cap < need) cap *= 2;
+  }
+  if (result == XT_OK) {
+    for (size_t s = 0; s < ctx->seg_n.size(); ++s) {
+      const XtChunk& c0 = ctx->chunks[ctx->seg_chunk0[s]];
+      const size_t cnt = (size_t)ctx->seg_n[s] * ctx->seg_L[s] * nS;
+      if (cudaMemcpyAsync(out[s], d_pred + (size_t)c0.loc_off * nS, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream) !=
+          cudaSuccess) {
+        set_error(ctx, "xt_predict: device to host copy failed");
+        result = XT_ERR_CUDA;
+        break;
+      }
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && result == XT_OK) {
+      set_error(ctx, "xt_predict: synchronisation failed");
+      result = XT_ERR_CUDA;
+    }
+  }
+  cudaFree(d_pred);
+  cudaFree(d_err);
+  cudaFree(d_scratch);
+  return result;
 }

@@ -343,23 +343,35 @@ def Proba_Cs(Cs, LocErr, ds, Fs, TrMat, pBL, isBL, cell_dims, nb_substeps, frame
 # --------------------------------------------------------------------------------------
 def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, max_nb_states=200, threshold=0.1,
                workers=1, input_LocErr=None, verbose=0, nb_max=1):
-    """Per-localisation state posteriors, ``{str(L): float64[n, L, nb_states]}``."""
+    """Per-localisation state posteriors, ``{str(L): float64[n, L, nb_states]}`` (forward time).
+
+    Implements the reference default ``nb_max = 1``: every track gets its own grouping plan
+    (tracking.py:803,866-867).  ``nb_max > 1`` (plan shared by ``nb_max`` tracks, "might affect the
+    predictions quality") is not provided by the CUDA engine and raises ``NotImplementedError``.
+    ``workers`` is accepted and ignored.
+    """
     sorted_tracks, l_list = _sorted_buckets(all_tracks)
     nb_substeps = 1  # substeps should not impact the step labelling (tracking.py:839)
     if not isinstance(params, Parameters):
         raise TypeError("params must be either of the class 'lmfit.parameter.Parameters' or a dictionary of the relevant parameters")
+    if nb_max != 1:
+        raise NotImplementedError("predict_Bs on the CUDA engine implements nb_max = 1 (the reference default) only")
     LocErr, ds, Fs, TrMat, pBL = extract_params(params, dt, nb_states, nb_substeps, input_LocErr)
     if len(ds) != nb_states:
         raise ValueError("nb_states (%d) must equal the number of D parameters (%d)" % (nb_states, len(ds)))
     out = {l: np.empty((0, int(l), nb_states)) for l in l_list}
     if not sorted_tracks:
         return out
+    for a in sorted_tracks:
+        if a.shape[1] < 2:
+            raise ValueError("minimal track length = 2, here track length = %s" % a.shape[1])
     min_len, max_len = int(l_list[0]), int(l_list[-1])
     p = build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold, max_nb_states,
                      sorted_tracks[0].shape[2])
     eng = _native.Engine(_default_device())
     try:
-        eng.upload(sorted_tracks, [0 if a.shape[1] == max_len else 1 for a in sorted_tracks], int(nb_max))
+        # chunk size only shapes the device layout here; plans are per track
+        eng.upload(sorted_tracks, [0 if a.shape[1] == max_len else 1 for a in sorted_tracks], MAX_TRACKS_PER_CHUNK)
         preds = eng.predict(p, nb_states)
     finally:
         eng.close()

@@ -185,3 +185,62 @@ def test_param_fitting_recovers_simulated_parameters(xt, capsys):
     assert abs(v["F0"] - 0.6) < 0.08
     assert 0.05 < v["p01"] < 0.2 and 0.05 < v["p10"] < 0.2
     assert np.isfinite(fit.residual[0])
+
+
+PRED_ATOL = 1e-6
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_predict_matches_reference_golden(path, native):
+    z = np.load(path)
+    if z["ref_preds"].size == 0:
+        pytest.skip("nb_substeps > 1: predict_Bs forces nb_substeps = 1")
+    m = case_model(z)
+    m.threshold, m.max_nb_states = 0.1, 200
+    n = z["ref_preds"].shape[0]
+    eng = native.Engine(0)
+    try:
+        eng.upload([z["C"][:n]], [int(z["isBL"])], 2000)
+        got = eng.predict(engine_params(m, z["C"].shape[2]), m.nS)[0]
+    finally:
+        eng.close()
+    assert got.shape == z["ref_preds"].shape
+    np.testing.assert_allclose(got, z["ref_preds"], rtol=0, atol=PRED_ATOL)
+    np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-9)
+
+
+def test_predict_bs_api_vs_oracle(xt):
+    from extrack_b200._lmfit_compat import Parameters
+
+    rng = np.random.default_rng(21)
+    tracks = {str(L): random_walk_tracks(n, L, 2, rng) for L, n in ((2, 3), (3, 4), (7, 40), (15, 70), (31, 33))}
+    tracks["9"] = np.zeros((0, 9, 2))
+    p = Parameters()
+    for k, v in dict(D0=1e-5, D1=0.25, LocErr=0.02, F0=0.6, p01=0.1, p10=0.12, pBL=0.05).items():
+        p.add(k, value=v)
+    p.add("F1", expr="1-F0")
+    got = xt.predict_Bs(tracks, 0.02, p, cell_dims=[1], nb_states=2, frame_len=8)
+    assert set(got) == set(tracks) and got["9"].shape == (0, 9, 2)
+    st, _ = xt._sorted_buckets(tracks)
+    LocErr, ds, Fs, TrMat, pBL = xt.extract_params(p, 0.02, 2, 1)
+    m = orc.Model(LocErr[0].reshape(-1), ds, Fs, TrMat, pBL, [1], 1, 8, 2, 0.1, 200)
+    want = orc.predict_states(st, m, nb_max=1)
+    for a, w in zip(st, want):
+        np.testing.assert_allclose(got[str(a.shape[1])], w, rtol=0, atol=PRED_ATOL)
+    with pytest.raises(NotImplementedError):
+        xt.predict_Bs(tracks, 0.02, p, nb_states=2, nb_max=50)
+    with pytest.raises(TypeError):
+        xt.predict_Bs(tracks, 0.02, {"D0": 1.0}, nb_states=2)
+
+
+def test_predict_three_state_3d_many_sequences(native):
+    m = make_model(nS=3, nsub=1, frame_len=7, threshold=0.05, max_nb_states=200, min_len=5)
+    C = random_walk_tracks(24, 22, 3, np.random.default_rng(5), Ds=m.ds**2 / 0.04)
+    want = np.concatenate([orc.chunk_recursion(C[i : i + 1], m, 1, 1)[2] for i in range(len(C))])
+    eng = native.Engine(0)
+    try:
+        eng.upload([C], [1], 2000)
+        got = eng.predict(engine_params(m, 3), 3)[0]
+    finally:
+        eng.close()
+    np.testing.assert_allclose(got, want, rtol=0, atol=PRED_ATOL)
