@@ -1,0 +1,84 @@
+"""N > 1 host logic on CPU: chunk sharding + one all-reduce per objective call, world_size 2, gloo.
+
+There is no GPU in the build container, so the CUDA engine is replaced *in this test only* by a
+stand-in that evaluates a rank's chunks with the oracle; what is under test is `TrackSet`'s
+partition of the reference chunk list over ranks and the reduction of the partial sums."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    from extrack_b200 import _native
+    from extrack_b200 import tracking as xt
+    from helpers import make_model, random_walk_tracks
+    from oracle import extrack_oracle as orc
+
+    model = make_model(frame_len=5, min_len=6)
+
+    class OracleEngine:  # same surface as _native.Engine, oracle inside (test double)
+        def __init__(self, device=0):
+            self.segs = []
+
+        def upload(self, segments, isBL, chunk_size):
+            self.segs = [(np.asarray(s), int(b)) for s, b in zip(segments, isBL)]
+            assert all(len(s) <= chunk_size for s, _ in self.segs)
+
+        def sum_logp(self, p):
+            return float(sum(orc.chunk_logp(s, model, b).sum() for s, b in self.segs))
+
+        def close(self):
+            pass
+
+    _native.Engine = OracleEngine
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)  # identical data on every rank
+    st = [random_walk_tracks(n, L, 2, rng) for L, n in ((6, 700), (9, 1500), (14, 1200))]
+    ts = xt.TrackSet(st, chunk=500)
+    total = ts.sum_logp(None)
+    q.put((rank, total, ts.my_chunks, len(ts.chunks)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_objective_equals_single_process():
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_model, random_walk_tracks
+    from oracle import extrack_oracle as orc
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(0)
+    st = [random_walk_tracks(n, L, 2, rng) for L, n in ((6, 700), (9, 1500), (14, 1200))]
+    want = -orc.neg_log_likelihood(st, make_model(frame_len=5, min_len=6), chunk=500)
+    (r0, t0, c0, n0), (r1, t1, c1, n1) = res
+    assert t0 == t1  # every rank sees the same all-reduced value
+    assert abs(t0 - want) <= 1e-12 * abs(want)
+    assert sorted(c0 + c1) == list(range(n0)) and c0 and c1  # disjoint cover of the reference chunk list
