@@ -21,6 +21,10 @@ struct xt_ctx {
   int d = 0;
   int64_t n_tracks = 0, track_steps = 0, n_locs = 0;
   std::vector<int> seg_chunk0;
+  std::vector<int64_t> upload_sig;  // shapes of the resident data set (allocation reuse)
+  double* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_done[2] = {nullptr, nullptr};
+  size_t stage_elems = 0;
   std::vector<int64_t> seg_n;
   std::vector<int> seg_L;
   std::vector<XtChunk> chunks;
@@ -102,7 +106,7 @@ static void free_data(xt_ctx* ctx) {
   ctx->d_soa = ctx->d_logp = ctx->d_partial = ctx->d_gstate = nullptr;
   ctx->d_chunks = nullptr; ctx->d_work = nullptr; ctx->d_summ = nullptr; ctx->h_summ = nullptr;
   ctx->gstate_bytes = 0;
-  ctx->chunks.clear(); ctx->work.clear(); ctx->summ.clear();
+  ctx->chunks.clear(); ctx->work.clear(); ctx->summ.clear(); ctx->upload_sig.clear();
   ctx->have_eval = false;
   free_plan(ctx);
 }
@@ -138,6 +142,10 @@ extern "C" void xt_destroy(xt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_data(ctx);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(ctx->stage[b]);
+    if (ctx->stage_done[b]) cudaEventDestroy(ctx->stage_done[b]);
+  }
   cudaFree(ctx->d_out);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -159,17 +167,6 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
     set_error(ctx, "xt_upload: need n_seg >= 1, 1 <= d <= 3, chunk_size >= 1");
     return XT_ERR_ARG;
   }
-  XT_CUDA_OK(cudaSetDevice(ctx->device));
-  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  free_data(ctx);
-  ctx->d = d;
-  ctx->n_tracks = 0;
-  ctx->n_locs = 0;
-  ctx->track_steps = 0;
-  ctx->maxL = 0;
-  int64_t soa_elems = 0, max_seg_elems = 0;
-  int rec = 0;
-  std::vector<int> seg_chunk0(n_seg);
   for (int s = 0; s < n_seg; ++s) {
     if (L[s] < 2) {
       set_error(ctx, "minimal track length = 2, here track length = " + std::to_string(L[s]));
@@ -179,73 +176,95 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
       set_error(ctx, "xt_upload: empty segment");
       return XT_ERR_ARG;
     }
-    seg_chunk0[s] = (int)ctx->chunks.size();
-    ctx->maxL = std::max(ctx->maxL, (int)L[s]);
-    max_seg_elems = std::max<int64_t>(max_seg_elems, n[s] * L[s] * d);
-    for (int64_t a = 0; a < n[s]; a += chunk_size) {
-      XtChunk ck{};
-      ck.L = L[s];
-      ck.nT = (int)std::min<int64_t>(chunk_size, n[s] - a);
-      ck.nTpad = (ck.nT + 31) & ~31;
-      ck.isBL = isBL[s];
-      ck.xyz_off = soa_elems;
-      ck.trk_off = ctx->n_tracks;
-      ck.loc_off = ctx->n_locs;
-      ck.rec0 = rec;
-      ck.nrec = std::max(0, ck.L - 3);
-      ck.seg = s;
-      ck.seg_t0 = (int)a;
-      rec += ck.nrec;
-      soa_elems += (int64_t)ck.L * d * ck.nTpad;
-      ctx->n_tracks += ck.nT;
-      ctx->n_locs += (int64_t)ck.nT * ck.L;
-      ctx->track_steps += (int64_t)ck.nT * (ck.L - 1);
-      for (int t0 = 0; t0 < ck.nT; t0 += 32) ctx->work.push_back(XtWork{(int)ctx->chunks.size(), t0});
-      ctx->chunks.push_back(ck);
-    }
   }
-  ctx->nrec_total = rec;
-  ctx->seg_chunk0 = seg_chunk0;
-  ctx->seg_n.assign(n, n + n_seg);
-  ctx->seg_L.assign(L, L + n_seg);
-  const size_t nch = ctx->chunks.size();
-  XT_CUDA_OK(cudaMalloc(&ctx->d_soa, sizeof(double) * (size_t)soa_elems));
-  XT_CUDA_OK(cudaMemsetAsync(ctx->d_soa, 0, sizeof(double) * (size_t)soa_elems, ctx->stream));
-  XT_CUDA_OK(cudaMalloc(&ctx->d_chunks, sizeof(XtChunk) * nch));
-  XT_CUDA_OK(cudaMalloc(&ctx->d_work, sizeof(XtWork) * ctx->work.size()));
-  XT_CUDA_OK(cudaMalloc(&ctx->d_logp, sizeof(double) * (size_t)ctx->n_tracks));
-  XT_CUDA_OK(cudaMalloc(&ctx->d_partial, sizeof(double) * ctx->work.size()));
-  XT_CUDA_OK(cudaMalloc(&ctx->d_summ, sizeof(XtChunkSummary) * nch));
-  XT_CUDA_OK(cudaMallocHost(&ctx->h_summ, sizeof(XtChunkSummary) * nch));
-  ctx->summ.resize(nch);
-  XT_CUDA_OK(cudaMemcpyAsync(ctx->d_chunks, ctx->chunks.data(), sizeof(XtChunk) * nch, cudaMemcpyHostToDevice,
-                             ctx->stream));
-  XT_CUDA_OK(cudaMemcpyAsync(ctx->d_work, ctx->work.data(), sizeof(XtWork) * ctx->work.size(),
-                             cudaMemcpyHostToDevice, ctx->stream));
+  XT_CUDA_OK(cudaSetDevice(ctx->device));
+  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  // Same shapes as the resident data set (a re-upload of new coordinates, e.g. one objective call
+  // per host buffer): keep every allocation, the chunk/work tables and the plan storage.
+  std::vector<int64_t> sig;
+  sig.push_back(n_seg); sig.push_back(d); sig.push_back(chunk_size);
+  for (int s = 0; s < n_seg; ++s) { sig.push_back(L[s]); sig.push_back(n[s]); sig.push_back(isBL[s]); }
+  const bool reuse = !ctx->chunks.empty() && sig == ctx->upload_sig;
+  int64_t max_seg_elems = 0;
+  for (int s = 0; s < n_seg; ++s) max_seg_elems = std::max<int64_t>(max_seg_elems, n[s] * L[s] * d);
+  if (!reuse) {
+    free_data(ctx);
+    ctx->upload_sig = sig;
+    ctx->d = d;
+    ctx->n_tracks = 0;
+    ctx->n_locs = 0;
+    ctx->track_steps = 0;
+    ctx->maxL = 0;
+    int64_t soa_elems = 0;
+    int rec = 0;
+    ctx->seg_chunk0.assign(n_seg, 0);
+    for (int s = 0; s < n_seg; ++s) {
+      ctx->seg_chunk0[s] = (int)ctx->chunks.size();
+      ctx->maxL = std::max(ctx->maxL, (int)L[s]);
+      for (int64_t a = 0; a < n[s]; a += chunk_size) {
+        XtChunk ck{};
+        ck.L = L[s];
+        ck.nT = (int)std::min<int64_t>(chunk_size, n[s] - a);
+        ck.nTpad = (ck.nT + 31) & ~31;
+        ck.isBL = isBL[s];
+        ck.xyz_off = soa_elems;
+        ck.trk_off = ctx->n_tracks;
+        ck.loc_off = ctx->n_locs;
+        ck.rec0 = rec;
+        ck.nrec = std::max(0, ck.L - 3);
+        ck.seg = s;
+        ck.seg_t0 = (int)a;
+        rec += ck.nrec;
+        soa_elems += (int64_t)ck.L * d * ck.nTpad;
+        ctx->n_tracks += ck.nT;
+        ctx->n_locs += (int64_t)ck.nT * ck.L;
+        ctx->track_steps += (int64_t)ck.nT * (ck.L - 1);
+        for (int t0 = 0; t0 < ck.nT; t0 += 32) ctx->work.push_back(XtWork{(int)ctx->chunks.size(), t0});
+        ctx->chunks.push_back(ck);
+      }
+    }
+    ctx->nrec_total = rec;
+    ctx->seg_n.assign(n, n + n_seg);
+    ctx->seg_L.assign(L, L + n_seg);
+    const size_t nch = ctx->chunks.size();
+    XT_CUDA_OK(cudaMalloc(&ctx->d_soa, sizeof(double) * (size_t)soa_elems));
+    XT_CUDA_OK(cudaMemsetAsync(ctx->d_soa, 0, sizeof(double) * (size_t)soa_elems, ctx->stream));  // padding lanes
+    XT_CUDA_OK(cudaMalloc(&ctx->d_chunks, sizeof(XtChunk) * nch));
+    XT_CUDA_OK(cudaMalloc(&ctx->d_work, sizeof(XtWork) * ctx->work.size()));
+    XT_CUDA_OK(cudaMalloc(&ctx->d_logp, sizeof(double) * (size_t)ctx->n_tracks));
+    XT_CUDA_OK(cudaMalloc(&ctx->d_partial, sizeof(double) * ctx->work.size()));
+    XT_CUDA_OK(cudaMalloc(&ctx->d_summ, sizeof(XtChunkSummary) * nch));
+    XT_CUDA_OK(cudaMallocHost(&ctx->h_summ, sizeof(XtChunkSummary) * nch));
+    ctx->summ.resize(nch);
+    XT_CUDA_OK(cudaMemcpyAsync(ctx->d_chunks, ctx->chunks.data(), sizeof(XtChunk) * nch, cudaMemcpyHostToDevice,
+                               ctx->stream));
+    XT_CUDA_OK(cudaMemcpyAsync(ctx->d_work, ctx->work.data(), sizeof(XtWork) * ctx->work.size(),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->have_eval = false;
   // stage each segment (AoS) and repack on the device; two staging buffers overlap copy and pack
-  double* stage[2] = {nullptr, nullptr};
-  cudaEvent_t done[2];
-  for (int b = 0; b < 2; ++b) {
-    XT_CUDA_OK(cudaMalloc(&stage[b], sizeof(double) * (size_t)max_seg_elems));
-    XT_CUDA_OK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+  if ((size_t)max_seg_elems > ctx->stage_elems) {
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(ctx->stage[b]);
+      ctx->stage[b] = nullptr;
+      XT_CUDA_OK(cudaMalloc(&ctx->stage[b], sizeof(double) * (size_t)max_seg_elems));
+      if (!ctx->stage_done[b]) XT_CUDA_OK(cudaEventCreateWithFlags(&ctx->stage_done[b], cudaEventDisableTiming));
+    }
+    ctx->stage_elems = (size_t)max_seg_elems;
   }
   for (int s = 0; s < n_seg; ++s) {
     const int b = s & 1;
     const size_t elems = (size_t)n[s] * L[s] * d;
-    XT_CUDA_OK(cudaEventSynchronize(done[b]));
-    XT_CUDA_OK(cudaMemcpyAsync(stage[b], xyz[s], sizeof(double) * elems, cudaMemcpyHostToDevice, ctx->stream));
+    XT_CUDA_OK(cudaEventSynchronize(ctx->stage_done[b]));
+    XT_CUDA_OK(cudaMemcpyAsync(ctx->stage[b], xyz[s], sizeof(double) * elems, cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256;
     const long long blocks = ((long long)elems + threads - 1) / threads;
-    k_pack<<<(unsigned)blocks, threads, 0, ctx->stream>>>(stage[b], ctx->d_soa, ctx->d_chunks, seg_chunk0[s],
+    k_pack<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->stage[b], ctx->d_soa, ctx->d_chunks, ctx->seg_chunk0[s],
                                                           chunk_size, (int)n[s], L[s], d);
-    XT_CUDA_OK(cudaEventRecord(done[b], ctx->stream));
+    XT_CUDA_OK(cudaEventRecord(ctx->stage_done[b], ctx->stream));
   }
   XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   XT_CUDA_OK(cudaGetLastError());
-  for (int b = 0; b < 2; ++b) {
-    cudaFree(stage[b]);
-    cudaEventDestroy(done[b]);
-  }
   return XT_OK;
 }
 

@@ -230,10 +230,8 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 
     const double th_lo = __dmul_rn(th, 1.0 - 1e-14), th_hi = __dmul_rn(th, 1.0 + 1e-14);
     // predicate "leader i captures sequence j" (all lanes of the warp must call it together)
-    auto pair_ok = [&](const double (&mi)[D], const double (&si)[KS], unsigned long long ci, int j) -> bool {
-      const unsigned long long cj = codeC[j];
-      if (use_window && cj == ci) return true;             // state_mask, tracking.py:679-681
-      if ((cj & rowmask) != (ci & rowmask)) return false;  // cur_state_mask, :673-674
+    // floating-point half of the predicate (m_mask and s_mask, tracking.py:689-691)
+    auto fp_ok = [&](const double (&mi)[D], const double (&si)[KS], int j) -> bool {
       double am = 0.0, as = 0.0;
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) {
@@ -262,10 +260,20 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
       return cnt_m >= min_cnt && cnt_s >= min_cnt;
     };
+    // predicate "leader i captures sequence j" (all lanes of the warp must call it together)
+    auto pair_ok = [&](const double (&mi)[D], const double (&si)[KS], unsigned long long ci, int j) -> bool {
+      const unsigned long long cj = codeC[j];
+      if (use_window && cj == ci) return true;             // state_mask, tracking.py:679-681
+      if ((cj & rowmask) != (ci & rowmask)) return false;  // cur_state_mask, :673-674
+      return fp_ok(mi, si, j);
+    };
 
     int nG = 0;
     if (nC <= 64) {
       // ---- batch mode ----
+      // window codes of sequences `lane` and `lane + 32` (never equal to a real code when absent)
+      const unsigned long long code_lo = (lane < nC) ? codeC[lane] : ~0ull;
+      const unsigned long long code_hi = (lane + 32 < nC) ? codeC[lane + 32] : ~0ull;
       // grouped / visited / nG / CSR offset are kept redundantly in registers by every thread
       // (the resolution below is deterministic), so a batch needs a single barrier.
       const unsigned long long full = (nC == 64) ? ~0ull : ((1ull << nC) - 1ull);
@@ -286,13 +294,22 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 #pragma unroll
           for (int k = 0; k < KS; ++k) si[k] = ST(bufC, cand, D + KS + k);
           const unsigned long long ci = codeC[cand];
-          unsigned long long todo = full & ~grouped;
+          unsigned long long cand_base = full & ~grouped;
           // sequences below the candidate are already grouped unless an earlier leader failed
-          if ((visited & ~grouped) == 0ull) todo &= ~((1ull << cand) - 1ull);
+          if ((visited & ~grouped) == 0ull) cand_base &= ~((1ull << cand) - 1ull);
+          // code tests for all sequences at once (lane = sequence, two per lane)
+          const unsigned st_lo = __ballot_sync(0xffffffffu, (code_lo & rowmask) == (ci & rowmask));
+          const unsigned st_hi = __ballot_sync(0xffffffffu, (code_hi & rowmask) == (ci & rowmask));
+          const unsigned wn_lo = __ballot_sync(0xffffffffu, use_window && code_lo == ci);
+          const unsigned wn_hi = __ballot_sync(0xffffffffu, use_window && code_hi == ci);
+          const unsigned long long state_eq = (unsigned long long)st_lo | ((unsigned long long)st_hi << 32);
+          const unsigned long long win_eq = (unsigned long long)wn_lo | ((unsigned long long)wn_hi << 32);
+          row = win_eq & cand_base;                                  // state_mask (:679-681)
+          unsigned long long todo = state_eq & ~win_eq & cand_base;  // need the m/s tests (:689-693)
           while (todo) {
             const int j = __ffsll((long long)todo) - 1;
             todo &= todo - 1ull;
-            if (pair_ok(mi, si, ci, j)) row |= 1ull << j;
+            if (fp_ok(mi, si, j)) row |= 1ull << j;
           }
         }
         unsigned long long* b_row = s_row + (batch & 1) * W;
