@@ -43,6 +43,27 @@ struct XtRecHdr {
   double th;    // threshold used at this step
 };
 
+// Replay record of one fusion step, consumed by the fused replay kernel (xt_replay_fused.cuh):
+// one contiguous blob per record so that a CTA can stage the next step's record in shared
+// memory while it computes the current one.  Layout in 16-byte words:
+//   words 0-1 : XtBlobHdr
+//   words 2.. : nG group records (8 bytes each) in *schedule order*: the groups of replay warp w
+//               are entries woff[w] .. woff[w+1]-1 (groups sorted by member count, descending,
+//               dealt round-robin to the warps)
+//   then      : nC member entries (4 bytes each, xt_pack_ent) in CSR order, for groups of > 2 members
+// Group record: lo = p0:12 | head0:8 | g:12; hi = kind:2 (1 single, 2 pair, 3 list) << 30 and
+//   pair: p1:12 | head1:8 << 12;   list: first member offset:12 | member count:13 << 12.
+#define XT_MAX_WPC 8
+struct XtBlobHdr {
+  uint16_t nG, nC;
+  uint16_t n16;   // 16-byte words of this record
+  uint16_t pad_;
+  uint16_t woff[XT_MAX_WPC + 1];
+  uint16_t pad2_[3];
+};
+static_assert(sizeof(XtBlobHdr) == 32, "XtBlobHdr must be two 16-byte words");
+__host__ __device__ inline int xt_blob_stride16(int cap) { return 2 + (cap + 1) / 2 + (cap + 3) / 4; }
+
 // entry of the CSR member list: parent slot | head << 16 | r << 24
 __host__ __device__ inline uint32_t xt_pack_ent(int p, int head, int r) {
   return (uint32_t)p | ((uint32_t)head << 16) | ((uint32_t)r << 24);
@@ -55,6 +76,7 @@ struct XtPlanPtrs {
   uint8_t* curG;     // [nrec_total][cap]   newest true state of each group's representative
   uint16_t* gid;     // [nrec_total][cap]   group of each incoming child (dump / tests)
   unsigned long long* grec;  // [nrec_total][cap] per group: p0:16|head0:8|n:8 | (p1:16|head1:8)<<32, n capped at 255
+  uint4* blob;       // [nrec_total][xt_blob_stride16(cap)] replay records (see XtBlobHdr)
   int32_t cap;
 };
 

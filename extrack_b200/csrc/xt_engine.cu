@@ -11,6 +11,7 @@
 #include "xt_plan.cuh"
 #include "xt_replay.cuh"
 #include "xt_replay_lin.cuh"
+#include "xt_replay_fused.cuh"
 #include "xt_predict.cuh"
 
 struct xt_ctx {
@@ -34,6 +35,8 @@ struct xt_ctx {
   double* d_soa = nullptr;
   XtChunk* d_chunks = nullptr;
   XtWork* d_work = nullptr;
+  XtWork* d_workf[2] = {nullptr, nullptr};  // fused replay: tiles of 32 / 64 tracks, longest chunks first
+  int n_workf[2] = {0, 0};
   double* d_logp = nullptr;
   double* d_partial = nullptr;
   double* d_out = nullptr;
@@ -53,6 +56,8 @@ struct xt_ctx {
   bool have_eval = false;
   bool force_global = false;  // test hook: run the log-domain global-memory replay variant
   int k2_wpc = 4;             // warps cooperating on one 32-track tile in the fast replay kernel
+  int k2_tpt = 1;             // tracks per thread of the fused replay kernel (tile = 32 * k2_tpt tracks)
+  int k2_variant = 0;         // 0: fused merge+update kernel (default), 1: first-generation linear-domain kernel
   xt_params last_p{};
   xt_stats stats{};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -92,7 +97,7 @@ __global__ void k_fp64_peak(double* out, int iters) {
 
 static void free_plan(xt_ctx* ctx) {
   cudaFree(ctx->plan.hdr); cudaFree(ctx->plan.goff); cudaFree(ctx->plan.ent);
-  cudaFree(ctx->plan.curG); cudaFree(ctx->plan.gid); cudaFree(ctx->plan.grec);
+  cudaFree(ctx->plan.curG); cudaFree(ctx->plan.gid); cudaFree(ctx->plan.grec); cudaFree(ctx->plan.blob);
   cudaFree(ctx->d_state1); cudaFree(ctx->d_hist1);
   ctx->plan = XtPlanPtrs{};
   ctx->d_state1 = ctx->d_hist1 = nullptr;
@@ -102,6 +107,8 @@ static void free_plan(xt_ctx* ctx) {
 static void free_data(xt_ctx* ctx) {
   cudaFree(ctx->d_soa); cudaFree(ctx->d_chunks); cudaFree(ctx->d_work); cudaFree(ctx->d_logp);
   cudaFree(ctx->d_partial); cudaFree(ctx->d_summ); cudaFree(ctx->d_gstate);
+  cudaFree(ctx->d_workf[0]); cudaFree(ctx->d_workf[1]);
+  ctx->d_workf[0] = ctx->d_workf[1] = nullptr;
   if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
   ctx->d_soa = ctx->d_logp = ctx->d_partial = ctx->d_gstate = nullptr;
   ctx->d_chunks = nullptr; ctx->d_work = nullptr; ctx->d_summ = nullptr; ctx->h_summ = nullptr;
@@ -240,6 +247,20 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
                                ctx->stream));
     XT_CUDA_OK(cudaMemcpyAsync(ctx->d_work, ctx->work.data(), sizeof(XtWork) * ctx->work.size(),
                                cudaMemcpyHostToDevice, ctx->stream));
+    // work tables of the fused replay kernel: longest chunks first (the last CTAs of the launch
+    // are then the short ones: smaller tail)
+    std::vector<int> order(nch);
+    for (size_t c = 0; c < nch; ++c) order[c] = (int)c;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ctx->chunks[x].L > ctx->chunks[y].L; });
+    for (int v = 0; v < 2; ++v) {
+      const int tile = 32 << v;
+      std::vector<XtWork> wf;
+      for (int c : order)
+        for (int t0 = 0; t0 < ctx->chunks[c].nT; t0 += tile) wf.push_back(XtWork{c, t0});
+      ctx->n_workf[v] = (int)wf.size();
+      XT_CUDA_OK(cudaMalloc(&ctx->d_workf[v], sizeof(XtWork) * wf.size()));
+      XT_CUDA_OK(cudaMemcpy(ctx->d_workf[v], wf.data(), sizeof(XtWork) * wf.size(), cudaMemcpyHostToDevice));
+    }
   }
   ctx->have_eval = false;
   // stage each segment (AoS) and repack on the device; two staging buffers overlap copy and pack
@@ -308,6 +329,7 @@ static int ensure_plan(xt_ctx* ctx, const xt_params* p, int cap) {
   XT_CUDA_OK(cudaMalloc(&ctx->plan.curG, sizeof(uint8_t) * nrec * cap));
   XT_CUDA_OK(cudaMalloc(&ctx->plan.gid, sizeof(uint16_t) * nrec * cap));
   XT_CUDA_OK(cudaMalloc(&ctx->plan.grec, sizeof(unsigned long long) * nrec * cap));
+  XT_CUDA_OK(cudaMalloc(&ctx->plan.blob, sizeof(uint4) * nrec * xt_blob_stride16(cap)));
   ctx->plan.cap = cap;
   XT_CUDA_OK(cudaMalloc(&ctx->d_state1, sizeof(double) * nch * 2 * cap * CO1 * 32));
   XT_CUDA_OK(cudaMalloc(&ctx->d_hist1, sizeof(double) * nch * 2 * cap * RH * p->nS));
@@ -334,6 +356,27 @@ static cudaError_t launch_k2_lin(xt_ctx* ctx, const K2Args& a, const xt_params& 
   if (e != cudaSuccess) return e;
   kern<<<grid, 32 * WPC, smem, ctx->stream>>>(a, p, lin);
   return cudaGetLastError();
+}
+
+template <int D, int KS, int WPC, int TPT>
+static cudaError_t launch_k2_fused_w(xt_ctx* ctx, const K2FArgs& a, const K2Tab& tab, size_t smem) {
+  auto kern = k2_replay_fused<D, KS, WPC, TPT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<a.n_work, 32 * WPC, smem, ctx->stream>>>(a, tab);
+  return cudaGetLastError();
+}
+
+template <int D, int KS>
+static cudaError_t launch_k2_fused(xt_ctx* ctx, const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt) {
+  if (tpt == 2) {
+    if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 2>(ctx, a, tab, smem);
+    if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 2>(ctx, a, tab, smem);
+    return launch_k2_fused_w<D, KS, 4, 2>(ctx, a, tab, smem);
+  }
+  if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 1>(ctx, a, tab, smem);
+  if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 1>(ctx, a, tab, smem);
+  return launch_k2_fused_w<D, KS, 4, 1>(ctx, a, tab, smem);
 }
 
 template <int D, int KS>
@@ -379,6 +422,7 @@ static int run_plan(xt_ctx* ctx, const xt_params* p, int bits) {
     a.cap = cap;
     a.RH = ctx->RH;
     a.bits = bits;
+    a.wpc = ctx->k2_wpc;
     const size_t smem = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
     cudaError_t e = cudaSuccess;
 #define CALL_K1(D_, KS_) e = launch_k1<D_, KS_>(ctx, a, *p, smem)
@@ -405,6 +449,22 @@ static int run_plan(xt_ctx* ctx, const xt_params* p, int bits) {
     cap = ncap;
   }
   std::copy(ctx->h_summ, ctx->h_summ + ctx->chunks.size(), ctx->summ.begin());
+  return XT_OK;
+}
+
+static int finish_eval(xt_ctx* ctx, const xt_params* p, int n_work, double* d_out, int64_t su, int64_t sg, int maxC) {
+  k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, n_work, d_out ? d_out : ctx->d_out);
+  XT_CUDA_OK(cudaGetLastError());
+  XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  ctx->stats.k2_launches = 2;
+  ctx->stats.n_tracks = ctx->n_tracks;
+  ctx->stats.track_steps = ctx->track_steps;
+  ctx->stats.seq_updates = su;
+  ctx->stats.seq_groups = sg;
+  ctx->stats.max_nB_in = maxC;
+  ctx->stats.n_chunks = (int)ctx->chunks.size();
+  ctx->last_p = *p;
+  ctx->have_eval = true;
   return XT_OK;
 }
 
@@ -446,6 +506,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
   a.summ = ctx->d_summ;
   a.logp = ctx->d_logp;
   a.partial = ctx->d_partial;
+  Pmax = std::max(Pmax, 4);  // the fused kernel parks its end-of-track partial sums in an idle state buffer
   a.Pcap = Pmax;
   a.n_work = (int)ctx->work.size();
   for (int s = 0; s < p->nS; ++s) {
@@ -463,8 +524,44 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
     lin.tau1[h] = std::exp(p->LT[h] + p->Lp_stay[h % K]);
   }
   for (int s = 0; s < p->nS; ++s) lin.leave[s] = std::exp(a.Lsum[s]);
-  const size_t state_bytes = (size_t)2 * Pmax * CO * 32 * sizeof(double);
   const int wpc = ctx->k2_wpc;
+  // tracks per thread: two if the state of a 64-track tile fits in shared memory
+  int tpt = ctx->k2_tpt;
+  if (tpt == 2 && xt_fused_smem(p->d, KS, Pmax, K, K * p->nS, wpc, 2) > (size_t)ctx->smem_optin) tpt = 1;
+  const size_t fsmem = xt_fused_smem(p->d, KS, Pmax, K, K * p->nS, wpc, tpt);
+  if (ctx->k2_variant == 0 && !ctx->force_global && fsmem <= (size_t)ctx->smem_optin &&
+      xt_fused_blob16(Pmax, K) <= 64 * wpc) {
+    K2Tab tab{};
+    for (int h = 0; h < K * p->nS; ++h) {
+      tab.tau0[h] = lin.tau0[h];
+      tab.tau1[h] = lin.tau1[h];
+      tab.dd[h] = p->dd[h];
+      tab.winit[h] = lin.winit[h];
+    }
+    for (int s = 0; s < p->nS; ++s) tab.leave[s] = lin.leave[s];
+    for (int k = 0; k < KS; ++k) tab.l2[k] = p->l2[k];
+    for (int j = 0; j < 16; ++j) tab.e2[j] = std::exp2((double)j / 16.0);
+    tab.nS = p->nS;
+    tab.nsub = p->nsub;
+    tab.K = K;
+    tab.min_len = p->min_len;
+    K2FArgs fa{};
+    fa.chunks = ctx->d_chunks;
+    fa.work = ctx->d_workf[tpt - 1];
+    fa.soa = ctx->d_soa;
+    fa.plan = ctx->plan;
+    fa.logp = ctx->d_logp;
+    fa.partial = ctx->d_partial;
+    fa.Pcap = Pmax;
+    fa.n_work = ctx->n_workf[tpt - 1];
+    cudaError_t ef = cudaSuccess;
+#define CALL_K2F(D_, KS_) ef = launch_k2_fused<D_, KS_>(ctx, fa, tab, fsmem, wpc, tpt)
+    XT_DISPATCH(p->d, p->n_loc, CALL_K2F);
+#undef CALL_K2F
+    XT_CUDA_OK(ef);
+    return finish_eval(ctx, p, fa.n_work, d_out, su, sg, maxC);
+  }
+  const size_t state_bytes = (size_t)2 * Pmax * CO * 32 * sizeof(double);
   const size_t smem = state_bytes + (size_t)2 * wpc * 32 * sizeof(double);
   const bool use_smem = smem <= (size_t)ctx->smem_optin && !ctx->force_global;
   int grid = a.n_work;
@@ -485,19 +582,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
   XT_DISPATCH(p->d, p->n_loc, CALL_K2);
 #undef CALL_K2
   XT_CUDA_OK(e);
-  k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, a.n_work, d_out ? d_out : ctx->d_out);
-  XT_CUDA_OK(cudaGetLastError());
-  XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  ctx->stats.k2_launches = 2;
-  ctx->stats.n_tracks = ctx->n_tracks;
-  ctx->stats.track_steps = ctx->track_steps;
-  ctx->stats.seq_updates = su;
-  ctx->stats.seq_groups = sg;
-  ctx->stats.max_nB_in = maxC;
-  ctx->stats.n_chunks = (int)ctx->chunks.size();
-  ctx->last_p = *p;
-  ctx->have_eval = true;
-  return XT_OK;
+  return finish_eval(ctx, p, a.n_work, d_out, su, sg, maxC);
 }
 
 extern "C" int xt_sum_logp(xt_ctx* ctx, const xt_params* p, double* out) {
@@ -522,6 +607,24 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return XT_ERR_ARG;
   if (std::strcmp(name, "force_global_replay") == 0) {
     ctx->force_global = value != 0;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k2_variant") == 0) {
+    if (value != 0 && value != 1) {
+      set_error(ctx, "xt_set_option: k2_variant must be 0 (fused) or 1 (first-generation linear)");
+      return XT_ERR_ARG;
+    }
+    ctx->k2_variant = value;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k2_tpt") == 0) {
+    if (value != 1 && value != 2) {
+      set_error(ctx, "xt_set_option: k2_tpt must be 1 or 2");
+      return XT_ERR_ARG;
+    }
+    ctx->k2_tpt = value;
     ctx->have_eval = false;
     return XT_OK;
   }

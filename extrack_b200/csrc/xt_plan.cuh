@@ -26,6 +26,7 @@ struct K1Args {
   int32_t cap;         // children capacity
   int32_t RH;          // history rows allocated per sequence
   int32_t bits;        // bits per history row in the window code
+  int32_t wpc;         // warps per tile of the fused replay kernel (schedule of the replay records)
 };
 
 __device__ __forceinline__ int xt_label(int x, int nS, bool wrap) {
@@ -416,6 +417,50 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         const unsigned long long e0 = ent[o], e1 = (n > 1) ? ent[o + 1] : 0u;
         grec[g] = (e0 & 0xFFFFFFull) | ((unsigned long long)(n > 255 ? 255 : n) << 24) | ((e1 & 0xFFFFFFull) << 32);
       }
+    }
+
+    {  // replay record of this step (XtBlobHdr, xt_common.cuh).  Schedule: groups sorted by
+       // (members descending, group ascending) are dealt round-robin to the replay warps.
+      uint4* blob = a.plan.blob + (size_t)rec * xt_blob_stride16(a.plan.cap);
+      const int wpc = a.wpc;
+      if (tid <= XT_MAX_WPC) {
+        XtBlobHdr* h = (XtBlobHdr*)blob;
+        // groups of warp w: ranks w, w + wpc, ...  => woff[w] = sum_{v<w} ceil((nG - v) / wpc)
+        int o = 0;
+        for (int v = 0; v < tid && v < wpc; ++v) o += (nG - v + wpc - 1) / wpc;
+        h->woff[tid] = (uint16_t)o;
+        if (tid == 0) {
+          h->nG = (uint16_t)nG;
+          h->nC = (uint16_t)nC;
+          h->n16 = (uint16_t)(2 + (nG + 1) / 2 + (nC + 3) / 4);
+        }
+      }
+      unsigned long long* brec = (unsigned long long*)(blob + 2);
+      for (int g = tid; g < nG; g += XT_K1_THREADS) {
+        const int o = gcnt[g], n = gcnt[g + 1] - o;
+        int rank = 0;
+        for (int j = 0; j < nG; ++j) {
+          const int nj = gcnt[j + 1] - gcnt[j];
+          rank += (nj > n) || (nj == n && j < g);
+        }
+        const int wq = rank % wpc, pos = rank / wpc;
+        int slot = pos;
+        for (int v = 0; v < wq; ++v) slot += (nG - v + wpc - 1) / wpc;
+        const uint32_t e0 = ent[o];
+        const unsigned lo = (e0 & 0xFFFu) | (((e0 >> 16) & 0xFFu) << 12) | ((unsigned)g << 20);
+        unsigned hi;
+        if (n == 1) {
+          hi = 1u << 30;
+        } else if (n == 2) {
+          const uint32_t e1 = ent[o + 1];
+          hi = (2u << 30) | (e1 & 0xFFFu) | (((e1 >> 16) & 0xFFu) << 12);
+        } else {
+          hi = (3u << 30) | (unsigned)o | ((unsigned)n << 12);
+        }
+        brec[slot] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+      }
+      uint32_t* bent = (uint32_t*)(blob + 2 + (nG + 1) / 2);
+      for (int c = tid; c < nC; c += XT_K1_THREADS) bent[c] = ent[c];
     }
 
     // ---- merge on the leader tracks (tracking.py:723-741) ----

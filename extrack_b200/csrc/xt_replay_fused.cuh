@@ -1,0 +1,590 @@
+// K2 (fast path, second generation) — fused merge + update replay kernel with per-sequence
+// extended exponents.
+//
+// Same recursion as xt_replay.cuh (log domain) restated like a scaled forward algorithm:
+//   * a sequence carries a linear weight W = Wm * 2^E (Wm in [1, 2) or 0, E a 32-bit integer
+//     kept next to the moments), so no per-track scale has to be agreed between warps: one CTA
+//     barrier per step, no log/exp pair per merge, exact for any dynamic range;
+//   * the Gaussian-product update (tracking.py:87-98) costs one reciprocal and one
+//     range-reduced exp polynomial per parent: exp(e) = p(r) * 2^k and k goes to the exponent;
+//   * the merge of fuse_tracks_th (tracking.py:723-741) needs no transcendental: the members'
+//     weights are the merge weights;
+//   * merge and the following update are fused: a warp merges a group from the previous step's
+//     parents and immediately updates it with the next localisation, so the state makes one
+//     shared-memory round trip per step (ping-pong buffers);
+//   * the plan kernel emits one contiguous replay record per step (XtBlobHdr, xt_common.cuh)
+//     with the groups already assigned to the replay warps (sorted by size, round-robin);
+//     the CTA stages the record of the next step in shared memory while it computes the
+//     current one, so the inner loops never wait on global memory.
+//
+// Mapping: a CTA of WPC warps owns a tile of 32*TPT tracks; a thread carries TPT tracks (lane,
+// lane + 32, ...), which gives every instruction stream TPT independent dependency chains and
+// amortises the warp-uniform work (record decoding, addresses, loop control) over TPT tracks.
+// Warp w processes the groups woff[w]..woff[w+1]-1 of the step's record.  State slot =
+// (m[D], u[KS], Wm) as 16-byte vectors [slot][vector][track] (conflict-free 128-bit
+// shared-memory accesses) + [slot][track] exponents.
+#pragma once
+#include "xt_common.cuh"
+#include "xt_replay.cuh"
+#include "xt_replay_lin.cuh"
+
+#define XT_ZERO_EXP (-(1 << 30))  // exponent of a sequence with zero weight
+
+struct K2Tab {  // per-evaluation tables and scalars of the fused replay kernel (built on the host)
+  double tau0[XT_MAX_HEADS];      // exp(LT[head])
+  double tau1[XT_MAX_HEADS];      // exp(LT[head] + Lp_stay[r])
+  double dd[XT_MAX_HEADS];        // xt_params::dd
+  double winit[XT_MAX_HEADS];     // exp(LT + LF)
+  double leave[XT_MAX_STATES];    // sum_r exp(L_leave[r + K*state])
+  double l2[XT_MAX_DIMS];
+  double e2[16];                  // 2^(j/16)
+  int32_t nS, nsub, K, min_len;
+};
+
+// ---- shared memory through 32-bit shared-window addresses (no generic-pointer arithmetic) ----
+__device__ __forceinline__ unsigned xt_smem_base(const void* p) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));  // computed once: keeps the base from being rematerialised
+  return a;
+}
+__device__ __forceinline__ void xt_lds128(unsigned a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ double xt_lds64(unsigned a) {
+  double x;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
+  return x;
+}
+__device__ __forceinline__ uint2 xt_lds64u(unsigned a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int xt_lds32(unsigned a) {
+  int x;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(x) : "r"(a));
+  return x;
+}
+__device__ __forceinline__ unsigned xt_lds16(unsigned a) {
+  unsigned x;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(x) : "r"(a));
+  return x;
+}
+__device__ __forceinline__ void xt_sts128(unsigned a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void xt_sts128u(unsigned a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void xt_sts64(unsigned a, double x) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory");
+}
+__device__ __forceinline__ void xt_sts32(unsigned a, int x) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+}
+
+// 2^d for -1022 <= d <= 0, +0.0 below (d never exceeds 0 here: exponents relative to a maximum)
+__device__ __forceinline__ double xt_pow2_le0(int d) {
+  return __hiloint2double(max(d + 1023, 0) << 20, 0);
+}
+
+// x <= 0 -> max(x, about -1e6): unsigned min on the high word (the sign bit is set, so a larger
+// magnitude is a larger unsigned word); one integer instruction instead of a NaN-aware DSETP/FSEL
+// sequence.  Keeps k = round(x / ln 2) far inside the int range of the exponent bookkeeping.
+__device__ __forceinline__ double xt_clamp_neg(double x) {
+  return __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC12E8480u), __double2loint(x));
+}
+
+// exp(x) = p * 2^k for -1e6 <= x <= 0 with p in [0.97, 2): x * 16/ln2 = 16 k + j + rho,
+// exp(x) = 2^k * 2^(j/16) * exp(r), |r| <= ln2/32, Taylor degree 7 (truncation 1.2e-18);
+// 2^(j/16) from a 16-entry shared-memory table (conflict-free: 16 distinct 8-byte words).
+__device__ __forceinline__ double xt_exp_split(double x, unsigned s_e2, int& k) {
+  double t = fma(x, 23.083120654223414, 6755399441055744.0);
+  const int n = __double2loint(t);
+  t -= 6755399441055744.0;
+  double r = fma(t, -0.04332169878499658, x);
+  r = fma(t, -1.4494042586539372e-18, r);
+  const double tj = xt_lds64(s_e2 + ((n & 15) << 3));
+  k = n >> 4;
+  // the three highest coefficients are truncated to their high word (immediate operands):
+  // their terms are below 4e-11, so 21 significant bits keep the error under 2e-17
+  double p = 0.00019841268658638;
+  p = fma(p, r, 0.00138888880610466);
+  p = fma(p, r, 0.00833333283662796);
+  p = fma(p, r, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return p * tj;
+}
+
+// v >= 0 (normal or zero) -> mantissa in [1, 2) and exponent base + unbiased exponent of v;
+// zero -> (0, XT_ZERO_EXP)
+__device__ __forceinline__ void xt_split_exponent(double v, int base, double& mant, int& E) {
+  const int hi = __double2hiint(v);
+  const int be = (hi >> 20) & 0x7ff;
+  mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+  E = base + be - 1023;
+  if (be == 0) {
+    mant = 0.0;
+    E = XT_ZERO_EXP;
+  }
+}
+
+template <int D, int KS>
+struct XtSeq {
+  double m[D];
+  double u[KS];
+  double W;
+  int E;
+};
+
+// State slot = NV 16-byte vectors [vector][track] (components m[D], u[KS], W in this order) at
+// va + i*VS, exponents at ea; both addresses already include the lane offset.  Track j of the
+// thread sits 32*j lanes further.
+template <int D, int KS, int TPT>
+struct XtSlotIO {
+  static constexpr int CO = D + KS + 1;
+  static constexpr int NV = (CO + 1) / 2;
+  static constexpr int VS = 32 * TPT * 16;   // bytes per vector row
+  static constexpr int SLOTB = NV * VS;      // bytes per slot
+  static constexpr int ESLOT = 32 * TPT * 4; // exponent bytes per slot
+  static __device__ __forceinline__ void load(unsigned va, unsigned ea, XtSeq<D, KS> (&s)[TPT]) {
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+      double c[2 * NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xt_lds128(va + i * VS + j * 512, c[2 * i], c[2 * i + 1]);
+#pragma unroll
+      for (int i = 0; i < D; ++i) s[j].m[i] = c[i];
+#pragma unroll
+      for (int i = 0; i < KS; ++i) s[j].u[i] = c[D + i];
+      s[j].W = c[D + KS];
+      s[j].E = xt_lds32(ea + j * 128);
+    }
+  }
+  static __device__ __forceinline__ void store(unsigned va, unsigned ea, const XtSeq<D, KS> (&s)[TPT]) {
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+      double c[2 * NV];
+#pragma unroll
+      for (int i = 0; i < D; ++i) c[i] = s[j].m[i];
+#pragma unroll
+      for (int i = 0; i < KS; ++i) c[D + i] = s[j].u[i];
+      c[D + KS] = s[j].W;
+      if (2 * NV > CO) c[CO] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xt_sts128(va + i * VS + j * 512, c[2 * i], c[2 * i + 1]);
+      xt_sts32(ea + j * 128, s[j].E);
+    }
+  }
+};
+
+// Gaussian-product update of merged sequences (m, s2, W * 2^E) with the localisations cl (one
+// per track of the thread, written stage by stage so that the TPT chains interleave); the
+// result is the parent record (m', u = l2*s2/q, W' * 2^E') shared by its children.
+template <int D, int KS, int TPT>
+__device__ __forceinline__ void xt_update(XtSeq<D, KS> (&s)[TPT], const double (&cl)[TPT][D], const double (&l2)[KS],
+                                          unsigned s_e2) {
+  double rq[TPT][KS], e[TPT];
+#pragma unroll
+  for (int j = 0; j < TPT; ++j)
+#pragma unroll
+    for (int k = 0; k < KS; ++k) rq[j][k] = xt_rcp(l2[k] + s[j].u[k]);
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+    double g[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      g[k] = s[j].u[k] * rq[j][k];
+      s[j].u[k] = l2[k] * g[k];
+    }
+    if (KS == 1) {
+      double q2 = 0.0;
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) {
+        const double df = cl[j][dim] - s[j].m[dim];
+        s[j].m[dim] = fma(df, g[0], s[j].m[dim]);
+        q2 = (dim == 0) ? df * df : fma(df, df, q2);
+      }
+      e[j] = q2 * (-0.5 * rq[j][0]);
+    } else {
+      double quad = 0.0;
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) {
+        const double df = cl[j][dim] - s[j].m[dim];
+        s[j].m[dim] = fma(df, g[dim], s[j].m[dim]);
+        quad = fma(df * df, rq[j][dim], quad);
+      }
+      e[j] = -0.5 * quad;
+    }
+  }
+  double p[TPT];
+  int k2[TPT];
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) p[j] = xt_exp_split(xt_clamp_neg(e[j]), s_e2, k2[j]);
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+    const double wn = (s[j].W * xt_normfac<D, KS>(rq[j])) * p[j];
+    xt_split_exponent(wn, s[j].E + k2[j], s[j].W, s[j].E);
+  }
+}
+
+struct K2FArgs {
+  const XtChunk* chunks;
+  const XtWork* work;   // tiles of 32*TPT tracks
+  const double* soa;
+  XtPlanPtrs plan;
+  double* logp;
+  double* partial;
+  int32_t Pcap;
+  int32_t n_work;
+};
+
+// shared memory of k2_replay_fused in bytes (host and device agree through these functions)
+__host__ __device__ inline int xt_fused_blob16(int Pcap, int K) { return 2 + (Pcap + 1) / 2 + (K * Pcap + 3) / 4; }
+__host__ __device__ inline size_t xt_fused_smem(int D, int KS, int Pcap, int K, int H, int wpc, int tpt) {
+  const int NV = (D + KS + 1 + 1) / 2;
+  return (size_t)2 * Pcap * NV * 512 * tpt         // state vectors, ping-pong
+         + (size_t)2 * xt_fused_blob16(Pcap, K) * 16  // staged replay records, ping-pong
+         + (size_t)2 * H * 16                      // (tau, dd) per head, without / with the stay term
+         + 128                                     // 2^(j/16)
+         + (size_t)2 * Pcap * 128 * tpt;           // exponents, ping-pong
+  // (the end-of-track partial sums, wpc * 384 * tpt bytes, reuse the idle state buffer: Pcap >= 2)
+}
+
+template <int D, int KS, int WPC, int TPT>
+__global__ void __launch_bounds__(32 * WPC) k2_replay_fused(const K2FArgs a, const __grid_constant__ K2Tab T) {
+  using IO = XtSlotIO<D, KS, TPT>;
+  using Seq = XtSeq<D, KS>;
+  constexpr int SLOTB = IO::SLOTB, ESLOT = IO::ESLOT;
+  constexpr int NT = 32 * WPC;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, w = tid >> 5;
+  const int wi = blockIdx.x;
+  const XtWork wk = a.work[wi];
+  const XtChunk ck = a.chunks[wk.chunk];
+  const int nS = T.nS, K = T.K, H = K * nS;
+  const size_t npad = (size_t)ck.nTpad;
+  const double* Cs = a.soa + ck.xyz_off;
+  int toff[TPT];
+  bool valid[TPT];
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+    const int t = wk.t0 + lane + 32 * j;
+    valid[j] = t < ck.nT;
+    toff[j] = valid[j] ? t : ck.nT - 1;
+  }
+  const size_t cstride = (size_t)D * npad;
+  const int L = ck.L;
+  const int Pcap = a.Pcap;
+  const int B16 = xt_fused_blob16(Pcap, K);
+
+  extern __shared__ double2 k2f_smem[];
+  const unsigned sb = xt_smem_base(k2f_smem);
+  const unsigned VB = (unsigned)Pcap * SLOTB, EB = (unsigned)Pcap * ESLOT;
+  const unsigned s_vec = sb + lane * 16;                // [2][Pcap][NV][32*TPT] x 16 B
+  const unsigned s_blob = sb + 2 * VB;                  // [2][B16] x 16 B
+  const unsigned s_tab = s_blob + 2 * B16 * 16;         // [2][H] x 16 B: (tau, dd)
+  const unsigned s_e2 = s_tab + 2 * H * 16;             // [16] x 8 B
+  const unsigned s_exp = s_e2 + 128 + lane * 4;         // [2][Pcap][32*TPT] x 4 B
+
+  // stage the first replay record (steps 3..L-1 use records 0..L-4) and the tables
+  // (up to two 16-byte words per thread: B16 <= 64 * WPC is checked by the host)
+  const int bstride = xt_blob_stride16(a.plan.cap);
+  const uint4* gblob = a.plan.blob + (size_t)ck.rec0 * bstride + tid;
+  const int nrec = ck.nrec;
+  uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
+  if (nrec > 0) {
+    if (tid < B16) pre0 = __ldg(gblob);
+    if (tid + NT < B16) pre1 = __ldg(gblob + NT);
+  }
+  for (int h = tid; h < 2 * H; h += NT) {
+    const int hh = h < H ? h : h - H;
+    xt_sts128(s_tab + h * 16, h < H ? T.tau0[hh] : T.tau1[hh], T.dd[hh]);
+  }
+  if (tid < 16) xt_sts64(s_e2 + tid * 8, T.e2[tid]);
+
+  double l2[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) l2[k] = T.l2[k];
+
+  double cl[TPT][D], cn[TPT][D];
+  double csum[TPT];  // NaN / Inf coordinates anywhere in the track poison the result
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim) cl[j][dim] = Cs[(size_t)dim * npad + toff[j]];  // C[0]
+  }
+  Cs += cstride;
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+    csum[j] = 0.0;
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim) {
+      cn[j][dim] = Cs[(size_t)dim * npad + toff[j]];  // C[1] (L >= 2)
+      csum[j] += cl[j][dim];
+    }
+  }
+  __syncthreads();  // tables visible (the update below reads 2^(j/16))
+
+  // ---- first localisation (tracking.py:478-529) and, if L >= 3, the update of step 2 ----
+  int nP = H;
+  for (int c = w; c < nP; c += WPC) {
+    Seq s[TPT];
+    const double ddc = T.dd[c];
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) s[j].m[dim] = cl[j][dim];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) s[j].u[k] = l2[k] + ddc;
+      xt_split_exponent(T.winit[c], 0, s[j].W, s[j].E);
+    }
+    if (L >= 3) xt_update<D, KS, TPT>(s, cn, l2, s_e2);
+    IO::store(s_vec + c * SLOTB, s_exp + c * ESLOT, s);
+  }
+  if (L >= 3) {
+    Cs += cstride;
+#pragma unroll
+    for (int j = 0; j < TPT; ++j)
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) {
+        csum[j] += cn[j][dim];                           // C[1]
+        cn[j][dim] = Cs[(size_t)dim * npad + toff[j]];  // C[2]
+      }
+  }
+  if (tid < B16) xt_sts128u(s_blob + tid * 16, pre0);
+  if (tid + NT < B16) xt_sts128u(s_blob + (tid + NT) * 16, pre1);
+  __syncthreads();
+
+  // ---- steps 3..L-1: merge by the replay record of step-1, update with C[step-1] ----
+  unsigned src_v = s_vec, src_e = s_exp, dst_v = s_vec + VB, dst_e = s_exp + EB;
+  for (int step = 3; step <= L - 1; ++step) {
+    const int ri = step - 3;
+    // prefetch: localisation and replay record of the next step
+    Cs += cstride;  // C[step] exists (step <= L-1)
+#pragma unroll
+    for (int j = 0; j < TPT; ++j)
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) {
+        cl[j][dim] = cn[j][dim];
+        csum[j] += cl[j][dim];
+        cn[j][dim] = Cs[(size_t)dim * npad + toff[j]];
+      }
+    const bool more = ri + 1 < nrec;
+    if (more) {
+      if (tid < B16) pre0 = __ldg(gblob + (size_t)(ri + 1) * bstride);
+      if (tid + NT < B16) pre1 = __ldg(gblob + (size_t)(ri + 1) * bstride + NT);
+    }
+
+    const unsigned rb = s_blob + (ri & 1) * (B16 * 16);
+    const int nG = (int)xt_lds16(rb);  // XtBlobHdr::nG
+    const unsigned grec = rb + 32;
+    const unsigned entb = grec + ((nG + 1) >> 1) * 16;
+    const unsigned tab = s_tab + (((step - 1) >= T.min_len) ? H * 16 : 0);
+    const int i1 = (int)xt_lds16(rb + 8 + 2 * (w + 1));  // XtBlobHdr::woff
+    for (int i = (int)xt_lds16(rb + 8 + 2 * w); i < i1; ++i) {
+      const uint2 gr = xt_lds64u(grec + i * 8);
+      const unsigned p0 = gr.x & 0xFFFu, h0 = (gr.x >> 12) & 0xFFu, g = gr.x >> 20;
+      const unsigned kind = gr.y >> 30;
+      Seq G[TPT];
+      IO::load(src_v + p0 * SLOTB, src_e + p0 * ESLOT, G);
+      double tau0, dd0;
+      xt_lds128(tab + h0 * 16, tau0, dd0);
+      if (kind == 1u) {
+        // single member: the child itself
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+          G[j].W *= tau0;
+#pragma unroll
+          for (int k = 0; k < KS; ++k) G[j].u[k] += dd0;
+        }
+      } else if (kind == 2u) {
+        const unsigned p1 = gr.y & 0xFFFu, h1 = (gr.y >> 12) & 0xFFu;
+        Seq B[TPT];
+        IO::load(src_v + p1 * SLOTB, src_e + p1 * ESLOT, B);
+        double tau1, dd1;
+        xt_lds128(tab + h1 * 16, tau1, dd1);
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+          const int Eg = max(G[j].E, B[j].E);
+          const double w0 = (G[j].W * xt_pow2_le0(G[j].E - Eg)) * tau0;
+          const double w1 = (B[j].W * xt_pow2_le0(B[j].E - Eg)) * tau1;
+          const double sw = w0 + w1;
+          const double rs = (sw > 1e-280) ? xt_rcp(sw) : 0.0;
+          const double lam = w1 * rs;
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) G[j].m[dim] = fma(B[j].m[dim] - G[j].m[dim], lam, G[j].m[dim]);
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            const double ua = G[j].u[k] + dd0;
+            G[j].u[k] = fma((B[j].u[k] + dd1) - ua, lam, ua);
+          }
+          G[j].W = sw;
+          G[j].E = Eg;
+        }
+      } else {
+        // member list: two passes (largest exponent, then the weighted sums)
+        const unsigned o = gr.y & 0xFFFu;
+        const int n = (int)((gr.y >> 12) & 0x1FFFu);
+        const unsigned eb = entb + o * 4;
+        int Eg[TPT];
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) Eg[j] = G[j].E;
+#pragma unroll 4
+        for (int k = 1; k < n; ++k) {
+          const unsigned ea = src_e + ((unsigned)xt_lds32(eb + k * 4) & 0xFFFFu) * ESLOT;
+#pragma unroll
+          for (int j = 0; j < TPT; ++j) Eg[j] = max(Eg[j], xt_lds32(ea + j * 128));
+        }
+        double sw[TPT], am[TPT][D], as[TPT][KS];
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+          sw[j] = (G[j].W * xt_pow2_le0(G[j].E - Eg[j])) * tau0;
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) am[j][dim] = sw[j] * G[j].m[dim];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            G[j].u[k] += dd0;
+            as[j][k] = sw[j] * G[j].u[k];
+          }
+        }
+#pragma unroll 2
+        for (int k = 1; k < n; ++k) {
+          const unsigned e = (unsigned)xt_lds32(eb + k * 4);
+          const unsigned pm = e & 0xFFFFu;
+          Seq M[TPT];
+          IO::load(src_v + pm * SLOTB, src_e + pm * ESLOT, M);
+          double taum, ddm;
+          xt_lds128(tab + ((e >> 16) & 0xFFu) * 16, taum, ddm);
+#pragma unroll
+          for (int j = 0; j < TPT; ++j) {
+            const double wj = (M[j].W * xt_pow2_le0(M[j].E - Eg[j])) * taum;
+            sw[j] += wj;
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) am[j][dim] = fma(wj, M[j].m[dim], am[j][dim]);
+#pragma unroll
+            for (int k2 = 0; k2 < KS; ++k2) as[j][k2] = fma(wj, M[j].u[k2] + ddm, as[j][k2]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+          if (sw[j] > 1e-280) {  // otherwise: zero-weight group, keep the first member's moments
+            const double rs = xt_rcp(sw[j]);
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) G[j].m[dim] = am[j][dim] * rs;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) G[j].u[k] = as[j][k] * rs;
+          }
+          G[j].W = sw[j];
+          G[j].E = Eg[j];
+        }
+      }
+      xt_update<D, KS, TPT>(G, cl, l2, s_e2);
+      IO::store(dst_v + g * SLOTB, dst_e + g * ESLOT, G);
+    }
+    nP = nG;
+    {  // swap the ping-pong buffers
+      unsigned tv = src_v; src_v = dst_v; dst_v = tv;
+      unsigned te = src_e; src_e = dst_e; dst_e = te;
+    }
+    if (more) {
+      const unsigned nb = s_blob + ((ri + 1) & 1) * (B16 * 16);
+      if (tid < B16) xt_sts128u(nb + tid * 16, pre0);
+      if (tid + NT < B16) xt_sts128u(nb + (tid + NT) * 16, pre1);
+    }
+    __syncthreads();
+  }
+  const uint8_t* curP = nullptr;
+  if (nrec > 0) curP = a.plan.curG + (size_t)(ck.rec0 + nrec - 1) * a.plan.cap;
+
+  // ---- end of track (tracking.py:613-639, :781-786): last localisation, leave term,
+  //      sum over the surviving sequences in extended-exponent arithmetic ----
+  const bool implicit = L >= 3;  // slots hold un-fused parents (m', u, W'): children are read on the fly
+  const unsigned tab = s_tab + (((L - 1) >= T.min_len) ? H * 16 : 0);
+  const int Kc = implicit ? K : 1;
+  double acc[TPT];
+  int KA[TPT];
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+    acc[j] = 0.0;
+    KA[j] = XT_ZERO_EXP;
+#pragma unroll
+    for (int dim = 0; dim < D; ++dim) csum[j] += cn[j][dim];  // C[L-1]
+  }
+  for (int p = w; p < nP; p += WPC) {
+    Seq S[TPT];
+    IO::load(src_v + p * SLOTB, src_e + p * ESLOT, S);
+    const int ps = curP ? (int)__ldg(&curP[p]) : (p % nS);
+    double df2[TPT][D];
+#pragma unroll
+    for (int j = 0; j < TPT; ++j)
+#pragma unroll
+      for (int dim = 0; dim < D; ++dim) {
+        const double df = cn[j][dim] - S[j].m[dim];
+        df2[j][dim] = df * df;
+      }
+    int newest_r = 0;  // r % nS, maintained incrementally
+    for (int r = 0; r < Kc; ++r) {
+      double dd = 0.0, th = 1.0;
+      int newest = ps;
+      if (implicit) {
+        xt_lds128(tab + (r + K * ps) * 16, th, dd);
+        newest = newest_r;
+      }
+      if (++newest_r == nS) newest_r = 0;
+      if (ck.isBL) th *= T.leave[newest];
+#pragma unroll
+      for (int j = 0; j < TPT; ++j) {
+        double rq[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) rq[k] = xt_rcp(S[j].u[k] + dd + l2[k]);
+        double quad = 0.0;
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) quad = fma(df2[j][dim], rq[(KS == 1) ? 0 : dim], quad);
+        int k2;
+        const double pe = xt_exp_split(xt_clamp_neg(-0.5 * quad), s_e2, k2);
+        const double v = ((S[j].W * th) * xt_normfac<D, KS>(rq)) * pe;
+        const int Kv = S[j].E + k2;
+        const int Kn = max(KA[j], Kv);
+        acc[j] = fma(acc[j], xt_pow2_le0(KA[j] - Kn), v * xt_pow2_le0(Kv - Kn));
+        KA[j] = Kn;
+      }
+    }
+  }
+  // cross-warp combination through the idle state buffer (every warp is past the last barrier
+  // and reads only the current buffer)
+  const unsigned s_redA = dst_v - lane * 16;              // [WPC][TPT][32] x 8 B
+  const unsigned s_redK = s_redA + WPC * 256 * TPT;       // [WPC][TPT][32] x 4 B
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+    xt_sts64(s_redA + ((w * TPT + j) * 32 + lane) * 8, acc[j]);
+    xt_sts32(s_redK + ((w * TPT + j) * 32 + lane) * 4, KA[j]);
+  }
+  __syncthreads();
+  if (w == 0) {
+    double lps = 0.0;
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+      int Kn = xt_lds32(s_redK + (j * 32 + lane) * 4);
+#pragma unroll
+      for (int k = 1; k < WPC; ++k) Kn = max(Kn, xt_lds32(s_redK + ((k * TPT + j) * 32 + lane) * 4));
+      double tot = 0.0;
+#pragma unroll
+      for (int k = 0; k < WPC; ++k)
+        tot = fma(xt_lds64(s_redA + ((k * TPT + j) * 32 + lane) * 8),
+                  xt_pow2_le0(xt_lds32(s_redK + ((k * TPT + j) * 32 + lane) * 4) - Kn), tot);
+      double lp = XT_LN2 * (double)Kn + log(tot) - (double)(L - 1) * (0.5 * (double)D) * XT_LN_2PI;
+      if (!(fabs(csum[j]) <= 1.7976931348623157e308)) lp = __longlong_as_double(0x7ff8000000000000ll);
+      if (valid[j]) {
+        a.logp[ck.trk_off + wk.t0 + lane + 32 * j] = lp;
+        lps += lp;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lps += __shfl_down_sync(0xffffffffu, lps, off);
+    if (lane == 0) a.partial[wi] = lps;
+  }
+}

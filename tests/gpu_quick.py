@@ -35,6 +35,20 @@ def one(nS, nsub, d, fl, L, nT, isBL, seed=0, **kw):
     got2 = eng.chunk_logp(0, nT, p)
     err = max(err, np.max(np.abs(got2 - ref) / np.abs(ref)))
     eng.set_option("force_global_replay", 0)
+    eng.set_option("k2_variant", 1)
+    got3 = eng.chunk_logp(0, nT, p)
+    err3 = np.max(np.abs(got3 - ref) / np.abs(ref))
+    if err3 > 1e-9:
+        print("   first-generation linear kernel relerr", err3)
+    err = max(err, err3)
+    eng.set_option("k2_variant", 0)
+    eng.set_option("k2_tpt", 2)
+    got4 = eng.chunk_logp(0, nT, p)
+    err4 = np.max(np.abs(got4 - ref) / np.abs(ref))
+    if err4 > 1e-9:
+        print("   fused kernel, two tracks per thread: relerr", err4)
+    err = max(err, err4)
+    eng.set_option("k2_tpt", 1)
     eng.chunk_logp(0, nT, p)
     mism = 0
     for rec in plan:
@@ -96,10 +110,12 @@ if __name__ == "__main__":
     t = time.time()
     ts = xt.TrackSet(sorted_tracks)
     print("upload", round(time.time() - t, 3), "s; chunks", len(ts.chunks))
-    for it in range(9):
-        if it >= 3:
-            ts.engine.set_option("k2_wpc", [2, 2, 8, 8, 4, 4][it - 3])
-            print("k2_wpc", [2, 2, 8, 8, 4, 4][it - 3])
+    sched = [(0, 4, 1)] * 3 + [(0, 4, 2)] * 2 + [(0, 2, 1)] * 2 + [(0, 8, 2)] * 2 + [(0, 8, 1)] * 2 + [(1, 4, 1)] * 2 + [(0, 4, 1)] * 2
+    for it, (variant, wpc, tpt) in enumerate(sched):
+        ts.engine.set_option("k2_variant", variant)
+        ts.engine.set_option("k2_wpc", wpc)
+        ts.engine.set_option("k2_tpt", tpt)
+        print("k2_variant", variant, "k2_wpc", wpc, "k2_tpt", tpt)
         t = time.time()
         v = ts.sum_logp(p)
         dtm = time.time() - t
