@@ -55,6 +55,8 @@ class XtStats(C.Structure):
         ("k2_launches", C.c_int32),
         ("ms_plan", C.c_float),
         ("ms_replay", C.c_float),
+        ("pipelined", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
@@ -65,6 +67,7 @@ EXPORTS = (
     "xt_last_error",
     "xt_upload",
     "xt_sum_logp",
+    "xt_sum_logp_host",
     "xt_sum_logp_async",
     "xt_chunk_logp",
     "xt_plan_dump",
@@ -99,6 +102,7 @@ def load_library() -> C.CDLL:
     lib.xt_last_error.restype = C.c_char_p
     lib.xt_upload.argtypes = [vp, i32, P(i32), P(i64), P(i32), P(vp), i32, i32]
     lib.xt_sum_logp.argtypes = [vp, P(XtParams), P(dbl)]
+    lib.xt_sum_logp_host.argtypes = [vp, i32, P(i32), P(i64), P(i32), P(vp), i32, i32, P(XtParams), P(dbl)]
     lib.xt_sum_logp_async.argtypes = [vp, P(XtParams), vp, vp]
     lib.xt_chunk_logp.argtypes = [vp, i32, P(XtParams), P(dbl)]
     lib.xt_plan_dump.argtypes = [vp, i32, i32, P(i32), P(i32), P(i32), i32, P(dbl)]
@@ -180,6 +184,27 @@ class Engine:
         self.d = d
 
     # -- evaluation ----------------------------------------------------------------------
+    def sum_logp_host(self, segments: Sequence[np.ndarray], isBL: Sequence[int], chunk_size: int, p: XtParams) -> float:
+        """Objective on host arrays: upload (overlapped with the kernels) + evaluation in one call."""
+        segs = [np.ascontiguousarray(s, dtype=np.float64) for s in segments]
+        if len(segs) == 0:
+            raise ValueError("No track could be detected. The loaded tracks seem empty.")
+        d = segs[0].shape[2]
+        for s in segs:
+            if s.ndim != 3 or s.shape[2] != d:
+                raise ValueError("all track arrays must have shape [n, L, d] with the same d")
+        n = len(segs)
+        Ls = (C.c_int32 * n)(*[s.shape[1] for s in segs])
+        ns = (C.c_int64 * n)(*[s.shape[0] for s in segs])
+        bl = (C.c_int32 * n)(*[int(b) for b in isBL])
+        ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in segs])
+        out = C.c_double()
+        self._check(self._lib.xt_sum_logp_host(self._h, n, Ls, ns, bl, ptrs, d, int(chunk_size), C.byref(p), C.byref(out)))
+        self.segments = [(s.shape[1], s.shape[0]) for s in segs]
+        self.chunk_size = int(chunk_size)
+        self.d = d
+        return out.value
+
     def sum_logp(self, p: XtParams) -> float:
         out = C.c_double()
         self._check(self._lib.xt_sum_logp(self._h, C.byref(p), C.byref(out)))

@@ -8,7 +8,7 @@
 #define XT_LEADERS 30      // tracking.py:677  test_chunks = 30
 #define XT_HARD_CAP 4096   // most live sequences after an expansion the engine accepts
 #define XT_K1_THREADS 256
-#define XT_K1_MIN_CTAS 4
+#define XT_K1_MIN_CTAS 3
 #define XT_TWO_PI 6.283185307179586  // 2*np.pi
 
 // One chunk = <= chunk_size tracks of one length bucket (tracking.py:1030-1036).

@@ -35,8 +35,27 @@ struct xt_ctx {
   double* d_soa = nullptr;
   XtChunk* d_chunks = nullptr;
   XtWork* d_work = nullptr;
-  XtWork* d_workf[2] = {nullptr, nullptr};  // fused replay: tiles of 32 / 64 tracks, longest chunks first
+  XtWork* d_workf[2] = {nullptr, nullptr};  // fused replay: tiles of 32 / 64 tracks, chunk order
   int n_workf[2] = {0, 0};
+  std::vector<int> corder;                  // chunk ids sorted by track length, longest first (stable)
+  int32_t* d_corder = nullptr;
+  std::vector<int> seg_pos0, seg_pos1;      // position range of every segment's chunks in corder
+  std::vector<int> chunk_w0[2];             // first tile of every corder position in d_workf (+ one past the end)
+  // pipelined evaluation: plan + replay launched per group of chunks on several streams, sized
+  // speculatively with the parent-slot count of the previous evaluation, verified afterwards
+  static constexpr int NCS = 4;
+  cudaStream_t cs[NCS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[NCS] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_seg;
+  int* d_spec = nullptr;
+  int* h_spec = nullptr;  // pinned
+  int spec_Pmax = 0;      // 0: unknown (first evaluation of a data set runs the two-phase path)
+  int spec_maxP = 0, spec_maxC = 0;  // most parents / children of the previous evaluation: sizes the plan kernel's
+                                     // shared-memory scratch (0: global-memory scratch)
+  int k1_smem_scratch = 1;
+  int pipeline = 1;
+  int n_groups = 4;
   double* d_logp = nullptr;
   double* d_partial = nullptr;
   double* d_out = nullptr;
@@ -107,7 +126,8 @@ static void free_plan(xt_ctx* ctx) {
 static void free_data(xt_ctx* ctx) {
   cudaFree(ctx->d_soa); cudaFree(ctx->d_chunks); cudaFree(ctx->d_work); cudaFree(ctx->d_logp);
   cudaFree(ctx->d_partial); cudaFree(ctx->d_summ); cudaFree(ctx->d_gstate);
-  cudaFree(ctx->d_workf[0]); cudaFree(ctx->d_workf[1]);
+  cudaFree(ctx->d_workf[0]); cudaFree(ctx->d_workf[1]); cudaFree(ctx->d_corder);
+  ctx->d_corder = nullptr;
   ctx->d_workf[0] = ctx->d_workf[1] = nullptr;
   if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
   ctx->d_soa = ctx->d_logp = ctx->d_partial = ctx->d_gstate = nullptr;
@@ -115,6 +135,8 @@ static void free_data(xt_ctx* ctx) {
   ctx->gstate_bytes = 0;
   ctx->chunks.clear(); ctx->work.clear(); ctx->summ.clear(); ctx->upload_sig.clear();
   ctx->have_eval = false;
+  ctx->spec_Pmax = 0;
+  ctx->spec_maxP = ctx->spec_maxC = 0;
   free_plan(ctx);
 }
 
@@ -138,6 +160,14 @@ extern "C" int xt_create(int device, xt_ctx** out) {
   XT_CUDA_OK(cudaMalloc(&c->d_out, sizeof(double)));
   XT_CUDA_OK(cudaMallocHost(&c->h_out, sizeof(double)));
   for (int i = 0; i < 3; ++i) XT_CUDA_OK(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < xt_ctx::NCS; ++i) {
+    XT_CUDA_OK(cudaStreamCreateWithFlags(&c->cs[i], cudaStreamNonBlocking));
+    XT_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+  }
+  XT_CUDA_OK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+  XT_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  XT_CUDA_OK(cudaMalloc(&c->d_spec, sizeof(int)));
+  XT_CUDA_OK(cudaMallocHost(&c->h_spec, sizeof(int)));
   XT_CUDA_OK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   XT_CUDA_OK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
   *out = c;
@@ -156,6 +186,15 @@ extern "C" void xt_destroy(xt_ctx* ctx) {
   cudaFree(ctx->d_out);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < xt_ctx::NCS; ++i) {
+    if (ctx->cs[i]) cudaStreamDestroy(ctx->cs[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (cudaEvent_t e : ctx->ev_seg) cudaEventDestroy(e);
+  cudaFree(ctx->d_spec);
+  if (ctx->h_spec) cudaFreeHost(ctx->h_spec);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -167,9 +206,11 @@ extern "C" int xt_host_alloc(void** out, uint64_t bytes) {
 }
 extern "C" int xt_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? XT_OK : XT_ERR_CUDA; }
 
-extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int64_t* n, const int32_t* isBL,
-                         const double* const* xyz, int32_t d, int32_t chunk_size) {
-  if (!ctx) return XT_ERR_ARG;
+// Validate the segment list and (re)build the chunk / work tables and the device allocations.
+// Same shapes as the resident data set (a re-upload of new coordinates, e.g. one objective call
+// per host buffer): every allocation, table and the plan storage are kept.
+static int setup_layout(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int64_t* n, const int32_t* isBL, int32_t d,
+                        int32_t chunk_size) {
   if (n_seg <= 0 || d < 1 || d > XT_MAX_DIMS || chunk_size < 1) {
     set_error(ctx, "xt_upload: need n_seg >= 1, 1 <= d <= 3, chunk_size >= 1");
     return XT_ERR_ARG;
@@ -186,8 +227,6 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
   }
   XT_CUDA_OK(cudaSetDevice(ctx->device));
   XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  // Same shapes as the resident data set (a re-upload of new coordinates, e.g. one objective call
-  // per host buffer): keep every allocation, the chunk/work tables and the plan storage.
   std::vector<int64_t> sig;
   sig.push_back(n_seg); sig.push_back(d); sig.push_back(chunk_size);
   for (int s = 0; s < n_seg; ++s) { sig.push_back(L[s]); sig.push_back(n[s]); sig.push_back(isBL[s]); }
@@ -204,7 +243,7 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
     ctx->maxL = 0;
     int64_t soa_elems = 0;
     int rec = 0;
-    ctx->seg_chunk0.assign(n_seg, 0);
+    ctx->seg_chunk0.assign(n_seg + 1, 0);
     for (int s = 0; s < n_seg; ++s) {
       ctx->seg_chunk0[s] = (int)ctx->chunks.size();
       ctx->maxL = std::max(ctx->maxL, (int)L[s]);
@@ -230,6 +269,7 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
         ctx->chunks.push_back(ck);
       }
     }
+    ctx->seg_chunk0[n_seg] = (int)ctx->chunks.size();
     ctx->nrec_total = rec;
     ctx->seg_n.assign(n, n + n_seg);
     ctx->seg_L.assign(L, L + n_seg);
@@ -247,23 +287,45 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
                                ctx->stream));
     XT_CUDA_OK(cudaMemcpyAsync(ctx->d_work, ctx->work.data(), sizeof(XtWork) * ctx->work.size(),
                                cudaMemcpyHostToDevice, ctx->stream));
-    // work tables of the fused replay kernel: longest chunks first (the last CTAs of the launch
-    // are then the short ones: smaller tail)
-    std::vector<int> order(nch);
-    for (size_t c = 0; c < nch; ++c) order[c] = (int)c;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ctx->chunks[x].L > ctx->chunks[y].L; });
+    // chunk order of the kernels: longest tracks first (their plan is the critical path and their
+    // replay CTAs run longest); the work tables of the fused replay kernel (tiles of 32 and 64
+    // tracks) follow that order, so a range of positions is a range of tiles
+    ctx->corder.resize(nch);
+    for (size_t c = 0; c < nch; ++c) ctx->corder[c] = (int)c;
+    std::stable_sort(ctx->corder.begin(), ctx->corder.end(),
+                     [&](int x, int y) { return ctx->chunks[x].L > ctx->chunks[y].L; });
+    ctx->seg_pos0.assign(n_seg, (int)nch);
+    ctx->seg_pos1.assign(n_seg, 0);
+    for (size_t q = 0; q < nch; ++q) {
+      const int sg = ctx->chunks[ctx->corder[q]].seg;
+      ctx->seg_pos0[sg] = std::min(ctx->seg_pos0[sg], (int)q);
+      ctx->seg_pos1[sg] = std::max(ctx->seg_pos1[sg], (int)q + 1);
+    }
+    XT_CUDA_OK(cudaMalloc(&ctx->d_corder, sizeof(int32_t) * nch));
+    XT_CUDA_OK(cudaMemcpy(ctx->d_corder, ctx->corder.data(), sizeof(int32_t) * nch, cudaMemcpyHostToDevice));
     for (int v = 0; v < 2; ++v) {
       const int tile = 32 << v;
       std::vector<XtWork> wf;
-      for (int c : order)
+      ctx->chunk_w0[v].assign(nch + 1, 0);
+      for (size_t q = 0; q < nch; ++q) {
+        const int c = ctx->corder[q];
+        ctx->chunk_w0[v][q] = (int)wf.size();
         for (int t0 = 0; t0 < ctx->chunks[c].nT; t0 += tile) wf.push_back(XtWork{c, t0});
+      }
+      ctx->chunk_w0[v][nch] = (int)wf.size();
       ctx->n_workf[v] = (int)wf.size();
       XT_CUDA_OK(cudaMalloc(&ctx->d_workf[v], sizeof(XtWork) * wf.size()));
       XT_CUDA_OK(cudaMemcpy(ctx->d_workf[v], wf.data(), sizeof(XtWork) * wf.size(), cudaMemcpyHostToDevice));
     }
+    while ((int)ctx->ev_seg.size() < n_seg) {
+      cudaEvent_t e;
+      XT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->ev_seg.push_back(e);
+    }
+    XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   }
   ctx->have_eval = false;
-  // stage each segment (AoS) and repack on the device; two staging buffers overlap copy and pack
+  // two staging buffers (AoS as on the host) overlap the copy of one segment with the repack of another
   if ((size_t)max_seg_elems > ctx->stage_elems) {
     for (int b = 0; b < 2; ++b) {
       cudaFree(ctx->stage[b]);
@@ -273,16 +335,35 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
     }
     ctx->stage_elems = (size_t)max_seg_elems;
   }
+  return XT_OK;
+}
+
+// Copy segment s to the device and repack it into the SoA blocks of its chunks, on `stream`;
+// `slot` alternates between the two staging buffers.
+static int enqueue_segment(xt_ctx* ctx, int s, const double* xyz, int slot, cudaStream_t stream) {
+  const int b = slot & 1;
+  const int64_t n = ctx->seg_n[s];
+  const int L = ctx->seg_L[s], d = ctx->d;
+  const size_t elems = (size_t)n * L * d;
+  const int chunk_size = (int)ctx->upload_sig[2];
+  XT_CUDA_OK(cudaEventSynchronize(ctx->stage_done[b]));
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->stage[b], xyz, sizeof(double) * elems, cudaMemcpyHostToDevice, stream));
+  const int threads = 256;
+  const long long blocks = ((long long)elems + threads - 1) / threads;
+  k_pack<<<(unsigned)blocks, threads, 0, stream>>>(ctx->stage[b], ctx->d_soa, ctx->d_chunks, ctx->seg_chunk0[s], chunk_size,
+                                                   (int)n, L, d);
+  XT_CUDA_OK(cudaEventRecord(ctx->stage_done[b], stream));
+  return XT_OK;
+}
+
+extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int64_t* n, const int32_t* isBL,
+                         const double* const* xyz, int32_t d, int32_t chunk_size) {
+  if (!ctx) return XT_ERR_ARG;
+  int rc = setup_layout(ctx, n_seg, L, n, isBL, d, chunk_size);
+  if (rc) return rc;
   for (int s = 0; s < n_seg; ++s) {
-    const int b = s & 1;
-    const size_t elems = (size_t)n[s] * L[s] * d;
-    XT_CUDA_OK(cudaEventSynchronize(ctx->stage_done[b]));
-    XT_CUDA_OK(cudaMemcpyAsync(ctx->stage[b], xyz[s], sizeof(double) * elems, cudaMemcpyHostToDevice, ctx->stream));
-    const int threads = 256;
-    const long long blocks = ((long long)elems + threads - 1) / threads;
-    k_pack<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->stage[b], ctx->d_soa, ctx->d_chunks, ctx->seg_chunk0[s],
-                                                          chunk_size, (int)n[s], L[s], d);
-    XT_CUDA_OK(cudaEventRecord(ctx->stage_done[b], ctx->stream));
+    rc = enqueue_segment(ctx, s, xyz[s], s, ctx->stream);
+    if (rc) return rc;
   }
   XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   XT_CUDA_OK(cudaGetLastError());
@@ -341,11 +422,11 @@ static int ensure_plan(xt_ctx* ctx, const xt_params* p, int cap) {
 }
 
 template <int D, int KS>
-static cudaError_t launch_k1(xt_ctx* ctx, const K1Args& a, const xt_params& p, size_t smem) {
+static cudaError_t launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream) {
   auto kern = k1_plan<D, KS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)ctx->chunks.size(), XT_K1_THREADS, smem, ctx->stream>>>(a, p);
+  kern<<<(unsigned)n_chunks, XT_K1_THREADS, smem, stream>>>(a, p);
   return cudaGetLastError();
 }
 
@@ -359,24 +440,24 @@ static cudaError_t launch_k2_lin(xt_ctx* ctx, const K2Args& a, const xt_params& 
 }
 
 template <int D, int KS, int WPC, int TPT>
-static cudaError_t launch_k2_fused_w(xt_ctx* ctx, const K2FArgs& a, const K2Tab& tab, size_t smem) {
+static cudaError_t launch_k2_fused_w(const K2FArgs& a, const K2Tab& tab, size_t smem, cudaStream_t stream) {
   auto kern = k2_replay_fused<D, KS, WPC, TPT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<a.n_work, 32 * WPC, smem, ctx->stream>>>(a, tab);
+  kern<<<a.n_work, 32 * WPC, smem, stream>>>(a, tab);
   return cudaGetLastError();
 }
 
 template <int D, int KS>
-static cudaError_t launch_k2_fused(xt_ctx* ctx, const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt) {
+static cudaError_t launch_k2_fused(const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt, cudaStream_t stream) {
   if (tpt == 2) {
-    if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 2>(ctx, a, tab, smem);
-    if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 2>(ctx, a, tab, smem);
-    return launch_k2_fused_w<D, KS, 4, 2>(ctx, a, tab, smem);
+    if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 2>(a, tab, smem, stream);
+    if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 2>(a, tab, smem, stream);
+    return launch_k2_fused_w<D, KS, 4, 2>(a, tab, smem, stream);
   }
-  if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 1>(ctx, a, tab, smem);
-  if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 1>(ctx, a, tab, smem);
-  return launch_k2_fused_w<D, KS, 4, 1>(ctx, a, tab, smem);
+  if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 1>(a, tab, smem, stream);
+  if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 1>(a, tab, smem, stream);
+  return launch_k2_fused_w<D, KS, 4, 1>(a, tab, smem, stream);
 }
 
 template <int D, int KS>
@@ -400,10 +481,84 @@ static cudaError_t launch_k2(xt_ctx* ctx, const K2Args& a, const xt_params& p, c
     else { CALL(3, 3); }                                             \
   } while (0)
 
-static int run_plan(xt_ctx* ctx, const xt_params* p, int bits) {
-  // run K1, growing the sequence capacity on overflow
+#ifdef XT_K1_PROF
+static long long* g_k1_prof = nullptr;
+extern "C" int xt_debug_k1_prof(long long* out, int n_chunks) {
+  return cudaMemcpy(out, g_k1_prof, sizeof(long long) * 8 * n_chunks, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+#endif
+static K1Args make_k1_args(xt_ctx* ctx, int bits) {
+  K1Args a{};
+  a.chunks = ctx->d_chunks;
+  a.soa = ctx->d_soa;
+  a.state = ctx->d_state1;
+  a.hist = ctx->d_hist1;
+  a.plan = ctx->plan;
+  a.summ = ctx->d_summ;
+  a.cap = ctx->cap;
+  a.RH = ctx->RH;
+  a.bits = bits;
+  a.wpc = ctx->k2_wpc;
+  a.corder = ctx->d_corder;
+#ifdef XT_K1_PROF
+  if (!g_k1_prof) cudaMalloc(&g_k1_prof, sizeof(long long) * 8 * 65536);
+  a.prof = g_k1_prof;
+#endif
+  return a;
+}
+// shared-memory scratch of the plan kernel: used when the previous evaluation tells how many
+// parents / children to expect and 3 CTAs per SM still fit
+static void k1_scratch_caps(xt_ctx* ctx, const xt_params* p, bool use_smem, int* scapP, int* scapC) {
+  *scapP = *scapC = 0;
+  if (!use_smem || !ctx->k1_smem_scratch || ctx->spec_maxC <= 0) return;
+  const int CO1 = p->d + 2 * p->n_loc + 1;
+  const size_t b = xt_k1_smem(ctx->cap, CO1, ctx->RH, p->nS, ctx->spec_maxP, ctx->spec_maxC);
+  if (b + 1024 > (size_t)(228 * 1024) / XT_K1_MIN_CTAS || b > (size_t)ctx->smem_optin) return;
+  *scapP = ctx->spec_maxP;
+  *scapC = ctx->spec_maxC;
+}
+
+static int enqueue_k1(xt_ctx* ctx, const xt_params* p, int bits, int c0, int nc, cudaStream_t stream, bool smem_scratch) {
+  K1Args a = make_k1_args(ctx, bits);
+  a.chunk0 = c0;
+  k1_scratch_caps(ctx, p, smem_scratch, &a.scapP, &a.scapC);
+  const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC);
+  cudaError_t e = cudaSuccess;
+#define CALL_K1(D_, KS_) e = launch_k1<D_, KS_>(a, *p, smem, nc, stream)
+  XT_DISPATCH(p->d, p->n_loc, CALL_K1);
+#undef CALL_K1
+  XT_CUDA_OK(e);
+  ctx->stats.k1_launches++;
+  return XT_OK;
+}
+
+static int initial_cap(xt_ctx* ctx, const xt_params* p) {
   const int K = ipow(p->nS, p->nsub);
-  int cap = std::max(ctx->cap, std::max(128, K * K * p->nS));
+  return std::max(ctx->cap, std::max(128, K * K * p->nS));
+}
+
+// scan the per-chunk summaries in h_summ: returns an error, or *need = capacity wanted (0: fine)
+static int scan_summaries(xt_ctx* ctx, int* need) {
+  *need = 0;
+  bool smem_short = false;
+  for (size_t c = 0; c < ctx->chunks.size(); ++c) {
+    const XtChunkSummary& s = ctx->h_summ[c];
+    if (s.err == 1) {
+      set_error(ctx, "problem with grouping: a state sequence ended ungrouped in chunk " + std::to_string(c) +
+                         " (threshold must be > 0 and the model finite)");
+      return XT_ERR_GROUPING;
+    }
+    if (s.err == 2) *need = std::max(*need, s.need_cap);
+    if (s.err == 3) smem_short = true;  // shared-memory scratch too small: rerun with the global one
+  }
+  if (!*need && smem_short) *need = -1;
+  return XT_OK;
+}
+
+static int run_plan(xt_ctx* ctx, const xt_params* p, int bits) {
+  // run K1 over all chunks, growing the sequence capacity on overflow
+  int cap = initial_cap(ctx, p);
+  bool smem_scratch = true;
   for (;;) {
     if (cap > XT_HARD_CAP) {
       set_error(ctx, "more than " + std::to_string(XT_HARD_CAP) + " live state sequences; lower frame_len or raise threshold");
@@ -412,38 +567,19 @@ static int run_plan(xt_ctx* ctx, const xt_params* p, int bits) {
     int rc = ensure_plan(ctx, p, cap);
     if (rc) return rc;
     cap = ctx->cap;
-    K1Args a{};
-    a.chunks = ctx->d_chunks;
-    a.soa = ctx->d_soa;
-    a.state = ctx->d_state1;
-    a.hist = ctx->d_hist1;
-    a.plan = ctx->plan;
-    a.summ = ctx->d_summ;
-    a.cap = cap;
-    a.RH = ctx->RH;
-    a.bits = bits;
-    a.wpc = ctx->k2_wpc;
-    const size_t smem = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
-    cudaError_t e = cudaSuccess;
-#define CALL_K1(D_, KS_) e = launch_k1<D_, KS_>(ctx, a, *p, smem)
-    XT_DISPATCH(p->d, p->n_loc, CALL_K1);
-#undef CALL_K1
-    XT_CUDA_OK(e);
-    ctx->stats.k1_launches++;
+    rc = enqueue_k1(ctx, p, bits, 0, (int)ctx->chunks.size(), ctx->stream, smem_scratch);
+    if (rc) return rc;
     XT_CUDA_OK(cudaMemcpyAsync(ctx->h_summ, ctx->d_summ, sizeof(XtChunkSummary) * ctx->chunks.size(),
                                cudaMemcpyDeviceToHost, ctx->stream));
     XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     int need = 0;
-    for (size_t c = 0; c < ctx->chunks.size(); ++c) {
-      const XtChunkSummary& s = ctx->h_summ[c];
-      if (s.err == 1) {
-        set_error(ctx, "problem with grouping: a state sequence ended ungrouped in chunk " + std::to_string(c) +
-                           " (threshold must be > 0 and the model finite)");
-        return XT_ERR_GROUPING;
-      }
-      if (s.err == 2) need = std::max(need, s.need_cap);
+    rc = scan_summaries(ctx, &need);
+    if (rc) return rc;
+    if (need < 0) {  // the shared-memory scratch (sized from the previous evaluation) was too small
+      smem_scratch = false;
+      continue;
     }
-    if (!need) break;
+    if (need == 0) break;
     int ncap = cap;
     while (ncap < need) ncap *= 2;
     cap = ncap;
@@ -456,7 +592,7 @@ static int finish_eval(xt_ctx* ctx, const xt_params* p, int n_work, double* d_ou
   k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, n_work, d_out ? d_out : ctx->d_out);
   XT_CUDA_OK(cudaGetLastError());
   XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  ctx->stats.k2_launches = 2;
+  ctx->stats.k2_launches++;  // the reduction
   ctx->stats.n_tracks = ctx->n_tracks;
   ctx->stats.track_steps = ctx->track_steps;
   ctx->stats.seq_updates = su;
@@ -468,7 +604,197 @@ static int finish_eval(xt_ctx* ctx, const xt_params* p, int n_work, double* d_ou
   return XT_OK;
 }
 
-static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t user_stream) {
+// work counters of an evaluation from the chunk summaries in ctx->summ
+static void work_counters(xt_ctx* ctx, const xt_params* p, int* Pmax, int* maxC, int64_t* su, int64_t* sg) {
+  *Pmax = 1;
+  *maxC = 0;
+  *su = *sg = 0;
+  for (size_t c = 0; c < ctx->chunks.size(); ++c) {
+    const XtChunkSummary& s = ctx->summ[c];
+    *Pmax = std::max(*Pmax, s.max_nP);
+    *maxC = std::max(*maxC, s.max_nC);
+    *su += s.sum_nC * ctx->chunks[c].nT;
+    *sg += s.sum_nG * ctx->chunks[c].nT;
+  }
+  const int K = ipow(p->nS, p->nsub);
+  *maxC = std::max(*maxC, K * p->nS);
+  ctx->spec_maxP = *Pmax;
+  ctx->spec_maxC = *maxC;
+  *Pmax = std::max(*Pmax, 4);  // the fused kernel parks its end-of-track partial sums in an idle state buffer
+}
+
+struct FusedLaunch {  // everything a fused replay launch needs besides its tile range
+  K2Tab tab;
+  K2FArgs fa;
+  size_t smem;
+  int wpc, tpt;
+};
+
+static void leave_sums(const xt_params* p, double* Lsum) {
+  const int K = ipow(p->nS, p->nsub);
+  for (int s = 0; s < p->nS; ++s) {
+    double mx = -INFINITY;
+    for (int r = 0; r < K; ++r) mx = std::max(mx, p->L_leave[r + K * s]);
+    double acc = 0;
+    for (int r = 0; r < K; ++r) acc += std::exp(p->L_leave[r + K * s] - mx);
+    Lsum[s] = std::log(acc) + mx;
+  }
+}
+
+// returns false if the fused kernel cannot run with Pmax parent slots (shared memory / staging limits)
+static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch* fl) {
+  const int K = ipow(p->nS, p->nsub), KS = p->n_loc, H = K * p->nS;
+  fl->wpc = ctx->k2_wpc;
+  fl->tpt = ctx->k2_tpt;
+  if (fl->tpt == 2 && xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, 2) > (size_t)ctx->smem_optin) fl->tpt = 1;
+  fl->smem = xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, fl->tpt);
+  if (ctx->k2_variant != 0 || ctx->force_global || fl->smem > (size_t)ctx->smem_optin ||
+      xt_fused_blob16(Pmax, K) > 64 * fl->wpc)
+    return false;
+  double Lsum[XT_MAX_STATES];
+  leave_sums(p, Lsum);
+  K2Tab& tab = fl->tab;
+  tab = K2Tab{};
+  for (int h = 0; h < H; ++h) {
+    tab.tau0[h] = std::exp(p->LT[h]);
+    tab.tau1[h] = std::exp(p->LT[h] + p->Lp_stay[h % K]);
+    tab.dd[h] = p->dd[h];
+    tab.winit[h] = std::exp(p->LT[h] + p->LF[h]);
+  }
+  for (int s = 0; s < p->nS; ++s) tab.leave[s] = std::exp(Lsum[s]);
+  for (int k = 0; k < KS; ++k) tab.l2[k] = p->l2[k];
+  for (int j = 0; j < 16; ++j) tab.e2[j] = std::exp2((double)j / 16.0);
+  tab.nS = p->nS;
+  tab.nsub = p->nsub;
+  tab.K = K;
+  tab.min_len = p->min_len;
+  K2FArgs& fa = fl->fa;
+  fa = K2FArgs{};
+  fa.chunks = ctx->d_chunks;
+  fa.work = ctx->d_workf[fl->tpt - 1];
+  fa.soa = ctx->d_soa;
+  fa.plan = ctx->plan;
+  fa.logp = ctx->d_logp;
+  fa.partial = ctx->d_partial;
+  fa.summ = ctx->d_summ;
+  fa.spec_fail = ctx->d_spec;
+  fa.Pcap = Pmax;
+  return true;
+}
+
+// fused replay of the chunks at positions [c0, c1) of corder on `stream`
+static int enqueue_fused(xt_ctx* ctx, const xt_params* p, const FusedLaunch& fl, int c0, int c1, cudaStream_t stream) {
+  K2FArgs fa = fl.fa;
+  const std::vector<int>& w0 = ctx->chunk_w0[fl.tpt - 1];
+  fa.work0 = w0[c0];
+  fa.n_work = w0[c1] - w0[c0];
+  if (fa.n_work <= 0) return XT_OK;
+  cudaError_t ef = cudaSuccess;
+#define CALL_K2F(D_, KS_) ef = launch_k2_fused<D_, KS_>(fa, fl.tab, fl.smem, fl.wpc, fl.tpt, stream)
+  XT_DISPATCH(p->d, p->n_loc, CALL_K2F);
+#undef CALL_K2F
+  XT_CUDA_OK(ef);
+  ctx->stats.k2_launches++;
+  return XT_OK;
+}
+
+#define XT_RETRY 1        // internal: the speculative single-pass evaluation has to be redone in two phases
+#define XT_RETRY_EARLY 2  // same, and nothing was enqueued yet (host buffers not copied)
+
+// Pipelined evaluation: for every group of chunks, plan and replay are enqueued back to back on
+// one of NCS streams, so the (latency-bound) plan kernel of one group overlaps the replay of
+// another.  The replay launches are sized with the parent-slot count of the previous evaluation
+// and check it against the plan's summary; the host verifies afterwards (one synchronisation per
+// evaluation) and falls back to the two-phase path if the guess was too small.
+// `xyz` != nullptr: the segments are first copied from these host buffers (upload stream) and
+// each segment is its own group, so that the copy of one segment overlaps the kernels of another.
+static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double* d_out, const double* const* xyz) {
+  int rc = ensure_plan(ctx, p, initial_cap(ctx, p));
+  if (rc) return rc;
+  FusedLaunch fl;
+  if (!prepare_fused(ctx, p, ctx->spec_Pmax, &fl)) return XT_RETRY_EARLY;
+  const int nch = (int)ctx->chunks.size(), n_seg = (int)ctx->seg_L.size();
+  XT_CUDA_OK(cudaMemsetAsync(ctx->d_spec, 0, sizeof(int), ctx->stream));
+  XT_CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  XT_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  for (int i = 0; i < xt_ctx::NCS; ++i) XT_CUDA_OK(cudaStreamWaitEvent(ctx->cs[i], ctx->ev_fork, 0));
+  // host buffers: segments are copied longest tracks first
+  std::vector<int> order(n_seg);
+  for (int s = 0; s < n_seg; ++s) order[s] = s;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ctx->seg_L[x] > ctx->seg_L[y]; });
+  if (xyz) {
+    XT_CUDA_OK(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_fork, 0));
+    for (int i = 0; i < n_seg; ++i) {
+      const int s = order[i];
+      rc = enqueue_segment(ctx, s, xyz[s], i, ctx->up_stream);
+      if (rc) return rc;
+      XT_CUDA_OK(cudaEventRecord(ctx->ev_seg[s], ctx->up_stream));
+      cudaStream_t st = ctx->cs[i % xt_ctx::NCS];
+      XT_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_seg[s], 0));
+      const int c0 = ctx->seg_pos0[s], c1 = ctx->seg_pos1[s];
+      rc = enqueue_k1(ctx, p, bits, c0, c1 - c0, st, true);
+      if (rc) return rc;
+      rc = enqueue_fused(ctx, p, fl, c0, c1, st);
+      if (rc) return rc;
+    }
+  } else {
+    // resident data: n_groups contiguous ranges of corder (longest tracks first) with about equal
+    // replay work
+    const int G = std::max(1, std::min(ctx->n_groups, nch));
+    int q0 = 0, g = 0;
+    int64_t done = 0;
+    for (int q = 0; q < nch; ++q) {
+      const XtChunk& ck = ctx->chunks[ctx->corder[q]];
+      done += (int64_t)ck.nT * (ck.L - 1);
+      const bool last = q + 1 == nch;
+      if (last || (g + 1 < G && done * G >= ctx->track_steps * (int64_t)(g + 1))) {
+        cudaStream_t st = ctx->cs[g % xt_ctx::NCS];
+        rc = enqueue_k1(ctx, p, bits, q0, q + 1 - q0, st, true);
+        if (rc) return rc;
+        rc = enqueue_fused(ctx, p, fl, q0, q + 1, st);
+        if (rc) return rc;
+        q0 = q + 1;
+        ++g;
+      }
+    }
+  }
+  for (int i = 0; i < xt_ctx::NCS; ++i) {
+    XT_CUDA_OK(cudaEventRecord(ctx->ev_join[i], ctx->cs[i]));
+    XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+  }
+  if (xyz) {
+    XT_CUDA_OK(cudaEventRecord(ctx->ev_seg[order[n_seg - 1]], ctx->up_stream));
+    XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_seg[order[n_seg - 1]], 0));
+  }
+  XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, ctx->n_workf[fl.tpt - 1], d_out ? d_out : ctx->d_out);
+  XT_CUDA_OK(cudaGetLastError());
+  XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_summ, ctx->d_summ, sizeof(XtChunkSummary) * nch, cudaMemcpyDeviceToHost, ctx->stream));
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  int need = 0;
+  rc = scan_summaries(ctx, &need);
+  if (rc) return rc;
+  if (need || *ctx->h_spec) return XT_RETRY;
+  std::copy(ctx->h_summ, ctx->h_summ + nch, ctx->summ.begin());
+  int Pmax, maxC;
+  int64_t su, sg;
+  work_counters(ctx, p, &Pmax, &maxC, &su, &sg);
+  ctx->spec_Pmax = Pmax;
+  ctx->stats.pipelined = 1;
+  ctx->stats.n_tracks = ctx->n_tracks;
+  ctx->stats.track_steps = ctx->track_steps;
+  ctx->stats.seq_updates = su;
+  ctx->stats.seq_groups = sg;
+  ctx->stats.max_nB_in = maxC;
+  ctx->stats.n_chunks = nch;
+  ctx->last_p = *p;
+  ctx->have_eval = true;
+  return XT_OK;
+}
+
+static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double* const* xyz) {
   if (!ctx) return XT_ERR_ARG;
   if (ctx->chunks.empty()) {
     set_error(ctx, "no tracks uploaded");
@@ -478,25 +804,38 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
   int rc = check_params(ctx, p, &bits);
   if (rc) return rc;
   XT_CUDA_OK(cudaSetDevice(ctx->device));
-  (void)user_stream;
   ctx->stats = xt_stats{};
+  if (ctx->pipeline && ctx->spec_Pmax > 0) {
+    rc = evaluate_pipelined(ctx, p, bits, d_out, xyz);
+    if (rc != XT_RETRY && rc != XT_RETRY_EARLY) return rc;
+    if (rc == XT_RETRY) xyz = nullptr;  // the data are resident now
+    ctx->stats = xt_stats{};
+  }
+  if (xyz) {  // host buffers, no history to size the launches with: plain upload first
+    for (int s = 0; s < (int)ctx->seg_L.size(); ++s) {
+      rc = enqueue_segment(ctx, s, xyz[s], s, ctx->stream);
+      if (rc) return rc;
+    }
+  }
+  // two-phase path: plan for all chunks, read the summaries back, then the replay
   XT_CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
   rc = run_plan(ctx, p, bits);
   if (rc) return rc;
   XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
-
-  // work counters + replay configuration
-  int Pmax = 1, maxC = 0;
-  int64_t su = 0, sg = 0;
-  for (size_t c = 0; c < ctx->chunks.size(); ++c) {
-    const XtChunkSummary& s = ctx->summ[c];
-    Pmax = std::max(Pmax, s.max_nP);
-    maxC = std::max(maxC, s.max_nC);
-    su += s.sum_nC * ctx->chunks[c].nT;
-    sg += s.sum_nG * ctx->chunks[c].nT;
+  int Pmax, maxC;
+  int64_t su, sg;
+  work_counters(ctx, p, &Pmax, &maxC, &su, &sg);
+  ctx->spec_Pmax = Pmax;
+  const int nch = (int)ctx->chunks.size();
+  FusedLaunch fl;
+  if (prepare_fused(ctx, p, Pmax, &fl)) {
+    XT_CUDA_OK(cudaMemsetAsync(ctx->d_spec, 0, sizeof(int), ctx->stream));
+    rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->stream);
+    if (rc) return rc;
+    return finish_eval(ctx, p, ctx->n_workf[fl.tpt - 1], d_out, su, sg, maxC);
   }
+  // first-generation linear-domain kernel (k2_variant 1) or log-domain global-memory fallback
   const int K = ipow(p->nS, p->nsub);
-  maxC = std::max(maxC, K * p->nS);
   const int KS = p->n_loc, CO = p->d + KS + 1;
   K2Args a{};
   a.chunks = ctx->d_chunks;
@@ -506,17 +845,9 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
   a.summ = ctx->d_summ;
   a.logp = ctx->d_logp;
   a.partial = ctx->d_partial;
-  Pmax = std::max(Pmax, 4);  // the fused kernel parks its end-of-track partial sums in an idle state buffer
   a.Pcap = Pmax;
   a.n_work = (int)ctx->work.size();
-  for (int s = 0; s < p->nS; ++s) {
-    double mx = -INFINITY;
-    for (int r = 0; r < K; ++r) mx = std::max(mx, p->L_leave[r + K * s]);
-    double acc = 0;
-    for (int r = 0; r < K; ++r) acc += std::exp(p->L_leave[r + K * s] - mx);
-    a.Lsum[s] = std::log(acc) + mx;
-  }
-  // linear-domain tables of the fast replay kernel
+  leave_sums(p, a.Lsum);
   K2Lin lin{};
   for (int h = 0; h < K * p->nS; ++h) {
     lin.winit[h] = std::exp(p->LT[h] + p->LF[h]);
@@ -525,42 +856,6 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
   }
   for (int s = 0; s < p->nS; ++s) lin.leave[s] = std::exp(a.Lsum[s]);
   const int wpc = ctx->k2_wpc;
-  // tracks per thread: two if the state of a 64-track tile fits in shared memory
-  int tpt = ctx->k2_tpt;
-  if (tpt == 2 && xt_fused_smem(p->d, KS, Pmax, K, K * p->nS, wpc, 2) > (size_t)ctx->smem_optin) tpt = 1;
-  const size_t fsmem = xt_fused_smem(p->d, KS, Pmax, K, K * p->nS, wpc, tpt);
-  if (ctx->k2_variant == 0 && !ctx->force_global && fsmem <= (size_t)ctx->smem_optin &&
-      xt_fused_blob16(Pmax, K) <= 64 * wpc) {
-    K2Tab tab{};
-    for (int h = 0; h < K * p->nS; ++h) {
-      tab.tau0[h] = lin.tau0[h];
-      tab.tau1[h] = lin.tau1[h];
-      tab.dd[h] = p->dd[h];
-      tab.winit[h] = lin.winit[h];
-    }
-    for (int s = 0; s < p->nS; ++s) tab.leave[s] = lin.leave[s];
-    for (int k = 0; k < KS; ++k) tab.l2[k] = p->l2[k];
-    for (int j = 0; j < 16; ++j) tab.e2[j] = std::exp2((double)j / 16.0);
-    tab.nS = p->nS;
-    tab.nsub = p->nsub;
-    tab.K = K;
-    tab.min_len = p->min_len;
-    K2FArgs fa{};
-    fa.chunks = ctx->d_chunks;
-    fa.work = ctx->d_workf[tpt - 1];
-    fa.soa = ctx->d_soa;
-    fa.plan = ctx->plan;
-    fa.logp = ctx->d_logp;
-    fa.partial = ctx->d_partial;
-    fa.Pcap = Pmax;
-    fa.n_work = ctx->n_workf[tpt - 1];
-    cudaError_t ef = cudaSuccess;
-#define CALL_K2F(D_, KS_) ef = launch_k2_fused<D_, KS_>(ctx, fa, tab, fsmem, wpc, tpt)
-    XT_DISPATCH(p->d, p->n_loc, CALL_K2F);
-#undef CALL_K2F
-    XT_CUDA_OK(ef);
-    return finish_eval(ctx, p, fa.n_work, d_out, su, sg, maxC);
-  }
   const size_t state_bytes = (size_t)2 * Pmax * CO * 32 * sizeof(double);
   const size_t smem = state_bytes + (size_t)2 * wpc * 32 * sizeof(double);
   const bool use_smem = smem <= (size_t)ctx->smem_optin && !ctx->force_global;
@@ -582,6 +877,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, cudaStream_t
   XT_DISPATCH(p->d, p->n_loc, CALL_K2);
 #undef CALL_K2
   XT_CUDA_OK(e);
+  ctx->stats.k2_launches++;
   return finish_eval(ctx, p, a.n_work, d_out, su, sg, maxC);
 }
 
@@ -594,10 +890,23 @@ extern "C" int xt_sum_logp(xt_ctx* ctx, const xt_params* p, double* out) {
   return XT_OK;
 }
 
+extern "C" int xt_sum_logp_host(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int64_t* n, const int32_t* isBL,
+                                const double* const* xyz, int32_t d, int32_t chunk_size, const xt_params* p, double* out) {
+  if (!ctx) return XT_ERR_ARG;
+  int rc = setup_layout(ctx, n_seg, L, n, isBL, d, chunk_size);
+  if (rc) return rc;
+  rc = evaluate(ctx, p, nullptr, xyz);
+  if (rc) return rc;
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  *out = *ctx->h_out;
+  return XT_OK;
+}
+
 extern "C" int xt_sum_logp_async(xt_ctx* ctx, const xt_params* p, double* d_out, void* cuda_stream) {
   // The result lands in d_out in stream order of the context's stream; if the caller passes its
   // own stream it is made to wait for the result.
-  int rc = evaluate(ctx, p, d_out, (cudaStream_t)cuda_stream);
+  int rc = evaluate(ctx, p, d_out, nullptr);
   if (rc) return rc;
   if (cuda_stream) XT_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->ev[2], 0));
   return XT_OK;
@@ -617,6 +926,22 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
     }
     ctx->k2_variant = value;
     ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k1_smem_scratch") == 0) {
+    ctx->k1_smem_scratch = value != 0;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "pipeline") == 0) {
+    ctx->pipeline = value != 0;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "n_groups") == 0) {
+    if (value < 1 || value > 64) {
+      set_error(ctx, "xt_set_option: n_groups must be in 1..64");
+      return XT_ERR_ARG;
+    }
+    ctx->n_groups = value;
     return XT_OK;
   }
   if (std::strcmp(name, "k2_tpt") == 0) {

@@ -16,6 +16,12 @@
 #pragma once
 #include "xt_common.cuh"
 
+#ifdef XT_K1_PROF
+#define K1_T(i) do { if (tid == 0) { const long long now__ = clock64(); prof[i] += now__ - tprev; tprev = now__; } } while (0)
+#else
+#define K1_T(i) do { } while (0)
+#endif
+
 struct K1Args {
   const XtChunk* chunks;
   const double* soa;
@@ -27,7 +33,22 @@ struct K1Args {
   int32_t RH;          // history rows allocated per sequence
   int32_t bits;        // bits per history row in the window code
   int32_t wpc;         // warps per tile of the fused replay kernel (schedule of the replay records)
+  int32_t chunk0;      // first position of this launch in `corder`
+  const int32_t* corder;  // chunk ids, longest tracks first: chunk id = corder[blockIdx.x + chunk0]
+  long long* prof;        // XT_K1_PROF builds: [n_chunks][8] cycles per phase (thread 0)
+  // shared-memory scratch (speculative: sized from the previous evaluation; 0 = global scratch).
+  // A chunk that needs more parents / children than this reports err = 3 and the host retries with
+  // the global-memory scratch.
+  int32_t scapP, scapC;
 };
+
+// dynamic shared memory of k1_plan (bytes)
+__host__ __device__ inline size_t xt_k1_smem(int cap, int CO, int RH, int nS, int scapP, int scapC) {
+  size_t b = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
+  b = (b + 15) & ~(size_t)15;
+  if (scapC > 0) b += (size_t)(scapP + scapC) * CO * 32 * 8 + (size_t)2 * scapP * RH * nS * 8;
+  return b;
+}
 
 __device__ __forceinline__ int xt_label(int x, int nS, bool wrap) {
   if (wrap) {
@@ -44,7 +65,8 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
   constexpr int W = XT_K1_THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
-  const XtChunk ck = a.chunks[blockIdx.x];
+  const int cid = a.corder[(int)blockIdx.x + a.chunk0];
+  const XtChunk ck = a.chunks[cid];
   const int nS = P.nS, nsub = P.nsub, cap = a.cap;
   int K = 1;
   for (int i = 0; i < nsub; ++i) K *= nS;
@@ -58,11 +80,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   int* grank = gid + cap;
   int* gcnt = grank + cap;            // [cap+1]: group sizes -> offsets
   unsigned char* curP = (unsigned char*)(gcnt + cap + 1);
-  __shared__ int s_flag;
-  __shared__ unsigned long long s_row[2 * W];
-  __shared__ int s_cand[2 * W];
+  __shared__ int s_flag, s_nG;
+  __shared__ unsigned long long s_rows[64];  // capture matrix of the matrix-mode grouping
 
-  XtChunkSummary* sm = &a.summ[blockIdx.x];
+  XtChunkSummary* sm = &a.summ[cid];
   const int nP0 = K * nS;
   if (tid == 0) {
     sm->err = 0;
@@ -100,10 +121,26 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       if (__ddiv_rn((double)c, denom) > 0.8) min_cnt = c;
   }
 
-  double* bufP = a.state + (size_t)blockIdx.x * 2 * cap * CO * 32;
+  // leader-track state and history rows: shared memory when the launch was sized for it (every
+  // producer -> consumer hand-off between phases is then a shared-memory round trip instead of
+  // an L2 one), else the per-chunk global scratch.  Generic pointers: same code for both.
+  double* bufP = a.state + (size_t)cid * 2 * cap * CO * 32;
   double* bufC = bufP + (size_t)cap * CO * 32;
-  double* histP = a.hist + (size_t)blockIdx.x * 2 * cap * a.RH * nS;
+  double* histP = a.hist + (size_t)cid * 2 * cap * a.RH * nS;
   double* histN = histP + (size_t)cap * a.RH * nS;
+  const int scapP = a.scapP, scapC = a.scapC;
+  if (scapC > 0) {
+    size_t o = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
+    o = (o + 15) & ~(size_t)15;
+    bufP = (double*)(k1_smem + o);
+    bufC = bufP + (size_t)scapP * CO * 32;
+    histP = bufC + (size_t)scapC * CO * 32;
+    histN = histP + (size_t)scapP * a.RH * nS;
+    if (nP0 > scapP) {
+      if (tid == 0) sm->err = 3;
+      return;
+    }
+  }
   const int bits = a.bits;
   const unsigned long long rowmask = (1ull << bits) - 1ull;
 
@@ -141,6 +178,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   int max_nP = nP, max_nC = 0;
   __syncthreads();
 
+#ifdef XT_K1_PROF
+  long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#endif
   for (int step = 2; step <= L - 2; ++step) {
     const int nC = nP * K;
     if (nC > cap) {
@@ -148,6 +189,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         sm->err = 2;
         sm->need_cap = nC;
       }
+      return;
+    }
+    if (scapC > 0 && nC > scapC) {  // more children than the shared-memory scratch was sized for
+      if (tid == 0) sm->err = 3;
       return;
     }
     sum_nC += nC;
@@ -228,6 +273,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     }
     if (nC > P.max_nb_states) th = __dmul_rn(th, 1.2);  // sticky escalation, tracking.py:581-582
     __syncthreads();
+    K1_T(0);
 
     const double th_lo = __dmul_rn(th, 1.0 - 1e-14), th_hi = __dmul_rn(th, 1.0 + 1e-14);
     // predicate "leader i captures sequence j" (all lanes of the warp must call it together)
@@ -261,6 +307,52 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
       return cnt_m >= min_cnt && cnt_s >= min_cnt;
     };
+    // the same predicate for up to four sequences at once (independent loads and dependency
+    // chains: the plan kernel is latency-bound); js[q] for q >= nj repeat a valid index
+    auto fp_ok4 = [&](const double (&mi)[D], const double (&si)[KS], const int (&js)[4], bool (&ok)[4]) {
+      double am[4], as[4], sj[4][KS];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        am[q] = 0.0;
+        as[q] = 0.0;
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) {
+          const double v = fabs(__dsub_rn(ST(bufC, js[q], dim), mi[dim]));
+          am[q] = (dim == 0) ? v : __dadd_rn(am[q], v);
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          sj[q][k] = ST(bufC, js[q], D + KS + k);
+          const double v = fabs(__dsub_rn(sj[q][k], si[k]));
+          as[q] = (k == 0) ? v : __dadd_rn(as[q], v);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        am[q] = (D == 2) ? __dmul_rn(am[q], 0.5) : ((D == 1) ? am[q] : __ddiv_rn(am[q], (double)D));
+        as[q] = (KS == 2) ? __dmul_rn(as[q], 0.5) : ((KS == 1) ? as[q] : __ddiv_rn(as[q], (double)KS));
+      }
+      int cnt_m[4] = {0, 0, 0, 0}, cnt_s[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        bool pm[4], ps[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double lo = __dmul_rn(th_lo, sj[q][k]), hi = __dmul_rn(th_hi, sj[q][k]);
+          pm[q] = am[q] < lo;
+          ps[q] = as[q] < lo;
+          if (!pm[q] && !(am[q] > hi)) pm[q] = __ddiv_rn(am[q], sj[q][k]) < th;
+          if (!ps[q] && !(as[q] > hi)) ps[q] = __ddiv_rn(as[q], sj[q][k]) < th;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          cnt_m[q] += __popc(__ballot_sync(0xffffffffu, act && pm[q]));
+          cnt_s[q] += __popc(__ballot_sync(0xffffffffu, act && ps[q]));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ok[q] = cnt_m[q] >= min_cnt && cnt_s[q] >= min_cnt;
+    };
     // predicate "leader i captures sequence j" (all lanes of the warp must call it together)
     auto pair_ok = [&](const double (&mi)[D], const double (&si)[KS], unsigned long long ci, int j) -> bool {
       const unsigned long long cj = codeC[j];
@@ -271,87 +363,105 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 
     int nG = 0;
     if (nC <= 64) {
-      // ---- batch mode ----
+      // ---- matrix mode ----
+      // Phase 1 (parallel, no dependency between leaders): row i of the capture matrix for every
+      // sequence i, restricted to j >= i.  The greedy loop of the reference visits leaders in
+      // ascending order and everything below a leader is already grouped (a leader that captures
+      // nothing, not even itself, is the reference's error path, tracking.py:725), so only the
+      // upper triangle is ever consulted.  Rows are dealt to the warps in zigzag order (row i has
+      // about (nC - i) / 2 floating-point tests).
       // window codes of sequences `lane` and `lane + 32` (never equal to a real code when absent)
       const unsigned long long code_lo = (lane < nC) ? codeC[lane] : ~0ull;
       const unsigned long long code_hi = (lane + 32 < nC) ? codeC[lane + 32] : ~0ull;
-      // grouped / visited / nG / CSR offset are kept redundantly in registers by every thread
-      // (the resolution below is deterministic), so a batch needs a single barrier.
       const unsigned long long full = (nC == 64) ? ~0ull : ((1ull << nC) - 1ull);
-      unsigned long long grouped = 0ull, visited = 0ull;
-      int off = 0, batch = 0;
-      bool bad = false;
-      for (;; ++batch) {
-        const unsigned long long candset = full & ~grouped & ~visited;
-        if (candset == 0ull) break;  // uniform
-        unsigned long long r = candset;
-        for (int k = 0; k < warp; ++k) r &= r - 1ull;
-        const int cand = r ? (__ffsll((long long)r) - 1) : -1;
-        unsigned long long row = 0ull;
-        if (cand >= 0) {
-          double mi[D], si[KS];
+      for (int base = 0, pass = 0; base < nC; base += W, ++pass) {
+        const int cnt = (nC - base) < W ? (nC - base) : W;
+        if (warp >= cnt) continue;  // warp-uniform
+        const int i = base + ((pass & 1) ? (cnt - 1 - warp) : warp);
+        double mi[D], si[KS];
 #pragma unroll
-          for (int dim = 0; dim < D; ++dim) mi[dim] = ST(bufC, cand, dim);
+        for (int dim = 0; dim < D; ++dim) mi[dim] = ST(bufC, i, dim);
 #pragma unroll
-          for (int k = 0; k < KS; ++k) si[k] = ST(bufC, cand, D + KS + k);
-          const unsigned long long ci = codeC[cand];
-          unsigned long long cand_base = full & ~grouped;
-          // sequences below the candidate are already grouped unless an earlier leader failed
-          if ((visited & ~grouped) == 0ull) cand_base &= ~((1ull << cand) - 1ull);
-          // code tests for all sequences at once (lane = sequence, two per lane)
-          const unsigned st_lo = __ballot_sync(0xffffffffu, (code_lo & rowmask) == (ci & rowmask));
-          const unsigned st_hi = __ballot_sync(0xffffffffu, (code_hi & rowmask) == (ci & rowmask));
-          const unsigned wn_lo = __ballot_sync(0xffffffffu, use_window && code_lo == ci);
-          const unsigned wn_hi = __ballot_sync(0xffffffffu, use_window && code_hi == ci);
-          const unsigned long long state_eq = (unsigned long long)st_lo | ((unsigned long long)st_hi << 32);
-          const unsigned long long win_eq = (unsigned long long)wn_lo | ((unsigned long long)wn_hi << 32);
-          row = win_eq & cand_base;                                  // state_mask (:679-681)
-          unsigned long long todo = state_eq & ~win_eq & cand_base;  // need the m/s tests (:689-693)
-          while (todo) {
-            const int j = __ffsll((long long)todo) - 1;
-            todo &= todo - 1ull;
-            if (fp_ok(mi, si, j)) row |= 1ull << j;
-          }
-        }
-        unsigned long long* b_row = s_row + (batch & 1) * W;
-        int* b_cand = s_cand + (batch & 1) * W;
-        if (lane == 0) {
-          b_row[warp] = row;
-          b_cand[warp] = cand;
-        }
-        __syncthreads();
-        // greedy resolution of the candidates in ascending order (tracking.py:667-698)
+        for (int k = 0; k < KS; ++k) si[k] = ST(bufC, i, D + KS + k);
+        const unsigned long long ci = codeC[i];
+        const unsigned long long upper = full & ~((1ull << i) - 1ull);
+        // code tests for all sequences at once (lane = sequence, two per lane)
+        const unsigned st_lo = __ballot_sync(0xffffffffu, (code_lo & rowmask) == (ci & rowmask));
+        const unsigned st_hi = __ballot_sync(0xffffffffu, (code_hi & rowmask) == (ci & rowmask));
+        const unsigned wn_lo = __ballot_sync(0xffffffffu, use_window && code_lo == ci);
+        const unsigned wn_hi = __ballot_sync(0xffffffffu, use_window && code_hi == ci);
+        const unsigned long long state_eq = (unsigned long long)st_lo | ((unsigned long long)st_hi << 32);
+        const unsigned long long win_eq = (unsigned long long)wn_lo | ((unsigned long long)wn_hi << 32);
+        unsigned long long row = win_eq & upper;                  // state_mask (:679-681)
+        unsigned long long todo = state_eq & ~win_eq & upper;     // need the m/s tests (:689-693)
+        while (todo) {  // four sequences per round
+          int js[4];
+          int nj = 0;
 #pragma unroll
-        for (int wq = 0; wq < W; ++wq) {
-          const int c = b_cand[wq];
-          if (c < 0) break;
-          if ((grouped >> c) & 1ull) continue;  // captured by an earlier leader of this batch
-          visited |= 1ull << c;
-          unsigned long long mem = b_row[wq] & ~grouped;
-          if (mem == 0ull) {  // empty group: the reference fails on the zero-size max (:725)
-            bad = true;
-            continue;
-          }
-          const int nmem = __popcll(mem);
-          grouped |= mem;
-          if (tid == wq) {  // one thread per accepted leader writes its member list
-            gcnt[nG] = off;
-            int o = off;
-            while (mem) {
-              const int j = __ffsll((long long)mem) - 1;
-              mem &= mem - 1ull;
-              gid[j] = nG;
-              const int p = j / K, rr = j - p * K;
-              ent[o++] = xt_pack_ent(p, rr + K * (int)curP[p], rr);
+          for (int q = 0; q < 4; ++q) {
+            if (todo) {
+              js[q] = __ffsll((long long)todo) - 1;
+              todo &= todo - 1ull;
+              nj = q + 1;
+            } else {
+              js[q] = js[0];
             }
           }
-          off += nmem;
-          ++nG;
+          bool ok[4];
+          fp_ok4(mi, si, js, ok);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < nj && ok[q]) row |= 1ull << js[q];
+        }
+        if (lane == 0) s_rows[i] = row;
+      }
+      __syncthreads();
+      K1_T(1);
+      // Phase 2: greedy resolution on the bit rows (tracking.py:667-698) by one warp (the other
+      // warps wait at the barrier and leave the issue slots to the co-resident chunks); lane l
+      // emits the CSR entries of sequences l and l + 32 when they are captured.
+      if (warp == 0) {
+        unsigned long long grouped = 0ull, rem = full;
+        int off = 0, ng = 0;
+        bool bad = false;
+        int jp[2], jr[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = lane + 32 * h;
+          jp[h] = (j < nC) ? j / K : 0;
+          jr[h] = j - jp[h] * K;
+        }
+        while (rem) {
+          const int i = __ffsll((long long)rem) - 1;
+          const unsigned long long mem = s_rows[i] & ~grouped;
+          if (mem == 0ull) {  // empty group: the reference fails on the zero-size max (:725)
+            bad = true;
+            rem &= rem - 1ull;
+            continue;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = lane + 32 * h;
+            if (j < nC && ((mem >> j) & 1ull)) {
+              gid[j] = ng;
+              ent[off + __popcll(mem & ((1ull << j) - 1ull))] = xt_pack_ent(jp[h], jr[h] + K * (int)curP[jp[h]], jr[h]);
+            }
+          }
+          if (lane == 0) gcnt[ng] = off;
+          off += __popcll(mem);
+          grouped |= mem;
+          rem &= ~mem;
+          ++ng;
+        }
+        if (lane == 0) {
+          gcnt[ng] = off;
+          s_nG = ng;
+          if (bad || grouped != full) s_flag = 1;  // tracking.py:700-701
         }
       }
-      if (tid == 0) gcnt[nG] = off;
-      if (bad || grouped != full) s_flag = 1;  // tracking.py:700-701
+      K1_T(2);
       __syncthreads();
+      nG = s_nG;
       for (int c = tid; c < nC; c += XT_K1_THREADS) pgid[c] = (uint16_t)gid[c];
       for (int g = tid; g <= nG; g += XT_K1_THREADS) goff[g] = (uint16_t)gcnt[g];
       if (s_flag) {
@@ -405,6 +515,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
       __syncthreads();  // ent visible to the CTA (read back below through global memory)
     }
+    if (scapC > 0 && nG > scapP) {  // more groups than parent slots in shared memory
+      if (tid == 0) sm->err = 3;
+      return;
+    }
     if (tid == 0) {
       a.plan.hdr[rec].nC = nC;
       a.plan.hdr[rec].nG = nG;
@@ -419,6 +533,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
     }
 
+    K1_T(3);
     {  // replay record of this step (XtBlobHdr, xt_common.cuh).  Schedule: groups sorted by
        // (members descending, group ascending) are dealt round-robin to the replay warps.
       uint4* blob = a.plan.blob + (size_t)rec * xt_blob_stride16(a.plan.cap);
@@ -437,6 +552,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
       unsigned long long* brec = (unsigned long long*)(blob + 2);
       for (int g = tid; g < nG; g += XT_K1_THREADS) {
+        codeC[g] = 0ull;  // the children's codes are dead: becomes the group's window code (history phase)
         const int o = gcnt[g], n = gcnt[g + 1] - o;
         int rank = 0;
         for (int j = 0; j < nG; ++j) {
@@ -463,6 +579,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       for (int c = tid; c < nC; c += XT_K1_THREADS) bent[c] = ent[c];
     }
 
+    K1_T(4);
     // ---- merge on the leader tracks (tracking.py:723-741) ----
     // `LP[:, subgroup]` is an F-ordered fancy-index copy in numpy, so every reduction over the
     // members runs sequentially in ascending member order (checked against numpy 2.3).
@@ -478,19 +595,33 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       double mx = ST(bufC, child(0), D + 2 * KS);
       for (int k = 1; k < n; ++k) mx = fmax(mx, ST(bufC, child(k), D + 2 * KS));
       double sw = 0.0, am[D], as2[KS];
-      for (int k = 0; k < n; ++k) {
-        const int c = child(k);
-        const double w = exp(__dsub_rn(ST(bufC, c, D + 2 * KS), mx));
-        sw = (k == 0) ? w : __dadd_rn(sw, w);
+      for (int k0 = 0; k0 < n; k0 += 4) {  // weights of four members at a time (independent exps);
+        double w4[4], m4[4][D], s4[4][KS];  // the sums still run in ascending member order
 #pragma unroll
-        for (int dim = 0; dim < D; ++dim) {
-          const double v = __dmul_rn(w, ST(bufC, c, dim));
-          am[dim] = (k == 0) ? v : __dadd_rn(am[dim], v);
+        for (int q = 0; q < 4; ++q) {
+          const int c = child(k0 + q < n ? k0 + q : k0);
+          w4[q] = exp(__dsub_rn(ST(bufC, c, D + 2 * KS), mx));
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) m4[q][dim] = ST(bufC, c, dim);
+#pragma unroll
+          for (int k2 = 0; k2 < KS; ++k2) s4[q][k2] = ST(bufC, c, D + k2);
         }
 #pragma unroll
-        for (int k2 = 0; k2 < KS; ++k2) {
-          const double v = __dmul_rn(w, ST(bufC, c, D + k2));
-          as2[k2] = (k == 0) ? v : __dadd_rn(as2[k2], v);
+        for (int q = 0; q < 4; ++q) {
+          if (k0 + q < n) {
+            const bool first = (k0 + q) == 0;
+            sw = first ? w4[q] : __dadd_rn(sw, w4[q]);
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) {
+              const double v = __dmul_rn(w4[q], m4[q][dim]);
+              am[dim] = first ? v : __dadd_rn(am[dim], v);
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < KS; ++k2) {
+              const double v = __dmul_rn(w4[q], s4[q][k2]);
+              as2[k2] = first ? v : __dadd_rn(as2[k2], v);
+            }
+          }
         }
       }
 #pragma unroll
@@ -499,68 +630,96 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       for (int k2 = 0; k2 < KS; ++k2) ST(bufP, g, D + k2) = __ddiv_rn(as2[k2], sw);
       ST(bufP, g, D + 2 * KS) = __dadd_rn(log(sw), mx);
     }
+#ifdef XT_K1_PROF
+    __syncthreads();
+#endif
+    K1_T(5);
     // ---- history rows of the groups (fit mode: mean one-hot over members and leader tracks,
     //      tracking.py:714-715,735-737), accumulated in numpy's (member, track) order ----
     const int rows_out = rows_cmp;  // truncated to frame_len
     const int Kh = hist_dim0_is_nT ? Kt : 1;
-    for (int idx = tid; idx < nG * rows_out * nS; idx += XT_K1_THREADS) {
-      const int s = idx % nS, row = (idx / nS) % rows_out, g = idx / (nS * rows_out);
+    __syncthreads();  // codeC[g] zeroed (record phase) before the argmax bits are OR-ed in
+    // one thread per (group, row): the nS values of the row, then their argmax (ties -> lowest
+    // state) goes straight into the group's window code.  The sums run in numpy's order for the
+    // fancy-indexed copy (member outer, track inner; adding to 0.0 first is exact), two states at
+    // a time so that the two sequential chains interleave.
+    for (int idx = tid; idx < nG * rows_out; idx += XT_K1_THREADS) {
+      const int row = idx % rows_out, g = idx / rows_out;
       const int o = gcnt[g], n = gcnt[g + 1] - o;
-      auto val = [&](int k) -> double {
-        const uint32_t e = ent[o + k];
-        const int p = (int)(e & 0xFFFF);
-        if (row < nsub) {
-          int x = p * K + (int)(e >> 24);
-          for (int r = 0; r < row; ++r) x /= nS;
-          return xt_label(x, nS, wrap) == s ? 1.0 : 0.0;
-        }
-        return histP[((size_t)p * a.RH + (row - nsub)) * nS + s];
-      };
-      double out;
-      if (n == 1) {
-        out = val(0);
-      } else {
-        double acc = 0.0;
-        bool first = true;
-        for (int k = 0; k < n; ++k) {  // numpy order for the fancy-indexed copy: member outer, track inner
-          const double v = val(k);
-          for (int tt = 0; tt < Kh; ++tt) {
-            acc = first ? v : __dadd_rn(acc, v);
-            first = false;
+      int best = 0;
+      double bv = 0.0;
+      for (int s0 = 0; s0 < nS; s0 += 2) {
+        const bool two = s0 + 1 < nS;
+        double accA = 0.0, accB = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const uint32_t e = ent[o + k];
+          const int p = (int)(e & 0xFFFF);
+          double vA, vB = 0.0;
+          if (row < nsub) {
+            int x = p * K + (int)(e >> 24);
+            for (int r = 0; r < row; ++r) x /= nS;
+            const int lab = xt_label(x, nS, wrap);
+            vA = lab == s0 ? 1.0 : 0.0;
+            vB = lab == s0 + 1 ? 1.0 : 0.0;
+          } else {
+            const double* hp = histP + ((size_t)p * a.RH + (row - nsub)) * nS + s0;
+            vA = hp[0];
+            if (two) vB = hp[1];
+          }
+          if (n == 1) {  // single member: the value itself (no mean)
+            accA = vA;
+            accB = vB;
+            break;
+          }
+          const bool fastA = vA == 0.0 || (vA == 1.0 && accA < 1e9 && accA == (double)(int)accA);
+          const bool fastB = vB == 0.0 || (vB == 1.0 && accB < 1e9 && accB == (double)(int)accB);
+          if (fastA && fastB) {  // zeros change nothing; ones on an integer partial sum are exact
+            accA += vA * (double)Kh;
+            accB += vB * (double)Kh;
+          } else {
+#pragma unroll 6
+            for (int tt = 0; tt < Kh; ++tt) {
+              accA = __dadd_rn(accA, vA);
+              accB = __dadd_rn(accB, vB);
+            }
           }
         }
-        out = __ddiv_rn(acc, (double)(Kh * n));
+        double outA = accA, outB = accB;
+        if (n > 1) {
+          const double den = (double)(Kh * n);
+          outA = __ddiv_rn(accA, den);
+          outB = __ddiv_rn(accB, den);
+        }
+        double* hn = histN + ((size_t)g * a.RH + row) * nS + s0;
+        hn[0] = outA;
+        if (s0 == 0 || outA > bv) {
+          bv = outA;
+          best = s0;
+        }
+        if (two) {
+          hn[1] = outB;
+          if (outB > bv) {
+            bv = outB;
+            best = s0 + 1;
+          }
+        }
       }
-      histN[((size_t)g * a.RH + row) * nS + s] = out;
+      if (best) atomicOr(&codeC[g], (unsigned long long)best << (bits * row));
     }
     __syncthreads();
-    // new parents: newest true state, window code (argmax per row, ties -> lowest state)
+    K1_T(6);
+    // new parents: newest true state and window code.  All reads of curP / codeP of this step are
+    // done (the last ones are in the grouping phase), so they are published directly.
     {
       uint8_t* pcur = a.plan.curG + (size_t)rec * a.plan.cap;
       for (int g = tid; g < nG; g += XT_K1_THREADS) {
         const uint32_t e = ent[gcnt[g]];
         const int c0 = (int)(e & 0xFFFF) * K + (int)(e >> 24);
         const unsigned char cs = (unsigned char)(c0 % nS);
-        unsigned long long code = 0;
-        for (int row = 0; row < rows_out; ++row) {
-          int best = 0;
-          double bv = histN[((size_t)g * a.RH + row) * nS];
-          for (int s = 1; s < nS; ++s) {
-            const double v = histN[((size_t)g * a.RH + row) * nS + s];
-            if (v > bv) { bv = v; best = s; }
-          }
-          code |= (unsigned long long)best << (bits * row);
-        }
-        // published after all reads of curP/codeP of this step are done (next barrier)
-        grank[g] = (int)cs;
-        codeC[g] = code;  // codeC is dead until the next expansion
         pcur[g] = cs;
+        curP[g] = cs;
+        codeP[g] = codeC[g];
       }
-    }
-    __syncthreads();
-    for (int g = tid; g < nG; g += XT_K1_THREADS) {
-      curP[g] = (unsigned char)grank[g];
-      codeP[g] = codeC[g];
     }
     {  // swap history buffers
       double* tmp = histP;
@@ -573,7 +732,11 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     sum_nG += nG;
     max_nP = nP > max_nP ? nP : max_nP;
     __syncthreads();
+    K1_T(7);
   }
+#ifdef XT_K1_PROF
+  if (tid == 0 && a.prof) for (int i = 0; i < 8; ++i) a.prof[(size_t)cid * 8 + i] = prof[i];
+#endif
   if (tid == 0) {
     // last step (no fusion) and the optional end-of-track expansion, for the work counters
     const int nC = nP * K;

@@ -238,8 +238,11 @@ struct K2FArgs {
   XtPlanPtrs plan;
   double* logp;
   double* partial;
+  const XtChunkSummary* summ;  // written by the plan kernel earlier in the same stream
+  int* spec_fail;      // set when a chunk needs more parent slots than this launch was sized for
   int32_t Pcap;
-  int32_t n_work;
+  int32_t n_work;      // CTAs of this launch
+  int32_t work0;       // first tile of this launch in the work table
 };
 
 // shared memory of k2_replay_fused in bytes (host and device agree through these functions)
@@ -255,16 +258,26 @@ __host__ __device__ inline size_t xt_fused_smem(int D, int KS, int Pcap, int K, 
 }
 
 template <int D, int KS, int WPC, int TPT>
-__global__ void __launch_bounds__(32 * WPC) k2_replay_fused(const K2FArgs a, const __grid_constant__ K2Tab T) {
+__global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_replay_fused(const K2FArgs a, const __grid_constant__ K2Tab T) {
   using IO = XtSlotIO<D, KS, TPT>;
   using Seq = XtSeq<D, KS>;
   constexpr int SLOTB = IO::SLOTB, ESLOT = IO::ESLOT;
   constexpr int NT = 32 * WPC;
   const int tid = threadIdx.x;
   const int lane = tid & 31, w = tid >> 5;
-  const int wi = blockIdx.x;
+  const int wi = (int)blockIdx.x + a.work0;
   const XtWork wk = a.work[wi];
   const XtChunk ck = a.chunks[wk.chunk];
+  {  // the launch may have been sized speculatively (parent slots of the previous evaluation)
+    const XtChunkSummary sm = a.summ[wk.chunk];
+    if (sm.err != 0 || sm.max_nP > a.Pcap) {
+      if (tid == 0) {
+        atomicExch(a.spec_fail, 1);
+        a.partial[wi] = 0.0;
+      }
+      return;
+    }
+  }
   const int nS = T.nS, K = T.K, H = K * nS;
   const size_t npad = (size_t)ck.nTpad;
   const double* Cs = a.soa + ck.xyz_off;

@@ -73,8 +73,10 @@ typedef struct xt_stats {
   int32_t n_chunks;
   int32_t k1_launches;   /* kernels launched by the last evaluation */
   int32_t k2_launches;
-  float ms_plan;         /* CUDA-event time of the plan kernel(s) */
-  float ms_replay;       /* CUDA-event time of the replay kernel(s) incl. the reduction */
+  float ms_plan;         /* CUDA-event time of the plan kernel(s); pipelined evaluation: plan + replay */
+  float ms_replay;       /* CUDA-event time of the replay kernel(s) incl. the reduction; pipelined: reduction */
+  int32_t pipelined;     /* 1: plan and replay were launched per group of chunks on several streams */
+  int32_t pad_;
 } xt_stats;
 
 /* Lifetime.  `device` is the CUDA ordinal this context drives. */
@@ -103,7 +105,17 @@ int xt_upload(xt_ctx* ctx, int32_t n_segments, const int32_t* L, const int64_t* 
  */
 int xt_sum_logp(xt_ctx* ctx, const xt_params* p, double* out);
 
-/* Same, but the result stays on the device: d_out is a device pointer to one double and the
+/*
+ * Objective on host buffers — the call cum_Proba_Cs makes when it is handed numpy arrays on every
+ * evaluation (tracking.py:991: all_tracks is an argument of the objective): same arguments as
+ * xt_upload plus the model.  The copy of one segment overlaps the plan / replay kernels of the
+ * segments already on the device.  The data set stays resident afterwards (xt_sum_logp,
+ * xt_chunk_logp ... work on it).
+ */
+int xt_sum_logp_host(xt_ctx* ctx, int32_t n_segments, const int32_t* L, const int64_t* n, const int32_t* isBL,
+                     const double* const* xyz, int32_t d, int32_t chunk_size, const xt_params* p, double* out);
+
+/* Same as xt_sum_logp, but the result stays on the device: d_out is a device pointer to one double and the
  * work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream) so a
  * collective can be chained without a host round trip.  No synchronisation on return. */
 int xt_sum_logp_async(xt_ctx* ctx, const xt_params* p, double* d_out, void* cuda_stream);
@@ -128,9 +140,13 @@ int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out);
 
 int xt_get_stats(xt_ctx* ctx, xt_stats* out);
 
-/* Engine options (tests / diagnostics).  "force_global_replay" = 1 runs the log-domain replay
- * kernel with its state in global memory (the path taken when the live sequences of a track do
- * not fit in shared memory) instead of the shared-memory linear-domain kernel. */
+/* Engine options (tests / diagnostics).
+ *  "force_global_replay" = 1: run the log-domain replay kernel with its state in global memory (the
+ *      path taken when the live sequences of a track do not fit in shared memory);
+ *  "k2_variant" = 1: first-generation linear-domain replay kernel instead of the fused one;
+ *  "k2_wpc" (2|4|8), "k2_tpt" (1|2): warps per tile / tracks per thread of the fused replay kernel;
+ *  "pipeline" = 0: always evaluate in two phases (plan for all chunks, then replay) instead of
+ *      per-group launches on several streams; "n_groups": number of groups of the pipelined path. */
 int xt_set_option(xt_ctx* ctx, const char* name, int value);
 
 /* Measured FP64 FMA throughput of this GPU in TFLOP/s (2 flops per DFMA), used as the

@@ -110,18 +110,50 @@ if __name__ == "__main__":
     t = time.time()
     ts = xt.TrackSet(sorted_tracks)
     print("upload", round(time.time() - t, 3), "s; chunks", len(ts.chunks))
-    sched = [(0, 4, 1)] * 3 + [(0, 4, 2)] * 2 + [(0, 2, 1)] * 2 + [(0, 8, 2)] * 2 + [(0, 8, 1)] * 2 + [(1, 4, 1)] * 2 + [(0, 4, 1)] * 2
-    for it, (variant, wpc, tpt) in enumerate(sched):
-        ts.engine.set_option("k2_variant", variant)
-        ts.engine.set_option("k2_wpc", wpc)
-        ts.engine.set_option("k2_tpt", tpt)
-        print("k2_variant", variant, "k2_wpc", wpc, "k2_tpt", tpt)
+    def timed(tag, n=4):
+        for it in range(n):
+            t = time.time()
+            v = ts.sum_logp(p)
+            dtm = time.time() - t
+            st = ts.engine.stats()
+            print(f"{tag} eval {it}: sum_logp={v!r} wall={dtm*1e3:.3f}ms plan={st['ms_plan']:.3f}ms replay={st['ms_replay']:.3f}ms "
+                  f"pipelined={st['pipelined']} launches={st['k1_launches']}+{st['k2_launches']} -> {st['track_steps']/dtm/1e9:.3f} G track-steps/s")
+        return v
+
+    ts.engine.set_option("pipeline", 0)
+    v = timed("two-phase")
+    ts.engine.set_option("pipeline", 1)
+    for g in (1, 2, 3, 4, 6, 8, 21):
+        ts.engine.set_option("n_groups", g)
+        v2 = timed(f"pipelined G={g}", 3)
+        if v2 != v:
+            print("   MISMATCH pipelined vs two-phase", v2, v)
+            bad += 1
+    ts.engine.set_option("n_groups", 4)
+    # host-buffer objective: upload overlapped with the kernels
+    pinned = []
+    for a in sorted_tracks:
+        b = _native.pinned_empty(a.shape)
+        b[...] = a
+        pinned.append(b)
+    bl = [0 if a.shape[1] == sorted_tracks[-1].shape[1] else 1 for a in sorted_tracks]
+    e2 = _native.Engine(0)
+    for it in range(5):
         t = time.time()
-        v = ts.sum_logp(p)
+        vh = e2.sum_logp_host(pinned, bl, 2000, p)
         dtm = time.time() - t
-        st = ts.engine.stats()
-        print(f"eval {it}: sum_logp={v!r} wall={dtm*1e3:.3f}ms plan={st['ms_plan']:.3f}ms replay={st['ms_replay']:.3f}ms "
-              f"track_steps={st['track_steps']} -> {st['track_steps']/dtm/1e9:.3f} G track-steps/s; seq_updates={st['seq_updates']} maxnB={st['max_nB_in']}")
+        st = e2.stats()
+        print(f"host eval {it}: sum_logp={vh!r} wall={dtm*1e3:.3f}ms pipelined={st['pipelined']} -> {st['track_steps']/dtm/1e9:.3f} G track-steps/s")
+    if vh != v:
+        print("   MISMATCH host vs resident", vh, v)
+        bad += 1
+    e2.set_option("pipeline", 0)
+    for it in range(2):
+        t = time.time()
+        vh = e2.sum_logp_host(pinned, bl, 2000, p)
+        dtm = time.time() - t
+        print(f"host eval two-phase {it}: sum_logp={vh!r} wall={dtm*1e3:.3f}ms")
+    e2.close()
     if n_tracks <= 200000:
         t = time.time()
         ref = -orc.neg_log_likelihood(sorted_tracks, model, workers=8)

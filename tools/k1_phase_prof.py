@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Per-phase cycle counts of the plan kernel (debug build: nvcc -DXT_K1_PROF).  Run on the GPU box:
+
+    python tools/k1_phase_prof.py [n_tracks]
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from extrack_b200 import _native, tracking as xt  # noqa: E402
+from extrack_b200.simulate import sim_tracks  # noqa: E402
+from helpers import engine_params, make_model  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+tracks = sim_tracks(n, seed=0, device="cuda", max_track_len=30, min_track_len=10, LocErr=0.02, Ds=[0, 0.25], nb_dims=2,
+                    initial_fractions=[0.6, 0.4], TrMat=[[0.9, 0.1], [0.1, 0.9]], dt=0.02, pBL=0.05, cell_dims=[1, None, None])
+st, _ = xt._sorted_buckets(tracks)
+model = make_model(nS=2, nsub=1, frame_len=8, min_len=st[0].shape[1], Ds=[1e-5, 0.25], Fs=[0.6, 0.4])
+p = engine_params(model, 2)
+ts = xt.TrackSet(st)
+ts.engine.set_option("pipeline", int(os.environ.get("PIPE", "0")))
+for _ in range(3):
+    ts.sum_logp(p)
+print(ts.engine.stats())
+lib = _native.load_library()
+nch = len(ts.chunks)
+buf = np.zeros((nch, 8), dtype=np.int64)
+assert lib.xt_debug_k1_prof(buf.ctypes.data_as(C.c_void_p), nch) == 0
+names = ["update+codes", "batch rows", "batch resolve", "csr/hdr/grec", "blob", "merge", "history", "new parents"]
+Ls = np.array([st[b].shape[1] for (b, a, z, _) in ts.chunks])
+for L in (10, 20, 30):
+    sel = buf[Ls == L]
+    if len(sel) == 0:
+        continue
+    m = sel.mean(0)
+    print(f"L={L}: {len(sel)} chunks, total {m.sum():.0f} cycles = {m.sum()/1.965e3:.1f} us; per fused step {m.sum()/(L-3):.0f}")
+    for nm, v in zip(names, m):
+        print(f"   {nm:14s} {v:10.0f}  {100*v/m.sum():5.1f}%  per step {v/(L-3):8.0f}")
