@@ -206,6 +206,8 @@ def main():
 
     ts = xt.TrackSet(st, rank=0, world_size=1, device=local)  # every rank owns its whole field of view
     eng = ts.engine
+    if os.environ.get("XT_BENCH_TWO_PHASE"):  # profiling aid: one plan launch + one replay launch per evaluation
+        eng.set_option("pipeline", 0)
     buf = torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}")
     stream = torch.cuda.current_stream().cuda_stream
 

@@ -65,10 +65,20 @@ def test_plan_equals_oracle_plan_and_both_replay_kernels_agree(path, native):
             assert th == rec["threshold"]
         eng.set_option("force_global_replay", 1)  # log-domain kernel with global-memory state
         slow = eng.chunk_logp(0, len(C), p)
+        eng.set_option("force_global_replay", 0)
+        others = []
+        for opts in (dict(k2_variant=1), dict(k2_tpt=2), dict(k2_wpc=2), dict(k2_wpc=8, k2_tpt=2)):
+            for k, v in opts.items():
+                eng.set_option(k, v)
+            others.append(eng.chunk_logp(0, len(C), p))
+            for k, v in dict(k2_variant=0, k2_tpt=1, k2_wpc=4).items():
+                eng.set_option(k, v)
     finally:
         eng.close()
     np.testing.assert_allclose(fast, ref, rtol=RTOL_LOGL)
     np.testing.assert_allclose(slow, ref, rtol=RTOL_LOGL)
+    for o in others:  # first-generation kernel, two tracks per thread, other warp counts
+        np.testing.assert_allclose(o, ref, rtol=RTOL_LOGL)
 
 
 @pytest.mark.parametrize("cfg", [
@@ -92,6 +102,87 @@ def test_chunk_parity_vs_oracle_seeded(cfg, native):
     finally:
         eng.close()
     np.testing.assert_allclose(got, ref, rtol=RTOL_LOGL)
+
+
+def test_extreme_dynamic_range_and_nan_inputs(native, xt):
+    """The linear-domain replay carries per-sequence exponents: jumps of hundreds of sigma (log
+    likelihoods of -1e5 per track) must agree with the log-domain oracle; NaN coordinates poison
+    the track (and the objective becomes inf, tracking.py:1084-1086)."""
+    import warnings
+
+    m = make_model(frame_len=6)
+    C = random_walk_tracks(64, 15, 2, np.random.default_rng(4))
+    C[::3, 7] += 5.0      # one 250-sigma jump
+    C[1::3, 4:] += 40.0   # a 2000-sigma jump
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = orc.chunk_logp(C, m, 1)
+    assert np.isfinite(ref).all() and ref.min() < -1e5
+    p = engine_params(m, 2)
+    eng = native.Engine(0)
+    try:
+        eng.upload([C], [1], len(C))
+        got = eng.chunk_logp(0, len(C), p)
+        eng.set_option("k2_tpt", 2)
+        got2 = eng.chunk_logp(0, len(C), p)
+        eng.set_option("k2_tpt", 1)
+        Cn = C.copy()
+        Cn[5, 3, 1] = np.nan
+        eng.upload([Cn], [1], len(C))
+        bad = eng.chunk_logp(0, len(C), p)
+    finally:
+        eng.close()
+    np.testing.assert_allclose(got, ref, rtol=RTOL_LOGL)
+    np.testing.assert_allclose(got2, ref, rtol=RTOL_LOGL)
+    assert np.isnan(bad[5]) and np.isfinite(np.delete(bad, 5)).all()
+
+
+def test_pipelined_host_and_two_phase_evaluations_agree(native):
+    """Per-group launches on several streams, the host-buffer objective (upload overlapped with the
+    kernels) and the two-phase evaluation give the same bits; a speculative launch that turns out
+    too small (more live sequences than the previous evaluation) is redone transparently."""
+    rng = np.random.default_rng(17)
+    st = [random_walk_tracks(n, L, 2, rng) for L, n in ((5, 700), (9, 2300), (14, 4100), (22, 2500), (30, 4500))]
+    bl = [1, 1, 1, 1, 0]
+    m = make_model(frame_len=8, min_len=5)
+    p = engine_params(m, 2)
+    eng = native.Engine(0)
+    try:
+        eng.upload(st, bl, 2000)
+        eng.set_option("pipeline", 0)
+        two_phase = eng.sum_logp(p)
+        assert eng.stats()["pipelined"] == 0
+        eng.set_option("pipeline", 1)
+        vals = []
+        for g in (1, 2, 4, 7):
+            eng.set_option("n_groups", g)
+            vals.append(eng.sum_logp(p))
+            assert eng.stats()["pipelined"] == 1
+        eng.set_option("k1_smem_scratch", 0)
+        vals.append(eng.sum_logp(p))
+        eng.set_option("k1_smem_scratch", 1)
+        per_chunk = np.concatenate([eng.chunk_logp(c, min(2000, len(a) - o), p)
+                                    for c, (a, o) in enumerate((a, o) for a in st for o in range(0, len(a), 2000))])
+        # fewer live sequences, then many more: the launch sized from the small plan must be redone
+        m_small = make_model(frame_len=3, min_len=5)
+        small = eng.sum_logp(engine_params(m_small, 2))
+        big = eng.sum_logp(p)
+        # host-buffer objective on a fresh engine: first call two-phase, later calls pipelined
+        e2 = native.Engine(0)
+        h = [e2.sum_logp_host(st, bl, 2000, p) for _ in range(3)]
+        assert e2.stats()["pipelined"] == 1
+        moved = [a + 0.25 for a in st]  # new coordinates, same shapes: allocations are reused
+        h_moved = e2.sum_logp_host(moved, bl, 2000, p)
+        e2.close()
+    finally:
+        eng.close()
+    assert all(v == two_phase for v in vals), (vals, two_phase)
+    assert big == two_phase
+    assert abs(per_chunk.sum() - two_phase) <= 1e-12 * abs(two_phase)
+    want_small = -orc.neg_log_likelihood(st, m_small)
+    assert abs(small - want_small) <= RTOL_LOGL * abs(want_small)
+    assert all(v == two_phase for v in h), (h, two_phase)
+    assert abs(h_moved - two_phase) <= 1e-9 * abs(two_phase)  # translation invariance
 
 
 def test_objective_multibucket_golden_through_api(xt, capsys):
