@@ -56,7 +56,7 @@ class XtStats(C.Structure):
         ("ms_plan", C.c_float),
         ("ms_replay", C.c_float),
         ("pipelined", C.c_int32),
-        ("pad_", C.c_int32),
+        ("ms_predict", C.c_float),
     ]
 
 

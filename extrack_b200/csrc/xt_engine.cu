@@ -24,6 +24,9 @@ struct xt_ctx {
   std::vector<int> seg_chunk0;
   std::vector<int64_t> upload_sig;  // shapes of the resident data set (allocation reuse)
   double* stage[2] = {nullptr, nullptr};
+  double* stage_all = nullptr;          // host-buffer objective: one staging area per segment (no reuse, no host waits)
+  size_t stage_all_elems = 0;
+  std::vector<size_t> seg_stage_off;
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
   size_t stage_elems = 0;
   std::vector<int64_t> seg_n;
@@ -80,6 +83,8 @@ struct xt_ctx {
   xt_params last_p{};
   xt_stats stats{};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_k3[2] = {nullptr, nullptr};
+  float ms_predict = 0.f;
 };
 
 static std::string g_create_error;
@@ -160,6 +165,7 @@ extern "C" int xt_create(int device, xt_ctx** out) {
   XT_CUDA_OK(cudaMalloc(&c->d_out, sizeof(double)));
   XT_CUDA_OK(cudaMallocHost(&c->h_out, sizeof(double)));
   for (int i = 0; i < 3; ++i) XT_CUDA_OK(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaEventCreate(&c->ev_k3[i]));
   for (int i = 0; i < xt_ctx::NCS; ++i) {
     XT_CUDA_OK(cudaStreamCreateWithFlags(&c->cs[i], cudaStreamNonBlocking));
     XT_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
@@ -183,9 +189,11 @@ extern "C" void xt_destroy(xt_ctx* ctx) {
     cudaFree(ctx->stage[b]);
     if (ctx->stage_done[b]) cudaEventDestroy(ctx->stage_done[b]);
   }
+  cudaFree(ctx->stage_all);
   cudaFree(ctx->d_out);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; ++i) if (ctx->ev_k3[i]) cudaEventDestroy(ctx->ev_k3[i]);
   for (int i = 0; i < xt_ctx::NCS; ++i) {
     if (ctx->cs[i]) cudaStreamDestroy(ctx->cs[i]);
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
@@ -353,6 +361,39 @@ static int enqueue_segment(xt_ctx* ctx, int s, const double* xyz, int slot, cuda
   k_pack<<<(unsigned)blocks, threads, 0, stream>>>(ctx->stage[b], ctx->d_soa, ctx->d_chunks, ctx->seg_chunk0[s], chunk_size,
                                                    (int)n, L, d);
   XT_CUDA_OK(cudaEventRecord(ctx->stage_done[b], stream));
+  return XT_OK;
+}
+
+// Host-buffer objective: every segment has its own staging area, so the copies run back to back on
+// the upload stream (the PCIe link never waits for a repack kernel or for the host) and the repack
+// is done on the compute stream that consumes the segment.
+static int ensure_stage_all(xt_ctx* ctx) {
+  const int n_seg = (int)ctx->seg_L.size();
+  size_t total = 0;
+  ctx->seg_stage_off.assign(n_seg, 0);
+  for (int s = 0; s < n_seg; ++s) {
+    ctx->seg_stage_off[s] = total;
+    total += (size_t)ctx->seg_n[s] * ctx->seg_L[s] * ctx->d;
+  }
+  if (total > ctx->stage_all_elems) {
+    cudaFree(ctx->stage_all);
+    ctx->stage_all = nullptr;
+    ctx->stage_all_elems = 0;
+    XT_CUDA_OK(cudaMalloc(&ctx->stage_all, sizeof(double) * total));
+    ctx->stage_all_elems = total;
+  }
+  return XT_OK;
+}
+
+static int enqueue_pack(xt_ctx* ctx, int s, cudaStream_t stream) {
+  const int64_t n = ctx->seg_n[s];
+  const int L = ctx->seg_L[s], d = ctx->d;
+  const size_t elems = (size_t)n * L * d;
+  const int threads = 256;
+  const long long blocks = ((long long)elems + threads - 1) / threads;
+  k_pack<<<(unsigned)blocks, threads, 0, stream>>>(ctx->stage_all + ctx->seg_stage_off[s], ctx->d_soa, ctx->d_chunks,
+                                                   ctx->seg_chunk0[s], (int)ctx->upload_sig[2], (int)n, L, d);
+  XT_CUDA_OK(cudaGetLastError());
   return XT_OK;
 }
 
@@ -723,14 +764,22 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
   for (int s = 0; s < n_seg; ++s) order[s] = s;
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ctx->seg_L[x] > ctx->seg_L[y]; });
   if (xyz) {
+    rc = ensure_stage_all(ctx);
+    if (rc) return rc;
     XT_CUDA_OK(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_fork, 0));
+    for (int i = 0; i < n_seg; ++i) {  // all copies first: the link stays busy while the host enqueues the kernels
+      const int s = order[i];
+      XT_CUDA_OK(cudaMemcpyAsync(ctx->stage_all + ctx->seg_stage_off[s], xyz[s],
+                                 sizeof(double) * (size_t)ctx->seg_n[s] * ctx->seg_L[s] * ctx->d, cudaMemcpyHostToDevice,
+                                 ctx->up_stream));
+      XT_CUDA_OK(cudaEventRecord(ctx->ev_seg[s], ctx->up_stream));
+    }
     for (int i = 0; i < n_seg; ++i) {
       const int s = order[i];
-      rc = enqueue_segment(ctx, s, xyz[s], i, ctx->up_stream);
-      if (rc) return rc;
-      XT_CUDA_OK(cudaEventRecord(ctx->ev_seg[s], ctx->up_stream));
       cudaStream_t st = ctx->cs[i % xt_ctx::NCS];
       XT_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_seg[s], 0));
+      rc = enqueue_pack(ctx, s, st);
+      if (rc) return rc;
       const int c0 = ctx->seg_pos0[s], c1 = ctx->seg_pos1[s];
       rc = enqueue_k1(ctx, p, bits, c0, c1 - c0, st, true);
       if (rc) return rc;
@@ -761,10 +810,6 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
   for (int i = 0; i < xt_ctx::NCS; ++i) {
     XT_CUDA_OK(cudaEventRecord(ctx->ev_join[i], ctx->cs[i]));
     XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
-  }
-  if (xyz) {
-    XT_CUDA_OK(cudaEventRecord(ctx->ev_seg[order[n_seg - 1]], ctx->up_stream));
-    XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_seg[order[n_seg - 1]], 0));
   }
   XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
   k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, ctx->n_workf[fl.tpt - 1], d_out ? d_out : ctx->d_out);
@@ -974,6 +1019,7 @@ extern "C" int xt_get_stats(xt_ctx* ctx, xt_stats* out) {
     cudaEventElapsedTime(&ctx->stats.ms_plan, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->stats.ms_replay, ctx->ev[1], ctx->ev[2]);
   }
+  ctx->stats.ms_predict = ctx->ms_predict;
   *out = ctx->stats;
   return XT_OK;
 }

@@ -67,9 +67,11 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       a.Lsum[s] = std::log(acc) + mx;
     }
     cudaError_t e = cudaSuccess;
+    cudaEventRecord(ctx->ev_k3[0], ctx->stream);
 #define CALL_K3(D_, KS_) e = launch_k3<D_, KS_>(ctx, a, *p, grid)
     XT_DISPATCH(p->d, p->n_loc, CALL_K3);
 #undef CALL_K3
+    cudaEventRecord(ctx->ev_k3[1], ctx->stream);
     if (e != cudaSuccess || cudaMemcpyAsync(h_err.data(), d_err, sizeof(int32_t) * 2 * (size_t)n_work, cudaMemcpyDeviceToHost,
                                             ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -88,7 +90,10 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       result = XT_ERR_GROUPING;
       break;
     }
-    if (!need) break;
+    if (!need) {
+      cudaEventElapsedTime(&ctx->ms_predict, ctx->ev_k3[0], ctx->ev_k3[1]);
+      break;
+    }
     while (cap < need) cap *= 2;
   }
   if (result == XT_OK) {

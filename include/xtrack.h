@@ -76,7 +76,7 @@ typedef struct xt_stats {
   float ms_plan;         /* CUDA-event time of the plan kernel(s); pipelined evaluation: plan + replay */
   float ms_replay;       /* CUDA-event time of the replay kernel(s) incl. the reduction; pipelined: reduction */
   int32_t pipelined;     /* 1: plan and replay were launched per group of chunks on several streams */
-  int32_t pad_;
+  float ms_predict;      /* CUDA-event time of the last xt_predict kernel launch (all tracks) */
 } xt_stats;
 
 /* Lifetime.  `device` is the CUDA ordinal this context drives. */
