@@ -16,6 +16,9 @@ XT_MAX_HEADS = 128
 XT_MAX_STATES = 8
 XT_MAX_DIMS = 3
 XT_FLAG_INT8_WRAP = 1
+XT_FLAG_VAR_LOC = 2
+XT_FLAG_VAR_DT = 4
+XT_FLAG_LOC_AFFINE = 8
 
 XT_ERR_CUDA, XT_ERR_ARG, XT_ERR_GROUPING, XT_ERR_CAPACITY, XT_ERR_STATE = -1, -2, -3, -4, -5
 
@@ -40,6 +43,9 @@ class XtParams(C.Structure):
         ("LF", C.c_double * XT_MAX_HEADS),
         ("Lp_stay", C.c_double * XT_MAX_HEADS),
         ("L_leave", C.c_double * XT_MAX_HEADS),
+        ("twoD", C.c_double * XT_MAX_STATES),
+        ("loc_slope", C.c_double),
+        ("loc_offset", C.c_double),
     ]
 
 
@@ -66,6 +72,8 @@ EXPORTS = (
     "xt_destroy",
     "xt_last_error",
     "xt_upload",
+    "xt_upload_aux",
+    "xt_set_stay_tables",
     "xt_sum_logp",
     "xt_sum_logp_host",
     "xt_sum_logp_async",
@@ -101,6 +109,8 @@ def load_library() -> C.CDLL:
     lib.xt_last_error.argtypes = [vp]
     lib.xt_last_error.restype = C.c_char_p
     lib.xt_upload.argtypes = [vp, i32, P(i32), P(i64), P(i32), P(vp), i32, i32]
+    lib.xt_upload_aux.argtypes = [vp, i32, P(vp), P(vp)]
+    lib.xt_set_stay_tables.argtypes = [vp, i32, i32, i32, P(dbl), P(dbl)]
     lib.xt_sum_logp.argtypes = [vp, P(XtParams), P(dbl)]
     lib.xt_sum_logp_host.argtypes = [vp, i32, P(i32), P(i64), P(i32), P(vp), i32, i32, P(XtParams), P(dbl)]
     lib.xt_sum_logp_async.argtypes = [vp, P(XtParams), vp, vp]
@@ -182,6 +192,47 @@ class Engine:
         self.segments = [(s.shape[1], s.shape[0]) for s in segs]
         self.chunk_size = int(chunk_size)
         self.d = d
+
+    def upload_aux(self, sigma: Optional[Sequence[np.ndarray]] = None, dt: Optional[Sequence[np.ndarray]] = None):
+        """Per-localisation inputs of the uploaded segments: ``sigma[s]`` float64 [n, L, k] peak-wise
+        localisation errors (k = 1 or d), ``dt[s]`` float64 [n, L] time steps."""
+        n = len(self.segments)
+        k = 0
+        sp = dp = None
+        keep = []
+        if sigma is not None:
+            sg = [np.ascontiguousarray(a, dtype=np.float64) for a in sigma]
+            k = sg[0].shape[2] if sg[0].ndim == 3 else -1
+            for a, (L, cnt) in zip(sg, self.segments):
+                if a.ndim != 3 or a.shape != (cnt, L, k):
+                    raise ValueError("Localization error is not specified correctly: input_LocErr arrays must have shape "
+                                     "[n, L, 1] or [n, L, d] matching all_tracks")
+            if len(sg) != n:
+                raise ValueError("input_LocErr must hold one array per track-length bucket")
+            sp = (C.c_void_p * n)(*[a.ctypes.data for a in sg])
+            keep.append(sg)
+        if dt is not None:
+            ds_ = [np.ascontiguousarray(a, dtype=np.float64) for a in dt]
+            if len(ds_) != n:
+                raise ValueError("dt must hold one array per track-length bucket")
+            for a, (L, cnt) in zip(ds_, self.segments):
+                if a.shape != (cnt, L):
+                    raise ValueError("dt is not informed properly. It must either be a float number or a dictionary of same "
+                                     "structure than `all_tracks` with each element being an array of dims (nb_tracks, track_len)")
+            dp = (C.c_void_p * n)(*[a.ctypes.data for a in ds_])
+            keep.append(ds_)
+        self._check(self._lib.xt_upload_aux(self._h, int(k), sp, dp))
+
+    def set_stay_tables(self, per_track: bool, Lp_stay: Optional[np.ndarray], L_leave: Optional[np.ndarray]):
+        """Per-chunk (objective) or per-track (predict) field-of-view tables, float64 [rows, K] / [rows, H]."""
+        if Lp_stay is None:
+            self._check(self._lib.xt_set_stay_tables(self._h, int(per_track), 0, 0, None, None))
+            return
+        a = np.ascontiguousarray(Lp_stay, dtype=np.float64)
+        b = np.ascontiguousarray(L_leave, dtype=np.float64)
+        pd = C.POINTER(C.c_double)
+        self._check(self._lib.xt_set_stay_tables(self._h, int(per_track), a.shape[1], b.shape[1], a.ctypes.data_as(pd),
+                                                 b.ctypes.data_as(pd)))
 
     # -- evaluation ----------------------------------------------------------------------
     def sum_logp_host(self, segments: Sequence[np.ndarray], isBL: Sequence[int], chunk_size: int, p: XtParams) -> float:

@@ -80,6 +80,49 @@ struct XtPlanPtrs {
   int32_t cap;
 };
 
+// Optional per-localisation inputs (xt_upload_aux) and field-of-view tables (xt_set_stay_tables)
+// of evaluations with XT_FLAG_VAR_LOC / XT_FLAG_VAR_DT.  Per chunk the block [L][R][nTpad] sits at
+// (xyz_off / d) * R: rows 0..ka-1 = sigma components, row ka = dt stored time-reversed, so that
+// the row of localisation j holds what the reference reads while it consumes C[j]
+// (tracking.py:495,:526,:549,:563,:634).
+struct XtAux {
+  const double* aux;
+  const double* stay;    // [n_chunks | n_tracks][K] Lp_stay, nullptr: xt_params::Lp_stay
+  const double* leave;   // [n_chunks | n_tracks][H] L_leave (plan / predict) or [..][nS] exp-sums (replay)
+  int32_t R, ka, d;
+};
+
+// sigma -> LocErr^2 exactly as the host does (extract_params :926-930, LocErr**2 :457)
+__device__ __forceinline__ double xt_sigma2f(uint32_t flags, double slope, double offset, double sg) {
+  if (flags & XT_FLAG_LOC_AFFINE) {
+    sg = __dadd_rn(__dmul_rn(sg, slope), offset);
+    if (sg < 0.000001) sg = 0.000001;  // np.clip(.., 0.000001, inf); NaN stays NaN
+  }
+  return __dmul_rn(sg, sg);
+}
+__device__ __forceinline__ double xt_sigma2(const xt_params& P, double sg) {
+  return xt_sigma2f(P.flags, P.loc_slope, P.loc_offset, sg);
+}
+
+// mean mid-sub-step displacement variance of `head` for the time step dtv, in numpy's operation
+// order: ds = sqrt(2 D dt) (:979-982), ds**2, (d2[k+1] + d2[k]) / 2, mean over the sub-steps (:549-553)
+__device__ __forceinline__ double xt_dd_exact(const xt_params& P, int head, double dtv) {
+  const int nS = P.nS, nsub = P.nsub;
+  int x = head;
+  double r0 = __dsqrt_rn(__dmul_rn(P.twoD[x % nS], dtv));
+  double prev = __dmul_rn(r0, r0), sum = 0.0;
+  x /= nS;
+  for (int k = 0; k < nsub; ++k) {
+    const double r1 = __dsqrt_rn(__dmul_rn(P.twoD[x % nS], dtv));
+    const double cur = __dmul_rn(r1, r1);
+    x /= nS;
+    const double pair = __dmul_rn(__dadd_rn(cur, prev), 0.5);
+    sum = (k == 0) ? pair : __dadd_rn(sum, pair);
+    prev = cur;
+  }
+  return nsub == 1 ? sum : __ddiv_rn(sum, (double)nsub);
+}
+
 struct XtWork {  // one replay CTA: 32 tracks of a chunk
   int32_t chunk;
   int32_t t0;

@@ -85,6 +85,13 @@ struct xt_ctx {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_k3[2] = {nullptr, nullptr};
   float ms_predict = 0.f;
+  // optional per-localisation inputs (xt_upload_aux) and field-of-view tables (xt_set_stay_tables)
+  double* d_aux = nullptr;
+  int aux_R = 0, aux_ka = 0, aux_has_dt = 0;
+  int64_t soa_elems = 0;
+  double* d_stay[2] = {nullptr, nullptr};   // [0] per chunk, [1] per track: Lp_stay [rows][K]
+  double* d_leave[2] = {nullptr, nullptr};  // [0] per chunk: linear sums [rows][nS]; [1] per track: log-sums [rows][nS]
+  int stay_K[2] = {0, 0}, stay_H[2] = {0, 0};
 };
 
 static std::string g_create_error;
@@ -108,6 +115,22 @@ __global__ void k_pack(const double* __restrict__ src, double* __restrict__ soa,
   soa[ck.xyz_off + (size_t)row * ck.nTpad + t] = src[(size_t)i * rows + row];
 }
 
+// aux repack: src [n][L][kin] -> rows row0..row0+kin-1 of the per-chunk blocks [L][R][nTpad] at
+// (xyz_off / d) * R; `reverse` stores localisation j at row block L-1-j (dt, see XtAux)
+__global__ void k_pack_aux(const double* __restrict__ src, double* __restrict__ aux, const XtChunk* __restrict__ chunks,
+                           int chunk0, int chunk_size, int n, int L, int kin, int R, int row0, int d, int reverse) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = L * kin;
+  if (idx >= (long long)n * rows) return;
+  const int i = (int)(idx % n);
+  const int row = (int)(idx / n);
+  const int j = row / kin, k = row - j * kin;
+  const int c = i / chunk_size, t = i - c * chunk_size;
+  const XtChunk ck = chunks[chunk0 + c];
+  const int jo = reverse ? (L - 1 - j) : j;
+  aux[(size_t)(ck.xyz_off / d) * R + ((size_t)jo * R + row0 + k) * ck.nTpad + t] = src[(size_t)i * rows + row];
+}
+
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
   double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
@@ -129,6 +152,14 @@ static void free_plan(xt_ctx* ctx) {
 }
 
 static void free_data(xt_ctx* ctx) {
+  cudaFree(ctx->d_aux);
+  ctx->d_aux = nullptr;
+  ctx->aux_R = ctx->aux_ka = ctx->aux_has_dt = 0;
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ctx->d_stay[i]); cudaFree(ctx->d_leave[i]);
+    ctx->d_stay[i] = ctx->d_leave[i] = nullptr;
+    ctx->stay_K[i] = ctx->stay_H[i] = 0;
+  }
   cudaFree(ctx->d_soa); cudaFree(ctx->d_chunks); cudaFree(ctx->d_work); cudaFree(ctx->d_logp);
   cudaFree(ctx->d_partial); cudaFree(ctx->d_summ); cudaFree(ctx->d_gstate);
   cudaFree(ctx->d_workf[0]); cudaFree(ctx->d_workf[1]); cudaFree(ctx->d_corder);
@@ -278,6 +309,7 @@ static int setup_layout(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int6
       }
     }
     ctx->seg_chunk0[n_seg] = (int)ctx->chunks.size();
+    ctx->soa_elems = soa_elems;
     ctx->nrec_total = rec;
     ctx->seg_n.assign(n, n + n_seg);
     ctx->seg_L.assign(L, L + n_seg);
@@ -411,10 +443,126 @@ extern "C" int xt_upload(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int
   return XT_OK;
 }
 
+extern "C" int xt_upload_aux(xt_ctx* ctx, int32_t k_sigma, const double* const* sigma, const double* const* dt) {
+  if (!ctx) return XT_ERR_ARG;
+  if (ctx->chunks.empty()) {
+    set_error(ctx, "xt_upload_aux: upload the tracks first");
+    return XT_ERR_STATE;
+  }
+  if (k_sigma < 0 || (k_sigma != 0 && k_sigma != 1 && k_sigma != ctx->d) || (k_sigma > 0 && !sigma) ||
+      (k_sigma == 0 && !dt)) {
+    set_error(ctx, "Localization error is not specified correctly: peak-wise errors must have 1 or d components per localisation");
+    return XT_ERR_ARG;
+  }
+  XT_CUDA_OK(cudaSetDevice(ctx->device));
+  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  const int R = k_sigma + (dt ? 1 : 0);
+  cudaFree(ctx->d_aux);
+  ctx->d_aux = nullptr;
+  const size_t elems = (size_t)(ctx->soa_elems / ctx->d) * R;
+  XT_CUDA_OK(cudaMalloc(&ctx->d_aux, sizeof(double) * elems));
+  XT_CUDA_OK(cudaMemsetAsync(ctx->d_aux, 0, sizeof(double) * elems, ctx->stream));
+  ctx->aux_R = R;
+  ctx->aux_ka = k_sigma;
+  ctx->aux_has_dt = dt ? 1 : 0;
+  ctx->have_eval = false;
+  const int chunk_size = (int)ctx->upload_sig[2];
+  int slot = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const double* const* src = pass == 0 ? sigma : dt;
+    const int kin = pass == 0 ? k_sigma : 1;
+    if (!src || kin == 0) continue;
+    for (int s = 0; s < (int)ctx->seg_L.size(); ++s, ++slot) {
+      const int b = slot & 1;
+      const int64_t n = ctx->seg_n[s];
+      const int L = ctx->seg_L[s];
+      const size_t cnt = (size_t)n * L * kin;
+      XT_CUDA_OK(cudaEventSynchronize(ctx->stage_done[b]));
+      XT_CUDA_OK(cudaMemcpyAsync(ctx->stage[b], src[s], sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+      const long long blocks = ((long long)cnt + 255) / 256;
+      k_pack_aux<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ctx->stage[b], ctx->d_aux, ctx->d_chunks, ctx->seg_chunk0[s],
+                                                             chunk_size, (int)n, L, kin, R, pass == 0 ? 0 : k_sigma, ctx->d,
+                                                             pass == 1);
+      XT_CUDA_OK(cudaEventRecord(ctx->stage_done[b], ctx->stream));
+    }
+  }
+  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  XT_CUDA_OK(cudaGetLastError());
+  return XT_OK;
+}
+
+extern "C" int xt_set_stay_tables(xt_ctx* ctx, int32_t per_track, int32_t K, int32_t H, const double* Lp_stay,
+                                  const double* L_leave) {
+  if (!ctx) return XT_ERR_ARG;
+  const int i = per_track ? 1 : 0;
+  XT_CUDA_OK(cudaSetDevice(ctx->device));
+  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->d_stay[i]); cudaFree(ctx->d_leave[i]);
+  ctx->d_stay[i] = ctx->d_leave[i] = nullptr;
+  ctx->stay_K[i] = ctx->stay_H[i] = 0;
+  ctx->have_eval = false;
+  if (!Lp_stay || !L_leave) return XT_OK;
+  if (ctx->chunks.empty() || K < 1 || H < K || H % K != 0) {
+    set_error(ctx, "xt_set_stay_tables: upload the tracks first; need K >= 1 and H a multiple of K");
+    return XT_ERR_ARG;
+  }
+  const size_t rows = per_track ? (size_t)ctx->n_tracks : ctx->chunks.size();
+  const int nS = H / K;
+  std::vector<double> lv(rows * nS);
+  for (size_t r = 0; r < rows; ++r)
+    for (int s = 0; s < nS; ++s) {  // end-of-track expansion folded: sum over r of exp(L_leave[r + K*s])
+      const double* v = L_leave + r * H + (size_t)K * s;
+      double mx = -INFINITY;
+      for (int q = 0; q < K; ++q) mx = std::max(mx, v[q]);
+      double acc = 0;
+      for (int q = 0; q < K; ++q) acc += std::exp(v[q] - mx);
+      lv[r * nS + s] = per_track ? std::log(acc) + mx : std::exp(std::log(acc) + mx);
+    }
+  XT_CUDA_OK(cudaMalloc(&ctx->d_stay[i], sizeof(double) * rows * K));
+  XT_CUDA_OK(cudaMalloc(&ctx->d_leave[i], sizeof(double) * rows * nS));
+  XT_CUDA_OK(cudaMemcpy(ctx->d_stay[i], Lp_stay, sizeof(double) * rows * K, cudaMemcpyHostToDevice));
+  XT_CUDA_OK(cudaMemcpy(ctx->d_leave[i], lv.data(), sizeof(double) * rows * nS, cudaMemcpyHostToDevice));
+  ctx->stay_K[i] = K;
+  ctx->stay_H[i] = H;
+  return XT_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // evaluation
 // ------------------------------------------------------------------------------------------
 static int ipow(int b, int e) { int r = 1; for (int i = 0; i < e; ++i) r *= b; return r; }
+
+static bool is_var(const xt_params* p) { return (p->flags & (XT_FLAG_VAR_LOC | XT_FLAG_VAR_DT)) != 0; }
+
+static XtAux make_aux(xt_ctx* ctx, const xt_params* p, int per_track) {
+  XtAux ax{};
+  ax.aux = ctx->d_aux;
+  ax.R = ctx->aux_R;
+  ax.ka = ctx->aux_ka;
+  ax.d = ctx->d;
+  if ((p->flags & XT_FLAG_VAR_DT) && ctx->d_stay[per_track]) {
+    ax.stay = ctx->d_stay[per_track];
+    ax.leave = ctx->d_leave[per_track];
+  }
+  return ax;
+}
+
+// dd per unit time of every head (replay kernels: dd = ddu * dt[track, loc] up to rounding)
+static void dd_unit(const xt_params* p, double* ddu) {
+  const int nS = p->nS, nsub = p->nsub, H = ipow(nS, nsub + 1);
+  for (int h = 0; h < H; ++h) {
+    int x = h;
+    double prev = p->twoD[x % nS], sum = 0;
+    x /= nS;
+    for (int k = 0; k < nsub; ++k) {
+      const double cur = p->twoD[x % nS];
+      x /= nS;
+      sum += (cur + prev) * 0.5;
+      prev = cur;
+    }
+    ddu[h] = sum / nsub;
+  }
+}
 
 static int check_params(xt_ctx* ctx, const xt_params* p, int* bits_out) {
   if (!p || p->nS < 1 || p->nS > XT_MAX_STATES || p->nsub < 1 || p->d != ctx->d ||
@@ -432,6 +580,18 @@ static int check_params(xt_ctx* ctx, const xt_params* p, int* bits_out) {
   if ((long long)bits * std::max(p->frame_len, p->nsub + 1) > 64) {
     set_error(ctx, "xt_params: frame_len too large for the window code (bits*frame_len must be <= 64)");
     return XT_ERR_ARG;
+  }
+  if (is_var(p)) {
+    if (!ctx->d_aux || ((p->flags & XT_FLAG_VAR_LOC) && ctx->aux_ka != p->n_loc) ||
+        ((p->flags & XT_FLAG_VAR_DT) && !ctx->aux_has_dt)) {
+      set_error(ctx, "xt_params: XT_FLAG_VAR_LOC / XT_FLAG_VAR_DT need matching xt_upload_aux data (n_loc = k_sigma)");
+      return XT_ERR_STATE;
+    }
+    if ((p->flags & XT_FLAG_VAR_DT) && ctx->d_stay[0] &&
+        (ctx->stay_K[0] != ipow(p->nS, p->nsub) || ctx->stay_H[0] != ipow(p->nS, p->nsub + 1))) {
+      set_error(ctx, "xt_set_stay_tables: K / H do not match the model");
+      return XT_ERR_ARG;
+    }
   }
   *bits_out = bits;
   return XT_OK;
@@ -462,9 +622,9 @@ static int ensure_plan(xt_ctx* ctx, const xt_params* p, int cap) {
   return XT_OK;
 }
 
-template <int D, int KS>
+template <int D, int KS, bool VAR>
 static cudaError_t launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream) {
-  auto kern = k1_plan<D, KS>;
+  auto kern = k1_plan<D, KS, VAR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)n_chunks, XT_K1_THREADS, smem, stream>>>(a, p);
@@ -490,7 +650,15 @@ static cudaError_t launch_k2_fused_w(const K2FArgs& a, const K2Tab& tab, size_t 
 }
 
 template <int D, int KS>
-static cudaError_t launch_k2_fused(const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt, cudaStream_t stream) {
+static cudaError_t launch_k2_fused(const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt, cudaStream_t stream,
+                                   bool var) {
+  if (var) {  // peak-wise LocErr / per-track dt: one configuration (4 warps per tile, one track per thread)
+    auto kern = k2_replay_fused<D, KS, 4, 1, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<a.n_work, 128, smem, stream>>>(a, tab);
+    return cudaGetLastError();
+  }
   if (tpt == 2) {
     if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 2>(a, tab, smem, stream);
     if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 2>(a, tab, smem, stream);
@@ -504,6 +672,10 @@ static cudaError_t launch_k2_fused(const K2FArgs& a, const K2Tab& tab, size_t sm
 template <int D, int KS>
 static cudaError_t launch_k2(xt_ctx* ctx, const K2Args& a, const xt_params& p, const K2Lin& lin, size_t smem,
                              bool use_smem, int grid, int wpc) {
+  if (is_var(&p)) {  // log-domain kernel, state in global memory
+    k2_replay<D, KS, false, true><<<grid, 32, 0, ctx->stream>>>(a, p);
+    return cudaGetLastError();
+  }
   if (use_smem) {
     if (wpc == 8) return launch_k2_lin<D, KS, 8>(ctx, a, p, lin, smem, grid);
     if (wpc == 2) return launch_k2_lin<D, KS, 2>(ctx, a, p, lin, smem, grid);
@@ -553,7 +725,8 @@ static void k1_scratch_caps(xt_ctx* ctx, const xt_params* p, bool use_smem, int*
   *scapP = *scapC = 0;
   if (!use_smem || !ctx->k1_smem_scratch || ctx->spec_maxC <= 0) return;
   const int CO1 = p->d + 2 * p->n_loc + 1;
-  const size_t b = xt_k1_smem(ctx->cap, CO1, ctx->RH, p->nS, ctx->spec_maxP, ctx->spec_maxC);
+  const size_t b = xt_k1_smem(ctx->cap, CO1, ctx->RH, p->nS, ctx->spec_maxP, ctx->spec_maxC,
+                              is_var(p) ? ipow(p->nS, p->nsub + 1) : 0);
   if (b + 1024 > (size_t)(228 * 1024) / XT_K1_MIN_CTAS || b > (size_t)ctx->smem_optin) return;
   *scapP = ctx->spec_maxP;
   *scapC = ctx->spec_maxC;
@@ -563,11 +736,20 @@ static int enqueue_k1(xt_ctx* ctx, const xt_params* p, int bits, int c0, int nc,
   K1Args a = make_k1_args(ctx, bits);
   a.chunk0 = c0;
   k1_scratch_caps(ctx, p, smem_scratch, &a.scapP, &a.scapC);
-  const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC);
+  const bool var = is_var(p);
+  const int varH = var ? ipow(p->nS, p->nsub + 1) : 0;
+  const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC, varH);
   cudaError_t e = cudaSuccess;
-#define CALL_K1(D_, KS_) e = launch_k1<D_, KS_>(a, *p, smem, nc, stream)
-  XT_DISPATCH(p->d, p->n_loc, CALL_K1);
+  if (var) {
+    a.ax = make_aux(ctx, p, 0);
+#define CALL_K1V(D_, KS_) e = launch_k1<D_, KS_, true>(a, *p, smem, nc, stream)
+    XT_DISPATCH(p->d, p->n_loc, CALL_K1V);
+#undef CALL_K1V
+  } else {
+#define CALL_K1(D_, KS_) e = launch_k1<D_, KS_, false>(a, *p, smem, nc, stream)
+    XT_DISPATCH(p->d, p->n_loc, CALL_K1);
 #undef CALL_K1
+  }
   XT_CUDA_OK(e);
   ctx->stats.k1_launches++;
   return XT_OK;
@@ -669,6 +851,7 @@ struct FusedLaunch {  // everything a fused replay launch needs besides its tile
   K2FArgs fa;
   size_t smem;
   int wpc, tpt;
+  bool var;
 };
 
 static void leave_sums(const xt_params* p, double* Lsum) {
@@ -687,10 +870,12 @@ static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch
   const int K = ipow(p->nS, p->nsub), KS = p->n_loc, H = K * p->nS;
   fl->wpc = ctx->k2_wpc;
   fl->tpt = ctx->k2_tpt;
+  fl->var = is_var(p);
+  if (fl->var) fl->tpt = 1;
   if (fl->tpt == 2 && xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, 2) > (size_t)ctx->smem_optin) fl->tpt = 1;
-  fl->smem = xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, fl->tpt);
+  fl->smem = xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, fl->tpt, fl->var);
   if (ctx->k2_variant != 0 || ctx->force_global || fl->smem > (size_t)ctx->smem_optin ||
-      xt_fused_blob16(Pmax, K) > 64 * fl->wpc)
+      xt_fused_blob16(Pmax, K) > 64 * fl->wpc || (fl->var && fl->wpc != 4))
     return false;
   double Lsum[XT_MAX_STATES];
   leave_sums(p, Lsum);
@@ -709,8 +894,13 @@ static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch
   tab.nsub = p->nsub;
   tab.K = K;
   tab.min_len = p->min_len;
+  tab.flags = p->flags;
+  tab.loc_slope = p->loc_slope;
+  tab.loc_offset = p->loc_offset;
+  if (p->flags & XT_FLAG_VAR_DT) dd_unit(p, tab.dd);
   K2FArgs& fa = fl->fa;
   fa = K2FArgs{};
+  if (fl->var) fa.ax = make_aux(ctx, p, 0);
   fa.chunks = ctx->d_chunks;
   fa.work = ctx->d_workf[fl->tpt - 1];
   fa.soa = ctx->d_soa;
@@ -731,7 +921,7 @@ static int enqueue_fused(xt_ctx* ctx, const xt_params* p, const FusedLaunch& fl,
   fa.n_work = w0[c1] - w0[c0];
   if (fa.n_work <= 0) return XT_OK;
   cudaError_t ef = cudaSuccess;
-#define CALL_K2F(D_, KS_) ef = launch_k2_fused<D_, KS_>(fa, fl.tab, fl.smem, fl.wpc, fl.tpt, stream)
+#define CALL_K2F(D_, KS_) ef = launch_k2_fused<D_, KS_>(fa, fl.tab, fl.smem, fl.wpc, fl.tpt, stream, fl.var)
   XT_DISPATCH(p->d, p->n_loc, CALL_K2F);
 #undef CALL_K2F
   XT_CUDA_OK(ef);
@@ -903,7 +1093,11 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
   const int wpc = ctx->k2_wpc;
   const size_t state_bytes = (size_t)2 * Pmax * CO * 32 * sizeof(double);
   const size_t smem = state_bytes + (size_t)2 * wpc * 32 * sizeof(double);
-  const bool use_smem = smem <= (size_t)ctx->smem_optin && !ctx->force_global;
+  const bool use_smem = smem <= (size_t)ctx->smem_optin && !ctx->force_global && !is_var(p);
+  if (is_var(p)) {
+    a.ax = make_aux(ctx, p, 0);
+    if (p->flags & XT_FLAG_VAR_DT) dd_unit(p, a.ddu);
+  }
   int grid = a.n_work;
   if (!use_smem) {
     grid = std::min(a.n_work, ctx->n_sm * 16);

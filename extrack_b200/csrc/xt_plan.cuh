@@ -40,13 +40,15 @@ struct K1Args {
   // A chunk that needs more parents / children than this reports err = 3 and the host retries with
   // the global-memory scratch.
   int32_t scapP, scapC;
+  XtAux ax;            // VAR instantiation only
 };
 
 // dynamic shared memory of k1_plan (bytes)
-__host__ __device__ inline size_t xt_k1_smem(int cap, int CO, int RH, int nS, int scapP, int scapC) {
+__host__ __device__ inline size_t xt_k1_smem(int cap, int CO, int RH, int nS, int scapP, int scapC, int varH = 0) {
   size_t b = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
   b = (b + 15) & ~(size_t)15;
   if (scapC > 0) b += (size_t)(scapP + scapC) * CO * 32 * 8 + (size_t)2 * scapP * RH * nS * 8;
+  b += (size_t)varH * 32 * 8;  // VAR: per-lane dd of every head
   return b;
 }
 
@@ -59,7 +61,7 @@ __device__ __forceinline__ int xt_label(int x, int nS, bool wrap) {
   return x % nS;
 }
 
-template <int D, int KS>
+template <int D, int KS, bool VAR>
 __global__ void __launch_bounds__(XT_K1_THREADS, XT_K1_MIN_CTAS)
 k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
@@ -150,13 +152,43 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 #pragma unroll
   for (int k = 0; k < KS; ++k) l2[k] = P.l2[k];
 
+  // VAR: peak-wise LocErr / per-localisation dt of the leader tracks.  Row j of the aux block
+  // belongs to localisation j; s_dd[head][lane] holds dd of the current step for every leader.
+  const bool var_loc = VAR && (P.flags & XT_FLAG_VAR_LOC), var_dt = VAR && (P.flags & XT_FLAG_VAR_DT);
+  const double* Ap = VAR ? a.ax.aux + (size_t)(ck.xyz_off / D) * a.ax.R + t : nullptr;
+  const double* Lps = (VAR && a.ax.stay) ? a.ax.stay + (size_t)cid * K : P.Lp_stay;
+  double* s_dd = nullptr;
+  if (VAR) {
+    size_t o = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
+    o = (o + 15) & ~(size_t)15;
+    if (scapC > 0) o += (size_t)(scapP + scapC) * CO * 32 * 8 + (size_t)2 * scapP * a.RH * nS * 8;
+    s_dd = (double*)(k1_smem + o);
+  }
+  auto var_step = [&](int j) {  // call by all threads, followed by a barrier before s_dd is read
+    if (var_loc) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) l2[k] = xt_sigma2(P, Ap[(size_t)(j * a.ax.R + k) * npad]);
+    }
+    for (int idx = tid; idx < nP0 * 32; idx += XT_K1_THREADS) {
+      const int h = idx >> 5, ln = idx & 31;
+      double v = P.dd[h];
+      if (var_dt) v = xt_dd_exact(P, h, Ap[(size_t)(j * a.ax.R + a.ax.ka) * npad - t + (ln < Kt ? ln : 0)]);
+      s_dd[idx] = v;
+    }
+  };
+#define DDH(head) (VAR ? s_dd[(head) * 32 + lane] : P.dd[head])
+  if (VAR) {
+    var_step(0);
+    __syncthreads();
+  }
+
   // ---- first localisation (tracking.py:478-529) ----
   int nP = nP0;
   for (int c = warp; c < nP; c += W) {
 #pragma unroll
     for (int dim = 0; dim < D; ++dim) ST(bufP, c, dim) = Cp[(size_t)(0 * D + dim) * npad];
 #pragma unroll
-    for (int k = 0; k < KS; ++k) ST(bufP, c, D + k) = __dadd_rn(l2[k], P.dd[c]);
+    for (int k = 0; k < KS; ++k) ST(bufP, c, D + k) = __dadd_rn(l2[k], DDH(c));
     ST(bufP, c, D + 2 * KS) = __dadd_rn(P.LT[c], P.LF[c]);
   }
   int LhP = nsub + 1;
@@ -212,6 +244,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 #pragma unroll
     for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((step - 1) * D + dim) * npad];
     const bool stay = step >= P.min_len;
+    if (VAR) {  // (the previous step ended with a barrier: nobody still reads s_dd)
+      var_step(step - 1);
+      __syncthreads();
+    }
     for (int p = warp; p < nP; p += W) {
       const double LPp = ST(bufP, p, D + 2 * KS);
       double mm[D], s2[KS], q[KS], nm[D];
@@ -244,7 +280,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       const int hbase = K * (int)curP[p];
       for (int r = 0; r < K; ++r) {
         const int c = p * K + r, head = r + hbase;
-        const double dd = P.dd[head];
+        const double dd = DDH(head);
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) ST(bufC, c, dim) = nm[dim];
 #pragma unroll
@@ -255,7 +291,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
           ST(bufC, c, D + KS + k) = __dsqrt_rn(ns2);
         }
         double add = __dadd_rn(P.LT[head], LC);
-        if (stay) add = __dadd_rn(add, P.Lp_stay[r]);
+        if (stay) add = __dadd_rn(add, Lps[r]);
         ST(bufC, c, D + 2 * KS) = __dadd_rn(LPp, add);
       }
     }
@@ -749,4 +785,5 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     sm->max_nC = max_nC;
   }
 #undef ST
+#undef DDH
 }

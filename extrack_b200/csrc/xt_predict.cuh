@@ -33,6 +33,7 @@ struct K3Args {
   int32_t bits;
   double Lsum[XT_MAX_STATES];
   size_t warp_scratch; // 8-byte units per warp (k3_layout(...).total)
+  XtAux ax;            // VAR instantiation only; stay = [n_tracks][K] Lp_stay, leave = [n_tracks][nS] log-sums
 };
 
 // per-warp scratch layout, in 8-byte units
@@ -61,7 +62,7 @@ __host__ __device__ inline K3Layout k3_layout(int cap, int CO, int fl, int nS, i
   return l;
 }
 
-template <int D, int KS>
+template <int D, int KS, bool VAR = false>
 __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, const __grid_constant__ xt_params P) {
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
   double l2[KS];
 #pragma unroll
   for (int k = 0; k < KS; ++k) l2[k] = P.l2[k];
+  const bool var_loc = VAR && (P.flags & XT_FLAG_VAR_LOC), var_dt = VAR && (P.flags & XT_FLAG_VAR_DT);
 
   for (int wi = blockIdx.x; wi < a.n_work; wi += gridDim.x) {
     const XtWork wk = a.work[wi];
@@ -106,6 +108,20 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
       const size_t npad = (size_t)ck.nTpad;
       double* out = a.pred + ((size_t)ck.loc_off + (size_t)t * L) * nS;
       int errc = 0;
+      // VAR: row j of the aux block = (sigma components, time-reversed dt) of localisation j
+      const double* Ap = VAR ? a.ax.aux + (size_t)(ck.xyz_off / D) * a.ax.R + t : nullptr;
+      const double* Lps = (VAR && a.ax.stay) ? a.ax.stay + (size_t)(ck.trk_off + t) * K : P.Lp_stay;
+      const double* Lsm = (VAR && a.ax.leave) ? a.ax.leave + (size_t)(ck.trk_off + t) * nS : a.Lsum;
+      double dtv = 0.0;
+      auto var_row = [&](int j) {
+        if (var_loc) {
+#pragma unroll
+          for (int k = 0; k < KS; ++k) l2[k] = xt_sigma2(P, Ap[(size_t)(j * a.ax.R + k) * npad]);
+        }
+        if (var_dt) dtv = Ap[(size_t)(j * a.ax.R + a.ax.ka) * npad];
+      };
+#define DDX(head) ((VAR && var_dt) ? xt_dd_exact(P, head, dtv) : P.dd[head])
+      if (VAR) var_row(0);
 
       // ---- first localisation (tracking.py:478-529) ----
       int nP = nS * nS;
@@ -113,7 +129,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) BP(c, dim) = Cp[(size_t)dim * npad];
 #pragma unroll
-        for (int k = 0; k < KS; ++k) BP(c, D + k) = __dadd_rn(l2[k], P.dd[c]);
+        for (int k = 0; k < KS; ++k) BP(c, D + k) = __dadd_rn(l2[k], DDX(c));
         BP(c, D + 2 * KS) = __dadd_rn(P.LT[c], P.LF[c]);
         curP[c] = c % nS;
         const int d0 = c % nS, d1 = c / nS;
@@ -142,11 +158,12 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((step - 1) * D + dim) * npad];
         const bool stay = step >= P.min_len;
+        if (VAR) var_row(step - 1);
         // ---- expansion + Gaussian update (tracking.py:540-570, :87-98), lane = child ----
         for (int c = lane; c < nC; c += 32) {
           const int p = c / K, r = c - p * K;
           const int head = r + K * curP[p];
-          const double dd = P.dd[head];
+          const double dd = DDX(head);
           double s2[KS], q[KS];
 #pragma unroll
           for (int k = 0; k < KS; ++k) {
@@ -180,7 +197,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
             BC(c, D + KS + k) = __dsqrt_rn(ns2);
           }
           double add = __dadd_rn(P.LT[head], __dsub_rn(logs, quad));
-          if (stay) add = __dadd_rn(add, P.Lp_stay[r]);
+          if (stay) add = __dadd_rn(add, Lps[r]);
           BC(c, D + 2 * KS) = __dadd_rn(BP(p, D + 2 * KS), add);
           codeC[c] = ((codeP[p] << bits) | (unsigned long long)xt_label(c, nS, wrap)) & cmask;
           gid[c] = -1;
@@ -350,6 +367,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
       double clast[D];
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) clast[dim] = Cp[(size_t)((L - 1) * D + dim) * npad];
+      if (VAR) var_row(L - 1);
       double vmax = -INFINITY;
       for (int c = lane; c < nP; c += 32) {
         double term = 0.0;
@@ -362,7 +380,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
           term = (dim == 0) ? tt : __dadd_rn(term, tt);
         }
         double v = FB[(size_t)(D + 2 * KS) * cap + c] + term;
-        if (ck.isBL) v += a.Lsum[c % nS];
+        if (ck.isBL) v += Lsm[c % nS];
         aC[c] = v;
         vmax = fmax(vmax, v);
       }
@@ -424,4 +442,5 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
   }
 #undef BP
 #undef BC
+#undef DDX
 }

@@ -1,7 +1,10 @@
 // Host driver of the state-annotation kernel (included by xt_engine.cu).
 template <int D, int KS>
 static cudaError_t launch_k3(xt_ctx* ctx, const K3Args& a, const xt_params& p, int grid) {
-  k3_predict<D, KS><<<grid, 32 * XT_K3_WARPS, 0, ctx->stream>>>(a, p);
+  if (is_var(&p))
+    k3_predict<D, KS, true><<<grid, 32 * XT_K3_WARPS, 0, ctx->stream>>>(a, p);
+  else
+    k3_predict<D, KS, false><<<grid, 32 * XT_K3_WARPS, 0, ctx->stream>>>(a, p);
   return cudaGetLastError();
 }
 
@@ -59,6 +62,7 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
     a.maxL = ctx->maxL + 1;
     a.bits = bits;
     a.warp_scratch = lay.total;
+    if (is_var(p)) a.ax = make_aux(ctx, p, 1);
     for (int s = 0; s < nS; ++s) {  // nsub == 1: K = nS
       double mx = -INFINITY;
       for (int r = 0; r < nS; ++r) mx = std::max(mx, p->L_leave[r + nS * s]);

@@ -23,9 +23,11 @@ struct K2Args {
   int32_t Pcap;        // parent slots per ping-pong buffer (max over chunks of max_nP)
   int32_t n_work;
   double Lsum[XT_MAX_STATES];  // log sum_r exp(L_leave[r + K*state]) (end-of-track expansion folded)
+  double ddu[XT_MAX_HEADS];    // VAR_DT: dd per unit time (from 2 D)
+  XtAux ax;                    // VAR instantiation only; ax.leave = per-chunk exp-sums [nS] (linear)
 };
 
-template <int D, int KS, bool SMEM>
+template <int D, int KS, bool SMEM, bool VAR = false>
 __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_constant__ xt_params P) {
   constexpr int CO = D + KS + 1;  // m[D], s2|u[KS], LP|base
   const int lane = threadIdx.x;
@@ -52,6 +54,23 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
   double l2[KS];
 #pragma unroll
   for (int k = 0; k < KS; ++k) l2[k] = P.l2[k];
+  // VAR: row j of the aux block = (sigma components, time-reversed dt) of localisation j
+  const bool var_loc = VAR && (P.flags & XT_FLAG_VAR_LOC), var_dt = VAR && (P.flags & XT_FLAG_VAR_DT);
+  const double* Ap = VAR ? a.ax.aux + (size_t)(ck.xyz_off / D) * a.ax.R + tt : nullptr;
+  const double* Lps = (VAR && a.ax.stay) ? a.ax.stay + (size_t)wk.chunk * K : P.Lp_stay;
+  double dtv = 1.0;  // dt of the localisation whose expansion is being consumed
+  auto var_row = [&](int j) {
+    if (var_loc) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) l2[k] = xt_sigma2(P, Ap[(size_t)(j * a.ax.R + k) * npad]);
+    }
+  };
+  auto var_dtrow = [&](int j) { return var_dt ? Ap[(size_t)(j * a.ax.R + a.ax.ka) * npad] : 1.0; };
+#define DDV(head) (VAR ? (var_dt ? a.ddu[head] * dtv : P.dd[head]) : P.dd[head])
+  if (VAR) {
+    var_row(0);
+    dtv = var_dtrow(0);
+  }
 
   // ---- first localisation ----
   int nP = K * nS;
@@ -64,7 +83,7 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) SA(cur, c, dim) = c0[dim];
 #pragma unroll
-      for (int k = 0; k < KS; ++k) SA(cur, c, D + k) = l2[k] + P.dd[c];
+      for (int k = 0; k < KS; ++k) SA(cur, c, D + k) = l2[k] + DDV(c);
       SA(cur, c, D + KS) = P.LT[c] + P.LF[c];
     }
   }
@@ -75,6 +94,10 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
     double cl[D];
 #pragma unroll
     for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((step - 1) * D + dim) * npad];
+    if (VAR) {
+      var_row(step - 1);
+      dtv = var_dtrow(step - 1);
+    }
     // phase A: per parent, the part of the update shared by all its children
     for (int p = 0; p < nP; ++p) {
       double quad = 0.0, logs = 0.0;
@@ -117,14 +140,14 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
 #pragma unroll
           for (int dim = 0; dim < D; ++dim) SA(nxt, g, dim) = SA(cur, p, dim);
 #pragma unroll
-          for (int k = 0; k < KS; ++k) SA(nxt, g, D + k) = SA(cur, p, D + k) + P.dd[head];
-          SA(nxt, g, D + KS) = SA(cur, p, D + KS) + (P.LT[head] + (stay ? P.Lp_stay[r] : 0.0));
+          for (int k = 0; k < KS; ++k) SA(nxt, g, D + k) = SA(cur, p, D + k) + DDV(head);
+          SA(nxt, g, D + KS) = SA(cur, p, D + KS) + (P.LT[head] + (stay ? Lps[r] : 0.0));
         } else {
           double mx = -INFINITY;
           for (int k = 0; k < n; ++k) {
             const uint32_t e = __ldg(&ent[o + k]);
             const int p = (int)(e & 0xFFFF), head = (int)((e >> 16) & 0xFF), r = (int)(e >> 24);
-            mx = fmax(mx, SA(cur, p, D + KS) + (P.LT[head] + (stay ? P.Lp_stay[r] : 0.0)));
+            mx = fmax(mx, SA(cur, p, D + KS) + (P.LT[head] + (stay ? Lps[r] : 0.0)));
           }
           double sw = 0.0, am[D], as[KS];
 #pragma unroll
@@ -134,13 +157,13 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
           for (int k = 0; k < n; ++k) {
             const uint32_t e = __ldg(&ent[o + k]);
             const int p = (int)(e & 0xFFFF), head = (int)((e >> 16) & 0xFF), r = (int)(e >> 24);
-            const double lp = SA(cur, p, D + KS) + (P.LT[head] + (stay ? P.Lp_stay[r] : 0.0));
+            const double lp = SA(cur, p, D + KS) + (P.LT[head] + (stay ? Lps[r] : 0.0));
             const double w = exp(lp - mx);
             sw += w;
 #pragma unroll
             for (int dim = 0; dim < D; ++dim) am[dim] += w * SA(cur, p, dim);
 #pragma unroll
-            for (int k2 = 0; k2 < KS; ++k2) as[k2] += w * (SA(cur, p, D + k2) + P.dd[head]);
+            for (int k2 = 0; k2 < KS; ++k2) as[k2] += w * (SA(cur, p, D + k2) + DDV(head));
           }
           const double rs = 1.0 / sw;
 #pragma unroll
@@ -164,6 +187,7 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
   double cl[D];
 #pragma unroll
   for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((L - 1) * D + dim) * npad];
+  if (VAR) var_row(L - 1);  // (dtv still belongs to localisation L-2: the implicit children of step L-1)
   const bool stay_last = (L - 1) >= P.min_len;
   double mx = -INFINITY, acc = 0.0;
   const int Kc = implicit ? K : 1;
@@ -174,8 +198,8 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
       int newest = ps;
       if (implicit) {
         const int head = r + K * ps;
-        dd = P.dd[head];
-        lpadd = P.LT[head] + (stay_last ? P.Lp_stay[r] : 0.0);
+        dd = DDV(head);
+        lpadd = P.LT[head] + (stay_last ? Lps[r] : 0.0);
         newest = r % nS;
       }
       double term = 0.0;
@@ -191,7 +215,7 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
         }
       }
       double v = SA(cur, p, D + KS) + lpadd + term;
-      if (ck.isBL) v += a.Lsum[newest];
+      if (ck.isBL) v += (VAR && a.ax.leave) ? log(a.ax.leave[(size_t)wk.chunk * nS + newest]) : a.Lsum[newest];
       const double nm = fmax(mx, v);
       acc = acc * exp(mx - nm) + exp(v - nm);
       mx = nm;
@@ -206,6 +230,7 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
   if (lane == 0) a.partial[wi] = lp;
   }
 #undef SA
+#undef DDV
 }
 
 // Deterministic final reduction of the per-CTA partial sums (second level of tracking.py:1069).

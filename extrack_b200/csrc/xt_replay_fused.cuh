@@ -39,6 +39,8 @@ struct K2Tab {  // per-evaluation tables and scalars of the fused replay kernel 
   double l2[XT_MAX_DIMS];
   double e2[16];                  // 2^(j/16)
   int32_t nS, nsub, K, min_len;
+  uint32_t flags;                 // xt_params::flags
+  double loc_slope, loc_offset;   // xt_params
 };
 
 // ---- shared memory through 32-bit shared-window addresses (no generic-pointer arithmetic) ----
@@ -184,21 +186,22 @@ struct XtSlotIO {
 // Gaussian-product update of merged sequences (m, s2, W * 2^E) with the localisations cl (one
 // per track of the thread, written stage by stage so that the TPT chains interleave); the
 // result is the parent record (m', u = l2*s2/q, W' * 2^E') shared by its children.
-template <int D, int KS, int TPT>
-__device__ __forceinline__ void xt_update(XtSeq<D, KS> (&s)[TPT], const double (&cl)[TPT][D], const double (&l2)[KS],
-                                          unsigned s_e2) {
+// (VAR: l2 is per track, l2[j][k]; otherwise one row shared by the thread's tracks)
+template <int D, int KS, int TPT, bool VAR = false>
+__device__ __forceinline__ void xt_update(XtSeq<D, KS> (&s)[TPT], const double (&cl)[TPT][D],
+                                          const double (&l2)[VAR ? TPT : 1][KS], unsigned s_e2) {
   double rq[TPT][KS], e[TPT];
 #pragma unroll
   for (int j = 0; j < TPT; ++j)
 #pragma unroll
-    for (int k = 0; k < KS; ++k) rq[j][k] = xt_rcp(l2[k] + s[j].u[k]);
+    for (int k = 0; k < KS; ++k) rq[j][k] = xt_rcp(l2[VAR ? j : 0][k] + s[j].u[k]);
 #pragma unroll
   for (int j = 0; j < TPT; ++j) {
     double g[KS];
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
       g[k] = s[j].u[k] * rq[j][k];
-      s[j].u[k] = l2[k] * g[k];
+      s[j].u[k] = l2[VAR ? j : 0][k] * g[k];
     }
     if (KS == 1) {
       double q2 = 0.0;
@@ -243,13 +246,15 @@ struct K2FArgs {
   int32_t Pcap;
   int32_t n_work;      // CTAs of this launch
   int32_t work0;       // first tile of this launch in the work table
+  XtAux ax;            // VAR instantiation only (stay / leave tables are per chunk)
 };
 
 // shared memory of k2_replay_fused in bytes (host and device agree through these functions)
 __host__ __device__ inline int xt_fused_blob16(int Pcap, int K) { return 2 + (Pcap + 1) / 2 + (K * Pcap + 3) / 4; }
-__host__ __device__ inline size_t xt_fused_smem(int D, int KS, int Pcap, int K, int H, int wpc, int tpt) {
+__host__ __device__ inline size_t xt_fused_smem(int D, int KS, int Pcap, int K, int H, int wpc, int tpt, bool var = false) {
   const int NV = (D + KS + 1 + 1) / 2;
-  return (size_t)2 * Pcap * NV * 512 * tpt         // state vectors, ping-pong
+  return (var ? 64 : 0)                            // VAR: per-chunk leave sums [nS]
+         + (size_t)2 * Pcap * NV * 512 * tpt       // state vectors, ping-pong
          + (size_t)2 * xt_fused_blob16(Pcap, K) * 16  // staged replay records, ping-pong
          + (size_t)2 * H * 16                      // (tau, dd) per head, without / with the stay term
          + 128                                     // 2^(j/16)
@@ -257,7 +262,7 @@ __host__ __device__ inline size_t xt_fused_smem(int D, int KS, int Pcap, int K, 
   // (the end-of-track partial sums, wpc * 384 * tpt bytes, reuse the idle state buffer: Pcap >= 2)
 }
 
-template <int D, int KS, int WPC, int TPT>
+template <int D, int KS, int WPC, int TPT, bool VAR = false>
 __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_replay_fused(const K2FArgs a, const __grid_constant__ K2Tab T) {
   using IO = XtSlotIO<D, KS, TPT>;
   using Seq = XtSeq<D, KS>;
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
   const unsigned s_tab = s_blob + 2 * B16 * 16;         // [2][H] x 16 B: (tau, dd)
   const unsigned s_e2 = s_tab + 2 * H * 16;             // [16] x 8 B
   const unsigned s_exp = s_e2 + 128 + lane * 4;         // [2][Pcap][32*TPT] x 4 B
+  const unsigned s_leave = s_e2 + 128 + 2 * EB;         // VAR: [nS] x 8 B per-chunk leave sums
 
   // stage the first replay record (steps 3..L-1 use records 0..L-4) and the tables
   // (up to two 16-byte words per thread: B16 <= 64 * WPC is checked by the host)
@@ -315,13 +321,36 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
   }
   for (int h = tid; h < 2 * H; h += NT) {
     const int hh = h < H ? h : h - H;
-    xt_sts128(s_tab + h * 16, h < H ? T.tau0[hh] : T.tau1[hh], T.dd[hh]);
+    double tau = h < H ? T.tau0[hh] : T.tau1[hh];
+    if (VAR && a.ax.stay && h >= H) tau = T.tau0[hh] * exp(a.ax.stay[(size_t)wk.chunk * K + hh % K]);  // per-chunk p_stay
+    xt_sts128(s_tab + h * 16, tau, T.dd[hh]);
   }
   if (tid < 16) xt_sts64(s_e2 + tid * 8, T.e2[tid]);
+  if (VAR && tid < nS) xt_sts64(s_leave + tid * 8, a.ax.leave ? a.ax.leave[(size_t)wk.chunk * nS + tid] : T.leave[tid]);
 
-  double l2[KS];
+  // l2 of the localisation the next update consumes (VAR: per track, from the aux block; the
+  // dd column of the tables then holds dd per unit time and is scaled by the track's dt)
+  double l2[VAR ? TPT : 1][KS];
 #pragma unroll
-  for (int k = 0; k < KS; ++k) l2[k] = T.l2[k];
+  for (int k = 0; k < KS; ++k) l2[0][k] = T.l2[k];
+  const bool var_loc = VAR && (T.flags & XT_FLAG_VAR_LOC), var_dt = VAR && (T.flags & XT_FLAG_VAR_DT);
+  const double* Ax = VAR ? a.ax.aux + (size_t)(ck.xyz_off / D) * a.ax.R : nullptr;
+  const size_t astride = VAR ? (size_t)a.ax.R * npad : 0;
+  double l2n[VAR ? TPT : 1][KS], dtc[VAR ? TPT : 1], dtq[VAR ? TPT : 1], dtn[VAR ? TPT : 1];
+  auto aux_row = [&](double (&lo)[VAR ? TPT : 1][KS], double (&dto)[VAR ? TPT : 1]) {  // row at Ax
+#pragma unroll
+    for (int j = 0; j < (VAR ? TPT : 1); ++j) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) lo[j][k] = var_loc ? xt_sigma2f(T.flags, T.loc_slope, T.loc_offset, Ax[(size_t)k * npad + toff[j]]) : T.l2[k];
+      dto[j] = var_dt ? Ax[(size_t)a.ax.ka * npad + toff[j]] : 1.0;
+    }
+  };
+#define DTQ(j) (VAR ? dtq[VAR ? (j) : 0] : 1.0)
+  if (VAR) {
+    aux_row(l2, dtq);    // row 0: first localisation
+    Ax += astride;
+    aux_row(l2n, dtc);   // row 1 (L >= 2)
+  }
 
   double cl[TPT][D], cn[TPT][D];
   double csum[TPT];  // NaN / Inf coordinates anywhere in the track poison the result
@@ -352,11 +381,15 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) s[j].m[dim] = cl[j][dim];
 #pragma unroll
-      for (int k = 0; k < KS; ++k) s[j].u[k] = l2[k] + ddc;
+      for (int k = 0; k < KS; ++k) s[j].u[k] = l2[VAR ? j : 0][k] + (VAR ? ddc * DTQ(j) : ddc);
       xt_split_exponent(T.winit[c], 0, s[j].W, s[j].E);
     }
-    if (L >= 3) xt_update<D, KS, TPT>(s, cn, l2, s_e2);
+    if (L >= 3) xt_update<D, KS, TPT, VAR>(s, cn, VAR ? l2n : l2, s_e2);
     IO::store(s_vec + c * SLOTB, s_exp + c * ESLOT, s);
+  }
+  if (VAR && L >= 3) {  // dtc = dt of localisation 1, l2n/dtn = row 2
+    Ax += astride;
+    aux_row(l2n, dtn);
   }
   if (L >= 3) {
     Cs += cstride;
@@ -386,6 +419,17 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
         csum[j] += cl[j][dim];
         cn[j][dim] = Cs[(size_t)dim * npad + toff[j]];
       }
+    if (VAR) {  // dtq = dt of C[step-2] (children being merged), l2 = of C[step-1] (update), next row prefetched
+#pragma unroll
+      for (int j = 0; j < (VAR ? TPT : 1); ++j) {
+        dtq[j] = dtc[j];
+        dtc[j] = dtn[j];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) l2[j][k] = l2n[j][k];
+      }
+      Ax += astride;
+      aux_row(l2n, dtn);
+    }
     const bool more = ri + 1 < nrec;
     if (more) {
       if (tid < B16) pre0 = __ldg(gblob + (size_t)(ri + 1) * bstride);
@@ -412,7 +456,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
         for (int j = 0; j < TPT; ++j) {
           G[j].W *= tau0;
 #pragma unroll
-          for (int k = 0; k < KS; ++k) G[j].u[k] += dd0;
+          for (int k = 0; k < KS; ++k) G[j].u[k] += VAR ? dd0 * DTQ(j) : dd0;
         }
       } else if (kind == 2u) {
         const unsigned p1 = gr.y & 0xFFFu, h1 = (gr.y >> 12) & 0xFFu;
@@ -432,8 +476,8 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
           for (int dim = 0; dim < D; ++dim) G[j].m[dim] = fma(B[j].m[dim] - G[j].m[dim], lam, G[j].m[dim]);
 #pragma unroll
           for (int k = 0; k < KS; ++k) {
-            const double ua = G[j].u[k] + dd0;
-            G[j].u[k] = fma((B[j].u[k] + dd1) - ua, lam, ua);
+            const double ua = G[j].u[k] + (VAR ? dd0 * DTQ(j) : dd0);
+            G[j].u[k] = fma((B[j].u[k] + (VAR ? dd1 * DTQ(j) : dd1)) - ua, lam, ua);
           }
           G[j].W = sw;
           G[j].E = Eg;
@@ -460,7 +504,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
           for (int dim = 0; dim < D; ++dim) am[j][dim] = sw[j] * G[j].m[dim];
 #pragma unroll
           for (int k = 0; k < KS; ++k) {
-            G[j].u[k] += dd0;
+            G[j].u[k] += VAR ? dd0 * DTQ(j) : dd0;
             as[j][k] = sw[j] * G[j].u[k];
           }
         }
@@ -479,7 +523,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
 #pragma unroll
             for (int dim = 0; dim < D; ++dim) am[j][dim] = fma(wj, M[j].m[dim], am[j][dim]);
 #pragma unroll
-            for (int k2 = 0; k2 < KS; ++k2) as[j][k2] = fma(wj, M[j].u[k2] + ddm, as[j][k2]);
+            for (int k2 = 0; k2 < KS; ++k2) as[j][k2] = fma(wj, M[j].u[k2] + (VAR ? ddm * DTQ(j) : ddm), as[j][k2]);
           }
         }
 #pragma unroll
@@ -495,7 +539,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
           G[j].E = Eg[j];
         }
       }
-      xt_update<D, KS, TPT>(G, cl, l2, s_e2);
+      xt_update<D, KS, TPT, VAR>(G, cl, l2, s_e2);
       IO::store(dst_v + g * SLOTB, dst_e + g * ESLOT, G);
     }
     nP = nG;
@@ -548,12 +592,13 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
         newest = newest_r;
       }
       if (++newest_r == nS) newest_r = 0;
-      if (ck.isBL) th *= T.leave[newest];
+      if (ck.isBL) th *= VAR ? xt_lds64(s_leave + newest * 8) : T.leave[newest];
 #pragma unroll
       for (int j = 0; j < TPT; ++j) {
         double rq[KS];
 #pragma unroll
-        for (int k = 0; k < KS; ++k) rq[k] = xt_rcp(S[j].u[k] + dd + l2[k]);
+        for (int k = 0; k < KS; ++k)
+          rq[k] = xt_rcp(S[j].u[k] + (VAR ? dd * dtc[VAR ? j : 0] : dd) + (VAR ? l2n[VAR ? j : 0][k] : l2[0][k]));
         double quad = 0.0;
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) quad = fma(df2[j][dim], rq[(KS == 1) ? 0 : dim], quad);

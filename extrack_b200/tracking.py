@@ -28,20 +28,10 @@ MAX_TRACKS_PER_CHUNK = 2000  # tracking.py:991 max_number_of_tracks_per_matrix
 # --------------------------------------------------------------------------------------
 # parameters -> model quantities (host; tracking.py:913-986)
 # --------------------------------------------------------------------------------------
-def extract_params(params, dt, nb_states, nb_substeps, input_LocErr=None, Matrix_type=1):
-    """lmfit ``Parameters`` -> ``(LocErr, ds, Fs, TrMat, pBL)`` with the reference's conventions.
-
-    ``LocErr`` is ``[array(1,1,k)]``; ``ds = sqrt(2 D dt)``; ``TrMat`` holds per-sub-step
-    transition probabilities.  Peak-wise ``input_LocErr`` and per-track ``dt`` are not
-    supported by the CUDA path yet and raise ``NotImplementedError``.
-    """
-    if input_LocErr is not None:
-        raise NotImplementedError("peak-wise input_LocErr is not supported by the CUDA engine yet (SURVEY.md §8f N1)")
-    if isinstance(dt, (list, dict)):
-        raise NotImplementedError("per-track dt is not supported by the CUDA engine yet (SURVEY.md §8f N1)")
+def _extract_scalars(params, nb_substeps, Matrix_type=1):
+    """lmfit ``Parameters`` -> ``(LocErr values, Ds, Fs, TrMat, pBL)`` (tracking.py:918-975)."""
     names = sorted(params.keys())
     loc = [params[n].value for n in names if n.startswith("LocErr")]
-    LocErr = [np.array(loc, dtype=float)[None, None]]
     Ds = np.array([params[n].value for n in names if n.startswith("D") and len(n) < 3], dtype=float)
     Fs = np.array([params[n].value for n in names if n.startswith("F")], dtype=float)
     nS = len(Ds)
@@ -72,41 +62,132 @@ def extract_params(params, dt, nb_states, nb_substeps, input_LocErr=None, Matrix
             G[diag, diag] = -np.sum(G, 1)
             TrMatG = linalg.expm(G)
             TrMat = np.mean([TrMat, TrMatG], axis=0) if Matrix_type == 3 else (TrMat * TrMatG) ** 0.5
-    ds = np.sqrt(2 * Ds * dt)
+    return np.array(loc, dtype=float), Ds, Fs, TrMat, pBL
+
+
+def _has_slope(params) -> bool:
+    return any(k == "slope_LocErr" for k in params.keys())
+
+
+def extract_params(params, dt, nb_states, nb_substeps, input_LocErr=None, Matrix_type=1):
+    """lmfit ``Parameters`` -> ``(LocErr, ds, Fs, TrMat, pBL)`` with the reference's conventions
+    (tracking.py:913-986).
+
+    ``LocErr`` is ``[array(1,1,k)]``, or with peak-wise ``input_LocErr`` (a list of ``[n, L, k]``
+    arrays, one per bucket) that list, transformed by ``slope_LocErr`` / ``offset_LocErr`` when
+    these parameters exist (:926-932).  ``ds = sqrt(2 D dt)``; with a list of per-track ``dt``
+    arrays ``[n, L]`` it is the list of ``[n, L, nS]`` arrays (:979-982).  ``TrMat`` holds
+    per-sub-step transition probabilities.
+    """
+    loc, Ds, Fs, TrMat, pBL = _extract_scalars(params, nb_substeps, Matrix_type)
+    LocErr = [loc[None, None]]
+    if input_LocErr is not None:
+        if _has_slope(params):
+            LocErr = [np.clip(a * params["slope_LocErr"].value + params["offset_LocErr"].value, 0.000001, np.inf)
+                      for a in input_LocErr]
+        else:
+            LocErr = input_LocErr
+    if type(dt) == list:
+        ds = [np.sqrt(2 * Ds[None, None] * t[:, :, None]) for t in dt]
+    else:
+        ds = np.sqrt(2 * Ds * dt)
     return LocErr, ds, Fs, TrMat, pBL
 
 
 def _p_stay(ds, nS, nsub, cell_dims):
-    """P(stay in the field of view) per sub-step state tuple (tracking.py:508-523)."""
+    """P(stay in the field of view) per sub-step state tuple (tracking.py:508-523).
+
+    ``ds``: ``[nS]`` -> ``[K]``; or ``[rows, nS]`` (one row per chunk / track when dt is per track,
+    :501-506) -> ``[rows, K]``, each row computed with the operations (and the summation order of
+    ``np.mean(.., 0)``) the reference applies to a single chunk.
+    """
     import scipy.stats
 
+    ds = np.asarray(ds, dtype=float)
+    one = ds.ndim == 1
+    ds2 = ds[None] if one else ds
     K = nS**nsub
     tup = np.arange(K)[:, None] // nS ** np.arange(nsub)[None, :] % nS
-    sub_ds = np.mean(ds[tup] ** 2, axis=1) ** 0.5
-    p_stay = np.ones(K)
-    for cell_len in cell_dims:
-        xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
-        cur = np.mean(
-            scipy.stats.norm.cdf((cell_len - xs[:, None]) / (sub_ds + 1e-200))
-            - scipy.stats.norm.cdf(-xs[:, None] / (sub_ds + 1e-200)),
-            0,
-        )
-        p_stay = p_stay * cur
-    return p_stay
+    out = np.ones((len(ds2), K))
+    for r0 in range(0, len(ds2), 512):
+        sub_ds = np.mean(ds2[r0 : r0 + 512][:, tup] ** 2, axis=2) ** 0.5  # [rows, K]
+        p_stay = np.ones(sub_ds.shape)
+        for cell_len in cell_dims:
+            xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
+            cur = np.mean(
+                scipy.stats.norm.cdf((cell_len - xs[:, None, None]) / (sub_ds + 1e-200))
+                - scipy.stats.norm.cdf(-xs[:, None, None] / (sub_ds + 1e-200)),
+                0,
+            )
+            p_stay = p_stay * cur
+        out[r0 : r0 + 512] = p_stay
+    return out[0] if one else out
+
+
+def _head_tables(ds, Fs, TrMat, nS, nsub):
+    """digits, dd, LT, LF per head (tracking.py:487-488,549-555,759-767); head h: digit k (base nS) =
+    state k sub-steps ago, digit nsub = newest state of the parent."""
+    nH = nS ** (nsub + 1)
+    dig = np.arange(nH)[:, None] // nS ** np.arange(nsub + 1)[None, :] % nS
+    d2 = ds[dig] ** 2
+    dd = np.mean((d2[:, 1:] + d2[:, :-1]) / 2, axis=1)
+    Tt = TrMat.T
+    LT = np.zeros(nH)
+    for k in range(nsub):
+        LT += np.log(Tt[dig[:, k], dig[:, k + 1]])
+    LF = np.log(Fs[dig[:, nsub]])
+    return dig, dd, LT, LF
+
+
+def _mid2(x):
+    """The two middle order statistics of x (equal for an odd count): np.median = their mean."""
+    x = np.sort(np.asarray(x, dtype=float).ravel())
+    return x[(len(x) - 1) // 2], x[len(x) // 2]
+
+
+def _median_ds(Ds, mids):
+    """median over tracks of sqrt(2 D dt) per state from the two middle dt values (sqrt is monotone)."""
+    mids = np.asarray(mids, dtype=float)
+    a = np.sqrt(2 * Ds[None] * mids[..., 0:1].reshape(-1, 1))
+    b = np.sqrt(2 * Ds[None] * mids[..., 1:2].reshape(-1, 1))
+    return (a + b) / 2
+
+
+def stay_tables(Ds, mids, TrMat, pBL, cell_dims, nb_substeps):
+    """Per-row (chunk or track) ``Lp_stay [rows, K]`` and ``L_leave [rows, H]`` when dt is per track:
+    the reference derives p_stay from the median diffusion length of the chunk's first time step
+    (tracking.py:501-506,515-524,630-631).  ``mids``: ``[rows, 2]`` middle order statistics of
+    ``dt[:, 0]`` per row."""
+    Ds = np.asarray(Ds, dtype=float)
+    nS, nsub = len(Ds), int(nb_substeps)
+    uniq, inv = np.unique(np.asarray(mids, dtype=float).reshape(-1, 2), axis=0, return_inverse=True)
+    inv = np.asarray(inv).reshape(-1)
+    p_stay = _p_stay(_median_ds(Ds, uniq), nS, nsub, cell_dims)  # [U, K]
+    dig, _, LT, _ = _head_tables(np.zeros(nS), np.ones(nS), np.asarray(TrMat, dtype=float), nS, nsub)
+    Lp_stay = np.log(p_stay * (1 - pBL))
+    e = p_stay[:, dig[:, 0]]
+    L_leave = np.log(pBL + (1 - e) - pBL * (1 - e)) + LT[None]
+    return Lp_stay[inv], L_leave[inv]
 
 
 def build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold,
-                 max_nb_states, nb_dims, int8_wrap=True) -> _native.XtParams:
+                 max_nb_states, nb_dims, int8_wrap=True, var_loc_k=0, var_dt=False, Ds=None,
+                 slope_offset=None) -> _native.XtParams:
     """Model quantities -> the engine's per-evaluation POD (``xt_params`` in include/xtrack.h).
 
     Restates the table-building half of ``P_Cs_inter_bound_stats_th`` (tracking.py:474-524,
-    549-555, 630-631) once per evaluation instead of once per chunk.
+    549-555, 630-631) once per evaluation instead of once per chunk.  ``var_loc_k`` > 0: the
+    localisation errors are the resident peak-wise ones (k components, ``LocErr`` is ignored,
+    optionally ``slope_offset``); ``var_dt``: dt is resident per localisation (``Ds`` required, ``ds``
+    = the guard's median diffusion lengths).
     """
     ds = np.asarray(ds, dtype=float)
     Fs = np.asarray(Fs, dtype=float)
     TrMat = np.asarray(TrMat, dtype=float)
     nS, nsub = len(ds), int(nb_substeps)
     loc = np.asarray(LocErr, dtype=float).reshape(-1)
+    if var_loc_k:
+        loc = np.zeros(int(var_loc_k))
     if len(loc) not in (1, nb_dims):
         raise ValueError(
             "Localization error is not specified correctly, in case of unique localization error specify a float "
@@ -121,22 +202,24 @@ def build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, 
     p.nS, p.nsub, p.d, p.n_loc = nS, nsub, int(nb_dims), len(loc)
     p.frame_len, p.min_len, p.max_nb_states = int(frame_len), int(min_len), int(min(max_nb_states, 2**31 - 1))
     p.flags = _native.XT_FLAG_INT8_WRAP if int8_wrap else 0
+    if var_loc_k:
+        p.flags |= _native.XT_FLAG_VAR_LOC
+        if slope_offset is not None:
+            p.flags |= _native.XT_FLAG_LOC_AFFINE
+            p.loc_slope, p.loc_offset = float(slope_offset[0]), float(slope_offset[1])
+    if var_dt:
+        p.flags |= _native.XT_FLAG_VAR_DT
+    if Ds is not None:
+        for k, v in enumerate(2 * np.asarray(Ds, dtype=float)):
+            p.twoD[k] = v
     p.threshold = float(threshold)
     for k, v in enumerate(loc**2):
         p.l2[k] = v
-    # head h: digit k (base nS) = state k sub-steps ago, digit nsub = newest state of the parent
-    dig = np.arange(nH)[:, None] // nS ** np.arange(nsub + 1)[None, :] % nS
-    d2 = ds[dig] ** 2
-    dd = np.mean((d2[:, 1:] + d2[:, :-1]) / 2, axis=1)
-    Tt = TrMat.T
-    LT = np.zeros(nH)
-    for k in range(nsub):
-        LT += np.log(Tt[dig[:, k], dig[:, k + 1]])
+    dig, dd, LT, LF = _head_tables(ds, Fs, TrMat, nS, nsub)
     p_stay = _p_stay(ds, nS, nsub, cell_dims)
     Lp_stay = np.log(p_stay * (1 - pBL))
     e = p_stay[dig[:, 0]]  # indexed by the newest *state value* (reference quirk, tracking.py:630)
     L_leave = np.log(pBL + (1 - e) - pBL * (1 - e)) + LT
-    LF = np.log(Fs[dig[:, nsub]])
     for h in range(nH):
         p.dd[h], p.LT[h], p.LF[h], p.L_leave[h] = dd[h], LT[h], LF[h], L_leave[h]
     for r in range(K):
@@ -193,7 +276,8 @@ class TrackSet:
     """
 
     def __init__(self, sorted_tracks: Sequence[np.ndarray], chunk: int = MAX_TRACKS_PER_CHUNK, device: Optional[int] = None,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, reverse: bool = True):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, reverse: bool = True,
+                 input_LocErr: Optional[Sequence[np.ndarray]] = None, dt_list: Optional[Sequence[np.ndarray]] = None):
         if len(sorted_tracks) < 1:
             raise ValueError("No track could be detected. The loaded tracks seem empty. Errors often come from wrong input paths.")
         for a in sorted_tracks:
@@ -218,6 +302,38 @@ class TrackSet:
         if segs:
             self.engine.upload(segs, bl, self.chunk)
         self._dist_buf = None
+        # peak-wise localisation errors [n, L, k] / per-localisation dt [n, L] per bucket (sorted like the tracks)
+        self.loc_k = 0
+        self.has_dt = dt_list is not None
+        self.dt_mids = self.dt_mid0 = None
+        if input_LocErr is not None or dt_list is not None:
+            cut = lambda arrs: [np.asarray(arrs[b])[a:z] for (b, a, z, _) in (self.chunks[i] for i in mine)]
+            if input_LocErr is not None:
+                for a, c in zip(input_LocErr, self.sorted_tracks):
+                    a = np.asarray(a)
+                    if a.ndim != 3 or a.shape[:2] != c.shape[:2] or a.shape[2] not in (1, c.shape[2]):
+                        raise ValueError(
+                            "Localization error is not specified correctly, in case of unique localization error specify "
+                            "a float number in estimated_vals['LocErr'].\n If one localization error per dimension, "
+                            "specify a list or 1D array of elements the localization error for each dimension.\n If "
+                            "localization error is predetermined by another method for each position the argument "
+                            "input_LocErr should be a dict for each track length of the 3D arrays corresponding to "
+                            "all_tracks (can be obtained from the reader functions using the opt_colname argument)")
+                self.loc_k = int(np.asarray(input_LocErr[0]).shape[2])
+            if dt_list is not None:
+                for a, c in zip(dt_list, self.sorted_tracks):
+                    if np.asarray(a).shape != c.shape[:2]:
+                        raise ValueError(
+                            "dt is not informed properly. It must either be a float number or a dictionary of same "
+                            "structure than `all_tracks` with each element being an array of dims (nb_tracks, track_len)")
+                dts = cut(dt_list)
+                # field-of-view term: median over the chunk of ds[:, 0] (tracking.py:501-506); guard: median of
+                # the first bucket's ds (:1012-1013).  sqrt is monotone: keep the middle order statistics of dt
+                self.dt_mids = np.array([_mid2(a[:, 0]) for a in dts]).reshape(-1, 2)
+                self.dt_mid0 = np.array(_mid2(np.asarray(dt_list[0])))
+            if segs:
+                self.engine.upload_aux(cut(input_LocErr) if input_LocErr is not None else None,
+                                       dts if dt_list is not None else None)
 
     # local chunk index of global chunk i (or None when another rank owns it)
     def local_index(self, i: int) -> Optional[int]:
@@ -270,14 +386,16 @@ def _default_device() -> int:
 _TRACKSET_CACHE: List = []  # [(key, refs, TrackSet)] most recent first
 
 
-def _trackset_for(all_tracks: Sequence[np.ndarray], chunk: int) -> TrackSet:
+def _trackset_for(all_tracks: Sequence[np.ndarray], chunk: int, input_LocErr=None, dt_list=None) -> TrackSet:
     """Resident data for a list of arrays handed to ``cum_Proba_Cs`` (upload once per fit)."""
-    key = tuple((id(a), a.shape, a.__array_interface__["data"][0]) for a in all_tracks) + (chunk,)
+    sig = lambda arrs: tuple((id(a), a.shape, a.__array_interface__["data"][0]) for a in arrs)
+    key = sig(all_tracks) + (chunk,) + (sig(input_LocErr) if input_LocErr is not None else (None,)) + (
+        sig(dt_list) if dt_list is not None else (None,))
     for k, refs, ts in _TRACKSET_CACHE:
         if k == key:
             return ts
-    ts = TrackSet(all_tracks, chunk)
-    _TRACKSET_CACHE.insert(0, (key, list(all_tracks), ts))
+    ts = TrackSet(all_tracks, chunk, input_LocErr=input_LocErr, dt_list=dt_list)
+    _TRACKSET_CACHE.insert(0, (key, [list(all_tracks), input_LocErr, dt_list], ts))
     while len(_TRACKSET_CACHE) > 2:
         _, _, old = _TRACKSET_CACHE.pop()
         old.close()
@@ -293,14 +411,28 @@ def cum_Proba_Cs(params, all_tracks, dt, cell_dims, input_LocErr, nb_states, nb_
     """-sum log L over all tracks for ``params`` (``np.inf`` for invalid parameters).
 
     ``all_tracks`` is the sorted list of ``[n, L, d]`` arrays (as ``param_fitting`` builds it);
+    ``input_LocErr`` (optional) the matching list of peak-wise localisation errors ``[n, L, k]`` and
+    ``dt`` a float or the matching list of ``[n, L]`` time steps (tracking.py:1024-1044).
     ``workers`` is accepted and ignored (the GPU replaces the process pool).
     """
-    LocErr, ds, Fs, TrMat, pBL = extract_params(params, dt, nb_states, nb_substeps, input_LocErr, Matrix_type)
-    ts = _trackset if _trackset is not None else _trackset_for(all_tracks, max_number_of_tracks_per_matrix)
+    loc, Ds, Fs, TrMat, pBL = _extract_scalars(params, nb_substeps, Matrix_type)
+    dt_list = dt if type(dt) == list else None
+    if input_LocErr is not None:
+        input_LocErr = [np.asarray(a, dtype=np.float64) for a in input_LocErr] if _trackset is None else input_LocErr
+    ts = _trackset if _trackset is not None else _trackset_for(all_tracks, max_number_of_tracks_per_matrix, input_LocErr,
+                                                               dt_list)
     quiet = ts.rank != 0
+    if dt_list is not None:
+        ds = _median_ds(Ds, ts.dt_mid0)[0]  # avg_ds = np.median(ds[0], axis=(0, 1)), tracking.py:1012-1013
+    else:
+        ds = np.sqrt(2 * Ds * dt)
     if np.all(TrMat > 0) and np.all(Fs > 0) and np.all(ds[1:] - ds[:-1] >= 0):
-        p = build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, ts.min_len, threshold,
-                         max_nb_states, ts.nb_dims)
+        slope = (params["slope_LocErr"].value, params["offset_LocErr"].value) if (ts.loc_k and _has_slope(params)) else None
+        p = build_tables(loc, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, ts.min_len, threshold,
+                         max_nb_states, ts.nb_dims, var_loc_k=ts.loc_k, var_dt=ts.has_dt, Ds=Ds, slope_offset=slope)
+        if ts.has_dt and ts.n_local_chunks:
+            ts.engine.set_stay_tables(False, *stay_tables(Ds, ts.dt_mids, TrMat, pBL, cell_dims, nb_substeps))
+        ts._last_p = p
         Cum_P = ts.sum_logp(p)
         if not quiet:
             if verbose == 1:
@@ -351,14 +483,17 @@ def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, 
     ``workers`` is accepted and ignored.
     """
     sorted_tracks, l_list = _sorted_buckets(all_tracks)
+    keys = [k for k in l_list if len(all_tracks[k]) > 0]
+    sorted_LocErrs = [np.asarray(input_LocErr[k], dtype=np.float64) for k in keys] if input_LocErr is not None else None
+    sorted_dt = [np.asarray(dt[k], dtype=np.float64) for k in keys] if type(dt) == dict else None
     nb_substeps = 1  # substeps should not impact the step labelling (tracking.py:839)
     if not isinstance(params, Parameters):
         raise TypeError("params must be either of the class 'lmfit.parameter.Parameters' or a dictionary of the relevant parameters")
     if nb_max != 1:
         raise NotImplementedError("predict_Bs on the CUDA engine implements nb_max = 1 (the reference default) only")
-    LocErr, ds, Fs, TrMat, pBL = extract_params(params, dt, nb_states, nb_substeps, input_LocErr)
-    if len(ds) != nb_states:
-        raise ValueError("nb_states (%d) must equal the number of D parameters (%d)" % (nb_states, len(ds)))
+    loc, Ds, Fs, TrMat, pBL = _extract_scalars(params, nb_substeps)
+    if len(Ds) != nb_states:
+        raise ValueError("nb_states (%d) must equal the number of D parameters (%d)" % (nb_states, len(Ds)))
     out = {l: np.empty((0, int(l), nb_states)) for l in l_list}
     if not sorted_tracks:
         return out
@@ -366,12 +501,30 @@ def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, 
         if a.shape[1] < 2:
             raise ValueError("minimal track length = 2, here track length = %s" % a.shape[1])
     min_len, max_len = int(l_list[0]), int(l_list[-1])
-    p = build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold, max_nb_states,
-                     sorted_tracks[0].shape[2])
+    loc_k = 0
+    if sorted_LocErrs is not None:
+        for a, c in zip(sorted_LocErrs, sorted_tracks):
+            if a.ndim != 3 or a.shape[:2] != c.shape[:2] or a.shape[2] not in (1, c.shape[2]):
+                raise ValueError("Localization error is not specified correctly: input_LocErr arrays must have shape "
+                                 "[n, L, 1] or [n, L, d] matching all_tracks")
+        loc_k = sorted_LocErrs[0].shape[2]
+    if sorted_dt is not None:
+        # one track per chunk (nb_max = 1): every track's own dt[0] sets its field-of-view term (:501-506)
+        ds = _median_ds(Ds, np.array(_mid2(sorted_dt[0])))[0]
+    else:
+        ds = np.sqrt(2 * Ds * dt)
+    slope = (params["slope_LocErr"].value, params["offset_LocErr"].value) if (loc_k and _has_slope(params)) else None
+    p = build_tables(loc, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold, max_nb_states,
+                     sorted_tracks[0].shape[2], var_loc_k=loc_k, var_dt=sorted_dt is not None, Ds=Ds, slope_offset=slope)
     eng = _native.Engine(_default_device())
     try:
         # chunk size only shapes the device layout here; plans are per track
         eng.upload(sorted_tracks, [0 if a.shape[1] == max_len else 1 for a in sorted_tracks], MAX_TRACKS_PER_CHUNK)
+        if sorted_LocErrs is not None or sorted_dt is not None:
+            eng.upload_aux(sorted_LocErrs, sorted_dt)
+        if sorted_dt is not None:
+            t0 = np.concatenate([a[:, 0] for a in sorted_dt])
+            eng.set_stay_tables(True, *stay_tables(Ds, np.stack([t0, t0], 1), TrMat, pBL, cell_dims, nb_substeps))
         preds = eng.predict(p, nb_states)
     finally:
         eng.close()
@@ -479,13 +632,16 @@ def param_fitting(all_tracks, dt, params=None, nb_states=2, nb_substeps=1, frame
     if params is None:
         params = generate_params(nb_states=nb_states, LocErr_type=1, LocErr_bounds=[0.005, 0.1], D_max=3,
                                  Fractions_bounds=[0.001, 0.99], estimated_transition_rates=0.1)
-    if input_LocErr is not None or isinstance(dt, dict):
-        extract_params(params, [] if isinstance(dt, dict) else dt, nb_states, nb_substeps, input_LocErr)  # raises
-    sorted_tracks, _ = _sorted_buckets(all_tracks)
+    sorted_tracks, l_list = _sorted_buckets(all_tracks)
     if len(sorted_tracks) < 1:
         raise ValueError("No track could be detected. The loaded tracks seem empty. Errors often come from wrong input paths.")
+    keys = [k for k in l_list if len(all_tracks[k]) > 0]
+    if input_LocErr is not None:  # dict like all_tracks -> list sorted like the tracks (tracking.py:1351-1366)
+        input_LocErr = [np.asarray(input_LocErr[k], dtype=np.float64) for k in keys]
+    if type(dt) == dict:
+        dt = [np.asarray(dt[k], dtype=np.float64) for k in keys]
     print("cell_dims", cell_dims)
-    ts = TrackSet(sorted_tracks, MAX_TRACKS_PER_CHUNK)
+    ts = TrackSet(sorted_tracks, MAX_TRACKS_PER_CHUNK, input_LocErr=input_LocErr, dt_list=dt if type(dt) == list else None)
     try:
         fit = minimize(cum_Proba_Cs, params,
                        args=(sorted_tracks, dt, cell_dims, input_LocErr, nb_states, nb_substeps, frame_len, verbose, workers,

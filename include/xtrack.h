@@ -32,6 +32,9 @@ extern "C" {
 #define XT_ERR_STATE (-5)     /* call order (e.g. evaluate before upload) */
 
 #define XT_FLAG_INT8_WRAP 1u /* reproduce the int8 wrap of history labels, tracking.py:543,619 */
+#define XT_FLAG_VAR_LOC 2u   /* peak-wise localisation error from xt_upload_aux replaces l2 (input_LocErr, tracking.py:455-463) */
+#define XT_FLAG_VAR_DT 4u    /* per-localisation dt from xt_upload_aux replaces dd (dt dict, tracking.py:494-499,:548-551) */
+#define XT_FLAG_LOC_AFFINE 8u /* sigma' = clip(sigma*loc_slope + loc_offset, 1e-6, inf), tracking.py:926-930 */
 
 typedef struct xt_ctx xt_ctx;
 
@@ -60,6 +63,9 @@ typedef struct xt_params {
   double LF[XT_MAX_HEADS];         /* log initial fraction of the oldest state of the head, :488 */
   double Lp_stay[XT_MAX_HEADS];    /* log(p_stay*(1-pBL)) per r (first K entries), :524 */
   double L_leave[XT_MAX_HEADS];    /* end-of-track leave term + LT per head, :630-631 */
+  /* peak-wise LocErr / per-track dt (XT_FLAG_VAR_*): */
+  double twoD[XT_MAX_STATES];      /* 2*D per state: ds = sqrt(twoD*dt[track, loc]), tracking.py:979-982 */
+  double loc_slope, loc_offset;    /* XT_FLAG_LOC_AFFINE: slope_LocErr / offset_LocErr, :926-930 */
 } xt_params;
 
 /* Work counters of the last evaluation (for seq-updates/s and the algorithmic flop count,
@@ -97,6 +103,26 @@ const char* xt_last_error(xt_ctx* ctx); /* ctx may be NULL: last creation error 
  */
 int xt_upload(xt_ctx* ctx, int32_t n_segments, const int32_t* L, const int64_t* n, const int32_t* isBL,
               const double* const* xyz, int32_t d, int32_t chunk_size);
+
+/*
+ * Optional per-localisation inputs of the resident tracks (call after xt_upload, same segments):
+ * sigma[s] = double[n][L][k_sigma] peak-wise localisation errors (input_LocErr of param_fitting /
+ * predict_Bs, tracking.py:1351-1366,:826-836; k_sigma = 1 or d, 0 = none) and dt[s] = double[n][L]
+ * per-localisation time steps (the dt dict, :1349-1368; NULL = none).  They are used by
+ * evaluations whose xt_params carry XT_FLAG_VAR_LOC / XT_FLAG_VAR_DT; n_loc must then equal
+ * k_sigma.  The reference reads dt with the reversed step counter on the un-reversed array
+ * (:495,:549): step s uses dt[:, L-s]; the engine stores dt time-reversed to the same effect.
+ */
+int xt_upload_aux(xt_ctx* ctx, int32_t k_sigma, const double* const* sigma, const double* const* dt);
+
+/*
+ * Field-of-view tables when dt is per track: the reference derives p_stay from the median
+ * diffusion length of each chunk (tracking.py:501-506), so Lp_stay (xt_params::Lp_stay, K = nS^nsub
+ * entries) and L_leave (H = K*nS entries) become per chunk (per_track = 0, rows in upload chunk
+ * order) for the objective, or per track (per_track = 1: predict_Bs with nb_max = 1 evaluates
+ * one track per chunk) for xt_predict.  Used by evaluations with XT_FLAG_VAR_DT; NULL clears.
+ */
+int xt_set_stay_tables(xt_ctx* ctx, int32_t per_track, int32_t K, int32_t H, const double* Lp_stay, const double* L_leave);
 
 /*
  * Objective — replaces the body of cum_Proba_Cs (tracking.py:1058-1070): plan kernel, replay

@@ -86,6 +86,54 @@ def main():
     np.savez_compressed(os.path.join(HERE, "objective_multibucket.npz"), keys=np.array(keys), fl=np.array(list(vals)),
                         neglogl=np.array(list(vals.values())), meta=str(meta), **{"C" + k: buckets[k] for k in keys})
     print("objective", vals)
+    make_var_cases(trk, meta)
+
+
+# peak-wise input_LocErr / per-track dt: objective and predictions through the
+# reference's own public functions (cum_Proba_Cs with lists, predict_Bs with dicts)
+VAR_CASES = [
+    dict(name="var_loc_k1", nS=2, nsub=1, d=2, fl=6, kloc=1, var_dt=False, slope=False, seed=21),
+    dict(name="var_loc_kd", nS=2, nsub=1, d=2, fl=6, kloc=2, var_dt=False, slope=False, seed=22),
+    dict(name="var_dt", nS=2, nsub=1, d=2, fl=6, kloc=0, var_dt=True, slope=False, seed=23),
+    dict(name="var_slope_dt", nS=2, nsub=1, d=2, fl=5, kloc=1, var_dt=True, slope=True, seed=24),
+    dict(name="var_dt_s3_nsub2", nS=3, nsub=2, d=2, fl=4, kloc=0, var_dt=True, slope=False, seed=25, chunk=30),
+    dict(name="var_all_s3_3d", nS=3, nsub=1, d=3, fl=5, kloc=3, var_dt=True, slope=False, seed=26, chunk=20),
+]
+
+
+def make_var_cases(trk, meta):
+    for c in VAR_CASES:
+        rng = np.random.default_rng(c["seed"])
+        nS, d = c["nS"], c["d"]
+        Ds = [1e-5, 0.25] if nS == 2 else [1e-5, 0.04, 0.25]
+        st = [random_walk_tracks(n, L, d, rng, Ds=Ds) for L, n in ((5, 40), (8, 50), (12, 35))]
+        kw = dict(nb_states=nS, nb_dims=d, estimated_Ds=Ds, estimated_Fs=[1 / nS] * (nS - 1), estimated_transition_rates=0.1)
+        if c["slope"]:
+            params = trk.generate_params(LocErr_type=4, slope_offsets_estimates=[1.1, 0.002], **kw)
+        else:
+            params = trk.generate_params(LocErr_type=1, estimated_LocErr=[0.02], **kw)
+        il = None if c["kloc"] == 0 else [0.02 * (1 + 0.5 * rng.random(a.shape[:2] + (c["kloc"],))) for a in st]
+        dts = 0.02 if not c["var_dt"] else [0.02 * (1 + 0.5 * rng.random(a.shape[:2])) for a in st]
+        chunk = c.get("chunk", 2000)
+        with contextlib.redirect_stdout(io.StringIO()):
+            val = float(trk.cum_Proba_Cs(params, st, dts, [1], il, nS, c["nsub"], c["fl"], 0, 1, 1, 0.2, 120, chunk))
+            preds = {}
+            if c["nsub"] == 1:
+                tr = {str(a.shape[1]): a for a in st}
+                ild = None if il is None else {str(a.shape[1]): x for a, x in zip(st, il)}
+                dtd = dts if not c["var_dt"] else {str(a.shape[1]): x for a, x in zip(st, dts)}
+                preds = trk.predict_Bs(tr, dtd, params, cell_dims=[1], nb_states=nS, frame_len=c["fl"], input_LocErr=ild)
+        pv = {k: float(params[k].value) for k in params}
+        arrays = {"C%d" % i: a for i, a in enumerate(st)}
+        if il is not None:
+            arrays.update({"S%d" % i: a for i, a in enumerate(il)})
+        if c["var_dt"]:
+            arrays.update({"T%d" % i: a for i, a in enumerate(dts)})
+        arrays.update({"P%d" % i: preds[str(a.shape[1])] for i, a in enumerate(st) if preds})
+        np.savez_compressed(os.path.join(HERE, c["name"] + ".npz"), nS=nS, nsub=c["nsub"], fl=c["fl"], kloc=c["kloc"],
+                            var_dt=int(c["var_dt"]), slope=int(c["slope"]), chunk=chunk, neglogl=val,
+                            param_names=np.array(list(pv)), param_values=np.array(list(pv.values())), meta=str(meta), **arrays)
+        print(c["name"], val)
 
 
 if __name__ == "__main__":

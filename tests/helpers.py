@@ -53,3 +53,52 @@ def gid_from_groups(groups, nB):
     for g, mem in enumerate(groups):
         gid[mem] = g
     return gid
+
+
+def load_var_case(path):
+    """Golden case with peak-wise LocErr / per-track dt (tests/golden/make_golden.py:make_var_cases):
+    tracks, optional sigma / dt lists, lmfit-style parameters, configuration and reference outputs."""
+    from extrack_b200._lmfit_compat import Parameters
+
+    z = np.load(path, allow_pickle=False)
+    nb = len([k for k in z.files if k.startswith("C")])
+    st = [z["C%d" % i] for i in range(nb)]
+    il = [z["S%d" % i] for i in range(nb)] if int(z["kloc"]) else None
+    dts = [z["T%d" % i] for i in range(nb)] if int(z["var_dt"]) else None
+    preds = [z["P%d" % i] for i in range(nb)] if "P0" in z.files else None
+    params = Parameters()
+    for k, v in zip(z["param_names"], z["param_values"]):
+        params.add(str(k), value=float(v))
+    cfg = dict(nS=int(z["nS"]), nsub=int(z["nsub"]), fl=int(z["fl"]), chunk=int(z["chunk"]), slope=int(z["slope"]),
+               neglogl=float(z["neglogl"]))
+    return st, il, dts, params, preds, cfg
+
+
+def var_oracle_inputs(st, il, dts, params, cfg, threshold=0.2, max_nb_states=120, nsub=None):
+    """Oracle model + per-bucket sigma / ds arrays from the same parameters (restating extract_params)."""
+    nS = cfg["nS"]
+    nsub = cfg["nsub"] if nsub is None else nsub
+    Ds = np.array([params["D%d" % i].value for i in range(nS)])
+    Fs = np.array([params["F%d" % i].value for i in range(nS)])
+    R = np.zeros((nS, nS))
+    for i in range(nS):
+        for j in range(nS):
+            if i != j:
+                R[i, j] = params["p%d%d" % (i, j)].value
+    Tr = 1 - np.exp(-R / nsub)
+    Tr[np.arange(nS), np.arange(nS)] = 0
+    Tr[np.arange(nS), np.arange(nS)] = 1 - Tr.sum(1)
+    sigs = None
+    if il is not None:
+        sigs = il
+        if cfg["slope"]:
+            sigs = [np.clip(a * params["slope_LocErr"].value + params["offset_LocErr"].value, 0.000001, np.inf) for a in il]
+    loc = np.array([params["LocErr"].value]) if "LocErr" in params.keys() else np.array([0.02])
+    if dts is not None:
+        ds_list = [np.sqrt(2 * Ds[None, None] * t[:, :, None]) for t in dts]
+        ds = np.median(ds_list[0], axis=(0, 1))
+    else:
+        ds_list = None
+        ds = np.sqrt(2 * Ds * 0.02)
+    model = orc.Model(loc, ds, Fs, Tr, params["pBL"].value, [1], nsub, cfg["fl"], st[0].shape[1], threshold, max_nb_states)
+    return model, sigs, ds_list

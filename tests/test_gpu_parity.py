@@ -7,13 +7,14 @@ import os
 import numpy as np
 import pytest
 
-from helpers import engine_params, gid_from_groups, make_model, random_walk_tracks
+from helpers import engine_params, gid_from_groups, load_var_case, make_model, random_walk_tracks, var_oracle_inputs
 from oracle import extrack_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if "objective" not in f)
+CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if "objective" not in f and "var_" not in f)
+VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
 RTOL_LOGL = 1e-9
 
 
@@ -335,3 +336,82 @@ def test_predict_three_state_3d_many_sequences(native):
     finally:
         eng.close()
     np.testing.assert_allclose(got, want, rtol=0, atol=PRED_ATOL)
+
+
+# ---- peak-wise input_LocErr / per-track dt ----
+@pytest.mark.parametrize("path", VAR_CASES, ids=[os.path.basename(p)[:-4] for p in VAR_CASES])
+def test_var_inputs_objective_and_predictions_match_reference_golden(path, xt):
+    """cum_Proba_Cs with an input_LocErr list / dt list and predict_Bs with dicts vs the values the
+    unmodified reference produced (tests/golden/make_golden.py:make_var_cases)."""
+    st, il, dts, params, preds, cfg = load_var_case(path)
+    got = xt.cum_Proba_Cs(params, st, dts if dts is not None else 0.02, [1], il, cfg["nS"], cfg["nsub"], cfg["fl"], 0, 1, 1,
+                          0.2, 120, cfg["chunk"])
+    assert abs(got - cfg["neglogl"]) <= RTOL_LOGL * abs(cfg["neglogl"])
+    if preds is not None:
+        tr = {str(a.shape[1]): a for a in st}
+        ild = None if il is None else {str(a.shape[1]): x for a, x in zip(st, il)}
+        dtd = 0.02 if dts is None else {str(a.shape[1]): x for a, x in zip(st, dts)}
+        pr = xt.predict_Bs(tr, dtd, params, cell_dims=[1], nb_states=cfg["nS"], frame_len=cfg["fl"], input_LocErr=ild)
+        for a, want in zip(st, preds):
+            np.testing.assert_allclose(pr[str(a.shape[1])], want, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("path", VAR_CASES, ids=[os.path.basename(p)[:-4] for p in VAR_CASES])
+def test_var_inputs_plan_equals_oracle_and_replay_kernels_agree(path, xt):
+    """Per chunk: plan identical to the oracle's, per-track log P within tolerance for the fused
+    linear-domain kernel and the log-domain fallback."""
+    st, il, dts, params, _, cfg = load_var_case(path)
+    model, sigs, ds_list = var_oracle_inputs(st, il, dts, params, cfg)
+    ts = xt.TrackSet(st, cfg["chunk"], input_LocErr=il, dt_list=dts)
+    try:
+        for variant in (0, 1):
+            ts.engine.set_option("force_global_replay", variant)
+            got = xt.cum_Proba_Cs(params, st, dts if dts is not None else 0.02, [1], il, cfg["nS"], cfg["nsub"], cfg["fl"], 0, 1,
+                                  1, 0.2, 120, cfg["chunk"], _trackset=ts)
+            assert abs(got - cfg["neglogl"]) <= RTOL_LOGL * abs(cfg["neglogl"])
+            for ci, (b, a, z, isBL) in enumerate(ts.chunks):
+                plan = []
+                ref = orc.chunk_logp(st[b][a:z], model, isBL, plan_out=plan, sig=None if sigs is None else sigs[b][a:z],
+                                     ds3=None if ds_list is None else ds_list[b][a:z])
+                lp = ts.engine.chunk_logp(ci, z - a, ts._last_p)
+                np.testing.assert_allclose(lp, ref, rtol=RTOL_LOGL)
+                for rec in plan:
+                    nB, nG, gid, th = ts.engine.plan_dump(ci, rec["step"])
+                    assert nB == rec["nB_in"] and nG == len(rec["groups"])
+                    np.testing.assert_array_equal(gid, gid_from_groups(rec["groups"], nB))
+    finally:
+        ts.close()
+
+
+def test_var_inputs_constant_arrays_reproduce_scalar_path(xt):
+    """input_LocErr filled with the scalar LocErr and dt filled with the scalar dt give the scalar
+    result (as in the reference, where both paths then see the same numbers)."""
+    from extrack_b200._lmfit_compat import Parameters
+
+    rng = np.random.default_rng(11)
+    st = [random_walk_tracks(n, L, 2, rng) for L, n in ((6, 300), (11, 2100), (19, 500))]
+    p = Parameters()
+    for k, v in dict(D0=1e-5, D1=0.25, LocErr=0.02, F0=0.6, F1=0.4, p01=0.1, p10=0.12, pBL=0.05).items():
+        p.add(k, value=v)
+    base = xt.cum_Proba_Cs(p, st, 0.02, [1], None, 2, 1, 7, 0)
+    il = [np.full(a.shape[:2] + (1,), 0.02) for a in st]
+    dts = [np.full(a.shape[:2], 0.02) for a in st]
+    a = xt.cum_Proba_Cs(p, st, 0.02, [1], il, 2, 1, 7, 0)
+    b = xt.cum_Proba_Cs(p, st, dts, [1], None, 2, 1, 7, 0)
+    c = xt.cum_Proba_Cs(p, st, dts, [1], il, 2, 1, 7, 0)
+    for v in (a, b, c):
+        assert abs(v - base) <= 1e-12 * abs(base)
+
+
+def test_var_inputs_bad_shapes_raise(xt):
+    from extrack_b200._lmfit_compat import Parameters
+
+    rng = np.random.default_rng(12)
+    st = [random_walk_tracks(20, 6, 2, rng)]
+    p = Parameters()
+    for k, v in dict(D0=1e-5, D1=0.25, LocErr=0.02, F0=0.6, F1=0.4, p01=0.1, p10=0.12, pBL=0.05).items():
+        p.add(k, value=v)
+    with pytest.raises(ValueError):  # [n, L] instead of [n, L, k] (the reference fails on broadcasting)
+        xt.cum_Proba_Cs(p, st, 0.02, [1], [np.full((20, 6), 0.02)], 2, 1, 6, 0)
+    with pytest.raises(ValueError):
+        xt.cum_Proba_Cs(p, st, [np.full((20, 5), 0.02)], [1], None, 2, 1, 6, 0)

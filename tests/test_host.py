@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_params_struct_layout_matches_header():
-    assert ctypes.sizeof(_native.XtParams) == 8 * 4 + 8 + 8 * 3 + 5 * 8 * _native.XT_MAX_HEADS
+    assert ctypes.sizeof(_native.XtParams) == 8 * 4 + 8 + 8 * 3 + 5 * 8 * _native.XT_MAX_HEADS + 8 * _native.XT_MAX_STATES + 2 * 8
     assert ctypes.sizeof(_native.XtStats) == 4 * 8 + 4 * 4 + 2 * 4 + 2 * 4
 
 
@@ -89,11 +89,38 @@ def test_per_dim_locerr_param_names():
     assert p3["LocErr1"].value == p3["LocErr0"].value
 
 
-def test_unsupported_inputs_raise():
-    with pytest.raises(NotImplementedError):
-        xt.extract_params(two_state_params(), 0.02, 2, 1, input_LocErr=[np.zeros((2, 3, 2))])
-    with pytest.raises(NotImplementedError):
-        xt.extract_params(two_state_params(), [np.zeros((2, 3))], 2, 1)
+def test_extract_params_peakwise_locerr_and_dt_lists():
+    """input_LocErr / dt lists (tracking.py:926-932,:979-982): pass-through, slope/offset clip, ds per track."""
+    rng = np.random.default_rng(0)
+    il = [0.02 + 0.01 * rng.random((4, 5, 1)), 0.02 + 0.01 * rng.random((3, 7, 1))]
+    dts = [0.02 * (1 + rng.random((4, 5))), 0.02 * (1 + rng.random((3, 7)))]
+    LocErr, ds, Fs, TrMat, pBL = xt.extract_params(two_state_params(), dts, 2, 1, input_LocErr=il)
+    assert LocErr is il
+    assert [a.shape for a in ds] == [(4, 5, 2), (3, 7, 2)]
+    np.testing.assert_array_equal(ds[1], np.sqrt(2 * np.array([1e-5, 0.25])[None, None] * dts[1][:, :, None]))
+    p4 = xt.generate_params(nb_states=2, LocErr_type=4, slope_offsets_estimates=[1.5, -0.04])
+    LocErr, *_ = xt.extract_params(p4, 0.02, 2, 1, input_LocErr=il)
+    np.testing.assert_array_equal(LocErr[0], np.clip(il[0] * 1.5 - 0.04, 0.000001, np.inf))
+    assert LocErr[0].min() == 0.000001  # some peaks are clipped
+
+
+def test_stay_tables_match_oracle_per_chunk_tables():
+    """Per-chunk field-of-view tables from the middle order statistics of dt[:, 0] == the oracle's
+    HeadTables built from np.median(ds3[:, 0], axis=0) (tracking.py:501-506), odd and even counts."""
+    rng = np.random.default_rng(1)
+    Ds = np.array([1e-5, 0.04, 0.25])
+    m = make_model(nS=3, nsub=2)
+    rows, want_stay, want_leave = [], [], []
+    for n in (1, 2, 7, 10):
+        t = 0.02 * (1 + rng.random((n, 6)))
+        ds3 = np.sqrt(2 * Ds[None, None] * t[:, :, None])
+        tb = orc.HeadTables(m, np.median(ds3[:, 0], axis=0))
+        rows.append(xt._mid2(t[:, 0]))
+        want_stay.append(tb.Lp_stay)
+        want_leave.append(tb.L_leave)
+    Lp, Ll = xt.stay_tables(Ds, np.array(rows), m.TrMat, m.pBL, m.cell_dims, 2)
+    np.testing.assert_array_equal(Lp, np.array(want_stay))
+    np.testing.assert_array_equal(Ll, np.array(want_leave))
 
 
 @pytest.mark.parametrize("kw", [dict(nS=2, nsub=1), dict(nS=3, nsub=2), dict(nS=3, nsub=1, loc_err=(0.02, 0.02, 0.03)), dict(nS=4, nsub=1)])

@@ -8,12 +8,13 @@ import os
 import numpy as np
 import pytest
 
-from helpers import make_model, random_walk_tracks
+from helpers import load_var_case, make_model, random_walk_tracks, var_oracle_inputs
 from oracle import extrack_oracle as orc
 from oracle import ref_loader
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if "objective" not in f)
+CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if "objective" not in f and "var_" not in f)
+VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
 
 
 def load_case(path):
@@ -25,6 +26,7 @@ def load_case(path):
 
 def test_golden_files_present():
     assert len(CASES) >= 10
+    assert len(VAR_CASES) >= 6
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
@@ -59,6 +61,21 @@ def test_oracle_objective_multibucket_golden():
                           st[0].shape[1], 0.2, 120)
         got = orc.neg_log_likelihood(st, model)
         assert abs(got - want) / abs(want) < 1e-13
+
+
+@pytest.mark.parametrize("path", VAR_CASES, ids=[os.path.basename(p)[:-4] for p in VAR_CASES])
+def test_oracle_matches_golden_var_inputs(path):
+    """Peak-wise input_LocErr / per-track dt: objective and predictions of the reference's
+    cum_Proba_Cs / predict_Bs (golden) vs the oracle."""
+    st, il, dts, params, preds, cfg = load_var_case(path)
+    model, sigs, ds_list = var_oracle_inputs(st, il, dts, params, cfg)
+    got = orc.neg_log_likelihood(st, model, chunk=cfg["chunk"], sigs=sigs, ds_list=ds_list)
+    assert abs(got - cfg["neglogl"]) <= 1e-13 * abs(cfg["neglogl"])
+    if preds is not None:
+        m2, sigs, ds_list = var_oracle_inputs(st, il, dts, params, cfg, threshold=0.1, max_nb_states=200, nsub=1)
+        gp = orc.predict_states(st, m2, 1, sigs, ds_list)
+        for a, b in zip(gp, preds):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
 
 
 def test_oracle_chunk_order_and_workers():
