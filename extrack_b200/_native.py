@@ -23,7 +23,8 @@ XT_FLAG_LOC_AFFINE = 8
 XT_ERR_CUDA, XT_ERR_ARG, XT_ERR_GROUPING, XT_ERR_CAPACITY, XT_ERR_STATE = -1, -2, -3, -4, -5
 
 LIB_NAME = "libxtrack_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# XT_LIB_PATH: another build of the same engine (A/B timing of kernel variants); never a fallback
+LIB_PATH = os.environ.get("XT_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 class XtParams(C.Structure):

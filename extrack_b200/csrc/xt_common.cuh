@@ -51,8 +51,9 @@ struct XtRecHdr {
 //               are entries woff[w] .. woff[w+1]-1 (groups sorted by member count, descending,
 //               dealt round-robin to the warps)
 //   then      : nC member entries (4 bytes each, xt_pack_ent) in CSR order, for groups of > 2 members
-// Group record: lo = p0:12 | head0:8 | g:12; hi = kind:2 (1 single, 2 pair, 3 list) << 30 and
-//   pair: p1:12 | head1:8 << 12;   list: first member offset:12 | member count:13 << 12.
+// Group record (fields pre-positioned so that the replay kernel gets byte offsets with one mask
+// each): lo = head0:7 | p0:12 << 7 | g:12 << 19; hi = kind:2 (1 single, 2 pair, 3 list) << 30 and
+//   pair: head1:7 | p1:12 << 7;   list: first member offset:12 | member count:13 << 12.
 #define XT_MAX_WPC 8
 struct XtBlobHdr {
   uint16_t nG, nC;

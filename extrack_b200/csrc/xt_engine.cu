@@ -46,10 +46,11 @@ struct xt_ctx {
   std::vector<int> chunk_w0[2];             // first tile of every corder position in d_workf (+ one past the end)
   // pipelined evaluation: plan + replay launched per group of chunks on several streams, sized
   // speculatively with the parent-slot count of the previous evaluation, verified afterwards
-  static constexpr int NCS = 4;
-  cudaStream_t cs[NCS] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int NCS = 32;  // streams created; n_streams of them are used
+  cudaStream_t cs[NCS] = {};
+  int n_streams = 4;
   cudaStream_t up_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join[NCS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[NCS] = {};
   std::vector<cudaEvent_t> ev_seg;
   int* d_spec = nullptr;
   int* h_spec = nullptr;  // pinned
@@ -80,6 +81,8 @@ struct xt_ctx {
   int k2_wpc = 4;             // warps cooperating on one 32-track tile in the fast replay kernel
   int k2_tpt = 1;             // tracks per thread of the fused replay kernel (tile = 32 * k2_tpt tracks)
   int k2_variant = 0;         // 0: fused merge+update kernel (default), 1: first-generation linear-domain kernel
+  bool last_fused = false;    // the previous evaluation ran the fused replay kernel
+  bool plan_has_grec = false; // the resident plan carries the first-generation kernel's inline group records
   xt_params last_p{};
   xt_stats stats{};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -697,7 +700,7 @@ static cudaError_t launch_k2(xt_ctx* ctx, const K2Args& a, const xt_params& p, c
 #ifdef XT_K1_PROF
 static long long* g_k1_prof = nullptr;
 extern "C" int xt_debug_k1_prof(long long* out, int n_chunks) {
-  return cudaMemcpy(out, g_k1_prof, sizeof(long long) * 8 * n_chunks, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+  return cudaMemcpy(out, g_k1_prof, sizeof(long long) * 12 * n_chunks, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
 #endif
 static K1Args make_k1_args(xt_ctx* ctx, int bits) {
@@ -712,9 +715,13 @@ static K1Args make_k1_args(xt_ctx* ctx, int bits) {
   a.RH = ctx->RH;
   a.bits = bits;
   a.wpc = ctx->k2_wpc;
+  // inline group records are only read by the first-generation linear-domain kernel (k2_variant 1, or
+  // the shared-memory fallback when the fused kernel's staging limits are exceeded)
+  a.want_grec = ctx->k2_variant == 1 || !ctx->last_fused;
+  ctx->plan_has_grec = a.want_grec != 0;
   a.corder = ctx->d_corder;
 #ifdef XT_K1_PROF
-  if (!g_k1_prof) cudaMalloc(&g_k1_prof, sizeof(long long) * 8 * 65536);
+  if (!g_k1_prof) cudaMalloc(&g_k1_prof, sizeof(long long) * 12 * 65536);
   a.prof = g_k1_prof;
 #endif
   return a;
@@ -948,7 +955,8 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
   XT_CUDA_OK(cudaMemsetAsync(ctx->d_spec, 0, sizeof(int), ctx->stream));
   XT_CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
   XT_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-  for (int i = 0; i < xt_ctx::NCS; ++i) XT_CUDA_OK(cudaStreamWaitEvent(ctx->cs[i], ctx->ev_fork, 0));
+  const int NS = ctx->n_streams;
+  for (int i = 0; i < NS; ++i) XT_CUDA_OK(cudaStreamWaitEvent(ctx->cs[i], ctx->ev_fork, 0));
   // host buffers: segments are copied longest tracks first
   std::vector<int> order(n_seg);
   for (int s = 0; s < n_seg; ++s) order[s] = s;
@@ -966,7 +974,7 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
     }
     for (int i = 0; i < n_seg; ++i) {
       const int s = order[i];
-      cudaStream_t st = ctx->cs[i % xt_ctx::NCS];
+      cudaStream_t st = ctx->cs[i % NS];
       XT_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_seg[s], 0));
       rc = enqueue_pack(ctx, s, st);
       if (rc) return rc;
@@ -982,22 +990,30 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
     const int G = std::max(1, std::min(ctx->n_groups, nch));
     int q0 = 0, g = 0;
     int64_t done = 0;
+    std::vector<int> gq;  // group boundaries in corder
+    gq.push_back(0);
     for (int q = 0; q < nch; ++q) {
       const XtChunk& ck = ctx->chunks[ctx->corder[q]];
       done += (int64_t)ck.nT * (ck.L - 1);
       const bool last = q + 1 == nch;
       if (last || (g + 1 < G && done * G >= ctx->track_steps * (int64_t)(g + 1))) {
-        cudaStream_t st = ctx->cs[g % xt_ctx::NCS];
-        rc = enqueue_k1(ctx, p, bits, q0, q + 1 - q0, st, true);
-        if (rc) return rc;
-        rc = enqueue_fused(ctx, p, fl, q0, q + 1, st);
-        if (rc) return rc;
+        gq.push_back(q + 1);
         q0 = q + 1;
         ++g;
       }
     }
+    (void)q0;
+    // all plan kernels first (they are latency-bound and run concurrently), then each group's
+    // replay behind its own plan
+    for (int pass = 0; pass < 2; ++pass)
+      for (int k = 0; k + 1 < (int)gq.size(); ++k) {
+        cudaStream_t st = ctx->cs[k % NS];
+        rc = pass == 0 ? enqueue_k1(ctx, p, bits, gq[k], gq[k + 1] - gq[k], st, true)
+                       : enqueue_fused(ctx, p, fl, gq[k], gq[k + 1], st);
+        if (rc) return rc;
+      }
   }
-  for (int i = 0; i < xt_ctx::NCS; ++i) {
+  for (int i = 0; i < NS; ++i) {
     XT_CUDA_OK(cudaEventRecord(ctx->ev_join[i], ctx->cs[i]));
     XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
   }
@@ -1067,7 +1083,13 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
     XT_CUDA_OK(cudaMemsetAsync(ctx->d_spec, 0, sizeof(int), ctx->stream));
     rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->stream);
     if (rc) return rc;
+    ctx->last_fused = true;
     return finish_eval(ctx, p, ctx->n_workf[fl.tpt - 1], d_out, su, sg, maxC);
+  }
+  if (ctx->last_fused || !ctx->plan_has_grec) {  // the plan was written without the records this path reads
+    ctx->last_fused = false;
+    rc = run_plan(ctx, p, bits);
+    if (rc) return rc;
   }
   // first-generation linear-domain kernel (k2_variant 1) or log-domain global-memory fallback
   const int K = ipow(p->nS, p->nsub);
@@ -1181,6 +1203,14 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
       return XT_ERR_ARG;
     }
     ctx->n_groups = value;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "n_streams") == 0) {
+    if (value < 1 || value > xt_ctx::NCS) {
+      set_error(ctx, "xt_set_option: n_streams must be in 1..32");
+      return XT_ERR_ARG;
+    }
+    ctx->n_streams = value;
     return XT_OK;
   }
   if (std::strcmp(name, "k2_tpt") == 0) {

@@ -40,12 +40,13 @@ struct K1Args {
   // A chunk that needs more parents / children than this reports err = 3 and the host retries with
   // the global-memory scratch.
   int32_t scapP, scapC;
+  int32_t want_grec;   // also emit the inline group records of the first-generation replay kernel
   XtAux ax;            // VAR instantiation only
 };
 
 // dynamic shared memory of k1_plan (bytes)
 __host__ __device__ inline size_t xt_k1_smem(int cap, int CO, int RH, int nS, int scapP, int scapC, int varH = 0) {
-  size_t b = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
+  size_t b = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64;
   b = (b + 15) & ~(size_t)15;
   if (scapC > 0) b += (size_t)(scapP + scapC) * CO * 32 * 8 + (size_t)2 * scapP * RH * nS * 8;
   b += (size_t)varH * 32 * 8;  // VAR: per-lane dd of every head
@@ -80,7 +81,8 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   unsigned long long* codeC = codeP + cap;
   int* gid = (int*)(codeC + cap);
   int* grank = gid + cap;
-  int* gcnt = grank + cap;            // [cap+1]: group sizes -> offsets
+  uint32_t* ent = (uint32_t*)(grank + cap);  // CSR member entries of the step (mirrored to the plan in global memory)
+  int* gcnt = (int*)(ent + cap);      // [cap+1]: group sizes -> offsets
   unsigned char* curP = (unsigned char*)(gcnt + cap + 1);
   __shared__ int s_flag, s_nG;
   __shared__ unsigned long long s_rows[64];  // capture matrix of the matrix-mode grouping
@@ -132,7 +134,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   double* histN = histP + (size_t)cap * a.RH * nS;
   const int scapP = a.scapP, scapC = a.scapC;
   if (scapC > 0) {
-    size_t o = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
+    size_t o = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64;
     o = (o + 15) & ~(size_t)15;
     bufP = (double*)(k1_smem + o);
     bufC = bufP + (size_t)scapP * CO * 32;
@@ -159,7 +161,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   const double* Lps = (VAR && a.ax.stay) ? a.ax.stay + (size_t)cid * K : P.Lp_stay;
   double* s_dd = nullptr;
   if (VAR) {
-    size_t o = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 1) + 64;
+    size_t o = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64;
     o = (o + 15) & ~(size_t)15;
     if (scapC > 0) o += (size_t)(scapP + scapC) * CO * 32 * 8 + (size_t)2 * scapP * a.RH * nS * 8;
     s_dd = (double*)(k1_smem + o);
@@ -211,7 +213,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   __syncthreads();
 
 #ifdef XT_K1_PROF
-  long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
 #endif
   for (int step = 2; step <= L - 2; ++step) {
@@ -235,7 +237,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     const bool use_window = LhC > P.frame_len;
     const unsigned long long cmask = (bits * rows_cmp >= 64) ? ~0ull : ((1ull << (bits * rows_cmp)) - 1ull);
     uint16_t* goff = a.plan.goff + (size_t)rec * (a.plan.cap + 1);
-    uint32_t* ent = a.plan.ent + (size_t)rec * a.plan.cap;
+    uint32_t* gent = a.plan.ent + (size_t)rec * a.plan.cap;
     uint16_t* pgid = a.plan.gid + (size_t)rec * a.plan.cap;
 
     // ---- expansion + Gaussian update on the leader tracks (tracking.py:540-570, :87-98);
@@ -467,6 +469,11 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
           jp[h] = (j < nC) ? j / K : 0;
           jr[h] = j - jp[h] * K;
         }
+        // the sequential part only tracks the masks; every lane remembers the group that captured its
+        // two sequences (lane, lane + 32) and emits gid / CSR entries once, after the loop
+        int myg[2] = {-1, -1}, myoff[2] = {0, 0};
+        unsigned long long mymem[2] = {0ull, 0ull};
+        const unsigned long long bit0 = 1ull << lane, bit1 = 1ull << (lane + 32);
         while (rem) {
           const int i = __ffsll((long long)rem) - 1;
           const unsigned long long mem = s_rows[i] & ~grouped;
@@ -475,19 +482,21 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
             rem &= rem - 1ull;
             continue;
           }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int j = lane + 32 * h;
-            if (j < nC && ((mem >> j) & 1ull)) {
-              gid[j] = ng;
-              ent[off + __popcll(mem & ((1ull << j) - 1ull))] = xt_pack_ent(jp[h], jr[h] + K * (int)curP[jp[h]], jr[h]);
-            }
-          }
+          if (mem & bit0) { myg[0] = ng; myoff[0] = off; mymem[0] = mem; }
+          if (mem & bit1) { myg[1] = ng; myoff[1] = off; mymem[1] = mem; }
           if (lane == 0) gcnt[ng] = off;
           off += __popcll(mem);
           grouped |= mem;
           rem &= ~mem;
           ++ng;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = lane + 32 * h;
+          if (j < nC && myg[h] >= 0) {
+            gid[j] = myg[h];
+            ent[myoff[h] + __popcll(mymem[h] & ((1ull << j) - 1ull))] = xt_pack_ent(jp[h], jr[h] + K * (int)curP[jp[h]], jr[h]);
+          }
         }
         if (lane == 0) {
           gcnt[ng] = off;
@@ -498,7 +507,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       K1_T(2);
       __syncthreads();
       nG = s_nG;
-      for (int c = tid; c < nC; c += XT_K1_THREADS) pgid[c] = (uint16_t)gid[c];
+      for (int c = tid; c < nC; c += XT_K1_THREADS) {
+        pgid[c] = (uint16_t)gid[c];
+        gent[c] = ent[c];
+      }
       for (int g = tid; g <= nG; g += XT_K1_THREADS) goff[g] = (uint16_t)gcnt[g];
       if (s_flag) {
         if (tid == 0) sm->err = 1;
@@ -546,50 +558,180 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       for (int g = tid; g <= nG; g += XT_K1_THREADS) goff[g] = (uint16_t)gcnt[g];
       for (int c = tid; c < nC; c += XT_K1_THREADS) {
         const int p = c / K, r = c - p * K;
-        ent[gcnt[gid[c]] + grank[c]] = xt_pack_ent(p, r + K * (int)curP[p], r);
+        const uint32_t e = xt_pack_ent(p, r + K * (int)curP[p], r);
+        const int pos = gcnt[gid[c]] + grank[c];
+        ent[pos] = e;
+        gent[pos] = e;
         pgid[c] = (uint16_t)gid[c];
       }
-      __syncthreads();  // ent visible to the CTA (read back below through global memory)
+      __syncthreads();  // ent visible to the CTA
     }
     if (scapC > 0 && nG > scapP) {  // more groups than parent slots in shared memory
       if (tid == 0) sm->err = 3;
       return;
     }
+    // The parents' window codes are dead since the update phase: codeP[g] becomes the window code
+    // of group g, i.e. of the next step's parent g (history rows OR their argmax bits into it).
+    for (int g = tid; g < nG; g += XT_K1_THREADS) codeP[g] = 0ull;
+    __syncthreads();
+    K1_T(3);
+    // From here to the next barrier the phases are independent of each other (they read ent / gcnt /
+    // bufC / histP and write disjoint outputs), so no barrier separates them and the warps overlap:
+    // history rows start at thread 0, the replay records at the last thread, the merge on all warps.
+    const int rtid = XT_K1_THREADS - 1 - tid;
     if (tid == 0) {
       a.plan.hdr[rec].nC = nC;
       a.plan.hdr[rec].nG = nG;
       a.plan.hdr[rec].th = th;
     }
-    {  // inline group records for the replay kernel: first two members + size in one 64-bit word
+    // ---- history rows of the groups (fit mode: mean one-hot over members and leader tracks,
+    //      tracking.py:714-715,735-737), accumulated in numpy's (member, track) order ----
+    const int rows_out = rows_cmp;  // truncated to frame_len
+    const int Kh = hist_dim0_is_nT ? Kt : 1;
+    // one thread per (group, row): the nS values of the row, then their argmax (ties -> lowest
+    // state) goes straight into the group's window code.  The sums run in numpy's order for the
+    // fancy-indexed copy (member outer, track inner; adding to 0.0 first is exact), two states at
+    // a time so that the two sequential chains interleave.
+#ifdef XT_K1_PROF
+    __shared__ unsigned long long s_hmax, s_hslow, s_hmem;
+    if (tid == 0) { s_hmax = 0; s_hslow = 0; s_hmem = 0; }
+    __syncthreads();
+    const long long h_t0 = clock64();
+    unsigned h_slow = 0, h_mem = 0, h_slowcyc = 0;
+#endif
+    int ro_sh = 0;  // rows padded to a power of two: (group, row) of a thread by shifts
+    while ((1 << ro_sh) < rows_out) ++ro_sh;
+    for (int idx = tid; (idx >> ro_sh) < nG; idx += XT_K1_THREADS) {
+      const int row = idx & ((1 << ro_sh) - 1), g = idx >> ro_sh;
+      if (row >= rows_out) continue;
+      const int o = gcnt[g], n = gcnt[g + 1] - o;
+      const bool lab_row = row < nsub;
+      const double* hrow = histP + (row - nsub) * nS;  // + p * pstride + state
+      const int pstride = a.RH * nS;
+      int best = 0;
+      double bv = 0.0;
+      for (int s0 = 0; s0 < nS; s0 += 2) {
+        const bool two = s0 + 1 < nS;
+        double accA = 0.0, accB = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const uint32_t e = ent[o + k];
+          const int p = (int)(e & 0xFFFF);
+          double vA, vB = 0.0;
+          if (lab_row) {  // one of the nsub newest rows: the label sits in the child's window code
+            const int lab = (int)((codeC[p * K + (int)(e >> 24)] >> (bits * row)) & rowmask);
+            vA = lab == s0 ? 1.0 : 0.0;
+            vB = lab == s0 + 1 ? 1.0 : 0.0;
+          } else {
+            const double* hp = hrow + p * pstride + s0;
+            vA = hp[0];
+            if (two) vB = hp[1];
+          }
+          if (n == 1) {  // single member: the value itself (no mean)
+            accA = vA;
+            accB = vB;
+            break;
+          }
+          // x is a multiple of 2^-20 below 2^31  <=>  x + 2^32 is exact.  If the summand and the partial
+          // sum both are, every intermediate sum of the Kh sequential additions is exactly
+          // representable, so one fused multiply-add gives the same result.
+          auto dyadic = [](double x) { return x < 2147483648.0 && __dsub_rn(__dadd_rn(x, 4294967296.0), 4294967296.0) == x; };
+          const bool fastA = vA == 0.0 || (dyadic(vA) && dyadic(accA));
+          const bool fastB = vB == 0.0 || (dyadic(vB) && dyadic(accB));
+#ifdef XT_K1_PROF
+          ++h_mem;
+          if (!(fastA && fastB)) ++h_slow;
+#endif
+          if (fastA && fastB) {  // zeros change nothing; dyadic values on dyadic partial sums are exact
+            accA = fma(vA, (double)Kh, accA);
+            accB = fma(vB, (double)Kh, accB);
+          } else {
+#ifdef XT_K1_PROF
+            const long long ts0 = clock64();
+#endif
+#pragma unroll 6
+            for (int tt = 0; tt < Kh; ++tt) {
+              accA = __dadd_rn(accA, vA);
+              accB = __dadd_rn(accB, vB);
+            }
+#ifdef XT_K1_PROF
+            h_slowcyc += (unsigned)(clock64() - ts0);
+#endif
+          }
+        }
+        double outA = accA, outB = accB;
+        if (n > 1) {
+          const double den = (double)(Kh * n);
+          outA = __ddiv_rn(accA, den);
+          outB = __ddiv_rn(accB, den);
+        }
+        double* hn = histN + ((size_t)g * a.RH + row) * nS + s0;
+        hn[0] = outA;
+        if (s0 == 0 || outA > bv) {
+          bv = outA;
+          best = s0;
+        }
+        if (two) {
+          hn[1] = outB;
+          if (outB > bv) {
+            bv = outB;
+            best = s0 + 1;
+          }
+        }
+      }
+      if (best) atomicOr(&codeP[g], (unsigned long long)best << (bits * row));
+    }
+#ifdef XT_K1_PROF
+    {
+      const unsigned long long dtc = (unsigned long long)(clock64() - h_t0);
+      const int myg = tid >> ro_sh;
+      const int myn = myg < nG ? gcnt[myg + 1] - gcnt[myg] : 0;
+      atomicMax(&s_hmax, (dtc << 32) | ((unsigned long long)(myn & 0xFF) << 24) | ((unsigned long long)(h_slow & 0xFF) << 16) | (unsigned long long)((h_slowcyc >> 4) & 0xFFFF));
+    }
+    atomicAdd(&s_hslow, (unsigned long long)h_slow);
+    atomicAdd(&s_hmem, (unsigned long long)h_mem);
+    __syncthreads();
+    if (tid == 0) {
+      prof[8] += s_hmax >> 32; prof[9] += s_hslow; prof[10] += s_hmem; prof[11] += nG * rows_out;
+      if (step == 12 && blockIdx.x < 4) printf("chunk %d step %d: slowest history thread %llu cycles n=%llu slow=%llu cycles in slow loops=%llu (nG=%d rows=%d Kh=%d)\n", cid, step, s_hmax >> 32, (s_hmax >> 24) & 0xFF, (s_hmax >> 16) & 0xFF, (s_hmax & 0xFFFF) << 4, nG, rows_out, Kh);
+    }
+#endif
+    K1_T(4);
+    if (a.want_grec) {  // inline group records of the first-generation replay kernel (k2_variant 1)
       unsigned long long* grec = a.plan.grec + (size_t)rec * a.plan.cap;
-      for (int g = tid; g < nG; g += XT_K1_THREADS) {
+      for (int g = rtid; g < nG; g += XT_K1_THREADS) {
         const int o = gcnt[g], n = gcnt[g + 1] - o;
         const unsigned long long e0 = ent[o], e1 = (n > 1) ? ent[o + 1] : 0u;
         grec[g] = (e0 & 0xFFFFFFull) | ((unsigned long long)(n > 255 ? 255 : n) << 24) | ((e1 & 0xFFFFFFull) << 32);
       }
     }
 
-    K1_T(3);
     {  // replay record of this step (XtBlobHdr, xt_common.cuh).  Schedule: groups sorted by
        // (members descending, group ascending) are dealt round-robin to the replay warps.
       uint4* blob = a.plan.blob + (size_t)rec * xt_blob_stride16(a.plan.cap);
       const int wpc = a.wpc;
-      if (tid <= XT_MAX_WPC) {
+      if (rtid <= XT_MAX_WPC) {
         XtBlobHdr* h = (XtBlobHdr*)blob;
         // groups of warp w: ranks w, w + wpc, ...  => woff[w] = sum_{v<w} ceil((nG - v) / wpc)
         int o = 0;
-        for (int v = 0; v < tid && v < wpc; ++v) o += (nG - v + wpc - 1) / wpc;
-        h->woff[tid] = (uint16_t)o;
-        if (tid == 0) {
+        for (int v = 0; v < rtid && v < wpc; ++v) o += (nG - v + wpc - 1) / wpc;
+        h->woff[rtid] = (uint16_t)o;
+        if (rtid == 0) {
           h->nG = (uint16_t)nG;
           h->nC = (uint16_t)nC;
           h->n16 = (uint16_t)(2 + (nG + 1) / 2 + (nC + 3) / 4);
         }
       }
       unsigned long long* brec = (unsigned long long*)(blob + 2);
-      for (int g = tid; g < nG; g += XT_K1_THREADS) {
-        codeC[g] = 0ull;  // the children's codes are dead: becomes the group's window code (history phase)
+      uint8_t* pcur = a.plan.curG + (size_t)rec * a.plan.cap;
+      for (int g = rtid; g < nG; g += XT_K1_THREADS) {
         const int o = gcnt[g], n = gcnt[g + 1] - o;
+        {  // new parent g: newest true state = its first member's (tracking.py:728); curP is not read
+           // again before the barrier that ends the step
+          const uint32_t e = ent[o];
+          const unsigned char cs = (unsigned char)(((int)(e & 0xFFFF) * K + (int)(e >> 24)) % nS);
+          pcur[g] = cs;
+          curP[g] = cs;
+        }
         int rank = 0;
         for (int j = 0; j < nG; ++j) {
           const int nj = gcnt[j + 1] - gcnt[j];
@@ -599,27 +741,30 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         int slot = pos;
         for (int v = 0; v < wq; ++v) slot += (nG - v + wpc - 1) / wpc;
         const uint32_t e0 = ent[o];
-        const unsigned lo = (e0 & 0xFFFu) | (((e0 >> 16) & 0xFFu) << 12) | ((unsigned)g << 20);
+        const unsigned lo = ((e0 >> 16) & 0x7Fu) | ((e0 & 0xFFFu) << 7) | ((unsigned)g << 19);
         unsigned hi;
         if (n == 1) {
           hi = 1u << 30;
         } else if (n == 2) {
           const uint32_t e1 = ent[o + 1];
-          hi = (2u << 30) | (e1 & 0xFFFu) | (((e1 >> 16) & 0xFFu) << 12);
+          hi = (2u << 30) | ((e1 >> 16) & 0x7Fu) | ((e1 & 0xFFFu) << 7);
         } else {
           hi = (3u << 30) | (unsigned)o | ((unsigned)n << 12);
         }
         brec[slot] = (unsigned long long)lo | ((unsigned long long)hi << 32);
       }
       uint32_t* bent = (uint32_t*)(blob + 2 + (nG + 1) / 2);
-      for (int c = tid; c < nC; c += XT_K1_THREADS) bent[c] = ent[c];
+      for (int c = rtid; c < nC; c += XT_K1_THREADS) bent[c] = ent[c];
     }
 
-    K1_T(4);
+    K1_T(5);
     // ---- merge on the leader tracks (tracking.py:723-741) ----
     // `LP[:, subgroup]` is an F-ordered fancy-index copy in numpy, so every reduction over the
     // members runs sequentially in ascending member order (checked against numpy 2.3).
-    for (int g = warp; g < nG; g += W) {
+    // (warps whose threads hold history rows merge fewer groups: with <= 128 rows the merge runs
+    // on the upper half of the CTA)
+    const int mw0 = ((nG << ro_sh) <= XT_K1_THREADS / 2) ? W / 2 : 0, mW = W - mw0;
+    for (int g = warp - mw0; g >= 0 && g < nG; g += mW) {
       const int o = gcnt[g], n = gcnt[g + 1] - o;
       if (n == 1) {
         const int c = (int)(ent[o] & 0xFFFF) * K + (int)(ent[o] >> 24);
@@ -666,97 +811,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       for (int k2 = 0; k2 < KS; ++k2) ST(bufP, g, D + k2) = __ddiv_rn(as2[k2], sw);
       ST(bufP, g, D + 2 * KS) = __dadd_rn(log(sw), mx);
     }
-#ifdef XT_K1_PROF
-    __syncthreads();
-#endif
-    K1_T(5);
-    // ---- history rows of the groups (fit mode: mean one-hot over members and leader tracks,
-    //      tracking.py:714-715,735-737), accumulated in numpy's (member, track) order ----
-    const int rows_out = rows_cmp;  // truncated to frame_len
-    const int Kh = hist_dim0_is_nT ? Kt : 1;
-    __syncthreads();  // codeC[g] zeroed (record phase) before the argmax bits are OR-ed in
-    // one thread per (group, row): the nS values of the row, then their argmax (ties -> lowest
-    // state) goes straight into the group's window code.  The sums run in numpy's order for the
-    // fancy-indexed copy (member outer, track inner; adding to 0.0 first is exact), two states at
-    // a time so that the two sequential chains interleave.
-    for (int idx = tid; idx < nG * rows_out; idx += XT_K1_THREADS) {
-      const int row = idx % rows_out, g = idx / rows_out;
-      const int o = gcnt[g], n = gcnt[g + 1] - o;
-      int best = 0;
-      double bv = 0.0;
-      for (int s0 = 0; s0 < nS; s0 += 2) {
-        const bool two = s0 + 1 < nS;
-        double accA = 0.0, accB = 0.0;
-        for (int k = 0; k < n; ++k) {
-          const uint32_t e = ent[o + k];
-          const int p = (int)(e & 0xFFFF);
-          double vA, vB = 0.0;
-          if (row < nsub) {
-            int x = p * K + (int)(e >> 24);
-            for (int r = 0; r < row; ++r) x /= nS;
-            const int lab = xt_label(x, nS, wrap);
-            vA = lab == s0 ? 1.0 : 0.0;
-            vB = lab == s0 + 1 ? 1.0 : 0.0;
-          } else {
-            const double* hp = histP + ((size_t)p * a.RH + (row - nsub)) * nS + s0;
-            vA = hp[0];
-            if (two) vB = hp[1];
-          }
-          if (n == 1) {  // single member: the value itself (no mean)
-            accA = vA;
-            accB = vB;
-            break;
-          }
-          const bool fastA = vA == 0.0 || (vA == 1.0 && accA < 1e9 && accA == (double)(int)accA);
-          const bool fastB = vB == 0.0 || (vB == 1.0 && accB < 1e9 && accB == (double)(int)accB);
-          if (fastA && fastB) {  // zeros change nothing; ones on an integer partial sum are exact
-            accA += vA * (double)Kh;
-            accB += vB * (double)Kh;
-          } else {
-#pragma unroll 6
-            for (int tt = 0; tt < Kh; ++tt) {
-              accA = __dadd_rn(accA, vA);
-              accB = __dadd_rn(accB, vB);
-            }
-          }
-        }
-        double outA = accA, outB = accB;
-        if (n > 1) {
-          const double den = (double)(Kh * n);
-          outA = __ddiv_rn(accA, den);
-          outB = __ddiv_rn(accB, den);
-        }
-        double* hn = histN + ((size_t)g * a.RH + row) * nS + s0;
-        hn[0] = outA;
-        if (s0 == 0 || outA > bv) {
-          bv = outA;
-          best = s0;
-        }
-        if (two) {
-          hn[1] = outB;
-          if (outB > bv) {
-            bv = outB;
-            best = s0 + 1;
-          }
-        }
-      }
-      if (best) atomicOr(&codeC[g], (unsigned long long)best << (bits * row));
-    }
-    __syncthreads();
     K1_T(6);
-    // new parents: newest true state and window code.  All reads of curP / codeP of this step are
-    // done (the last ones are in the grouping phase), so they are published directly.
-    {
-      uint8_t* pcur = a.plan.curG + (size_t)rec * a.plan.cap;
-      for (int g = tid; g < nG; g += XT_K1_THREADS) {
-        const uint32_t e = ent[gcnt[g]];
-        const int c0 = (int)(e & 0xFFFF) * K + (int)(e >> 24);
-        const unsigned char cs = (unsigned char)(c0 % nS);
-        pcur[g] = cs;
-        curP[g] = cs;
-        codeP[g] = codeC[g];
-      }
-    }
     {  // swap history buffers
       double* tmp = histP;
       histP = histN;
@@ -771,7 +826,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     K1_T(7);
   }
 #ifdef XT_K1_PROF
-  if (tid == 0 && a.prof) for (int i = 0; i < 8; ++i) a.prof[(size_t)cid * 8 + i] = prof[i];
+  if (tid == 0 && a.prof) for (int i = 0; i < 12; ++i) a.prof[(size_t)cid * 12 + i] = prof[i];
 #endif
   if (tid == 0) {
     // last step (no fusion) and the optional end-of-track expansion, for the work counters

@@ -441,15 +441,21 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
     const unsigned grec = rb + 32;
     const unsigned entb = grec + ((nG + 1) >> 1) * 16;
     const unsigned tab = s_tab + (((step - 1) >= T.min_len) ? H * 16 : 0);
-    const int i1 = (int)xt_lds16(rb + 8 + 2 * (w + 1));  // XtBlobHdr::woff
-    for (int i = (int)xt_lds16(rb + 8 + 2 * w); i < i1; ++i) {
-      const uint2 gr = xt_lds64u(grec + i * 8);
-      const unsigned p0 = gr.x & 0xFFFu, h0 = (gr.x >> 12) & 0xFFu, g = gr.x >> 20;
+    // group records of this warp: addresses walk [ga, ge); the loop-invariant bases are pinned in
+    // registers (the compiler otherwise rematerialises them from uniform registers every iteration)
+    unsigned ga = grec + xt_lds16(rb + 8 + 2 * w) * 8;  // XtBlobHdr::woff
+    const unsigned ge = grec + xt_lds16(rb + 8 + 2 * (w + 1)) * 8;
+    unsigned tabp = tab;
+    asm volatile("mov.u32 %0, %0;" : "+r"(tabp));
+    for (; ga < ge; ga += 8) {
+      const uint2 gr = xt_lds64u(ga);
+      const unsigned p0o = gr.x & 0x7FF80u;  // p0 * 128
+      const unsigned g = gr.x >> 19;
       const unsigned kind = gr.y >> 30;
       Seq G[TPT];
-      IO::load(src_v + p0 * SLOTB, src_e + p0 * ESLOT, G);
+      IO::load(src_v + p0o * (SLOTB / 128), src_e + p0o * (ESLOT / 128), G);
       double tau0, dd0;
-      xt_lds128(tab + h0 * 16, tau0, dd0);
+      xt_lds128(tabp + (gr.x & 0x7Fu) * 16, tau0, dd0);
       if (kind == 1u) {
         // single member: the child itself
 #pragma unroll
@@ -459,11 +465,11 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
           for (int k = 0; k < KS; ++k) G[j].u[k] += VAR ? dd0 * DTQ(j) : dd0;
         }
       } else if (kind == 2u) {
-        const unsigned p1 = gr.y & 0xFFFu, h1 = (gr.y >> 12) & 0xFFu;
+        const unsigned p1o = gr.y & 0x7FF80u;
         Seq B[TPT];
-        IO::load(src_v + p1 * SLOTB, src_e + p1 * ESLOT, B);
+        IO::load(src_v + p1o * (SLOTB / 128), src_e + p1o * (ESLOT / 128), B);
         double tau1, dd1;
-        xt_lds128(tab + h1 * 16, tau1, dd1);
+        xt_lds128(tabp + (gr.y & 0x7Fu) * 16, tau1, dd1);
 #pragma unroll
         for (int j = 0; j < TPT; ++j) {
           const int Eg = max(G[j].E, B[j].E);
@@ -515,7 +521,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
           Seq M[TPT];
           IO::load(src_v + pm * SLOTB, src_e + pm * ESLOT, M);
           double taum, ddm;
-          xt_lds128(tab + ((e >> 16) & 0xFFu) * 16, taum, ddm);
+          xt_lds128(tabp + ((e >> 16) & 0xFFu) * 16, taum, ddm);
 #pragma unroll
           for (int j = 0; j < TPT; ++j) {
             const double wj = (M[j].W * xt_pow2_le0(M[j].E - Eg[j])) * taum;

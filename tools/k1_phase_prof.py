@@ -28,15 +28,17 @@ for _ in range(3):
 print(ts.engine.stats())
 lib = _native.load_library()
 nch = len(ts.chunks)
-buf = np.zeros((nch, 8), dtype=np.int64)
+buf = np.zeros((nch, 12), dtype=np.int64)
 assert lib.xt_debug_k1_prof(buf.ctypes.data_as(C.c_void_p), nch) == 0
-names = ["update+codes", "batch rows", "batch resolve", "csr/hdr/grec", "blob", "merge", "history", "new parents"]
+names = ["update+codes", "batch rows", "batch resolve", "copy+zero+barriers", "history (thread 0)", "records (thread 0)", "merge (warp 0)", "end barrier"]
 Ls = np.array([st[b].shape[1] for (b, a, z, _) in ts.chunks])
 for L in (10, 20, 30):
     sel = buf[Ls == L]
     if len(sel) == 0:
         continue
     m = sel.mean(0)
-    print(f"L={L}: {len(sel)} chunks, total {m.sum():.0f} cycles = {m.sum()/1.965e3:.1f} us; per fused step {m.sum()/(L-3):.0f}")
-    for nm, v in zip(names, m):
-        print(f"   {nm:14s} {v:10.0f}  {100*v/m.sum():5.1f}%  per step {v/(L-3):8.0f}")
+    print(f"L={L}: {len(sel)} chunks, total {m[:8].sum():.0f} cycles = {m[:8].sum()/1.965e3:.1f} us; per fused step {m[:8].sum()/(L-3):.0f}")
+    tot = m[:8].sum()
+    for nm, v in zip(names, m[:8]):
+        print(f"   {nm:22s} {v:10.0f}  {100*v/tot:5.1f}%  per step {v/(L-3):8.0f}")
+    print(f"   history: slowest thread {m[8]/(L-3):.0f} cycles/step; member visits {m[10]/(L-3):.0f}/step of which slow path {m[9]/(L-3):.0f}; items {m[11]/(L-3):.0f}/step")
