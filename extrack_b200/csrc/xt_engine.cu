@@ -48,7 +48,7 @@ struct xt_ctx {
   // speculatively with the parent-slot count of the previous evaluation, verified afterwards
   static constexpr int NCS = 32;  // streams created; n_streams of them are used
   cudaStream_t cs[NCS] = {};
-  int n_streams = 4;
+  int n_streams = 8;
   cudaStream_t up_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[NCS] = {};
   std::vector<cudaEvent_t> ev_seg;
@@ -59,7 +59,7 @@ struct xt_ctx {
                                      // shared-memory scratch (0: global-memory scratch)
   int k1_smem_scratch = 1;
   int pipeline = 1;
-  int n_groups = 4;
+  int n_groups = 6;
   double* d_logp = nullptr;
   double* d_partial = nullptr;
   double* d_out = nullptr;
@@ -901,6 +901,10 @@ static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch
   tab.nsub = p->nsub;
   tab.K = K;
   tab.min_len = p->min_len;
+  {
+    const double kc[6] = XT_EXP_CONSTS;
+    for (int i = 0; i < 6; ++i) tab.kc[i] = kc[i];
+  }
   tab.flags = p->flags;
   tab.loc_slope = p->loc_slope;
   tab.loc_offset = p->loc_offset;

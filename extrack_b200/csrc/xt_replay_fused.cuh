@@ -41,7 +41,12 @@ struct K2Tab {  // per-evaluation tables and scalars of the fused replay kernel 
   int32_t nS, nsub, K, min_len;
   uint32_t flags;                 // xt_params::flags
   double loc_slope, loc_offset;   // xt_params
+  // constants of xt_exp_split: read as constant-bank operands of the FP64 instructions (64-bit
+  // immediates would be rebuilt with two moves per use inside the register-bound inner loop)
+  double kc[6];
 };
+#define XT_EXP_CONSTS {23.083120654223414, 6755399441055744.0, -0.04332169878499658, -1.4494042586539372e-18, \
+                       4.1666666666666664e-02, 1.6666666666666666e-01}
 
 // ---- shared memory through 32-bit shared-window addresses (no generic-pointer arithmetic) ----
 __device__ __forceinline__ unsigned xt_smem_base(const void* p) {
@@ -100,12 +105,12 @@ __device__ __forceinline__ double xt_clamp_neg(double x) {
 // exp(x) = p * 2^k for -1e6 <= x <= 0 with p in [0.97, 2): x * 16/ln2 = 16 k + j + rho,
 // exp(x) = 2^k * 2^(j/16) * exp(r), |r| <= ln2/32, Taylor degree 7 (truncation 1.2e-18);
 // 2^(j/16) from a 16-entry shared-memory table (conflict-free: 16 distinct 8-byte words).
-__device__ __forceinline__ double xt_exp_split(double x, unsigned s_e2, int& k) {
-  double t = fma(x, 23.083120654223414, 6755399441055744.0);
+__device__ __forceinline__ double xt_exp_split(double x, unsigned s_e2, int& k, const K2Tab& T) {
+  double t = fma(x, T.kc[0], T.kc[1]);
   const int n = __double2loint(t);
-  t -= 6755399441055744.0;
-  double r = fma(t, -0.04332169878499658, x);
-  r = fma(t, -1.4494042586539372e-18, r);
+  t -= T.kc[1];
+  double r = fma(t, T.kc[2], x);
+  r = fma(t, T.kc[3], r);
   const double tj = xt_lds64(s_e2 + ((n & 15) << 3));
   k = n >> 4;
   // the three highest coefficients are truncated to their high word (immediate operands):
@@ -113,8 +118,8 @@ __device__ __forceinline__ double xt_exp_split(double x, unsigned s_e2, int& k) 
   double p = 0.00019841268658638;
   p = fma(p, r, 0.00138888880610466);
   p = fma(p, r, 0.00833333283662796);
-  p = fma(p, r, 4.1666666666666664e-02);
-  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, T.kc[4]);
+  p = fma(p, r, T.kc[5]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
@@ -189,7 +194,7 @@ struct XtSlotIO {
 // (VAR: l2 is per track, l2[j][k]; otherwise one row shared by the thread's tracks)
 template <int D, int KS, int TPT, bool VAR = false>
 __device__ __forceinline__ void xt_update(XtSeq<D, KS> (&s)[TPT], const double (&cl)[TPT][D],
-                                          const double (&l2)[VAR ? TPT : 1][KS], unsigned s_e2) {
+                                          const double (&l2)[VAR ? TPT : 1][KS], unsigned s_e2, const K2Tab& T) {
   double rq[TPT][KS], e[TPT];
 #pragma unroll
   for (int j = 0; j < TPT; ++j)
@@ -226,7 +231,7 @@ __device__ __forceinline__ void xt_update(XtSeq<D, KS> (&s)[TPT], const double (
   double p[TPT];
   int k2[TPT];
 #pragma unroll
-  for (int j = 0; j < TPT; ++j) p[j] = xt_exp_split(xt_clamp_neg(e[j]), s_e2, k2[j]);
+  for (int j = 0; j < TPT; ++j) p[j] = xt_exp_split(xt_clamp_neg(e[j]), s_e2, k2[j], T);
 #pragma unroll
   for (int j = 0; j < TPT; ++j) {
     const double wn = (s[j].W * xt_normfac<D, KS>(rq[j])) * p[j];
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
       for (int k = 0; k < KS; ++k) s[j].u[k] = l2[VAR ? j : 0][k] + (VAR ? ddc * DTQ(j) : ddc);
       xt_split_exponent(T.winit[c], 0, s[j].W, s[j].E);
     }
-    if (L >= 3) xt_update<D, KS, TPT, VAR>(s, cn, VAR ? l2n : l2, s_e2);
+    if (L >= 3) xt_update<D, KS, TPT, VAR>(s, cn, VAR ? l2n : l2, s_e2, T);
     IO::store(s_vec + c * SLOTB, s_exp + c * ESLOT, s);
   }
   if (VAR && L >= 3) {  // dtc = dt of localisation 1, l2n/dtn = row 2
@@ -545,7 +550,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
           G[j].E = Eg[j];
         }
       }
-      xt_update<D, KS, TPT, VAR>(G, cl, l2, s_e2);
+      xt_update<D, KS, TPT, VAR>(G, cl, l2, s_e2, T);
       IO::store(dst_v + g * SLOTB, dst_e + g * ESLOT, G);
     }
     nP = nG;
@@ -609,7 +614,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_repla
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) quad = fma(df2[j][dim], rq[(KS == 1) ? 0 : dim], quad);
         int k2;
-        const double pe = xt_exp_split(xt_clamp_neg(-0.5 * quad), s_e2, k2);
+        const double pe = xt_exp_split(xt_clamp_neg(-0.5 * quad), s_e2, k2, T);
         const double v = ((S[j].W * th) * xt_normfac<D, KS>(rq)) * pe;
         const int Kv = S[j].E + k2;
         const int Kn = max(KA[j], Kv);
