@@ -473,14 +473,43 @@ def Proba_Cs(Cs, LocErr, ds, Fs, TrMat, pBL, isBL, cell_dims, nb_substeps, frame
 # --------------------------------------------------------------------------------------
 # state annotation (tracking.py:792-906)
 # --------------------------------------------------------------------------------------
+def _gather_predictions(preds_local, sorted_tracks, world, nb_states):
+    """All ranks' slices of every bucket -> full arrays in input order (rank r holds rows predict_shard(n, r, world))."""
+    import torch
+    import torch.distributed as dist
+
+    dev = torch.device("cuda", _default_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    out = []
+    for a, mine in zip(sorted_tracks, preds_local):
+        n, L = a.shape[0], a.shape[1]
+        rows = [predict_shard(n, r, world) for r in range(world)]
+        pad = max(hi - lo for lo, hi in rows)
+        buf = torch.zeros((pad, L, nb_states), dtype=torch.float64, device=dev)
+        buf[: len(mine)] = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        out.append(np.concatenate([parts[r][: hi - lo].cpu().numpy() for r, (lo, hi) in enumerate(rows)]))
+    return out
+
+
+def predict_shard(n: int, rank: int, world_size: int):
+    """Rows ``[lo, hi)`` of an ``n``-track bucket annotated by ``rank`` (contiguous, balanced)."""
+    return n * rank // world_size, n * (rank + 1) // world_size
+
+
 def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, max_nb_states=200, threshold=0.1,
-               workers=1, input_LocErr=None, verbose=0, nb_max=1):
+               workers=1, input_LocErr=None, verbose=0, nb_max=1, gather=True):
     """Per-localisation state posteriors, ``{str(L): float64[n, L, nb_states]}`` (forward time).
 
     Implements the reference default ``nb_max = 1``: every track gets its own grouping plan
     (tracking.py:803,866-867).  ``nb_max > 1`` (plan shared by ``nb_max`` tracks, "might affect the
     predictions quality") is not provided by the CUDA engine and raises ``NotImplementedError``.
     ``workers`` is accepted and ignored.
+
+    With ``torch.distributed`` initialised (one process per GPU) every rank annotates a contiguous
+    slice of each length bucket (``predict_shard``); tracks are independent, so the data path has no
+    collective.  ``gather=True`` (default) reassembles the full dictionary on every rank in input
+    order (one all-gather per bucket); ``gather=False`` returns only this rank's rows.
     """
     sorted_tracks, l_list = _sorted_buckets(all_tracks)
     keys = [k for k in l_list if len(all_tracks[k]) > 0]
@@ -516,18 +545,27 @@ def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, 
     slope = (params["slope_LocErr"].value, params["offset_LocErr"].value) if (loc_k and _has_slope(params)) else None
     p = build_tables(loc, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold, max_nb_states,
                      sorted_tracks[0].shape[2], var_loc_k=loc_k, var_dt=sorted_dt is not None, Ds=Ds, slope_offset=slope)
-    eng = _native.Engine(_default_device())
-    try:
-        # chunk size only shapes the device layout here; plans are per track
-        eng.upload(sorted_tracks, [0 if a.shape[1] == max_len else 1 for a in sorted_tracks], MAX_TRACKS_PER_CHUNK)
-        if sorted_LocErrs is not None or sorted_dt is not None:
-            eng.upload_aux(sorted_LocErrs, sorted_dt)
-        if sorted_dt is not None:
-            t0 = np.concatenate([a[:, 0] for a in sorted_dt])
-            eng.set_stay_tables(True, *stay_tables(Ds, np.stack([t0, t0], 1), TrMat, pBL, cell_dims, nb_substeps))
-        preds = eng.predict(p, nb_states)
-    finally:
-        eng.close()
+    rank, world = _dist_info(None, None)
+    cuts = [predict_shard(len(a), rank, world) for a in sorted_tracks]
+    mine = [b for b, (lo, hi) in enumerate(cuts) if hi > lo]
+    loc = lambda arrs: [arrs[b][cuts[b][0]:cuts[b][1]] for b in mine] if arrs is not None else None
+    preds_local = [np.empty((0, a.shape[1], nb_states)) for a in sorted_tracks]
+    if mine:
+        eng = _native.Engine(_default_device())
+        try:
+            # chunk size only shapes the device layout here; plans are per track
+            eng.upload(loc(sorted_tracks), [0 if sorted_tracks[b].shape[1] == max_len else 1 for b in mine],
+                       MAX_TRACKS_PER_CHUNK)
+            if sorted_LocErrs is not None or sorted_dt is not None:
+                eng.upload_aux(loc(sorted_LocErrs), loc(sorted_dt))
+            if sorted_dt is not None:
+                t0 = np.concatenate([a[:, 0] for a in loc(sorted_dt)])
+                eng.set_stay_tables(True, *stay_tables(Ds, np.stack([t0, t0], 1), TrMat, pBL, cell_dims, nb_substeps))
+            for b, pr in zip(mine, eng.predict(p, nb_states)):
+                preds_local[b] = pr
+        finally:
+            eng.close()
+    preds = preds_local if (world == 1 or not gather) else _gather_predictions(preds_local, sorted_tracks, world, nb_states)
     for a, pr in zip(sorted_tracks, preds):
         out[str(a.shape[1])] = pr
     return out
