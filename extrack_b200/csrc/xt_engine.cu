@@ -58,6 +58,8 @@ struct xt_ctx {
   int spec_maxP = 0, spec_maxC = 0;  // most parents / children of the previous evaluation: sizes the plan kernel's
                                      // shared-memory scratch (0: global-memory scratch)
   int k1_smem_scratch = 1;
+  int k1_threads = 0;         // plan kernel threads per chunk: 0 = automatic (256, or 1024 for <= n_sm chunks)
+  int k1_batch = 1;           // plan kernel, > 64 sequences: batched candidate leaders (0: one leader at a time)
   int pipeline = 1;
   int n_groups = 6;
   double* d_logp = nullptr;
@@ -625,13 +627,18 @@ static int ensure_plan(xt_ctx* ctx, const xt_params* p, int cap) {
   return XT_OK;
 }
 
-template <int D, int KS, bool VAR>
-static cudaError_t launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream) {
-  auto kern = k1_plan<D, KS, VAR>;
+template <int D, int KS, bool VAR, int NT>
+static cudaError_t launch_k1_nt(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream) {
+  auto kern = k1_plan<D, KS, VAR, NT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)n_chunks, XT_K1_THREADS, smem, stream>>>(a, p);
+  kern<<<(unsigned)n_chunks, NT, smem, stream>>>(a, p);
   return cudaGetLastError();
+}
+template <int D, int KS, bool VAR>
+static cudaError_t launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream, int nthreads) {
+  if (nthreads == 1024) return launch_k1_nt<D, KS, VAR, 1024>(a, p, smem, n_chunks, stream);
+  return launch_k1_nt<D, KS, VAR, XT_K1_THREADS>(a, p, smem, n_chunks, stream);
 }
 
 template <int D, int KS, int WPC>
@@ -720,6 +727,7 @@ static K1Args make_k1_args(xt_ctx* ctx, int bits) {
   a.want_grec = ctx->k2_variant == 1 || !ctx->last_fused;
   ctx->plan_has_grec = a.want_grec != 0;
   a.corder = ctx->d_corder;
+  a.batch_mode = ctx->k1_batch;
 #ifdef XT_K1_PROF
   if (!g_k1_prof) cudaMalloc(&g_k1_prof, sizeof(long long) * 12 * 65536);
   a.prof = g_k1_prof;
@@ -728,13 +736,22 @@ static K1Args make_k1_args(xt_ctx* ctx, int bits) {
 }
 // shared-memory scratch of the plan kernel: used when the previous evaluation tells how many
 // parents / children to expect and 3 CTAs per SM still fit
+// threads per chunk of the plan kernel: 1024 when every chunk can have an SM of its own
+static int k1_threads(xt_ctx* ctx) {
+  if (ctx->k1_threads) return ctx->k1_threads;
+  return (int)ctx->chunks.size() <= ctx->n_sm ? 1024 : XT_K1_THREADS;
+}
+
 static void k1_scratch_caps(xt_ctx* ctx, const xt_params* p, bool use_smem, int* scapP, int* scapC) {
   *scapP = *scapC = 0;
   if (!use_smem || !ctx->k1_smem_scratch || ctx->spec_maxC <= 0) return;
   const int CO1 = p->d + 2 * p->n_loc + 1;
+  const int nt = k1_threads(ctx);
   const size_t b = xt_k1_smem(ctx->cap, CO1, ctx->RH, p->nS, ctx->spec_maxP, ctx->spec_maxC,
-                              is_var(p) ? ipow(p->nS, p->nsub + 1) : 0);
-  if (b + 1024 > (size_t)(228 * 1024) / XT_K1_MIN_CTAS || b > (size_t)ctx->smem_optin) return;
+                              is_var(p) ? ipow(p->nS, p->nsub + 1) : 0, nt);
+  // (2 KB: static shared memory of the kernel + the per-CTA reservation)
+  const int ctas = nt == XT_K1_THREADS ? XT_K1_MIN_CTAS : 1;
+  if (b + 2048 > (size_t)(228 * 1024) / ctas || b > (size_t)ctx->smem_optin) return;
   *scapP = ctx->spec_maxP;
   *scapC = ctx->spec_maxC;
 }
@@ -745,15 +762,16 @@ static int enqueue_k1(xt_ctx* ctx, const xt_params* p, int bits, int c0, int nc,
   k1_scratch_caps(ctx, p, smem_scratch, &a.scapP, &a.scapC);
   const bool var = is_var(p);
   const int varH = var ? ipow(p->nS, p->nsub + 1) : 0;
-  const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC, varH);
+  const int nt = k1_threads(ctx);
+  const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC, varH, nt);
   cudaError_t e = cudaSuccess;
   if (var) {
     a.ax = make_aux(ctx, p, 0);
-#define CALL_K1V(D_, KS_) e = launch_k1<D_, KS_, true>(a, *p, smem, nc, stream)
+#define CALL_K1V(D_, KS_) e = launch_k1<D_, KS_, true>(a, *p, smem, nc, stream, nt)
     XT_DISPATCH(p->d, p->n_loc, CALL_K1V);
 #undef CALL_K1V
   } else {
-#define CALL_K1(D_, KS_) e = launch_k1<D_, KS_, false>(a, *p, smem, nc, stream)
+#define CALL_K1(D_, KS_) e = launch_k1<D_, KS_, false>(a, *p, smem, nc, stream, nt)
     XT_DISPATCH(p->d, p->n_loc, CALL_K1);
 #undef CALL_K1
   }
@@ -1190,6 +1208,20 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
       return XT_ERR_ARG;
     }
     ctx->k2_variant = value;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k1_threads") == 0) {
+    if (value != 0 && value != 256 && value != 1024) {
+      set_error(ctx, "xt_set_option: k1_threads must be 0 (automatic), 256 or 1024");
+      return XT_ERR_ARG;
+    }
+    ctx->k1_threads = value;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k1_batch") == 0) {
+    ctx->k1_batch = value != 0;
     ctx->have_eval = false;
     return XT_OK;
   }

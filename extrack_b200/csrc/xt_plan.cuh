@@ -41,13 +41,21 @@ struct K1Args {
   // the global-memory scratch.
   int32_t scapP, scapC;
   int32_t want_grec;   // also emit the inline group records of the first-generation replay kernel
+  int32_t batch_mode;  // grouping of more than 64 sequences: 1 = batched candidate leaders, 0 = one leader at a time
   XtAux ax;            // VAR instantiation only
 };
 
-// dynamic shared memory of k1_plan (bytes)
-__host__ __device__ inline size_t xt_k1_smem(int cap, int CO, int RH, int nS, int scapP, int scapC, int varH = 0) {
+// dynamic shared memory of k1_plan (bytes): per-sequence arrays + the bit rows of the batch-mode
+// grouping (grouped mask + one row per warp, (cap + 63) / 64 words each), then the optional scratch
+__host__ __device__ inline size_t xt_k1_base(int cap, int nthreads = XT_K1_THREADS) {
   size_t b = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64;
   b = (b + 15) & ~(size_t)15;
+  b += (size_t)((cap + 63) / 64) * 8 * (nthreads / 32 + 1);
+  return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t xt_k1_smem(int cap, int CO, int RH, int nS, int scapP, int scapC, int varH = 0,
+                                             int nthreads = XT_K1_THREADS) {
+  size_t b = xt_k1_base(cap, nthreads);
   if (scapC > 0) b += (size_t)(scapP + scapC) * CO * 32 * 8 + (size_t)2 * scapP * RH * nS * 8;
   b += (size_t)varH * 32 * 8;  // VAR: per-lane dd of every head
   return b;
@@ -62,11 +70,13 @@ __device__ __forceinline__ int xt_label(int x, int nS, bool wrap) {
   return x % nS;
 }
 
-template <int D, int KS, bool VAR>
-__global__ void __launch_bounds__(XT_K1_THREADS, XT_K1_MIN_CTAS)
+// NT threads per chunk: 256 (several chunks per SM) or 1024 when the data set has fewer chunks than
+// the GPU has SMs (long tracks: the per-step phases then run in a quarter of the rounds)
+template <int D, int KS, bool VAR, int NT>
+__global__ void __launch_bounds__(NT, NT == XT_K1_THREADS ? XT_K1_MIN_CTAS : 1)
 k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
-  constexpr int W = XT_K1_THREADS / 32;
+  constexpr int W = NT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
   const int cid = a.corder[(int)blockIdx.x + a.chunk0];
   const XtChunk ck = a.chunks[cid];
@@ -84,8 +94,12 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   uint32_t* ent = (uint32_t*)(grank + cap);  // CSR member entries of the step (mirrored to the plan in global memory)
   int* gcnt = (int*)(ent + cap);      // [cap+1]: group sizes -> offsets
   unsigned char* curP = (unsigned char*)(gcnt + cap + 1);
-  __shared__ int s_flag, s_nG;
+  __shared__ int s_flag, s_nG, s_left, s_cand[NT / 32];
   __shared__ unsigned long long s_rows[64];  // capture matrix of the matrix-mode grouping
+  // batch mode: grouped bit mask and one bit row per candidate (= per warp), BW words each
+  const int BW = (cap + 63) / 64;
+  unsigned long long* s_grp = (unsigned long long*)(k1_smem + ((((size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64) + 15) & ~(size_t)15));
+  unsigned long long* s_brow = s_grp + BW;
 
   XtChunkSummary* sm = &a.summ[cid];
   const int nP0 = K * nS;
@@ -134,8 +148,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   double* histN = histP + (size_t)cap * a.RH * nS;
   const int scapP = a.scapP, scapC = a.scapC;
   if (scapC > 0) {
-    size_t o = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64;
-    o = (o + 15) & ~(size_t)15;
+    const size_t o = xt_k1_base(cap, NT);
     bufP = (double*)(k1_smem + o);
     bufC = bufP + (size_t)scapP * CO * 32;
     histP = bufC + (size_t)scapC * CO * 32;
@@ -161,8 +174,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   const double* Lps = (VAR && a.ax.stay) ? a.ax.stay + (size_t)cid * K : P.Lp_stay;
   double* s_dd = nullptr;
   if (VAR) {
-    size_t o = (size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64;
-    o = (o + 15) & ~(size_t)15;
+    size_t o = xt_k1_base(cap, NT);
     if (scapC > 0) o += (size_t)(scapP + scapC) * CO * 32 * 8 + (size_t)2 * scapP * a.RH * nS * 8;
     s_dd = (double*)(k1_smem + o);
   }
@@ -171,7 +183,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 #pragma unroll
       for (int k = 0; k < KS; ++k) l2[k] = xt_sigma2(P, Ap[(size_t)(j * a.ax.R + k) * npad]);
     }
-    for (int idx = tid; idx < nP0 * 32; idx += XT_K1_THREADS) {
+    for (int idx = tid; idx < nP0 * 32; idx += NT) {
       const int h = idx >> 5, ln = idx & 31;
       double v = P.dd[h];
       if (var_dt) v = xt_dd_exact(P, h, Ap[(size_t)(j * a.ax.R + a.ax.ka) * npad - t + (ln < Kt ? ln : 0)]);
@@ -194,7 +206,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     ST(bufP, c, D + 2 * KS) = __dadd_rn(P.LT[c], P.LF[c]);
   }
   int LhP = nsub + 1;
-  for (int c = tid; c < nP; c += XT_K1_THREADS) {
+  for (int c = tid; c < nP; c += NT) {
     curP[c] = (unsigned char)(c % nS);
     unsigned long long code = 0;
     int x = c;
@@ -298,7 +310,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
     }
     // window codes of the children: nsub new labels in front of the parent's rows
-    for (int c = tid; c < nC; c += XT_K1_THREADS) {
+    for (int c = tid; c < nC; c += NT) {
       const int p = c / K;
       unsigned long long code = codeP[p] << (bits * nsub);
       int x = c;
@@ -507,17 +519,147 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       K1_T(2);
       __syncthreads();
       nG = s_nG;
-      for (int c = tid; c < nC; c += XT_K1_THREADS) {
+      for (int c = tid; c < nC; c += NT) {
         pgid[c] = (uint16_t)gid[c];
         gent[c] = ent[c];
       }
-      for (int g = tid; g <= nG; g += XT_K1_THREADS) goff[g] = (uint16_t)gcnt[g];
+      for (int g = tid; g <= nG; g += NT) goff[g] = (uint16_t)gcnt[g];
       if (s_flag) {
         if (tid == 0) sm->err = 1;
         return;
       }
     } else {
-      // ---- split mode ----
+      // ---- batch mode (nC > 64): the next W not yet grouped sequences are candidate leaders, one
+      //      per warp; every warp evaluates the row of its candidate against the sequences that are
+      //      still ungrouped (four floating-point tests in flight), then one warp resolves the
+      //      candidates in ascending order on the bit rows (a candidate captured by an earlier
+      //      leader of the batch is dropped: the reference never visits it as a leader) ----
+      const int NW = (nC + 63) >> 6;  // 64-bit words per row
+      if (a.batch_mode) {
+        for (int wd = tid; wd < NW; wd += NT) s_grp[wd] = 0ull;
+        if (tid == 0) { s_nG = 0; s_left = nC; }
+        __syncthreads();
+        for (;;) {
+          if (s_left == 0) break;  // uniform (written before the barrier that ends the previous round)
+          // candidate of this warp: the (warp)-th zero bit of the grouped mask (words scanned by lanes)
+          int cand = -1;
+          {
+            int before = 0;  // zero bits in the words below the current 32-word window
+            for (int w0 = 0; w0 < NW && cand < 0; w0 += 32) {
+              const int wd = w0 + lane;
+              unsigned long long z = 0ull;
+              if (wd < NW) {
+                z = ~s_grp[wd];
+                if (wd == NW - 1 && (nC & 63)) z &= (1ull << (nC & 63)) - 1ull;
+              }
+              const int cnt = __popcll(z);
+              int pre = cnt;  // inclusive prefix over the lanes
+#pragma unroll
+              for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, o2);
+                if (lane >= o2) pre += v;
+              }
+              const int lo = before + pre - cnt;  // zero bits before this lane's word
+              const bool mine = warp >= lo && warp < lo + cnt;
+              int bitpos = -1;
+              if (mine) {  // the (warp - lo)-th set bit of z
+                unsigned long long zz = z;
+                for (int q = 0; q < warp - lo; ++q) zz &= zz - 1ull;
+                bitpos = wd * 64 + __ffsll((long long)zz) - 1;
+              }
+              const unsigned who = __ballot_sync(0xffffffffu, mine);
+              if (who) cand = __shfl_sync(0xffffffffu, bitpos, __ffs(who) - 1);
+              before += __shfl_sync(0xffffffffu, pre, 31);
+            }
+          }
+          if (lane == 0) s_cand[warp] = cand;
+          if (cand >= 0) {
+            const int i = cand;
+            double mi[D], si[KS];
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) mi[dim] = ST(bufC, i, dim);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) si[k] = ST(bufC, i, D + KS + k);
+            const unsigned long long ci = codeC[i];
+            unsigned* brow = (unsigned*)&s_brow[warp * BW];
+            for (int b = 0; b < 2 * NW; ++b) {
+              if (b < (i >> 5)) {  // below the candidate: already grouped (uniform)
+                if (lane == 0) brow[b] = 0u;
+                continue;
+              }
+              const int j = 32 * b + lane;
+              const bool valid = j < nC && j >= i && !((s_grp[j >> 6] >> (j & 63)) & 1ull);
+              const unsigned long long cj = valid ? codeC[j] : ~0ull;
+              const unsigned win = __ballot_sync(0xffffffffu, valid && use_window && cj == ci);
+              unsigned todo = __ballot_sync(0xffffffffu, valid && (cj & rowmask) == (ci & rowmask)) & ~win;
+              unsigned row = win;
+              while (todo) {
+                int js[4];
+                int nj = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (todo) {
+                    js[q] = 32 * b + __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    nj = q + 1;
+                  } else {
+                    js[q] = js[0];
+                  }
+                }
+                bool ok[4];
+                fp_ok4(mi, si, js, ok);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (q < nj && ok[q]) row |= 1u << (js[q] & 31);
+              }
+              if (lane == 0) brow[b] = row;
+            }
+          }
+          __syncthreads();
+          if (warp == 0) {
+            int ng = s_nG, left = s_left;
+            bool bad = false;
+            for (int t2 = 0; t2 < W; ++t2) {
+              const int i = s_cand[t2];
+              if (i < 0) break;
+              if ((s_grp[i >> 6] >> (i & 63)) & 1ull) continue;  // captured by an earlier leader of this batch
+              int cnt = 0;
+              for (int w0 = 0; w0 < NW; w0 += 32) {
+                const int wd = w0 + lane;
+                unsigned long long mem = 0ull;
+                if (wd < NW) {
+                  mem = s_brow[t2 * BW + wd] & ~s_grp[wd];
+                  s_grp[wd] |= mem;
+                }
+                cnt += __popcll(mem);
+                unsigned nz = __ballot_sync(0xffffffffu, mem != 0ull);
+                while (nz) {  // publish the members word by word: lanes l, l + 32 own bits l, l + 32
+                  const int src = __ffs(nz) - 1;
+                  nz &= nz - 1u;
+                  const unsigned long long m2 = __shfl_sync(0xffffffffu, mem, src);
+                  const int base = (w0 + src) * 64;
+                  if ((m2 >> lane) & 1ull) gid[base + lane] = ng;
+                  if ((m2 >> (lane + 32)) & 1ull) gid[base + lane + 32] = ng;
+                }
+              }
+#pragma unroll
+              for (int o2 = 16; o2 > 0; o2 >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o2);
+              if (cnt == 0) bad = true;  // empty group: the reference fails on the zero-size max (:725)
+              left -= cnt;
+              ++ng;
+              __syncwarp();
+            }
+            if (lane == 0) {
+              s_nG = ng;
+              s_left = bad ? 0 : left;
+              if (bad) s_flag = 1;
+            }
+          }
+          __syncthreads();
+        }
+        nG = s_nG;
+      } else
+      // ---- split mode (diagnostic option k1_batch = 0): one leader at a time, its row split over the warps ----
       for (int i = 0; i < nC; ++i) {
         if (gid[i] >= 0) continue;  // uniform
         double mi[D], si[KS];
@@ -534,16 +676,16 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         __syncthreads();
       }
       // every sequence must have been grouped (tracking.py:700-701)
-      for (int c = tid; c < nC; c += XT_K1_THREADS)
+      for (int c = tid; c < nC; c += NT)
         if (gid[c] < 0) s_flag = 1;
-      for (int g = tid; g <= nC; g += XT_K1_THREADS) gcnt[g] = 0;
+      for (int g = tid; g <= nC; g += NT) gcnt[g] = 0;
       __syncthreads();
       if (s_flag) {
         if (tid == 0) sm->err = 1;
         return;
       }
       // CSR member lists: rank inside the group (ascending child id), sizes, offsets
-      for (int c = tid; c < nC; c += XT_K1_THREADS) {
+      for (int c = tid; c < nC; c += NT) {
         const int g = gid[c];
         int rk = 0;
         for (int c2 = 0; c2 < c; ++c2) rk += (gid[c2] == g);
@@ -555,8 +697,8 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         for (int g = 0; g < nG; ++g) gcnt[g + 1] += gcnt[g];
       }
       __syncthreads();
-      for (int g = tid; g <= nG; g += XT_K1_THREADS) goff[g] = (uint16_t)gcnt[g];
-      for (int c = tid; c < nC; c += XT_K1_THREADS) {
+      for (int g = tid; g <= nG; g += NT) goff[g] = (uint16_t)gcnt[g];
+      for (int c = tid; c < nC; c += NT) {
         const int p = c / K, r = c - p * K;
         const uint32_t e = xt_pack_ent(p, r + K * (int)curP[p], r);
         const int pos = gcnt[gid[c]] + grank[c];
@@ -572,13 +714,13 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     }
     // The parents' window codes are dead since the update phase: codeP[g] becomes the window code
     // of group g, i.e. of the next step's parent g (history rows OR their argmax bits into it).
-    for (int g = tid; g < nG; g += XT_K1_THREADS) codeP[g] = 0ull;
+    for (int g = tid; g < nG; g += NT) codeP[g] = 0ull;
     __syncthreads();
     K1_T(3);
     // From here to the next barrier the phases are independent of each other (they read ent / gcnt /
     // bufC / histP and write disjoint outputs), so no barrier separates them and the warps overlap:
     // history rows start at thread 0, the replay records at the last thread, the merge on all warps.
-    const int rtid = XT_K1_THREADS - 1 - tid;
+    const int rtid = NT - 1 - tid;
     if (tid == 0) {
       a.plan.hdr[rec].nC = nC;
       a.plan.hdr[rec].nG = nG;
@@ -601,7 +743,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 #endif
     int ro_sh = 0;  // rows padded to a power of two: (group, row) of a thread by shifts
     while ((1 << ro_sh) < rows_out) ++ro_sh;
-    for (int idx = tid; (idx >> ro_sh) < nG; idx += XT_K1_THREADS) {
+    for (int idx = tid; (idx >> ro_sh) < nG; idx += NT) {
       const int row = idx & ((1 << ro_sh) - 1), g = idx >> ro_sh;
       if (row >= rows_out) continue;
       const int o = gcnt[g], n = gcnt[g + 1] - o;
@@ -698,7 +840,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     K1_T(4);
     if (a.want_grec) {  // inline group records of the first-generation replay kernel (k2_variant 1)
       unsigned long long* grec = a.plan.grec + (size_t)rec * a.plan.cap;
-      for (int g = rtid; g < nG; g += XT_K1_THREADS) {
+      for (int g = rtid; g < nG; g += NT) {
         const int o = gcnt[g], n = gcnt[g + 1] - o;
         const unsigned long long e0 = ent[o], e1 = (n > 1) ? ent[o + 1] : 0u;
         grec[g] = (e0 & 0xFFFFFFull) | ((unsigned long long)(n > 255 ? 255 : n) << 24) | ((e1 & 0xFFFFFFull) << 32);
@@ -723,7 +865,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
       unsigned long long* brec = (unsigned long long*)(blob + 2);
       uint8_t* pcur = a.plan.curG + (size_t)rec * a.plan.cap;
-      for (int g = rtid; g < nG; g += XT_K1_THREADS) {
+      for (int g = rtid; g < nG; g += NT) {
         const int o = gcnt[g], n = gcnt[g + 1] - o;
         {  // new parent g: newest true state = its first member's (tracking.py:728); curP is not read
            // again before the barrier that ends the step
@@ -754,7 +896,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         brec[slot] = (unsigned long long)lo | ((unsigned long long)hi << 32);
       }
       uint32_t* bent = (uint32_t*)(blob + 2 + (nG + 1) / 2);
-      for (int c = rtid; c < nC; c += XT_K1_THREADS) bent[c] = ent[c];
+      for (int c = rtid; c < nC; c += NT) bent[c] = ent[c];
     }
 
     K1_T(5);
@@ -763,7 +905,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     // members runs sequentially in ascending member order (checked against numpy 2.3).
     // (warps whose threads hold history rows merge fewer groups: with <= 128 rows the merge runs
     // on the upper half of the CTA)
-    const int mw0 = ((nG << ro_sh) <= XT_K1_THREADS / 2) ? W / 2 : 0, mW = W - mw0;
+    const int mw0 = ((nG << ro_sh) <= NT / 2) ? W / 2 : 0, mW = W - mw0;
     for (int g = warp - mw0; g >= 0 && g < nG; g += mW) {
       const int o = gcnt[g], n = gcnt[g + 1] - o;
       if (n == 1) {
