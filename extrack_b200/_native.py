@@ -64,6 +64,8 @@ class XtStats(C.Structure):
         ("ms_replay", C.c_float),
         ("pipelined", C.c_int32),
         ("ms_predict", C.c_float),
+        ("k3_launches", C.c_int32),
+        ("k3_cap", C.c_int32),
     ]
 
 

@@ -58,6 +58,8 @@ struct xt_ctx {
   int spec_maxP = 0, spec_maxC = 0;  // most parents / children of the previous evaluation: sizes the plan kernel's
                                      // shared-memory scratch (0: global-memory scratch)
   int k1_smem_scratch = 1;
+  int k3_hot_smem = 1;        // state-annotation kernel: forward-pass state of every warp in shared memory
+  int k3_ctas_per_sm = 4;     // resident CTAs per SM of the state-annotation kernel (its per-warp scratch should stay in L2)
   int k1_threads = 0;         // plan kernel threads per chunk: 0 = automatic (256, or 1024 for <= n_sm chunks)
   int k1_batch = 1;           // plan kernel, > 64 sequences: batched candidate leaders (0: one leader at a time)
   int pipeline = 1;
@@ -90,6 +92,7 @@ struct xt_ctx {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_k3[2] = {nullptr, nullptr};
   float ms_predict = 0.f;
+  int k3_launches = 0, k3_cap = 0;
   // optional per-localisation inputs (xt_upload_aux) and field-of-view tables (xt_set_stay_tables)
   double* d_aux = nullptr;
   int aux_R = 0, aux_ka = 0, aux_has_dt = 0;
@@ -1220,6 +1223,18 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
     ctx->have_eval = false;
     return XT_OK;
   }
+  if (std::strcmp(name, "k3_hot_smem") == 0) {
+    ctx->k3_hot_smem = value != 0;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k3_ctas_per_sm") == 0) {
+    if (value < 1 || value > 8) {
+      set_error(ctx, "xt_set_option: k3_ctas_per_sm must be in 1..8");
+      return XT_ERR_ARG;
+    }
+    ctx->k3_ctas_per_sm = value;
+    return XT_OK;
+  }
   if (std::strcmp(name, "k1_batch") == 0) {
     ctx->k1_batch = value != 0;
     ctx->have_eval = false;
@@ -1280,6 +1295,8 @@ extern "C" int xt_get_stats(xt_ctx* ctx, xt_stats* out) {
     cudaEventElapsedTime(&ctx->stats.ms_replay, ctx->ev[1], ctx->ev[2]);
   }
   ctx->stats.ms_predict = ctx->ms_predict;
+  ctx->stats.k3_launches = ctx->k3_launches;
+  ctx->stats.k3_cap = ctx->k3_cap;
   *out = ctx->stats;
   return XT_OK;
 }

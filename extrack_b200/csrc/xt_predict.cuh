@@ -32,38 +32,49 @@ struct K3Args {
   int32_t maxL;
   int32_t bits;
   double Lsum[XT_MAX_STATES];
-  size_t warp_scratch; // 8-byte units per warp (k3_layout(...).total)
+  size_t warp_scratch; // 8-byte units per warp in `scratch`: cold part (+ hot part unless hot_smem)
+  int32_t hot_smem;    // 1: the hot part of every warp is in dynamic shared memory
   XtAux ax;            // VAR instantiation only; stay = [n_tracks][K] Lp_stay, leave = [n_tracks][nS] log-sums
 };
 
-// per-warp scratch layout, in 8-byte units
+// per-warp scratch layout, in 8-byte units: the *hot* part (state of the forward pass, touched at
+// every step) lives in shared memory when the launch could be sized for it (hot_smem), the *cold*
+// part (records of the fusions for the backward sweep: written once, read once) in global memory
 struct K3Layout {
-  size_t bufP, bufC, histP, histN, codeP, codeC, recW, aC, aP, gid, order, goff, curP, recN, recGid, total;
+  size_t bufP, bufC, histP, histN, codeP, codeC, aC, aP, gid, order, goff, curP, hot_total;
+  size_t recW, recN, recGid, cold_total;
 };
 __host__ __device__ inline K3Layout k3_layout(int cap, int CO, int fl, int nS, int maxL) {
   K3Layout l;
   size_t o = 0;
-  l.bufP = o;   o += (size_t)cap * CO;
+  // parents / groups: at most cap / nS of them (see the history rows below)
+  l.bufP = o;   o += (size_t)(cap / nS + 1) * CO;
   l.bufC = o;   o += (size_t)cap * CO;
-  l.histP = o;  o += (size_t)cap * fl * nS;
-  l.histN = o;  o += (size_t)cap * fl * nS;
-  l.codeP = o;  o += cap;
+  // history rows exist per parent / group only: at most cap / nS of them (a step with more groups
+  // could not expand into cap children and reports the overflow, see the check after the grouping)
+  l.histP = o;  o += (size_t)(cap / nS + 1) * fl * nS;
+  l.histN = o;  o += (size_t)(cap / nS + 1) * fl * nS;
+  l.codeP = o;  o += cap / nS + 1;
   l.codeC = o;  o += cap;
-  l.recW = o;   o += (size_t)maxL * cap;
   l.aC = o;     o += cap;
-  l.aP = o;     o += cap;
+  l.aP = o;     o += cap / nS + 1;
   l.gid = o;    o += (cap + 1) / 2;        // int32[cap]
   l.order = o;  o += (cap + 1) / 2;
   l.goff = o;   o += (cap + 2) / 2;        // int32[cap+1]
   l.curP = o;   o += (cap + 1) / 2;
+  l.hot_total = (o + 1) & ~(size_t)1;
+  o = 0;
+  l.recW = o;   o += (size_t)maxL * cap;
   l.recN = o;   o += (maxL + 2) / 2;       // int32[maxL+1]
   l.recGid = o; o += ((size_t)maxL * cap + 3) / 4;  // uint16[maxL][cap]
-  l.total = o + 4;
+  l.cold_total = o + 4;
   return l;
 }
 
 template <int D, int KS, bool VAR = false>
 __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, const __grid_constant__ xt_params P) {
+  extern __shared__ double k3_smem[];
+  const int nwarps = blockDim.x >> 5;  // <= XT_K3_WARPS (fewer when the hot scratch of 8 warps exceeds shared memory)
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nS = P.nS, K = P.nS, cap = a.cap, fl = P.frame_len, bits = a.bits;
@@ -72,24 +83,26 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
 
   // ---- per-warp scratch carve-up ----
   const K3Layout lay = k3_layout(cap, CO, fl, nS, a.maxL);
-  double* base = a.scratch + (size_t)(blockIdx.x * XT_K3_WARPS + warp) * a.warp_scratch;
+  double* cold = a.scratch + (size_t)(blockIdx.x * nwarps + warp) * a.warp_scratch;
+  double* base = a.hot_smem ? k3_smem + (size_t)warp * lay.hot_total : cold + lay.cold_total;
   double* bufP = base + lay.bufP;            // [CO][cap]
   double* bufC = base + lay.bufC;
   double* histP = base + lay.histP;          // [cap][fl][nS]
   double* histN = base + lay.histN;
   unsigned long long* codeP = (unsigned long long*)(base + lay.codeP);
   unsigned long long* codeC = (unsigned long long*)(base + lay.codeC);
-  double* recW = base + lay.recW;            // [maxL][cap]
   double* aC = base + lay.aC;
   double* aP = base + lay.aP;
   int* gid = (int*)(base + lay.gid);
   int* order = (int*)(base + lay.order);
   int* goff = (int*)(base + lay.goff);       // [cap+1]
   int* curP = (int*)(base + lay.curP);
-  int* recN = (int*)(base + lay.recN);       // children per fused step
-  uint16_t* recGid = (uint16_t*)(base + lay.recGid);
+  double* recW = cold + lay.recW;            // [maxL][cap]
+  int* recN = (int*)(cold + lay.recN);       // children per fused step
+  uint16_t* recGid = (uint16_t*)(cold + lay.recGid);
 
-#define BP(slot, comp) bufP[(size_t)(comp) * cap + (slot)]
+  const int capP = cap / nS + 1;  // parent / group slots
+#define BP(slot, comp) bufP[(size_t)(comp) * capP + (slot)]
 #define BC(slot, comp) bufC[(size_t)(comp) * cap + (slot)]
 
   double l2[KS];
@@ -101,7 +114,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
     const XtWork wk = a.work[wi];
     const XtChunk ck = a.chunks[wk.chunk];
     const int L = ck.L;
-    for (int tsub = warp; tsub < 32; tsub += XT_K3_WARPS) {
+    for (int tsub = warp; tsub < 32; tsub += nwarps) {
       const int t = wk.t0 + tsub;
       if (t >= ck.nT) break;  // warp-uniform
       const double* Cp = a.soa + ck.xyz_off + t;
@@ -211,6 +224,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         }
 
         // ---- greedy grouping from this track alone (tracking.py:667-698 with one leader track) ----
+        const double th_lo = __dmul_rn(th, 1.0 - 1e-14), th_hi = __dmul_rn(th, 1.0 + 1e-14);
         int nG = 0, off = 0;
         for (int i = 0; i < nC; ++i) {
           if (gid[i] >= 0) continue;  // warp-uniform (memory made visible by __syncwarp)
@@ -245,10 +259,16 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
                 }
                 as = (KS == 2) ? __dmul_rn(as, 0.5) : ((KS == 1) ? as : __ddiv_rn(as, (double)KS));
                 // one leader track: mean(bool over KS comps) > 0.8  <=>  every component passes
+                // fl(x / s) < th decided without a division unless x is within 1e-14 (relative) of th*s
                 ok = true;
 #pragma unroll
-                for (int k = 0; k < KS; ++k)
-                  ok = ok && (__ddiv_rn(am, sj[k]) < th) && (__ddiv_rn(as, sj[k]) < th);
+                for (int k = 0; k < KS; ++k) {
+                  const double lo = __dmul_rn(th_lo, sj[k]), hi = __dmul_rn(th_hi, sj[k]);
+                  bool pm = am < lo, ps = as < lo;
+                  if (!pm && !(am > hi)) pm = __ddiv_rn(am, sj[k]) < th;
+                  if (!ps && !(as > hi)) ps = __ddiv_rn(as, sj[k]) < th;
+                  ok = ok && pm && ps;
+                }
               }
             }
             const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -265,6 +285,10 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         if (lane == 0) goff[nG] = off;
         for (int c = lane; c < nC; c += 32)
           if (gid[c] < 0) errc = 1;  // tracking.py:700-701
+        if (errc == 0 && nG * K > cap) {  // the next expansion would not fit (history rows are sized for it)
+          errc = 2;
+          if (lane == 0) atomicMax(&a.err_need[wi], nG * K);
+        }
         errc = __reduce_max_sync(0xffffffffu, errc);
         __syncwarp();
         if (errc) break;
@@ -292,6 +316,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
               const int c = order[o + k];
               const double w = exp(__dsub_rn(BC(c, D + 2 * KS), mx));
               recW[(size_t)step * cap + c] = w;
+              aC[c] = w;  // (aC is only used after the forward pass: free scratch here)
               recGid[(size_t)step * cap + c] = (uint16_t)g;
               sw = (k == 0) ? w : __dadd_rn(sw, w);
 #pragma unroll
@@ -322,7 +347,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
                   const int c = order[o + k];
                   const double hv = (row == 0) ? ((xt_label(c, nS, wrap) == s) ? 1.0 : 0.0)
                                                : histP[((size_t)(c / K) * fl + row - 1) * nS + s];
-                  const double v = __dmul_rn(exp(__dsub_rn(BC(c, D + 2 * KS), mx)), hv);
+                  const double v = __dmul_rn(aC[c], hv);  // aC[c] = exp(LP_c - max) of this fusion (set above)
                   acc = (k == 0) ? v : __dadd_rn(acc, v);
                 }
                 histN[((size_t)g * fl + row) * nS + s] = __ddiv_rn(acc, sw);
@@ -364,6 +389,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
       // ---- end of track: last-localisation term, optional leave expansion (tracking.py:613-639) ----
       const bool have_children = L > 2;  // final sequences live in bufC (children of the last step) or bufP (L == 2)
       double* FB = have_children ? bufC : bufP;
+      const int fbs = have_children ? cap : capP;  // slot pitch of that buffer
       double clast[D];
 #pragma unroll
       for (int dim = 0; dim < D; ++dim) clast[dim] = Cp[(size_t)((L - 1) * D + dim) * npad];
@@ -374,12 +400,12 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) {
           const int k = (KS == 1) ? 0 : dim;
-          const double q = __dadd_rn(FB[(size_t)(D + k) * cap + c], l2[k]);
-          const double df = __dsub_rn(clast[dim], FB[(size_t)dim * cap + c]);
+          const double q = __dadd_rn(FB[(size_t)(D + k) * fbs + c], l2[k]);
+          const double df = __dsub_rn(clast[dim], FB[(size_t)dim * fbs + c]);
           const double tt = __dsub_rn(__dmul_rn(-0.5, log(__dmul_rn(XT_TWO_PI, q))), __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, q)));
           term = (dim == 0) ? tt : __dadd_rn(term, tt);
         }
-        double v = FB[(size_t)(D + 2 * KS) * cap + c] + term;
+        double v = FB[(size_t)(D + 2 * KS) * fbs + c] + term;
         if (ck.isBL) v += Lsm[c % nS];
         aC[c] = v;
         vmax = fmax(vmax, v);

@@ -1,11 +1,15 @@
 // Host driver of the state-annotation kernel (included by xt_engine.cu).
-template <int D, int KS>
-static cudaError_t launch_k3(xt_ctx* ctx, const K3Args& a, const xt_params& p, int grid) {
-  if (is_var(&p))
-    k3_predict<D, KS, true><<<grid, 32 * XT_K3_WARPS, 0, ctx->stream>>>(a, p);
-  else
-    k3_predict<D, KS, false><<<grid, 32 * XT_K3_WARPS, 0, ctx->stream>>>(a, p);
+template <int D, int KS, bool VAR>
+static cudaError_t launch_k3_v(xt_ctx* ctx, const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem) {
+  auto kern = k3_predict<D, KS, VAR>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32 * nwarps, smem, ctx->stream>>>(a, p);
   return cudaGetLastError();
+}
+template <int D, int KS>
+static cudaError_t launch_k3(xt_ctx* ctx, const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem) {
+  return is_var(&p) ? launch_k3_v<D, KS, true>(ctx, a, p, grid, nwarps, smem) : launch_k3_v<D, KS, false>(ctx, a, p, grid, nwarps, smem);
 }
 
 extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
@@ -24,7 +28,6 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
   XT_CUDA_OK(cudaSetDevice(ctx->device));
   const int nS = p->nS, KS = p->n_loc, CO = p->d + 2 * KS + 1;
   const int n_work = (int)ctx->work.size();
-  const int grid = std::min(n_work, ctx->n_sm * 4);
   double* d_pred = nullptr;
   int32_t* d_err = nullptr;
   double* d_scratch = nullptr;
@@ -33,6 +36,7 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
   std::vector<int32_t> h_err(2 * (size_t)n_work);
   int cap = std::max(64, nS * nS * nS);
   int result = XT_OK;
+  ctx->k3_launches = 0;
   for (;;) {
     if (cap > XT_HARD_CAP) {
       set_error(ctx, "more than " + std::to_string(XT_HARD_CAP) + " live state sequences; lower frame_len or raise threshold");
@@ -40,7 +44,33 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       break;
     }
     const K3Layout lay = k3_layout(cap, CO, p->frame_len, nS, ctx->maxL + 1);
-    const size_t bytes = sizeof(double) * lay.total * (size_t)grid * XT_K3_WARPS;
+    // hot scratch in shared memory: as many warps per CTA (<= 8) as fit, CTAs per SM accordingly;
+    // if not even one warp fits, everything stays in global memory (4 CTAs of 8 warps per SM)
+    const size_t hot_bytes = sizeof(double) * lay.hot_total;
+    const size_t smem_cap = (size_t)ctx->smem_optin;
+    int nwarps = XT_K3_WARPS, ctas_per_sm = ctx->k3_ctas_per_sm, hot_smem = 0;
+    if (ctx->k3_hot_smem && hot_bytes <= smem_cap) {
+      // warps per CTA (<= 8) that maximise the resident warps per SM under the shared-memory and
+      // register limits (the kernel is latency-bound: more resident warps = more throughput)
+      hot_smem = 1;
+      const int regs = 128;  // __launch_bounds__(256) lets the compiler use up to 128 registers per thread
+      int best = 0;
+      for (int nw = XT_K3_WARPS; nw >= 1; --nw) {
+        if (hot_bytes * nw > smem_cap) continue;
+        const int by_smem = (int)(((size_t)228 * 1024) / (hot_bytes * nw + 1024));
+        const int by_regs = 65536 / (regs * 32 * nw);
+        const int ctas = std::max(1, std::min(by_smem, by_regs));
+        if (ctas * nw > best) {
+          best = ctas * nw;
+          nwarps = nw;
+          ctas_per_sm = ctas;
+        }
+      }
+    }
+    const size_t smem = hot_smem ? hot_bytes * nwarps : 0;
+    const int grid = std::min(n_work, ctx->n_sm * ctas_per_sm);
+    const size_t warp_units = lay.cold_total + (hot_smem ? 0 : lay.hot_total);
+    const size_t bytes = sizeof(double) * warp_units * (size_t)grid * nwarps;
     cudaFree(d_scratch);
     d_scratch = nullptr;
     if (cudaMalloc(&d_scratch, bytes) != cudaSuccess) {
@@ -61,7 +91,8 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
     a.cap = cap;
     a.maxL = ctx->maxL + 1;
     a.bits = bits;
-    a.warp_scratch = lay.total;
+    a.warp_scratch = warp_units;
+    a.hot_smem = hot_smem;
     if (is_var(p)) a.ax = make_aux(ctx, p, 1);
     for (int s = 0; s < nS; ++s) {  // nsub == 1: K = nS
       double mx = -INFINITY;
@@ -71,8 +102,10 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       a.Lsum[s] = std::log(acc) + mx;
     }
     cudaError_t e = cudaSuccess;
+    ctx->k3_launches++;
+    ctx->k3_cap = cap;
     cudaEventRecord(ctx->ev_k3[0], ctx->stream);
-#define CALL_K3(D_, KS_) e = launch_k3<D_, KS_>(ctx, a, *p, grid)
+#define CALL_K3(D_, KS_) e = launch_k3<D_, KS_>(ctx, a, *p, grid, nwarps, smem)
     XT_DISPATCH(p->d, p->n_loc, CALL_K3);
 #undef CALL_K3
     cudaEventRecord(ctx->ev_k3[1], ctx->stream);

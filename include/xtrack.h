@@ -83,6 +83,8 @@ typedef struct xt_stats {
   float ms_replay;       /* CUDA-event time of the replay kernel(s) incl. the reduction; pipelined: reduction */
   int32_t pipelined;     /* 1: plan and replay were launched per group of chunks on several streams */
   float ms_predict;      /* CUDA-event time of the last xt_predict kernel launch (all tracks) */
+  int32_t k3_launches;   /* kernel launches of the last xt_predict call (> 1: the sequence capacity had to grow) */
+  int32_t k3_cap;        /* sequence capacity of the last xt_predict launch */
 } xt_stats;
 
 /* Lifetime.  `device` is the CUDA ordinal this context drives. */

@@ -415,3 +415,36 @@ def test_var_inputs_bad_shapes_raise(xt):
         xt.cum_Proba_Cs(p, st, 0.02, [1], [np.full((20, 6), 0.02)], 2, 1, 6, 0)
     with pytest.raises(ValueError):
         xt.cum_Proba_Cs(p, st, [np.full((20, 5), 0.02)], [1], None, 2, 1, 6, 0)
+
+
+@pytest.mark.parametrize("opts", [dict(k1_threads=256), dict(k1_threads=1024), dict(k1_threads=256, k1_batch=0),
+                                  dict(k1_threads=1024, k1_batch=0), dict(k1_threads=256, k1_smem_scratch=0)])
+@pytest.mark.parametrize("path", [p for p in CASES if any(t in p for t in ("s2_fl8_L20", "s3_nsub2_wrap", "s3_3d.", "s4", "s2_escalate"))],
+                         ids=lambda p: os.path.basename(p)[:-4] if isinstance(p, str) else None)
+def test_plan_kernel_variants_give_the_oracle_plan(path, opts, native):
+    """Threads per chunk (256 as in the 510-chunk bench, 1024 for few chunks), batched vs one-by-one
+    leaders above 64 sequences, shared- vs global-memory scratch: same plan as the oracle, same log P."""
+    z = np.load(path)
+    m = case_model(z)
+    C, isBL = z["C"], int(z["isBL"])
+    plan = []
+    ref = orc.chunk_logp(C, m, isBL, plan_out=plan)
+    p = engine_params(m, C.shape[2])
+    eng = native.Engine(0)
+    try:
+        eng.upload([C], [isBL], len(C))
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        for rep in range(2):  # the second evaluation runs with the shared-memory scratch sized by the first
+            got = eng.chunk_logp(0, len(C), p) if rep == 0 else None
+            if rep == 1:
+                eng.set_option("pipeline", 0)
+                eng.sum_logp(p)
+                got = eng.chunk_logp(0, len(C), p)
+            np.testing.assert_allclose(got, ref, rtol=RTOL_LOGL)
+            for rec in plan:
+                nB, nG, gid, th = eng.plan_dump(0, rec["step"])
+                assert nB == rec["nB_in"] and nG == len(rec["groups"])
+                np.testing.assert_array_equal(gid, gid_from_groups(rec["groups"], nB))
+    finally:
+        eng.close()

@@ -95,6 +95,12 @@ def predict_config(n_tracks, reps=3):
     eng.upload(st, [0 if a.shape[1] == st[-1].shape[1] else 1 for a in st], xt.MAX_TRACKS_PER_CHUNK)
     locs = sum(a.shape[0] * a.shape[1] for a in st)
     eng.predict(p, 2)
+    if os.environ.get("K3_SWEEP"):  # kernel time vs resident CTAs per SM (per-warp scratch vs L2 capacity)
+        for c in (1, 2, 3, 4, 6, 8):
+            eng.set_option("k3_ctas_per_sm", c)
+            eng.predict(p, 2)
+            print(f"k3_ctas_per_sm={c}: kernel {eng.stats().get('ms_predict'):.1f} ms", file=sys.stderr, flush=True)
+        eng.set_option("k3_ctas_per_sm", int(os.environ["K3_SWEEP"]))
     t = time.perf_counter()
     for _ in range(reps):
         out = eng.predict(p, 2)
@@ -102,7 +108,8 @@ def predict_config(n_tracks, reps=3):
     s = eng.stats()
     res = {"config": "4: predict_Bs 2-state fl=8 th=0.1 max_nb_states=200 nb_max=1", "tracks": n_tracks, "localisations": locs,
            "ms_per_call_incl_d2h": wall * 1e3, "localisations_per_s": locs / wall,
-           "kernel_ms": s.get("ms_predict"), "d2h_bytes": locs * 2 * 8,
+           "kernel_ms": s.get("ms_predict"), "kernel_launches": s.get("k3_launches"), "sequence_capacity": s.get("k3_cap"),
+           "d2h_bytes": locs * 2 * 8,
            "mean_posterior_state0": float(np.mean([o[..., 0].mean() for o in out]))}
     eng.close()
     print(json.dumps(res), flush=True)
