@@ -1045,6 +1045,7 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
   XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
   k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, ctx->n_workf[fl.tpt - 1], d_out ? d_out : ctx->d_out);
   XT_CUDA_OK(cudaGetLastError());
+  ctx->stats.k2_launches++;  // the reduction
   XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_summ, ctx->d_summ, sizeof(XtChunkSummary) * nch, cudaMemcpyDeviceToHost, ctx->stream));
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
