@@ -641,6 +641,13 @@ static cudaError_t launch_k1_nt(const K1Args& a, const xt_params& p, size_t smem
 template <int D, int KS, bool VAR>
 static cudaError_t launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream, int nthreads) {
   if (nthreads == 1024) return launch_k1_nt<D, KS, VAR, 1024>(a, p, smem, n_chunks, stream);
+  if (!VAR && a.scapC > 0) {  // scratch in shared memory, known at compile time
+    auto kern = k1_plan<D, KS, false, XT_K1_THREADS, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)n_chunks, XT_K1_THREADS, smem, stream>>>(a, p);
+    return cudaGetLastError();
+  }
   return launch_k1_nt<D, KS, VAR, XT_K1_THREADS>(a, p, smem, n_chunks, stream);
 }
 

@@ -72,7 +72,9 @@ __device__ __forceinline__ int xt_label(int x, int nS, bool wrap) {
 
 // NT threads per chunk: 256 (several chunks per SM) or 1024 when the data set has fewer chunks than
 // the GPU has SMs (long tracks: the per-step phases then run in a quarter of the rounds)
-template <int D, int KS, bool VAR, int NT>
+// SS: the scratch is known at compile time to be in shared memory (scapC > 0): the accesses then compile
+// to shared-memory instructions with 32-bit addresses instead of generic loads / stores.
+template <int D, int KS, bool VAR, int NT, bool SS = false>
 __global__ void __launch_bounds__(NT, NT == XT_K1_THREADS ? XT_K1_MIN_CTAS : 1)
 k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
@@ -142,21 +144,29 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   // leader-track state and history rows: shared memory when the launch was sized for it (every
   // producer -> consumer hand-off between phases is then a shared-memory round trip instead of
   // an L2 one), else the per-chunk global scratch.  Generic pointers: same code for both.
-  double* bufP = a.state + (size_t)cid * 2 * cap * CO * 32;
-  double* bufC = bufP + (size_t)cap * CO * 32;
-  double* histP = a.hist + (size_t)cid * 2 * cap * a.RH * nS;
-  double* histN = histP + (size_t)cap * a.RH * nS;
   const int scapP = a.scapP, scapC = a.scapC;
-  if (scapC > 0) {
-    const size_t o = xt_k1_base(cap, NT);
-    bufP = (double*)(k1_smem + o);
+  double *bufP, *bufC, *histP, *histN;
+  if (SS) {
+    bufP = (double*)(k1_smem + xt_k1_base(cap, NT));
     bufC = bufP + (size_t)scapP * CO * 32;
     histP = bufC + (size_t)scapC * CO * 32;
     histN = histP + (size_t)scapP * a.RH * nS;
-    if (nP0 > scapP) {
-      if (tid == 0) sm->err = 3;
-      return;
+  } else {
+    bufP = a.state + (size_t)cid * 2 * cap * CO * 32;
+    bufC = bufP + (size_t)cap * CO * 32;
+    histP = a.hist + (size_t)cid * 2 * cap * a.RH * nS;
+    histN = histP + (size_t)cap * a.RH * nS;
+    if (scapC > 0) {
+      const size_t o = xt_k1_base(cap, NT);
+      bufP = (double*)(k1_smem + o);
+      bufC = bufP + (size_t)scapP * CO * 32;
+      histP = bufC + (size_t)scapC * CO * 32;
+      histN = histP + (size_t)scapP * a.RH * nS;
     }
+  }
+  if (scapC > 0 && nP0 > scapP) {
+    if (tid == 0) sm->err = 3;
+    return;
   }
   const int bits = a.bits;
   const unsigned long long rowmask = (1ull << bits) - 1ull;

@@ -101,7 +101,7 @@ def _p_stay(ds, nS, nsub, cell_dims):
     :501-506) -> ``[rows, K]``, each row computed with the operations (and the summation order of
     ``np.mean(.., 0)``) the reference applies to a single chunk.
     """
-    import scipy.stats
+    from scipy.special import ndtr  # what scipy.stats.norm.cdf evaluates (same bits, without the 0.1 ms wrapper)
 
     ds = np.asarray(ds, dtype=float)
     one = ds.ndim == 1
@@ -115,8 +115,7 @@ def _p_stay(ds, nS, nsub, cell_dims):
         for cell_len in cell_dims:
             xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
             cur = np.mean(
-                scipy.stats.norm.cdf((cell_len - xs[:, None, None]) / (sub_ds + 1e-200))
-                - scipy.stats.norm.cdf(-xs[:, None, None] / (sub_ds + 1e-200)),
+                ndtr((cell_len - xs[:, None, None]) / (sub_ds + 1e-200)) - ndtr(-xs[:, None, None] / (sub_ds + 1e-200)),
                 0,
             )
             p_stay = p_stay * cur
