@@ -279,6 +279,26 @@ def test_param_fitting_recovers_simulated_parameters(xt, capsys):
     assert np.isfinite(fit.residual[0])
 
 
+def test_param_fitting_with_peakwise_locerr_and_dt_dict(xt, capsys):
+    """param_fitting with an input_LocErr dict (fitted through slope_LocErr / offset_LocErr) and a
+    dt dict (tracking.py:1346-1368): the effective localisation error and D1 come out right."""
+    from extrack_b200.simulate import sim_tracks
+
+    tracks = sim_tracks(10000, seed=3, device="cuda", max_track_len=16, min_track_len=6, LocErr=0.02, Ds=[0, 0.25], nb_dims=2,
+                        initial_fractions=[0.6, 0.4], TrMat=[[0.9, 0.1], [0.1, 0.9]], dt=0.02, pBL=0.05, cell_dims=[1, None, None])
+    sig = {k: np.full(v.shape[:2] + (1,), 0.01) for k, v in tracks.items()}   # reported errors are half the true ones
+    dts = {k: np.full(v.shape[:2], 0.02) for k, v in tracks.items()}
+    params = xt.generate_params(nb_states=2, LocErr_type=4, estimated_Ds=[0.001, 0.4], estimated_Fs=[0.5],
+                                estimated_transition_rates=0.15, slope_offsets_estimates=[1.5, 0.002])
+    fit = xt.param_fitting(tracks, dts, params=params, nb_states=2, frame_len=5, verbose=0, cell_dims=[1], input_LocErr=sig)
+    capsys.readouterr()
+    v = {k: fit.params[k].value for k in fit.params}
+    eff = 0.01 * v["slope_LocErr"] + v["offset_LocErr"]
+    assert abs(eff - 0.02) < 2e-3, (eff, v)
+    assert abs(v["D1"] - 0.25) < 0.03 and v["D0"] < 2e-3
+    assert np.isfinite(fit.residual[0])
+
+
 PRED_ATOL = 1e-6
 
 
