@@ -268,7 +268,10 @@ __host__ __device__ inline size_t xt_fused_smem(int D, int KS, int Pcap, int K, 
 }
 
 template <int D, int KS, int WPC, int TPT, bool VAR = false>
-__global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? 24 : 16) / WPC) k2_replay_fused(const K2FArgs a, const __grid_constant__ K2Tab T) {
+#ifndef XT_K2_WARPS_T1
+#define XT_K2_WARPS_T1 24  // resident warps per SM the register budget is set for (one track per thread)
+#endif
+__global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / WPC) k2_replay_fused(const K2FArgs a, const __grid_constant__ K2Tab T) {
   using IO = XtSlotIO<D, KS, TPT>;
   using Seq = XtSeq<D, KS>;
   constexpr int SLOTB = IO::SLOTB, ESLOT = IO::ESLOT;

@@ -87,6 +87,7 @@ def main():
                         neglogl=np.array(list(vals.values())), meta=str(meta), **{"C" + k: buckets[k] for k in keys})
     print("objective", vals)
     make_var_cases(trk, meta)
+    make_fit_case(trk, meta)
 
 
 # peak-wise input_LocErr / per-track dt: objective and predictions through the
@@ -134,6 +135,29 @@ def make_var_cases(trk, meta):
                             var_dt=int(c["var_dt"]), slope=int(c["slope"]), chunk=chunk, neglogl=val,
                             param_names=np.array(list(pv)), param_values=np.array(list(pv.values())), meta=str(meta), **arrays)
         print(c["name"], val)
+
+
+def make_fit_case(trk, meta):
+    """BASELINE config 1: 2-state param_fitting on Tutorials/tracks.csv (frame_len 6, bfgs) by the
+    UNMODIFIED reference, driven by the same lmfit stand-in the repo uses where lmfit is absent.
+    Stores the tracks as read by the reference's own reader, the start values, the fitted parameters
+    and the final objective."""
+    rd = ref_loader.load_readers()
+    with contextlib.redirect_stdout(io.StringIO()):
+        tracks, _, _ = rd.read_table(os.path.join(ref_loader.REFERENCE_ROOT, "Tutorials", "tracks.csv"), lengths=np.arange(5, 50),
+                                     dist_th=0.3, frames_boundaries=[0, 10000], fmt="csv", colnames=["X", "Y", "frame", "track_ID"],
+                                     opt_colnames=[], remove_no_disp=True)
+        params = trk.generate_params(nb_states=2, LocErr_type=1, nb_dims=2, LocErr_bounds=[0.005, 0.1], D_max=10,
+                                     Fractions_bounds=[0.001, 0.99])
+        start = {k: float(params[k].value) for k in params}
+        fit = trk.param_fitting(tracks, 0.02, params=params, nb_states=2, nb_substeps=1, frame_len=6, verbose=0, workers=1,
+                                method="bfgs", cell_dims=[1], threshold=0.2, max_nb_states=120)
+    fitted = {k: float(fit.params[k].value) for k in fit.params}
+    keys = sorted((k for k in tracks if len(tracks[k])), key=int)
+    np.savez_compressed(os.path.join(HERE, "fit_tracks_csv.npz"), keys=np.array(keys), names=np.array(list(fitted)),
+                        start=np.array([start[k] for k in fitted]), fitted=np.array(list(fitted.values())),
+                        neglogl=float(fit.residual[0]), meta=str(meta), **{"C" + k: np.asarray(tracks[k]) for k in keys})
+    print("fit", fitted, float(fit.residual[0]))
 
 
 if __name__ == "__main__":

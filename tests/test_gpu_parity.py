@@ -279,6 +279,28 @@ def test_param_fitting_recovers_simulated_parameters(xt, capsys):
     assert np.isfinite(fit.residual[0])
 
 
+def test_param_fitting_matches_reference_fit_on_tutorial_tracks(xt, capsys):
+    """BASELINE config 1: 2-state bfgs fit of Tutorials/tracks.csv (frame_len 6) from the reference's
+    default start values.  Golden = the unmodified reference driven by the same minimiser stand-in
+    (lmfit is not installable here): fitted parameters to 1e-3 relative, final objective to 1e-7."""
+    path = os.path.join(GOLDEN, "fit_tracks_csv.npz")
+    if not os.path.isfile(path):
+        pytest.skip("fit golden not generated")
+    z = np.load(path)
+    tracks = {str(k): z["C" + k] for k in z["keys"]}
+    params = xt.generate_params(nb_states=2, LocErr_type=1, nb_dims=2, LocErr_bounds=[0.005, 0.1], D_max=10,
+                                Fractions_bounds=[0.001, 0.99])
+    for n, s0 in zip(z["names"], z["start"]):
+        assert params[str(n)].value == s0  # same start as the reference run
+    fit = xt.param_fitting(tracks, 0.02, params=params, nb_states=2, nb_substeps=1, frame_len=6, verbose=0, method="bfgs",
+                           cell_dims=[1], threshold=0.2, max_nb_states=120)
+    capsys.readouterr()
+    want = dict(zip([str(n) for n in z["names"]], z["fitted"]))
+    assert abs(fit.residual[0] - float(z["neglogl"])) <= 1e-7 * abs(float(z["neglogl"]))
+    for k, w in want.items():
+        assert abs(fit.params[k].value - w) <= 1e-3 * max(abs(w), 1e-3), (k, fit.params[k].value, w)
+
+
 def test_param_fitting_with_peakwise_locerr_and_dt_dict(xt, capsys):
     """param_fitting with an input_LocErr dict (fitted through slope_LocErr / offset_LocErr) and a
     dt dict (tracking.py:1346-1368): the effective localisation error and D1 come out right."""

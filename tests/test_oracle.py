@@ -78,6 +78,28 @@ def test_oracle_matches_golden_var_inputs(path):
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
 
 
+def test_oracle_reproduces_reference_fit_objective_on_tutorial_tracks():
+    """BASELINE config 1 (golden: tests/golden/make_golden.py:make_fit_case): at the parameters the
+    reference's own param_fitting converged to on Tutorials/tracks.csv, the oracle's objective equals
+    the reference's final objective."""
+    path = os.path.join(GOLDEN, "fit_tracks_csv.npz")
+    if not os.path.isfile(path):
+        pytest.skip("fit golden not generated")
+    z = np.load(path)
+    st = [z["C" + k] for k in z["keys"]]
+    assert sum(len(a) for a in st) == 613
+    v = dict(zip([str(n) for n in z["names"]], z["fitted"]))
+    Ds = np.array([v["D0"], v["D1"]])
+    R = np.array([[0, v["p01"]], [v["p10"], 0]])
+    Tr = 1 - np.exp(-R)
+    Tr[[0, 1], [0, 1]] = 0
+    Tr[[0, 1], [0, 1]] = 1 - Tr.sum(1)
+    model = orc.Model(np.array([v["LocErr"]]), np.sqrt(2 * Ds * 0.02), np.array([v["F0"], v["F1"]]), Tr, v["pBL"], [1], 1, 6,
+                      st[0].shape[1], 0.2, 120)
+    got = orc.neg_log_likelihood(st, model)
+    assert abs(got - float(z["neglogl"])) <= 1e-12 * abs(float(z["neglogl"]))
+
+
 def test_oracle_chunk_order_and_workers():
     rng = np.random.default_rng(0)
     st = [random_walk_tracks(n, L, 2, rng) for L, n in ((6, 50), (9, 2300))]

@@ -115,12 +115,40 @@ def predict_config(n_tracks, reps=3):
     print(json.dumps(res), flush=True)
 
 
+def fit_config_1():
+    """BASELINE config 1: param_fitting on the tutorial tracks (golden fixture with the reference's fit)."""
+    import contextlib
+    import io
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fit_tracks_csv.npz"))
+    tracks = {str(k): z["C" + k] for k in z["keys"]}
+    want = dict(zip([str(n) for n in z["names"]], z["fitted"]))
+    out = {}
+    for rep in range(2):  # the second run has the library and the CUDA context warm
+        params = xt.generate_params(nb_states=2, LocErr_type=1, nb_dims=2, LocErr_bounds=[0.005, 0.1], D_max=10,
+                                    Fractions_bounds=[0.001, 0.99])
+        buf = io.StringIO()
+        t = time.perf_counter()
+        with contextlib.redirect_stdout(buf):
+            fit = xt.param_fitting(tracks, 0.02, params=params, nb_states=2, nb_substeps=1, frame_len=6, verbose=0, method="bfgs",
+                                   cell_dims=[1], threshold=0.2, max_nb_states=120)
+        wall = time.perf_counter() - t
+        out = {"config": "1: 2-state param_fitting on Tutorials/tracks.csv (613 tracks, 33 buckets, frame_len 6, bfgs)",
+               "fit_seconds": wall, "objective_evaluations": buf.getvalue().count(".") + buf.getvalue().count("x"),
+               "neglogl": float(fit.residual[0]), "neglogl_reference_fit": float(z["neglogl"]),
+               "max_rel_param_diff_vs_reference_fit": max(abs(fit.params[k].value - w) / max(abs(w), 1e-3) for k, w in want.items()),
+               "reference_fit_seconds_single_core_build_container": 772.4}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="3,4,5")
     ap.add_argument("--scale", type=float, default=1.0)
     a = ap.parse_args()
     only = set(a.only.split(","))
+    if "1" in only:
+        fit_config_1()
     if "3" in only:
         likelihood_config(
             "3: 3-state 2D nb_substeps=2 frame_len=6 max_nb_states=500", int(100_000 * a.scale),

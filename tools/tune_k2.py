@@ -65,13 +65,13 @@ if os.environ.get("TUNE_VARIANTS"):
             print("   MISMATCH", v, ref)
     eng.set_option("k2_wpc", 4)
     eng.set_option("k2_tpt", 1)
-for ns in (4, 8, 16):
+for ns in ((8,) if os.environ.get("TUNE_QUICK") else (4, 8, 16)):
     try:
         eng.set_option("n_streams", ns)
     except Exception:
         if ns != 4:
             continue
-    for g in (2, 3, 4, 6, 8, 12, 16):
+    for g in ((6,) if os.environ.get("TUNE_QUICK") else (2, 3, 4, 6, 8, 12, 16)):
         if g > ns * 2:
             continue
         eng.set_option("n_groups", g)
