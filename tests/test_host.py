@@ -221,3 +221,97 @@ def test_simulator_statistics():
     assert all(np.array_equal(same[k], again[k]) for k in same)
     many = sim_tracks(5000, block=3000, seed=1, max_track_len=12, min_track_len=5)
     assert sum(len(v) for v in many.values()) == 5000
+
+
+# ---- table reader ----
+def _synthetic_table(tmp_path, rng, n_tracks=300):
+    import pandas as pd
+
+    rows = []
+    for tid in rng.permutation(n_tracks):
+        L = int(rng.integers(1, 30))
+        pos = np.cumsum(rng.normal(size=(L, 2)) * 0.05, 0)
+        if tid % 17 == 0 and L > 3:
+            pos[3:] = pos[2]          # no displacement: removed by remove_no_disp
+        if tid % 23 == 0 and L > 4:
+            pos[4:] += 5.0            # one long step: removed by dist_th
+        f0 = int(rng.integers(0, 120))
+        fr = np.arange(f0, f0 + L)
+        perm = rng.permutation(L)     # rows of a track are not in frame order in the file
+        for k in perm:
+            rows.append((pos[k, 0], pos[k, 1], fr[k], int(tid), float(rng.random())))
+    df = pd.DataFrame(rows, columns=["X", "Y", "frame", "track_ID", "QUALITY"])
+    path = str(tmp_path / "table.csv")
+    df.to_csv(path, index=False)
+    return path
+
+
+def test_read_table_bucketing_rules(tmp_path):
+    """Own expectation (loop restating readers.py:173-203) on a synthetic table: exact lengths,
+    truncation of longer tracks, the in-between rule, the three filters, frame sorting."""
+    import contextlib
+    import io
+
+    import pandas as pd
+
+    from extrack_b200 import readers
+
+    rng = np.random.default_rng(0)
+    path = _synthetic_table(tmp_path, rng)
+    lengths = np.array([4, 5, 6, 9, 12])
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        tracks, frames, opt = readers.read_table(path, lengths=lengths, dist_th=1.0, frames_boundaries=[5, 100], fmt="csv",
+                                                 colnames=["X", "Y", "frame", "track_ID"], opt_colnames=["QUALITY"])
+    df = pd.read_csv(path)
+    want = {int(l): [] for l in lengths}
+    for tid, g in df.groupby("track_ID"):
+        g = g.sort_values("frame")
+        m = g[["X", "Y", "frame"]].values.astype(float)
+        d2 = (m[1:, :2] - m[:-1, :2]) ** 2
+        if len(m) > 1 and np.mean(d2 == 0) > 0.05:
+            continue
+        if not (5 <= m[0, 2] <= 100) or np.any(np.sum(d2, 1) ** 0.5 > 1.0):
+            continue
+        n = len(m)
+        if n in lengths:
+            want[n].append(m[:, :2])
+        elif n > 12:
+            want[12].append(m[:12, :2])
+        elif 4 < n < 12:
+            l = int(lengths[np.argmin(np.floor(n / lengths)) - 1])
+            want[l].append(m[:l, :2])
+    assert list(tracks) == [str(l) for l in lengths if want[int(l)]]
+    assert [int(x) for x in out.getvalue().split()] == [int(k) for k in tracks]
+    for k, arr in tracks.items():
+        np.testing.assert_array_equal(arr, np.array(want[int(k)]))
+        assert frames[k].shape == arr.shape[:2] and np.all(np.diff(frames[k], axis=1) == 1)
+    assert opt["QUALITY"]["12"].shape[1] == 12
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not present on this box")
+def test_read_table_matches_reference_reader(tmp_path):
+    import contextlib
+    import io
+
+    from extrack_b200 import readers
+
+    rd = ref_loader.load_readers()
+    cases = [(os.path.join(ref_loader.REFERENCE_ROOT, "Tutorials", "tracks.csv"),
+              dict(lengths=np.arange(5, 50), dist_th=0.3, frames_boundaries=[0, 10000], fmt="csv",
+                   colnames=["X", "Y", "frame", "track_ID"], opt_colnames=[], remove_no_disp=True)),
+             (_synthetic_table(tmp_path, np.random.default_rng(1)),
+              dict(lengths=np.array([4, 5, 6, 9, 12]), dist_th=1.0, frames_boundaries=[5, 100], fmt="csv",
+                   colnames=["X", "Y", "frame", "track_ID"], opt_colnames=["QUALITY"], remove_no_disp=True)),
+             (_synthetic_table(tmp_path, np.random.default_rng(2)),
+              dict(lengths=np.arange(3, 20), dist_th=np.inf, frames_boundaries=[-np.inf, np.inf], fmt=",",
+                   colnames=["X", "Y", "frame", "track_ID"], opt_colnames=[], remove_no_disp=False))]
+    for path, kw in cases:
+        with contextlib.redirect_stdout(io.StringIO()) as o1:
+            t1, f1, m1 = rd.read_table(path, **{k: (list(v) if isinstance(v, list) else v) for k, v in kw.items()})
+        with contextlib.redirect_stdout(io.StringIO()) as o2:
+            t2, f2, m2 = readers.read_table(path, **kw)
+        assert list(t1) == list(t2) and o1.getvalue() == o2.getvalue()
+        for k in t1:
+            np.testing.assert_array_equal(t1[k], t2[k])
+            np.testing.assert_array_equal(f1[k], f2[k])
+    assert sum(len(v) for v in t2.values()) > 0
