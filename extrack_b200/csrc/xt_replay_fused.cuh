@@ -413,6 +413,10 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
   if (tid + NT < B16) xt_sts128u(s_blob + (tid + NT) * 16, pre1);
   __syncthreads();
 
+  // loop-invariant parts of the record prefetch / staging
+  const bool st0 = tid < B16, st1 = tid + NT < B16;
+  const unsigned s_stage = s_blob + tid * 16;
+  const uint4* gnext = gblob;
   // ---- steps 3..L-1: merge by the replay record of step-1, update with C[step-1] ----
   unsigned src_v = s_vec, src_e = s_exp, dst_v = s_vec + VB, dst_e = s_exp + EB;
   for (int step = 3; step <= L - 1; ++step) {
@@ -439,9 +443,10 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       aux_row(l2n, dtn);
     }
     const bool more = ri + 1 < nrec;
+    gnext += bstride;  // record of the next step (running pointer: no 64-bit multiply per step)
     if (more) {
-      if (tid < B16) pre0 = __ldg(gblob + (size_t)(ri + 1) * bstride);
-      if (tid + NT < B16) pre1 = __ldg(gblob + (size_t)(ri + 1) * bstride + NT);
+      if (st0) pre0 = __ldg(gnext);
+      if (st1) pre1 = __ldg(gnext + NT);
     }
 
     const unsigned rb = s_blob + (ri & 1) * (B16 * 16);
@@ -562,9 +567,9 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       unsigned te = src_e; src_e = dst_e; dst_e = te;
     }
     if (more) {
-      const unsigned nb = s_blob + ((ri + 1) & 1) * (B16 * 16);
-      if (tid < B16) xt_sts128u(nb + tid * 16, pre0);
-      if (tid + NT < B16) xt_sts128u(nb + (tid + NT) * 16, pre1);
+      const unsigned nb = s_stage + ((ri + 1) & 1) * (B16 * 16);
+      if (st0) xt_sts128u(nb, pre0);
+      if (st1) xt_sts128u(nb + NT * 16, pre1);
     }
     __syncthreads();
   }
