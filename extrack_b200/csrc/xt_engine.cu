@@ -58,6 +58,7 @@ struct xt_ctx {
   int spec_maxP = 0, spec_maxC = 0;  // most parents / children of the previous evaluation: sizes the plan kernel's
                                      // shared-memory scratch (0: global-memory scratch)
   int k1_smem_scratch = 1;
+  int k2_global_ctas = 32;    // one-warp CTAs per SM of the global-memory replay kernel (latency-bound: as many as fit)
   int k3_hot_smem = 1;        // state-annotation kernel: forward-pass state of every warp in shared memory
   int k3_ctas_per_sm = 4;     // resident CTAs per SM of the state-annotation kernel (its per-warp scratch should stay in L2)
   int k1_threads = 0;         // plan kernel threads per chunk: 0 = automatic (256, or 1024 for <= n_sm chunks)
@@ -1155,7 +1156,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
   }
   int grid = a.n_work;
   if (!use_smem) {
-    grid = std::min(a.n_work, ctx->n_sm * 16);
+    grid = std::min(a.n_work, ctx->n_sm * ctx->k2_global_ctas);
     const size_t need = (size_t)grid * state_bytes;
     if (need > ctx->gstate_bytes) {
       cudaFree(ctx->d_gstate);
@@ -1229,6 +1230,14 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
     }
     ctx->k1_threads = value;
     ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k2_global_ctas") == 0) {
+    if (value < 1 || value > 32) {
+      set_error(ctx, "xt_set_option: k2_global_ctas must be in 1..32");
+      return XT_ERR_ARG;
+    }
+    ctx->k2_global_ctas = value;
     return XT_OK;
   }
   if (std::strcmp(name, "k3_hot_smem") == 0) {
