@@ -98,29 +98,44 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
       var_row(step - 1);
       dtv = var_dtrow(step - 1);
     }
-    // phase A: per parent, the part of the update shared by all its children
-    for (int p = 0; p < nP; ++p) {
-      double quad = 0.0, logs = 0.0;
-      double rq[KS], s2[KS];
+    // phase A: per parent, the part of the update shared by all its children.  Four parents per round:
+    // all loads first (the state lives in global memory: independent loads in flight hide its latency)
+    for (int p0 = 0; p0 < nP; p0 += 4) {
+      double mm4[4][D], s24[4][KS], lp4[4];
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        s2[k] = SA(cur, p, D + k);
-        const double q = l2[k] + s2[k];
-        rq[k] = 1.0 / q;
-        logs += log(XT_TWO_PI * q);
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const int p = (p0 + u4 < nP) ? p0 + u4 : p0;
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) mm4[u4][dim] = SA(cur, p, dim);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) s24[u4][k] = SA(cur, p, D + k);
+        lp4[u4] = SA(cur, p, D + KS);
       }
 #pragma unroll
-      for (int dim = 0; dim < D; ++dim) {
-        const int k = (KS == 1) ? 0 : dim;
-        const double mm = SA(cur, p, dim);
-        const double df = cl[dim] - mm;
-        quad += df * df * rq[k];
-        SA(cur, p, dim) = (mm * l2[k] + cl[dim] * s2[k]) * rq[k];
-      }
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const int p = p0 + u4;
+        if (p < nP) {
+          double quad = 0.0, logs = 0.0;
+          double rq[KS];
 #pragma unroll
-      for (int k = 0; k < KS; ++k) SA(cur, p, D + k) = l2[k] * s2[k] * rq[k];
-      const double LC = (KS == 1) ? -0.5 * ((double)D * logs + quad) : -0.5 * (logs + quad);
-      SA(cur, p, D + KS) += LC;
+          for (int k = 0; k < KS; ++k) {
+            const double q = l2[k] + s24[u4][k];
+            rq[k] = 1.0 / q;
+            logs += log(XT_TWO_PI * q);
+          }
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) {
+            const int k = (KS == 1) ? 0 : dim;
+            const double df = cl[dim] - mm4[u4][dim];
+            quad += df * df * rq[k];
+            SA(cur, p, dim) = (mm4[u4][dim] * l2[k] + cl[dim] * s24[u4][k]) * rq[k];
+          }
+#pragma unroll
+          for (int k = 0; k < KS; ++k) SA(cur, p, D + k) = l2[k] * s24[u4][k] * rq[k];
+          const double LC = (KS == 1) ? -0.5 * ((double)D * logs + quad) : -0.5 * (logs + quad);
+          SA(cur, p, D + KS) = lp4[u4] + LC;
+        }
+      }
     }
     const bool stay = step >= P.min_len;
     if (step <= L - 2) {
@@ -144,10 +159,17 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
           SA(nxt, g, D + KS) = SA(cur, p, D + KS) + (P.LT[head] + (stay ? Lps[r] : 0.0));
         } else {
           double mx = -INFINITY;
-          for (int k = 0; k < n; ++k) {
-            const uint32_t e = __ldg(&ent[o + k]);
-            const int p = (int)(e & 0xFFFF), head = (int)((e >> 16) & 0xFF), r = (int)(e >> 24);
-            mx = fmax(mx, SA(cur, p, D + KS) + (P.LT[head] + (stay ? Lps[r] : 0.0)));
+          for (int k0 = 0; k0 < n; k0 += 4) {  // four members per round, loads first
+            double b4[4], a4[4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+              const uint32_t e = __ldg(&ent[o + (k0 + u4 < n ? k0 + u4 : k0)]);
+              const int p = (int)(e & 0xFFFF), head = (int)((e >> 16) & 0xFF), r = (int)(e >> 24);
+              b4[u4] = SA(cur, p, D + KS);
+              a4[u4] = P.LT[head] + (stay ? Lps[r] : 0.0);
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) mx = fmax(mx, b4[u4] + a4[u4]);
           }
           double sw = 0.0, am[D], as[KS];
 #pragma unroll
