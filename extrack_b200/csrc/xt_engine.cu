@@ -80,6 +80,12 @@ struct xt_ctx {
   // K2 global-state fallback
   double* d_gstate = nullptr;
   size_t gstate_bytes = 0;
+  // fused replay kernel with its state in global memory (GST): state blocks + per-SM slot bitmaps
+  char* d_fstate = nullptr;
+  size_t fstate_bytes = 0;
+  unsigned* d_fslots = nullptr;
+  int k2_gst_below_ctas = 3;  // prefer the GST instantiation when fewer than this many shared-memory CTAs fit on an SM
+  int k2_gst = 1;             // 0: never use the GST instantiation (falls back to the log-domain kernel)
   int smem_optin = 0, n_sm = 0;
   bool have_eval = false;
   bool force_global = false;  // test hook: run the log-domain global-memory replay variant
@@ -171,6 +177,8 @@ static void free_data(xt_ctx* ctx) {
   }
   cudaFree(ctx->d_soa); cudaFree(ctx->d_chunks); cudaFree(ctx->d_work); cudaFree(ctx->d_logp);
   cudaFree(ctx->d_partial); cudaFree(ctx->d_summ); cudaFree(ctx->d_gstate);
+  cudaFree(ctx->d_fstate); cudaFree(ctx->d_fslots);
+  ctx->d_fstate = nullptr; ctx->d_fslots = nullptr; ctx->fstate_bytes = 0;
   cudaFree(ctx->d_workf[0]); cudaFree(ctx->d_workf[1]); cudaFree(ctx->d_corder);
   ctx->d_corder = nullptr;
   ctx->d_workf[0] = ctx->d_workf[1] = nullptr;
@@ -673,6 +681,13 @@ static cudaError_t launch_k2_fused_w(const K2FArgs& a, const K2Tab& tab, size_t 
 template <int D, int KS>
 static cudaError_t launch_k2_fused(const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt, cudaStream_t stream,
                                    bool var) {
+  if (a.gstate) {  // state in global memory: one configuration (4 warps per tile, one track per thread)
+    auto kern = k2_replay_fused<D, KS, 4, 1, false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<a.n_work, 128, smem, stream>>>(a, tab);
+    return cudaGetLastError();
+  }
   if (var) {  // peak-wise LocErr / per-track dt: one configuration (4 warps per tile, one track per thread)
     auto kern = k2_replay_fused<D, KS, 4, 1, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -888,6 +903,7 @@ struct FusedLaunch {  // everything a fused replay launch needs besides its tile
   size_t smem;
   int wpc, tpt;
   bool var;
+  bool gst;  // state in global memory (the live sequences of a tile exceed shared memory)
 };
 
 static void leave_sums(const xt_params* p, double* Lsum) {
@@ -910,9 +926,35 @@ static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch
   if (fl->var) fl->tpt = 1;
   if (fl->tpt == 2 && xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, 2) > (size_t)ctx->smem_optin) fl->tpt = 1;
   fl->smem = xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, fl->tpt, fl->var);
-  if (ctx->k2_variant != 0 || ctx->force_global || fl->smem > (size_t)ctx->smem_optin ||
-      xt_fused_blob16(Pmax, K) > 64 * fl->wpc || (fl->var && fl->wpc != 4))
-    return false;
+  fl->gst = false;
+  if (ctx->k2_variant != 0 || ctx->force_global || (fl->var && fl->wpc != 4)) return false;
+  const int smem_ctas = fl->smem ? (int)(((size_t)228 * 1024) / (fl->smem + 1024)) : 0;
+  if (fl->smem > (size_t)ctx->smem_optin || xt_fused_blob16(Pmax, K) > 64 * fl->wpc ||
+      (!fl->var && fl->wpc == 4 && smem_ctas < ctx->k2_gst_below_ctas)) {
+    // the live sequences of a tile do not fit in shared memory: same kernel with its state in global memory
+    const size_t stride = xt_fused_gstride(p->d, KS, Pmax);
+    const size_t need = stride * 32 * (size_t)ctx->n_sm;
+    if (!ctx->k2_gst || fl->var || fl->wpc != 4 || Pmax > 4095 || need > ((size_t)8 << 30) ||
+        xt_fused_smem_gst(Pmax, K, H) > (size_t)ctx->smem_optin)
+      return false;
+    if (need > ctx->fstate_bytes) {
+      cudaFree(ctx->d_fstate);
+      ctx->d_fstate = nullptr;
+      ctx->fstate_bytes = 0;
+      if (cudaMalloc(&ctx->d_fstate, need) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      ctx->fstate_bytes = need;
+    }
+    if (!ctx->d_fslots) {
+      if (cudaMalloc(&ctx->d_fslots, sizeof(unsigned) * ctx->n_sm) != cudaSuccess) return false;
+      cudaMemset(ctx->d_fslots, 0, sizeof(unsigned) * ctx->n_sm);
+    }
+    fl->gst = true;
+    fl->tpt = 1;
+    fl->smem = xt_fused_smem_gst(Pmax, K, H);
+  }
   double Lsum[XT_MAX_STATES];
   leave_sums(p, Lsum);
   K2Tab& tab = fl->tab;
@@ -941,6 +983,11 @@ static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch
   K2FArgs& fa = fl->fa;
   fa = K2FArgs{};
   if (fl->var) fa.ax = make_aux(ctx, p, 0);
+  if (fl->gst) {
+    fa.gstate = ctx->d_fstate;
+    fa.gslots = ctx->d_fslots;
+    fa.gstride = xt_fused_gstride(p->d, KS, Pmax);
+  }
   fa.chunks = ctx->d_chunks;
   fa.work = ctx->d_workf[fl->tpt - 1];
   fa.soa = ctx->d_soa;
@@ -1229,6 +1276,16 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
       return XT_ERR_ARG;
     }
     ctx->k1_threads = value;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k2_gst_below_ctas") == 0) {
+    ctx->k2_gst_below_ctas = value;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k2_gst") == 0) {
+    ctx->k2_gst = value != 0;
     ctx->have_eval = false;
     return XT_OK;
   }

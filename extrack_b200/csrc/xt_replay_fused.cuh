@@ -90,6 +90,29 @@ __device__ __forceinline__ void xt_sts32(unsigned a, int x) {
   asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
 }
 
+// State memory of the replay kernel: shared memory (32-bit shared-window address `a`) or, in the GST
+// instantiation (live sequences of a tile do not fit in shared memory), a per-CTA block of global
+// memory at `gb` (`a` is then a byte offset).  Plain loads / stores: the CTA barrier between the steps
+// orders them.
+template <bool GST> __device__ __forceinline__ void xs_ld128(const char* gb, unsigned a, double& x, double& y) {
+  if (GST) { const double2 v = *reinterpret_cast<const double2*>(gb + a); x = v.x; y = v.y; } else xt_lds128(a, x, y);
+}
+template <bool GST> __device__ __forceinline__ double xs_ld64(const char* gb, unsigned a) {
+  return GST ? *reinterpret_cast<const double*>(gb + a) : xt_lds64(a);
+}
+template <bool GST> __device__ __forceinline__ int xs_ld32(const char* gb, unsigned a) {
+  return GST ? *reinterpret_cast<const int*>(gb + a) : xt_lds32(a);
+}
+template <bool GST> __device__ __forceinline__ void xs_st128(char* gb, unsigned a, double x, double y) {
+  if (GST) *reinterpret_cast<double2*>(gb + a) = make_double2(x, y); else xt_sts128(a, x, y);
+}
+template <bool GST> __device__ __forceinline__ void xs_st64(char* gb, unsigned a, double x) {
+  if (GST) *reinterpret_cast<double*>(gb + a) = x; else xt_sts64(a, x);
+}
+template <bool GST> __device__ __forceinline__ void xs_st32(char* gb, unsigned a, int x) {
+  if (GST) *reinterpret_cast<int*>(gb + a) = x; else xt_sts32(a, x);
+}
+
 // 2^d for -1022 <= d <= 0, +0.0 below (d never exceeds 0 here: exponents relative to a maximum)
 __device__ __forceinline__ double xt_pow2_le0(int d) {
   return __hiloint2double(max(d + 1023, 0) << 20, 0);
@@ -150,28 +173,28 @@ struct XtSeq {
 // State slot = NV 16-byte vectors [vector][track] (components m[D], u[KS], W in this order) at
 // va + i*VS, exponents at ea; both addresses already include the lane offset.  Track j of the
 // thread sits 32*j lanes further.
-template <int D, int KS, int TPT>
+template <int D, int KS, int TPT, bool GST = false>
 struct XtSlotIO {
   static constexpr int CO = D + KS + 1;
   static constexpr int NV = (CO + 1) / 2;
   static constexpr int VS = 32 * TPT * 16;   // bytes per vector row
   static constexpr int SLOTB = NV * VS;      // bytes per slot
   static constexpr int ESLOT = 32 * TPT * 4; // exponent bytes per slot
-  static __device__ __forceinline__ void load(unsigned va, unsigned ea, XtSeq<D, KS> (&s)[TPT]) {
+  static __device__ __forceinline__ void load(const char* gb, unsigned va, unsigned ea, XtSeq<D, KS> (&s)[TPT]) {
 #pragma unroll
     for (int j = 0; j < TPT; ++j) {
       double c[2 * NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) xt_lds128(va + i * VS + j * 512, c[2 * i], c[2 * i + 1]);
+      for (int i = 0; i < NV; ++i) xs_ld128<GST>(gb, va + i * VS + j * 512, c[2 * i], c[2 * i + 1]);
 #pragma unroll
       for (int i = 0; i < D; ++i) s[j].m[i] = c[i];
 #pragma unroll
       for (int i = 0; i < KS; ++i) s[j].u[i] = c[D + i];
       s[j].W = c[D + KS];
-      s[j].E = xt_lds32(ea + j * 128);
+      s[j].E = xs_ld32<GST>(gb, ea + j * 128);
     }
   }
-  static __device__ __forceinline__ void store(unsigned va, unsigned ea, const XtSeq<D, KS> (&s)[TPT]) {
+  static __device__ __forceinline__ void store(char* gb, unsigned va, unsigned ea, const XtSeq<D, KS> (&s)[TPT]) {
 #pragma unroll
     for (int j = 0; j < TPT; ++j) {
       double c[2 * NV];
@@ -182,8 +205,8 @@ struct XtSlotIO {
       c[D + KS] = s[j].W;
       if (2 * NV > CO) c[CO] = 0.0;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) xt_sts128(va + i * VS + j * 512, c[2 * i], c[2 * i + 1]);
-      xt_sts32(ea + j * 128, s[j].E);
+      for (int i = 0; i < NV; ++i) xs_st128<GST>(gb, va + i * VS + j * 512, c[2 * i], c[2 * i + 1]);
+      xs_st32<GST>(gb, ea + j * 128, s[j].E);
     }
   }
 };
@@ -252,10 +275,22 @@ struct K2FArgs {
   int32_t n_work;      // CTAs of this launch
   int32_t work0;       // first tile of this launch in the work table
   XtAux ax;            // VAR instantiation only (stay / leave tables are per chunk)
+  // GST instantiation only: state blocks in global memory, one per resident CTA
+  char* gstate;        // [n_sm * 32][gstride] bytes
+  unsigned* gslots;    // [n_sm] bitmap of the blocks in use on every SM
+  size_t gstride;
 };
 
 // shared memory of k2_replay_fused in bytes (host and device agree through these functions)
 __host__ __device__ inline int xt_fused_blob16(int Pcap, int K) { return 2 + (Pcap + 1) / 2 + (K * Pcap + 3) / 4; }
+// GST instantiation: one staged record + tables in shared memory, the state in global memory
+__host__ __device__ inline size_t xt_fused_smem_gst(int Pcap, int K, int H) {
+  return (size_t)xt_fused_blob16(Pcap, K) * 16 + (size_t)2 * H * 16 + 128 + 64;
+}
+__host__ __device__ inline size_t xt_fused_gstride(int D, int KS, int Pcap) {
+  const int NV = (D + KS + 1 + 1) / 2;
+  return (size_t)2 * Pcap * (NV * 512 + 128);
+}
 __host__ __device__ inline size_t xt_fused_smem(int D, int KS, int Pcap, int K, int H, int wpc, int tpt, bool var = false) {
   const int NV = (D + KS + 1 + 1) / 2;
   return (var ? 64 : 0)                            // VAR: per-chunk leave sums [nS]
@@ -267,15 +302,16 @@ __host__ __device__ inline size_t xt_fused_smem(int D, int KS, int Pcap, int K, 
   // (the end-of-track partial sums, wpc * 384 * tpt bytes, reuse the idle state buffer: Pcap >= 2)
 }
 
-template <int D, int KS, int WPC, int TPT, bool VAR = false>
+template <int D, int KS, int WPC, int TPT, bool VAR = false, bool GST = false>
 #ifndef XT_K2_WARPS_T1
 #define XT_K2_WARPS_T1 24  // resident warps per SM the register budget is set for (one track per thread)
 #endif
 __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / WPC) k2_replay_fused(const K2FArgs a, const __grid_constant__ K2Tab T) {
-  using IO = XtSlotIO<D, KS, TPT>;
+  using IO = XtSlotIO<D, KS, TPT, GST>;
   using Seq = XtSeq<D, KS>;
   constexpr int SLOTB = IO::SLOTB, ESLOT = IO::ESLOT;
   constexpr int NT = 32 * WPC;
+  static_assert(!GST || (TPT == 1 && !VAR), "the global-state instantiation is built for one track per thread, scalar inputs");
   const int tid = threadIdx.x;
   const int lane = tid & 31, w = tid >> 5;
   const int wi = (int)blockIdx.x + a.work0;
@@ -310,12 +346,33 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
   extern __shared__ double2 k2f_smem[];
   const unsigned sb = xt_smem_base(k2f_smem);
   const unsigned VB = (unsigned)Pcap * SLOTB, EB = (unsigned)Pcap * ESLOT;
-  const unsigned s_vec = sb + lane * 16;                // [2][Pcap][NV][32*TPT] x 16 B
-  const unsigned s_blob = sb + 2 * VB;                  // [2][B16] x 16 B
-  const unsigned s_tab = s_blob + 2 * B16 * 16;         // [2][H] x 16 B: (tau, dd)
-  const unsigned s_e2 = s_tab + 2 * H * 16;             // [16] x 8 B
-  const unsigned s_exp = s_e2 + 128 + lane * 4;         // [2][Pcap][32*TPT] x 4 B
-  const unsigned s_leave = s_e2 + 128 + 2 * EB;         // VAR: [nS] x 8 B per-chunk leave sums
+  // shared memory: state vectors [2][Pcap][NV][32*TPT] x 16 B, staged records [2][B16] x 16 B, tables,
+  // exponents [2][Pcap][32*TPT] x 4 B.  GST: the state (vectors, then exponents) is a block of global
+  // memory and s_vec / s_exp are byte offsets into it; shared memory holds one record and the tables.
+  const unsigned s_vec = GST ? lane * 16 : sb + lane * 16;
+  const unsigned s_blob = GST ? sb : sb + 2 * VB;
+  const unsigned s_tab = s_blob + (GST ? 1 : 2) * B16 * 16;  // [2][H] x 16 B: (tau, dd)
+  const unsigned s_e2 = s_tab + 2 * H * 16;                   // [16] x 8 B
+  const unsigned s_exp = GST ? 2 * VB + lane * 4 : s_e2 + 128 + lane * 4;
+  const unsigned s_leave = s_e2 + 128 + (GST ? 0 : 2 * EB);   // VAR: [nS] x 8 B per-chunk leave sums
+  // GST: take one of this SM's state blocks (at most 32 CTAs are resident on an SM, so a bit is free)
+  char* gb = nullptr;
+  __shared__ int s_slot;
+  unsigned smid = 0;
+  if (GST) {
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (tid == 0) {
+      int b = 0;
+      for (;;) {
+        const unsigned old = atomicOr(&a.gslots[smid], 1u << b);
+        if (!(old & (1u << b))) break;
+        b = (b + 1) & 31;
+      }
+      s_slot = b;
+    }
+    __syncthreads();
+    gb = a.gstate + ((size_t)smid * 32 + s_slot) * a.gstride;
+  }
 
   // stage the first replay record (steps 3..L-1 use records 0..L-4) and the tables
   // (up to two 16-byte words per thread: B16 <= 64 * WPC is checked by the host)
@@ -323,7 +380,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
   const uint4* gblob = a.plan.blob + (size_t)ck.rec0 * bstride + tid;
   const int nrec = ck.nrec;
   uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
-  if (nrec > 0) {
+  if (!GST && nrec > 0) {
     if (tid < B16) pre0 = __ldg(gblob);
     if (tid + NT < B16) pre1 = __ldg(gblob + NT);
   }
@@ -393,7 +450,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       xt_split_exponent(T.winit[c], 0, s[j].W, s[j].E);
     }
     if (L >= 3) xt_update<D, KS, TPT, VAR>(s, cn, VAR ? l2n : l2, s_e2, T);
-    IO::store(s_vec + c * SLOTB, s_exp + c * ESLOT, s);
+    IO::store(gb, s_vec + c * SLOTB, s_exp + c * ESLOT, s);
   }
   if (VAR && L >= 3) {  // dtc = dt of localisation 1, l2n/dtn = row 2
     Ax += astride;
@@ -409,8 +466,10 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
         cn[j][dim] = Cs[(size_t)dim * npad + toff[j]];  // C[2]
       }
   }
-  if (tid < B16) xt_sts128u(s_blob + tid * 16, pre0);
-  if (tid + NT < B16) xt_sts128u(s_blob + (tid + NT) * 16, pre1);
+  if (!GST) {
+    if (tid < B16) xt_sts128u(s_blob + tid * 16, pre0);
+    if (tid + NT < B16) xt_sts128u(s_blob + (tid + NT) * 16, pre1);
+  }
   __syncthreads();
 
   // loop-invariant parts of the record prefetch / staging
@@ -443,13 +502,20 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       aux_row(l2n, dtn);
     }
     const bool more = ri + 1 < nrec;
-    gnext += bstride;  // record of the next step (running pointer: no 64-bit multiply per step)
-    if (more) {
-      if (st0) pre0 = __ldg(gnext);
-      if (st1) pre1 = __ldg(gnext + NT);
+    if (GST) {  // stage this step's record (any size) with the whole CTA
+      const uint4* gr = a.plan.blob + (size_t)(ck.rec0 + ri) * bstride;
+      const int n16 = (int)(__ldg(gr).y & 0xFFFFu);  // XtBlobHdr::n16
+      for (int i = tid; i < n16; i += NT) xt_sts128u(s_blob + i * 16, __ldg(gr + i));
+      __syncthreads();
+    } else {
+      gnext += bstride;  // record of the next step (running pointer: no 64-bit multiply per step)
+      if (more) {
+        if (st0) pre0 = __ldg(gnext);
+        if (st1) pre1 = __ldg(gnext + NT);
+      }
     }
 
-    const unsigned rb = s_blob + (ri & 1) * (B16 * 16);
+    const unsigned rb = s_blob + (GST ? 0 : (ri & 1) * (B16 * 16));
     const int nG = (int)xt_lds16(rb);  // XtBlobHdr::nG
     const unsigned grec = rb + 32;
     const unsigned entb = grec + ((nG + 1) >> 1) * 16;
@@ -466,7 +532,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       const unsigned g = gr.x >> 19;
       const unsigned kind = gr.y >> 30;
       Seq G[TPT];
-      IO::load(src_v + p0o * (SLOTB / 128), src_e + p0o * (ESLOT / 128), G);
+      IO::load(gb, src_v + p0o * (SLOTB / 128), src_e + p0o * (ESLOT / 128), G);
       double tau0, dd0;
       xt_lds128(tabp + (gr.x & 0x7Fu) * 16, tau0, dd0);
       if (kind == 1u) {
@@ -480,7 +546,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       } else if (kind == 2u) {
         const unsigned p1o = gr.y & 0x7FF80u;
         Seq B[TPT];
-        IO::load(src_v + p1o * (SLOTB / 128), src_e + p1o * (ESLOT / 128), B);
+        IO::load(gb, src_v + p1o * (SLOTB / 128), src_e + p1o * (ESLOT / 128), B);
         double tau1, dd1;
         xt_lds128(tabp + (gr.y & 0x7Fu) * 16, tau1, dd1);
 #pragma unroll
@@ -513,7 +579,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
         for (int k = 1; k < n; ++k) {
           const unsigned ea = src_e + ((unsigned)xt_lds32(eb + k * 4) & 0xFFFFu) * ESLOT;
 #pragma unroll
-          for (int j = 0; j < TPT; ++j) Eg[j] = max(Eg[j], xt_lds32(ea + j * 128));
+          for (int j = 0; j < TPT; ++j) Eg[j] = max(Eg[j], xs_ld32<GST>(gb, ea + j * 128));
         }
         double sw[TPT], am[TPT][D], as[TPT][KS];
 #pragma unroll
@@ -532,7 +598,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
           const unsigned e = (unsigned)xt_lds32(eb + k * 4);
           const unsigned pm = e & 0xFFFFu;
           Seq M[TPT];
-          IO::load(src_v + pm * SLOTB, src_e + pm * ESLOT, M);
+          IO::load(gb, src_v + pm * SLOTB, src_e + pm * ESLOT, M);
           double taum, ddm;
           xt_lds128(tabp + ((e >> 16) & 0xFFu) * 16, taum, ddm);
 #pragma unroll
@@ -559,14 +625,14 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
         }
       }
       xt_update<D, KS, TPT, VAR>(G, cl, l2, s_e2, T);
-      IO::store(dst_v + g * SLOTB, dst_e + g * ESLOT, G);
+      IO::store(gb, dst_v + g * SLOTB, dst_e + g * ESLOT, G);
     }
     nP = nG;
     {  // swap the ping-pong buffers
       unsigned tv = src_v; src_v = dst_v; dst_v = tv;
       unsigned te = src_e; src_e = dst_e; dst_e = te;
     }
-    if (more) {
+    if (!GST && more) {
       const unsigned nb = s_stage + ((ri + 1) & 1) * (B16 * 16);
       if (st0) xt_sts128u(nb, pre0);
       if (st1) xt_sts128u(nb + NT * 16, pre1);
@@ -592,7 +658,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
   }
   for (int p = w; p < nP; p += WPC) {
     Seq S[TPT];
-    IO::load(src_v + p * SLOTB, src_e + p * ESLOT, S);
+    IO::load(gb, src_v + p * SLOTB, src_e + p * ESLOT, S);
     const int ps = curP ? (int)__ldg(&curP[p]) : (p % nS);
     double df2[TPT][D];
 #pragma unroll
@@ -637,22 +703,22 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
   const unsigned s_redK = s_redA + WPC * 256 * TPT;       // [WPC][TPT][32] x 4 B
 #pragma unroll
   for (int j = 0; j < TPT; ++j) {
-    xt_sts64(s_redA + ((w * TPT + j) * 32 + lane) * 8, acc[j]);
-    xt_sts32(s_redK + ((w * TPT + j) * 32 + lane) * 4, KA[j]);
+    xs_st64<GST>(gb, s_redA + ((w * TPT + j) * 32 + lane) * 8, acc[j]);
+    xs_st32<GST>(gb, s_redK + ((w * TPT + j) * 32 + lane) * 4, KA[j]);
   }
   __syncthreads();
   if (w == 0) {
     double lps = 0.0;
 #pragma unroll
     for (int j = 0; j < TPT; ++j) {
-      int Kn = xt_lds32(s_redK + (j * 32 + lane) * 4);
+      int Kn = xs_ld32<GST>(gb, s_redK + (j * 32 + lane) * 4);
 #pragma unroll
-      for (int k = 1; k < WPC; ++k) Kn = max(Kn, xt_lds32(s_redK + ((k * TPT + j) * 32 + lane) * 4));
+      for (int k = 1; k < WPC; ++k) Kn = max(Kn, xs_ld32<GST>(gb, s_redK + ((k * TPT + j) * 32 + lane) * 4));
       double tot = 0.0;
 #pragma unroll
       for (int k = 0; k < WPC; ++k)
-        tot = fma(xt_lds64(s_redA + ((k * TPT + j) * 32 + lane) * 8),
-                  xt_pow2_le0(xt_lds32(s_redK + ((k * TPT + j) * 32 + lane) * 4) - Kn), tot);
+        tot = fma(xs_ld64<GST>(gb, s_redA + ((k * TPT + j) * 32 + lane) * 8),
+                  xt_pow2_le0(xs_ld32<GST>(gb, s_redK + ((k * TPT + j) * 32 + lane) * 4) - Kn), tot);
       double lp = XT_LN2 * (double)Kn + log(tot) - (double)(L - 1) * (0.5 * (double)D) * XT_LN_2PI;
       if (!(fabs(csum[j]) <= 1.7976931348623157e308)) lp = __longlong_as_double(0x7ff8000000000000ll);
       if (valid[j]) {
@@ -663,5 +729,9 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) lps += __shfl_down_sync(0xffffffffu, lps, off);
     if (lane == 0) a.partial[wi] = lps;
+  }
+  if (GST) {  // give the state block back (after warp 0 has read the partial sums parked in it)
+    __syncthreads();
+    if (tid == 0) atomicAnd(&a.gslots[smid], ~(1u << s_slot));
   }
 }

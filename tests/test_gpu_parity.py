@@ -460,7 +460,9 @@ def test_var_inputs_bad_shapes_raise(xt):
 
 
 @pytest.mark.parametrize("opts", [dict(k1_threads=256), dict(k1_threads=1024), dict(k1_threads=256, k1_batch=0),
-                                  dict(k1_threads=1024, k1_batch=0), dict(k1_threads=256, k1_smem_scratch=0)])
+                                  dict(k1_threads=1024, k1_batch=0), dict(k1_threads=256, k1_smem_scratch=0),
+                                  dict(k2_gst_below_ctas=99),   # fused replay with its state in global memory
+                                  dict(k2_gst=0, k2_gst_below_ctas=0)])  # shared-memory state or the log-domain kernel only
 @pytest.mark.parametrize("path", [p for p in CASES if any(t in p for t in ("s2_fl8_L20", "s3_nsub2_wrap", "s3_3d.", "s4", "s2_escalate"))],
                          ids=lambda p: os.path.basename(p)[:-4] if isinstance(p, str) else None)
 def test_plan_kernel_variants_give_the_oracle_plan(path, opts, native):

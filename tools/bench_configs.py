@@ -43,6 +43,8 @@ def params_from(LocErr, Ds, Fs, Tr, pBL):
 
 
 def time_eval(eng, p, reps):
+    if os.environ.get("K2_GST_BELOW"):
+        eng.set_option("k2_gst_below_ctas", int(os.environ["K2_GST_BELOW"]))
     eng.sum_logp(p)  # two-phase (sizes the launches)
     eng.sum_logp(p)
     torch.cuda.synchronize()
