@@ -66,6 +66,7 @@ class XtStats(C.Structure):
         ("ms_predict", C.c_float),
         ("k3_launches", C.c_int32),
         ("k3_cap", C.c_int32),
+        ("fp32", C.c_int32),
     ]
 
 

@@ -12,6 +12,7 @@
 #include "xt_replay.cuh"
 #include "xt_replay_lin.cuh"
 #include "xt_replay_fused.cuh"
+#include "xt_replay_f32.cuh"
 #include "xt_predict.cuh"
 
 struct xt_ctx {
@@ -86,6 +87,7 @@ struct xt_ctx {
   unsigned* d_fslots = nullptr;
   int k2_gst_below_ctas = 3;  // prefer the GST instantiation when fewer than this many shared-memory CTAs fit on an SM
   int k2_gst = 1;             // 0: never use the GST instantiation (falls back to the log-domain kernel)
+  int k2_fp32 = 0;            // 1: optional single-precision replay (xt_replay_f32.cuh) where it applies
   int smem_optin = 0, n_sm = 0;
   bool have_eval = false;
   bool force_global = false;  // test hook: run the log-domain global-memory replay variant
@@ -680,7 +682,14 @@ static cudaError_t launch_k2_fused_w(const K2FArgs& a, const K2Tab& tab, size_t 
 
 template <int D, int KS>
 static cudaError_t launch_k2_fused(const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt, cudaStream_t stream,
-                                   bool var) {
+                                   bool var, bool f32) {
+  if (f32) {  // optional single-precision replay: one configuration (4 warps per tile, one track per thread)
+    auto kern = k2_replay_f32<D, KS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<a.n_work, 128, smem, stream>>>(a, tab);
+    return cudaGetLastError();
+  }
   if (a.gstate) {  // state in global memory: one configuration (4 warps per tile, one track per thread)
     auto kern = k2_replay_fused<D, KS, 4, 1, false, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -904,7 +913,26 @@ struct FusedLaunch {  // everything a fused replay launch needs besides its tile
   int wpc, tpt;
   bool var;
   bool gst;  // state in global memory (the live sequences of a tile exceed shared memory)
+  bool f32;  // single-precision replay kernel
 };
+
+// FP32 replay applies when every table entry is zero or comfortably inside the FP32 range (the weights
+// themselves carry an extended exponent, the per-step factors do not)
+static bool f32_tables_ok(const xt_params* p, const double* Lsum) {
+  const int K = ipow(p->nS, p->nsub), H = K * p->nS;
+  auto fac_ok = [](double v) { return v == 0.0 || (v >= 1e-20 && v <= 1e3); };
+  for (int h = 0; h < H; ++h) {
+    if (!fac_ok(std::exp(p->LT[h])) || !fac_ok(std::exp(p->LT[h] + p->Lp_stay[h % K])) ||
+        !fac_ok(std::exp(p->LT[h] + p->LF[h])))
+      return false;
+    if (!(p->dd[h] >= 0.0 && p->dd[h] <= 1e6)) return false;
+  }
+  for (int s = 0; s < p->nS; ++s)
+    if (!fac_ok(std::exp(Lsum[s]))) return false;
+  for (int k = 0; k < p->n_loc; ++k)
+    if (!(p->l2[k] >= 1e-12 && p->l2[k] <= 1e6)) return false;
+  return true;
+}
 
 static void leave_sums(const xt_params* p, double* Lsum) {
   const int K = ipow(p->nS, p->nsub);
@@ -927,10 +955,20 @@ static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch
   if (fl->tpt == 2 && xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, 2) > (size_t)ctx->smem_optin) fl->tpt = 1;
   fl->smem = xt_fused_smem(p->d, KS, Pmax, K, H, fl->wpc, fl->tpt, fl->var);
   fl->gst = false;
+  fl->f32 = false;
   if (ctx->k2_variant != 0 || ctx->force_global || (fl->var && fl->wpc != 4)) return false;
+  double Lsum[XT_MAX_STATES];
+  leave_sums(p, Lsum);
+  if (ctx->k2_fp32 && !fl->var && fl->wpc == 4 && xt_f32_smem(p->d, KS, Pmax, K, H) <= (size_t)ctx->smem_optin &&
+      xt_fused_blob16(Pmax, K) <= 256 && f32_tables_ok(p, Lsum)) {
+    fl->f32 = true;
+    fl->wpc = 4;
+    fl->tpt = 1;
+    fl->smem = xt_f32_smem(p->d, KS, Pmax, K, H);
+  }
   const int smem_ctas = fl->smem ? (int)(((size_t)228 * 1024) / (fl->smem + 1024)) : 0;
-  if (fl->smem > (size_t)ctx->smem_optin || xt_fused_blob16(Pmax, K) > 64 * fl->wpc ||
-      (!fl->var && fl->wpc == 4 && smem_ctas < ctx->k2_gst_below_ctas)) {
+  if (!fl->f32 && (fl->smem > (size_t)ctx->smem_optin || xt_fused_blob16(Pmax, K) > 64 * fl->wpc ||
+                   (!fl->var && fl->wpc == 4 && smem_ctas < ctx->k2_gst_below_ctas))) {
     // the live sequences of a tile do not fit in shared memory: same kernel with its state in global memory
     const size_t stride = xt_fused_gstride(p->d, KS, Pmax);
     const size_t need = stride * 32 * (size_t)ctx->n_sm;
@@ -955,8 +993,6 @@ static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch
     fl->tpt = 1;
     fl->smem = xt_fused_smem_gst(Pmax, K, H);
   }
-  double Lsum[XT_MAX_STATES];
-  leave_sums(p, Lsum);
   K2Tab& tab = fl->tab;
   tab = K2Tab{};
   for (int h = 0; h < H; ++h) {
@@ -1008,11 +1044,12 @@ static int enqueue_fused(xt_ctx* ctx, const xt_params* p, const FusedLaunch& fl,
   fa.n_work = w0[c1] - w0[c0];
   if (fa.n_work <= 0) return XT_OK;
   cudaError_t ef = cudaSuccess;
-#define CALL_K2F(D_, KS_) ef = launch_k2_fused<D_, KS_>(fa, fl.tab, fl.smem, fl.wpc, fl.tpt, stream, fl.var)
+#define CALL_K2F(D_, KS_) ef = launch_k2_fused<D_, KS_>(fa, fl.tab, fl.smem, fl.wpc, fl.tpt, stream, fl.var, fl.f32)
   XT_DISPATCH(p->d, p->n_loc, CALL_K2F);
 #undef CALL_K2F
   XT_CUDA_OK(ef);
   ctx->stats.k2_launches++;
+  ctx->stats.fp32 = fl.f32 ? 1 : 0;
   return XT_OK;
 }
 
@@ -1281,6 +1318,11 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
   }
   if (std::strcmp(name, "k2_gst_below_ctas") == 0) {
     ctx->k2_gst_below_ctas = value;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "fp32_replay") == 0) {
+    ctx->k2_fp32 = value != 0;
     ctx->have_eval = false;
     return XT_OK;
   }

@@ -276,7 +276,8 @@ class TrackSet:
 
     def __init__(self, sorted_tracks: Sequence[np.ndarray], chunk: int = MAX_TRACKS_PER_CHUNK, device: Optional[int] = None,
                  rank: Optional[int] = None, world_size: Optional[int] = None, reverse: bool = True,
-                 input_LocErr: Optional[Sequence[np.ndarray]] = None, dt_list: Optional[Sequence[np.ndarray]] = None):
+                 input_LocErr: Optional[Sequence[np.ndarray]] = None, dt_list: Optional[Sequence[np.ndarray]] = None,
+                 precision: Optional[str] = None):
         if len(sorted_tracks) < 1:
             raise ValueError("No track could be detected. The loaded tracks seem empty. Errors often come from wrong input paths.")
         for a in sorted_tracks:
@@ -295,6 +296,9 @@ class TrackSet:
             device = _default_device()
         self.engine = _native.Engine(device)
         self.device = device
+        self.precision = _check_precision(precision if precision is not None else _PRECISION)
+        if self.precision == "fp32":
+            self.engine.set_option("fp32_replay", 1)
         segs = [self.sorted_tracks[b][a:z] for (b, a, z, _) in (self.chunks[i] for i in mine)]
         bl = [self.chunks[i][3] for i in mine]
         self.n_local_chunks = len(segs)
@@ -380,6 +384,34 @@ def _default_device() -> int:
     import os
 
     return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+# Arithmetic of the replay kernel: "fp64" (reference precision, default) or "fp32" (optional path of the
+# north star: total log-likelihood within 1e-4 relative of the FP64 result; the fusion plan stays FP64).
+# The reference signatures have no such argument, so it is a module switch (or EXTRACK_B200_PRECISION).
+import os as _os
+
+_PRECISION = _os.environ.get("EXTRACK_B200_PRECISION", "fp64")
+
+
+def _check_precision(name: str) -> str:
+    if name not in ("fp64", "fp32"):
+        raise ValueError("precision must be 'fp64' or 'fp32', got %r" % (name,))
+    return name
+
+
+def set_precision(name: str) -> None:
+    """Select the replay arithmetic of the data sets created from now on (``param_fitting`` /
+    ``cum_Proba_Cs``); ``predict_Bs`` always runs in FP64."""
+    global _PRECISION
+    _PRECISION = _check_precision(name)
+    for _, _, old in _TRACKSET_CACHE:
+        old.close()
+    del _TRACKSET_CACHE[:]
+
+
+def get_precision() -> str:
+    return _PRECISION
 
 
 _TRACKSET_CACHE: List = []  # [(key, refs, TrackSet)] most recent first

@@ -85,6 +85,7 @@ typedef struct xt_stats {
   float ms_predict;      /* CUDA-event time of the last xt_predict kernel launch (all tracks) */
   int32_t k3_launches;   /* kernel launches of the last xt_predict call (> 1: the sequence capacity had to grow) */
   int32_t k3_cap;        /* sequence capacity of the last xt_predict launch */
+  int32_t fp32;          /* 1: the last evaluation's replay ran in the optional FP32 kernel ("fp32_replay") */
 } xt_stats;
 
 /* Lifetime.  `device` is the CUDA ordinal this context drives. */
@@ -174,7 +175,12 @@ int xt_get_stats(xt_ctx* ctx, xt_stats* out);
  *  "k2_variant" = 1: first-generation linear-domain replay kernel instead of the fused one;
  *  "k2_wpc" (2|4|8), "k2_tpt" (1|2): warps per tile / tracks per thread of the fused replay kernel;
  *  "pipeline" = 0: always evaluate in two phases (plan for all chunks, then replay) instead of
- *      per-group launches on several streams; "n_groups": number of groups of the pipelined path. */
+ *      per-group launches on several streams; "n_groups": number of groups of the pipelined path;
+ *  "fp32_replay" = 1: optional single-precision replay (north star: FP32 path, total log-likelihood
+ *      within 1e-4 relative of the FP64 result).  The plan stays FP64 (same fusion decisions as the
+ *      reference); the per-sequence moments and weight mantissas are FP32 with the same 32-bit extended
+ *      exponent.  Applies to scalar LocErr / dt models whose state fits in shared memory and whose
+ *      tables are representable in FP32; otherwise the FP64 kernel runs (xt_stats::fp32 tells which). */
 int xt_set_option(xt_ctx* ctx, const char* name, int value);
 
 /* Measured FP64 FMA throughput of this GPU in TFLOP/s (2 flops per DFMA), used as the

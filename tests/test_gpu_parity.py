@@ -492,3 +492,104 @@ def test_plan_kernel_variants_give_the_oracle_plan(path, opts, native):
                 np.testing.assert_array_equal(gid, gid_from_groups(rec["groups"], nB))
     finally:
         eng.close()
+
+
+# ---- optional FP32 replay (north star: total log-likelihood within 1e-4 relative of FP64) ----
+RTOL_FP32 = 1e-4
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_fp32_replay_within_stated_tolerance(path, native):
+    """`fp32_replay`: FP64 plan, FP32 moments / weight mantissas with the extended exponent.  Per-track
+    log P and the chunk total stay within 1e-4 relative of the reference; where the FP32 kernel does
+    not apply (state larger than shared memory) the FP64 kernel runs and the bits are the FP64 ones."""
+    z = np.load(path)
+    m = case_model(z)
+    C, isBL = z["C"], int(z["isBL"])
+    ref = z["ref_logp"]
+    p = engine_params(m, C.shape[2])
+    eng = native.Engine(0)
+    try:
+        eng.upload([C], [isBL], len(C))
+        f64 = eng.chunk_logp(0, len(C), p)
+        eng.set_option("fp32_replay", 1)
+        got = eng.chunk_logp(0, len(C), p)
+        used = eng.stats()["fp32"]
+        tot = eng.sum_logp(p)   # second evaluation: pipelined path
+        used2 = eng.stats()["fp32"]
+        got2 = eng.chunk_logp(0, len(C), p)
+    finally:
+        eng.close()
+    assert used == used2
+    np.testing.assert_array_equal(got, got2)
+    if used:
+        assert np.abs(got - ref).max() <= RTOL_FP32 * max(1.0, np.abs(ref).max())
+        assert abs(got.sum() - ref.sum()) <= RTOL_FP32 * abs(ref.sum())
+        assert abs(tot - ref.sum()) <= RTOL_FP32 * abs(ref.sum())
+        assert not np.array_equal(got, f64)  # it really was another arithmetic
+    else:
+        np.testing.assert_array_equal(got, f64)
+
+
+def test_fp32_replay_objective_extreme_range_and_nan(native):
+    """FP32 objective of 4x10^4 synthetic tracks (20 chunks) vs the FP64 one; jumps of hundreds of sigma
+    (the extended exponent keeps the range); NaN coordinates poison the track; a localisation far from
+    the origin does not cost precision (coordinates are taken relative to the first localisation)."""
+    rng = np.random.default_rng(11)
+    m = make_model(frame_len=8)
+    p = engine_params(m, 2)
+    segs = [random_walk_tracks(n, L, 2, rng) for n, L in ((9000, 10), (14000, 17), (17000, 30))]
+    eng = native.Engine(0)
+    try:
+        eng.upload(segs, [1, 1, 0], 2000)
+        a64 = eng.sum_logp(p)
+        eng.set_option("fp32_replay", 1)
+        a32 = eng.sum_logp(p)
+        assert eng.stats()["fp32"] == 1
+        b32 = eng.sum_logp(p)
+        eng.upload([s + 1000.0 for s in segs], [1, 1, 0], 2000)  # 10^3 fields of view away
+        s32 = eng.sum_logp(p)
+        eng.set_option("fp32_replay", 0)
+        s64 = eng.sum_logp(p)
+        assert eng.stats()["fp32"] == 0
+
+        C = random_walk_tracks(64, 15, 2, np.random.default_rng(4))
+        C[::3, 7] += 5.0      # one 250-sigma jump
+        C[1::3, 4:] += 40.0   # a 2000-sigma jump
+        C[5, 3, 1] = np.nan
+        eng.upload([C], [1], len(C))
+        m6 = make_model(frame_len=6)
+        r64 = eng.chunk_logp(0, len(C), engine_params(m6, 2))
+        eng.set_option("fp32_replay", 1)
+        r32 = eng.chunk_logp(0, len(C), engine_params(m6, 2))
+        assert eng.stats()["fp32"] == 1
+    finally:
+        eng.close()
+    assert a32 == b32                                   # deterministic
+    assert abs(a32 - a64) <= RTOL_FP32 * abs(a64)
+    assert abs(s32 - s64) <= RTOL_FP32 * abs(s64)
+    assert np.isnan(r32[5]) and np.isnan(r64[5])
+    keep = np.arange(64) != 5
+    assert r64[keep].min() < -1e5
+    np.testing.assert_allclose(r32[keep], r64[keep], rtol=RTOL_FP32)
+
+
+def test_precision_switch_of_the_api_mirror(xt):
+    """`tracking.set_precision('fp32')`: same objective through cum_Proba_Cs within the stated tolerance."""
+    from extrack_b200._lmfit_compat import Parameters  # noqa: F401  (parameters come from generate_params)
+
+    rng = np.random.default_rng(3)
+    tracks = {str(L): random_walk_tracks(300, L, 2, rng) for L in (8, 12, 21)}
+    params = xt.generate_params(nb_states=2, LocErr_type=1, nb_dims=2, LocErr_bounds=[0.005, 0.1], D_max=10,
+                                Fractions_bounds=[0.001, 0.99])
+    args = (params, [tracks[k] for k in sorted(tracks, key=int)], 0.02, [1], None, 2, 1, 6)
+    try:
+        v64 = xt.cum_Proba_Cs(*args, verbose=0)
+        xt.set_precision("fp32")
+        assert xt.get_precision() == "fp32"
+        v32 = xt.cum_Proba_Cs(*args, verbose=0)
+    finally:
+        xt.set_precision("fp64")
+    assert v32 != v64 and abs(v32 - v64) <= RTOL_FP32 * abs(v64)
+    with pytest.raises(ValueError):
+        xt.set_precision("fp16")

@@ -56,6 +56,18 @@ def pipelined(tag, reps=30):
 
 
 ref = two_phase("wpc=4 tpt=1")
+if os.environ.get("TUNE_GST"):
+    eng.set_option("k2_gst_below_ctas", 99)
+    v = two_phase("wpc=4 tpt=1 state in global memory")
+    print("   rel diff vs shared-memory state", abs(v - ref) / abs(ref))
+    eng.set_option("k2_gst_below_ctas", 3)
+if os.environ.get("TUNE_FP32"):
+    eng.set_option("fp32_replay", 1)
+    v = two_phase("fp32 replay (FP64 plan)")
+    print("   fp32 kernel used:", eng.stats()["fp32"], " rel diff vs FP64", abs(v - ref) / abs(ref))
+    eng.set_option("n_groups", 6)
+    pipelined("fp32 pipelined G=6")
+    eng.set_option("fp32_replay", 0)
 if os.environ.get("TUNE_VARIANTS"):
     for wpc, tpt in ((4, 2), (8, 1), (8, 2), (2, 1), (2, 2)):
         eng.set_option("k2_wpc", wpc)
