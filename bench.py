@@ -240,6 +240,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     total = float(buf.item())
     stats = eng.stats()
+    total_local = eng.sum_logp(p)  # this rank's own sum (== total on one GPU)
     # per-kernel device times (CUDA events recorded by the engine on its own stream around the
     # single plan launch and the single replay launch of the two-phase mode)
     eng.set_option("pipeline", 0)
@@ -254,6 +255,28 @@ def main():
     ms_plan /= ksteps
     ms_replay /= ksteps
     eng.set_option("pipeline", 1)
+    # ---- optional FP32 replay (north star: FP32 path within 1e-4 relative): same data, same plan kernel ----
+    eng.set_option("fp32_replay", 1)
+    for _ in range(3):
+        step32 = eng.sum_logp(p)
+    f32_used = eng.stats()["fp32"]
+    fsteps = max(3, min(50, args.steps))
+    torch.cuda.synchronize()
+    fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fe0.record()
+    for _ in range(fsteps):
+        eng.sum_logp_async(p, buf.data_ptr(), stream)
+    fe1.record()
+    torch.cuda.synchronize()
+    f32_ms = fe0.elapsed_time(fe1) / fsteps
+    eng.set_option("pipeline", 0)
+    f32_replay = 0.0
+    for i in range(5):
+        eng.sum_logp(p)
+        if i >= 2:
+            f32_replay += eng.stats()["ms_replay"] / 3
+    eng.set_option("pipeline", 1)
+    eng.set_option("fp32_replay", 0)
     sampler.stop_flag = True
     tms = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
     tsteps = torch.tensor([float(stats["track_steps"])], dtype=torch.float64, device=f"cuda:{local}")
@@ -348,6 +371,11 @@ def main():
                          "algorithmic_flops_per_launch": flops,
                          "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (replay_ms * 1e-3) / 1e9,
                                  "peak_gbs": peaks.get("hbm_gbs")}},
+            "fp32_path": {"value": stats["track_steps"] / (f32_ms * 1e-3), "unit": UNIT, "ms_per_step": f32_ms,
+                          "replay_and_reduce_ms": f32_replay, "kernel_used": bool(f32_used),
+                          "rel_diff_vs_fp64": abs(step32 - total_local) / abs(total_local), "stated_tolerance": 1e-4,
+                          "what": "same evaluation on this rank with xt_set_option('fp32_replay', 1): FP64 plan kernel, FP32 replay "
+                                  "kernel k2_replay_f32 (not the headline: `value`, `e2e` and `roofline` are FP64)"},
             "cpu_baseline": cpu,
             "parity_rel_err_vs_oracle_on_cpu_sample": parity,
         }
