@@ -2,7 +2,7 @@
 // xt_replay_fused.cuh with the per-sequence state (m[D], u[KS], Wm) in FP32 and the same 32-bit
 // extended exponent next to it, so the dynamic range is as unlimited as in the FP64 kernel and only
 // the mantissas are short.  Stated tolerance: total log-likelihood within 1e-4 relative of the FP64
-// result (BASELINE north star); observed ~1e-7 on the synthetic fields of view.
+// result (BASELINE north star); observed 8.5e-10 on 10^6 synthetic tracks.
 //
 //   * the plan (which sequences fuse) still comes from the FP64 plan kernel: the plan decisions are
 //     those of the reference, only the arithmetic carried along the plan is shortened;
@@ -19,7 +19,7 @@
 //
 // One configuration: 4 warps per tile of 32 tracks, one track per thread, scalar LocErr / dt, state in
 // shared memory.  The host (prepare_fused) selects it only when the tables are representable in FP32
-// (every non-zero factor in [1e-30, 1e30]) and the state fits; otherwise the FP64 kernel runs.
+// (every non-zero factor in [1e-20, 1e3]) and the state fits; otherwise the FP64 kernel runs.
 #pragma once
 #include "xt_replay_fused.cuh"
 
@@ -53,6 +53,12 @@ __device__ __forceinline__ float xf_sqrt(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+
+// global -> shared staging without registers (the issuing thread waits, the CTA barrier publishes)
+__device__ __forceinline__ void xf_cp_async16(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void xf_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // 2^d for -126 <= d <= 0, +0 below
 __device__ __forceinline__ float xf_pow2_le0(int d) { return __int_as_float(max(d + 127, 0) << 23); }
@@ -225,12 +231,13 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
   const unsigned s_exp = s_tab + 2 * H * 8 + lane * 4;  // [2][Pcap][32] x 4 B
 
   const int bstride = xt_blob_stride16(a.plan.cap);
-  const uint4* gblob = a.plan.blob + (size_t)ck.rec0 * bstride + tid;
+  // replay records are staged by warp 0 alone with cp.async (no registers, no work for the other warps)
+  const uint4* gnext = a.plan.blob + (size_t)ck.rec0 * bstride + lane;
   const int nrec = ck.nrec;
-  uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
-  if (nrec > 0) {
-    if (tid < B16) pre0 = __ldg(gblob);
-    if (tid + NT < B16) pre1 = __ldg(gblob + NT);
+  const unsigned B16b = (unsigned)B16 * 16;
+  if (w == 0 && nrec > 0) {
+    for (int i = lane; i < B16; i += 32) xf_cp_async16(s_blob + i * 16, gnext + (i - lane));
+    gnext += bstride;
   }
   for (int h = tid; h < 2 * H; h += NT) {
     const int hh = h < H ? h : h - H;
@@ -238,23 +245,27 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
   }
   float l2[KS];
 #pragma unroll
-  for (int k = 0; k < KS; ++k) l2[k] = (float)T.l2[k];
+  for (int k = 0; k < KS; ++k) {
+    l2[k] = (float)T.l2[k];
+    asm volatile("mov.f32 %0, %0;" : "+f"(l2[k]));  // converted once (otherwise rematerialised per group)
+  }
 
   // localisations relative to the first one (FP64 difference, then rounded)
-  double c0[D], csum = 0.0;  // NaN / Inf coordinates anywhere in the track poison the result
-  float cl[D], cn[D];
+  // NaN / Inf coordinates anywhere in the track poison the result: the differences to the first
+  // localisation are then not finite either, and their running FP32 sum records it (a finite offset
+  // beyond the FP32 range, > 3e38, counts as not finite on this path)
+  double c0[D];
+  float cl[D], cn[D], csum = 0.0f;
 #pragma unroll
   for (int dim = 0; dim < D; ++dim) {
     c0[dim] = Cs[(size_t)dim * npad];
-    csum += c0[dim];
     cl[dim] = 0.0f;
   }
   Cs += cstride;
 #pragma unroll
   for (int dim = 0; dim < D; ++dim) {
-    const double c = Cs[(size_t)dim * npad];  // C[1] (L >= 2)
-    csum += c;
-    cn[dim] = (float)(c - c0[dim]);
+    cn[dim] = (float)(Cs[(size_t)dim * npad] - c0[dim]);  // C[1] (L >= 2)
+    csum += cn[dim] * 0.0f + (float)(c0[dim] * 0.0);      // (0 or NaN)
   }
 
   // ---- first localisation (tracking.py:478-529) and, if L >= 3, the update of step 2 ----
@@ -274,22 +285,20 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
     Cs += cstride;
 #pragma unroll
     for (int dim = 0; dim < D; ++dim) {
-      const double c = Cs[(size_t)dim * npad];  // C[2]
-      csum += c;
-      cn[dim] = (float)(c - c0[dim]);
+      cn[dim] = (float)(Cs[(size_t)dim * npad] - c0[dim]);  // C[2]
+      csum += cn[dim] * 0.0f;
     }
   }
-  if (tid < B16) xt_sts128u(s_blob + tid * 16, pre0);
-  if (tid + NT < B16) xt_sts128u(s_blob + (tid + NT) * 16, pre1);
+  if (w == 0) xf_cp_async_wait();
   __syncthreads();
 
-  const bool st0 = tid < B16, st1 = tid + NT < B16;
-  const unsigned s_stage = s_blob + tid * 16;
-  const uint4* gnext = gblob;
   // ---- steps 3..L-1: merge by the replay record of step-1, update with C[step-1] ----
+  // ping-pong buffers: toggled by XOR with the difference of the two addresses
   unsigned src_v = s_vec, src_e = s_exp, dst_v = s_vec + VB, dst_e = s_exp + EB;
-  for (int step = 3; step <= L - 1; ++step) {
-    const int ri = step - 3;
+  const unsigned xv = src_v ^ dst_v, xe = src_e ^ dst_e, xr = s_blob ^ (s_blob + B16b);
+  unsigned rb = s_blob;
+  const int last = L - 1;
+  for (int step = 3; step <= last; ++step) {
     // prefetch: localisation and replay record of the next step
     Cs += cstride;  // C[step] exists (step <= L-1)
     double cd[D];
@@ -298,14 +307,11 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
       cl[dim] = cn[dim];
       cd[dim] = Cs[(size_t)dim * npad];
     }
-    const bool more = ri + 1 < nrec;
-    gnext += bstride;
-    if (more) {
-      if (st0) pre0 = __ldg(gnext);
-      if (st1) pre1 = __ldg(gnext + NT);
+    if (w == 0 && step < last) {  // record of the next step into the other buffer
+      for (int i = lane; i < B16; i += 32) xf_cp_async16((rb ^ xr) + i * 16, gnext + (i - lane));
+      gnext += bstride;
     }
 
-    const unsigned rb = s_blob + (ri & 1) * (B16 * 16);
     const int nG = (int)xt_lds16(rb);  // XtBlobHdr::nG
     const unsigned grec = rb + 32;
     const unsigned entb = grec + ((nG + 1) >> 1) * 16;
@@ -393,20 +399,15 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
       IO::store(dst_v + g * SLOTB, dst_e + g * ESLOT, G);
     }
     nP = nG;
-    {  // swap the ping-pong buffers
-      unsigned tv = src_v; src_v = dst_v; dst_v = tv;
-      unsigned te = src_e; src_e = dst_e; dst_e = te;
-    }
+    src_v ^= xv; dst_v ^= xv;  // swap the ping-pong buffers
+    src_e ^= xe; dst_e ^= xe;
+    rb ^= xr;
 #pragma unroll
     for (int dim = 0; dim < D; ++dim) {
-      csum += cd[dim];
       cn[dim] = (float)(cd[dim] - c0[dim]);
+      csum = fmaf(cn[dim], 0.0f, csum);
     }
-    if (more) {
-      const unsigned nb = s_stage + ((ri + 1) & 1) * (B16 * 16);
-      if (st0) xt_sts128u(nb, pre0);
-      if (st1) xt_sts128u(nb + NT * 16, pre1);
-    }
+    if (w == 0) xf_cp_async_wait();
     __syncthreads();
   }
   const uint8_t* curP = nullptr;
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
       tot = fma((double)xf_lds32f(s_redA + (k * 32 + lane) * 4),
                 xt_pow2_le0(xt_lds32(s_redK + (k * 32 + lane) * 4) - Kn), tot);
     double lp = XT_LN2 * (double)Kn + log(tot) - (double)(L - 1) * (0.5 * (double)D) * XT_LN_2PI;
-    if (!(fabs(csum) <= 1.7976931348623157e308)) lp = __longlong_as_double(0x7ff8000000000000ll);
+    if (csum != 0.0f) lp = __longlong_as_double(0x7ff8000000000000ll);  // csum is 0 or NaN
     double lps = 0.0;
     if (valid) {
       a.logp[ck.trk_off + t] = lp;
