@@ -20,7 +20,7 @@ XT_FLAG_VAR_LOC = 2
 XT_FLAG_VAR_DT = 4
 XT_FLAG_LOC_AFFINE = 8
 
-XT_ERR_CUDA, XT_ERR_ARG, XT_ERR_GROUPING, XT_ERR_CAPACITY, XT_ERR_STATE = -1, -2, -3, -4, -5
+XT_ERR_CUDA, XT_ERR_ARG, XT_ERR_GROUPING, XT_ERR_CAPACITY, XT_ERR_STATE, XT_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 
 LIB_NAME = "libxtrack_b200.so"
 # XT_LIB_PATH: another build of the same engine (A/B timing of kernel variants); never a fallback
@@ -85,6 +85,8 @@ EXPORTS = (
     "xt_plan_dump",
     "xt_predict",
     "xt_get_stats",
+    "xt_seglen_hist",
+    "xt_seglen_last_ms",
     "xt_set_option",
     "xt_fp64_peak_tflops",
     "xt_host_alloc",
@@ -122,6 +124,8 @@ def load_library() -> C.CDLL:
     lib.xt_plan_dump.argtypes = [vp, i32, i32, P(i32), P(i32), P(i32), i32, P(dbl)]
     lib.xt_predict.argtypes = [vp, P(XtParams), P(vp)]
     lib.xt_get_stats.argtypes = [vp, P(XtStats)]
+    lib.xt_seglen_hist.argtypes = [vp, P(XtParams), P(dbl), P(dbl), i32, i32, vp, vp, P(i32)]
+    lib.xt_seglen_last_ms.argtypes = [vp, P(C.c_float)]
     lib.xt_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     lib.xt_fp64_peak_tflops.argtypes = [vp, P(dbl)]
     lib.xt_host_alloc.argtypes = [P(vp), C.c_uint64]
@@ -144,6 +148,8 @@ def _raise(code: int, msg: str):
     # error conventions of the reference: malformed input / grouping -> ValueError
     if code in (XT_ERR_ARG, XT_ERR_GROUPING, XT_ERR_CAPACITY):
         raise ValueError(msg)
+    if code == XT_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
     raise EngineError(code, msg)
 
 
@@ -288,6 +294,33 @@ class Engine:
         ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
         self._check(self._lib.xt_predict(self._h, C.byref(p), ptrs))
         return outs
+
+    def seglen_hist(self, p: XtParams, leave_LL: np.ndarray, Lmax: int, nS: int, n_chunks: int, dbg_chunk: int = -1,
+                    dbg_shape=None):
+        """Per-chunk segment-length histograms [n_chunks, Lmax, nS] (histograms.py:26-258 per chunk); with
+        ``dbg_chunk`` >= 0 and ``dbg_shape = (nT, L)`` also that chunk's final LP [nT, nBf] and histories [nT, nBf, L]."""
+        hist = np.zeros((n_chunks, Lmax, nS), dtype=np.float64)
+        lv = np.ascontiguousarray(leave_LL, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        nf = C.c_int32(0)
+        if dbg_chunk < 0:
+            self._check(self._lib.xt_seglen_hist(self._h, C.byref(p), lv.ctypes.data_as(dp), hist.ctypes.data_as(dp), int(Lmax),
+                                                 -1, None, None, C.byref(nf)))
+            return hist
+        nT, L = dbg_shape
+        # first call sizes the outputs (n_final), second call fills them
+        self._check(self._lib.xt_seglen_hist(self._h, C.byref(p), lv.ctypes.data_as(dp), hist.ctypes.data_as(dp), int(Lmax),
+                                             int(dbg_chunk), None, None, C.byref(nf)))
+        LP = np.empty((nT, nf.value), dtype=np.float64)
+        Bs = np.empty((nT, nf.value, L), dtype=np.int8)
+        self._check(self._lib.xt_seglen_hist(self._h, C.byref(p), lv.ctypes.data_as(dp), hist.ctypes.data_as(dp), int(Lmax),
+                                             int(dbg_chunk), C.c_void_p(LP.ctypes.data), C.c_void_p(Bs.ctypes.data), C.byref(nf)))
+        return hist, LP, Bs
+
+    def seglen_last_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.xt_seglen_last_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def stats(self) -> dict:
         st = XtStats()

@@ -13,6 +13,7 @@
 #include "xt_replay_lin.cuh"
 #include "xt_replay_fused.cuh"
 #include "xt_replay_f32.cuh"
+#include "xt_seglen.cuh"
 #include "xt_predict.cuh"
 
 struct xt_ctx {
@@ -101,6 +102,7 @@ struct xt_ctx {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_k3[2] = {nullptr, nullptr};
   float ms_predict = 0.f;
+  float ms_seglen = 0.f;
   int k3_launches = 0, k3_cap = 0;
   // optional per-localisation inputs (xt_upload_aux) and field-of-view tables (xt_set_stay_tables)
   double* d_aux = nullptr;
@@ -1490,3 +1492,4 @@ extern "C" int xt_fp64_peak_tflops(xt_ctx* ctx, double* out) {
 }
 
 #include "xt_predict_host.inl"
+#include "xt_seglen_host.inl"

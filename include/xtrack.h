@@ -30,6 +30,7 @@ extern "C" {
 #define XT_ERR_GROUPING (-3)  /* a sequence ended ungrouped: tracking.py:700-701 ValueError */
 #define XT_ERR_CAPACITY (-4)  /* more live sequences than the engine's hard cap */
 #define XT_ERR_STATE (-5)     /* call order (e.g. evaluate before upload) */
+#define XT_ERR_UNSUPPORTED (-6) /* a documented gap of the engine (maps to NotImplementedError in Python) */
 
 #define XT_FLAG_INT8_WRAP 1u /* reproduce the int8 wrap of history labels, tracking.py:543,619 */
 #define XT_FLAG_VAR_LOC 2u   /* peak-wise localisation error from xt_upload_aux replaces l2 (input_LocErr, tracking.py:455-463) */
@@ -168,6 +169,25 @@ int xt_plan_dump(xt_ctx* ctx, int32_t chunk, int32_t step, int32_t* nB_in, int32
 int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out);
 
 int xt_get_stats(xt_ctx* ctx, xt_stats* out);
+
+/*
+ * Segment-length histogram of the uploaded tracks — replaces extrack/histograms.py:26-258
+ * (P_segment_len: literal top-`max_nb_states` pruning per track, :183-206, and the run-length tally
+ * :248-258) as called per chunk of 50 tracks by len_hist (:265-373; upload with chunk_size = 50).
+ * Uses p->nS, d, n_loc, l2, dd, LT, LF, Lp_stay, min_len (= min_l, :274), max_nb_states; nb_substeps
+ * must be 1 and LocErr / dt scalar (or per dimension).  leave_LL[newest + nS * previous] =
+ * log(pBL + (1 - e) - pBL (1 - e)) with e = p_stay[s] if newest == previous == s else p_stay[0] (:224-232).
+ * hist receives double[n_chunks][Lmax][nS] (row k-1 = segments of k localisations, rows >= L-1 of a
+ * chunk of L-localisation tracks stay zero); len_hist = sum over chunks.  Test seam (P_segment_len's
+ * other outputs) for the tracks of chunk dbg_chunk >= 0: dbg_LP[nT][nBf] final log-probabilities and
+ * dbg_Bs[nT][nBf][L] state histories (column 0 = newest), *n_final = nBf; pass -1 / NULL otherwise.
+ * Returns XT_ERR_UNSUPPORTED if a final log-probability exceeds 600 (the reference then rescales per
+ * column over the tracks of a chunk, :243-244), XT_ERR_CAPACITY if the live sequences of one track
+ * (max_nb_states * nS) do not fit in shared memory.
+ */
+int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* leave_LL, double* hist, int32_t Lmax,
+                   int32_t dbg_chunk, double* dbg_LP, int8_t* dbg_Bs, int32_t* n_final);
+int xt_seglen_last_ms(xt_ctx* ctx, float* ms); /* CUDA-event time of the last xt_seglen_hist kernel */
 
 /* Engine options (tests / diagnostics).
  *  "force_global_replay" = 1: run the log-domain replay kernel with its state in global memory (the

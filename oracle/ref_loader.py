@@ -76,3 +76,15 @@ def load_readers():
         except Exception:
             sys.modules["xmltodict"] = types.ModuleType("xmltodict")
     return _load("readers", "extrack/readers.py")
+
+
+def load_histograms():
+    """``extrack/histograms.py`` (it imports ``extrack.tracking``: a package stub points at the loaded module)."""
+    trk = load_tracking()
+    if "extrack" not in sys.modules:
+        pkg = types.ModuleType("extrack")
+        pkg.__path__ = []  # a package, so that ``from extrack.tracking import ...`` resolves through sys.modules
+        pkg.tracking = trk
+        sys.modules["extrack"] = pkg
+        sys.modules["extrack.tracking"] = trk
+    return _load("histograms", "extrack/histograms.py")
