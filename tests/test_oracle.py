@@ -13,7 +13,8 @@ from oracle import extrack_oracle as orc
 from oracle import ref_loader
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if "objective" not in f and "var_" not in f and "fit_" not in f)
+CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
+               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f)
 VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
 
 
