@@ -1287,9 +1287,13 @@ extern "C" int xt_sum_logp_host(xt_ctx* ctx, int32_t n_seg, const int32_t* L, co
 extern "C" int xt_sum_logp_async(xt_ctx* ctx, const xt_params* p, double* d_out, void* cuda_stream) {
   // The result lands in d_out in stream order of the context's stream; if the caller passes its
   // own stream it is made to wait for the result.
+  if (!ctx) return XT_ERR_ARG;
+  XT_CUDA_OK(cudaSetDevice(ctx->device));
+  XT_CUDA_OK(cudaEventRecord(ctx->ev_fork, (cudaStream_t)cuda_stream));  // (ev_fork is re-recorded by the evaluation)
+  XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0));
   int rc = evaluate(ctx, p, d_out, nullptr);
   if (rc) return rc;
-  if (cuda_stream) XT_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->ev[2], 0));
+  XT_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->ev[2], 0));
   return XT_OK;
 }
 

@@ -145,9 +145,11 @@ int xt_sum_logp(xt_ctx* ctx, const xt_params* p, double* out);
 int xt_sum_logp_host(xt_ctx* ctx, int32_t n_segments, const int32_t* L, const int64_t* n, const int32_t* isBL,
                      const double* const* xyz, int32_t d, int32_t chunk_size, const xt_params* p, double* out);
 
-/* Same as xt_sum_logp, but the result stays on the device: d_out is a device pointer to one double and the
- * work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream) so a
- * collective can be chained without a host round trip.  No synchronisation on return. */
+/* Same as xt_sum_logp, but the result stays on the device: d_out is a device pointer to one double that is
+ * used in the stream order of `cuda_stream` (a cudaStream_t; NULL = the legacy default stream): the
+ * engine's own streams first wait for the work already enqueued on `cuda_stream` (e.g. the collective
+ * of the previous call, which still reads or writes d_out), and `cuda_stream` is made to wait for the
+ * result, so a collective can be chained without a host round trip. */
 int xt_sum_logp_async(xt_ctx* ctx, const xt_params* p, double* d_out, void* cuda_stream);
 
 /* Test seam = Proba_Cs (tracking.py:769-787): log P per track of chunk `chunk` after the last
