@@ -103,6 +103,7 @@ struct xt_ctx {
   cudaEvent_t ev_k3[2] = {nullptr, nullptr};
   float ms_predict = 0.f;
   float ms_seglen = 0.f;
+  bool seglen_rescaled = false;  // the last xt_seglen_hist call applied the > 600 rescale to some chunk
   int k3_launches = 0, k3_cap = 0;
   // optional per-localisation inputs (xt_upload_aux) and field-of-view tables (xt_set_stay_tables)
   double* d_aux = nullptr;

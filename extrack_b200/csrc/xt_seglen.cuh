@@ -3,7 +3,12 @@
 // the *literal* top-max_nb_states pruning per track (descending sort of LP + log-density of the next
 // localisation, histograms.py:183-206) and a tally of the run lengths of every surviving state sequence.
 //
-// One CTA per track (persistent over the track list).  The live sequences of the track — moments,
+// One CTA per chunk of <= 50 tracks (persistent over the chunk list), one track at a time: the chunk is
+// the reference's unit for the rescale of final log-probabilities above 600 (histograms.py:243-244: if
+// any LP of the chunk exceeds 600, every column j is shifted by max over the chunk's tracks of LP[:, j]
+// minus 600 — a per-column shift, reproduced): the CTA tallies optimistically while it tracks the column
+// maxima, and repeats the chunk with the shifts if the chunk maximum exceeded 600.
+// The live sequences of the track — moments,
 // log-probabilities LP / LL, newest state — sit in shared memory as two sets (parents / children).
 // Instead of the reference's history matrix cur_Bs[nT, nB, L], which it re-gathers at every pruning
 // step, each step writes one lattice record per surviving sequence (parent slot | newest state << 16)
@@ -15,7 +20,6 @@
 // Reproduced quirks: LL keeps the *last* k ranks of the order while everything else keeps the first k
 // (histograms.py:202); end_p_stay = p_stay[s] only if newest == previous == s, else p_stay[0] (:224);
 // no transition term in the leave expansion (:220); runs of length L are not counted (:251).
-// Not reproduced (flagged, the host raises): the per-column rescale of the final LP above 600 (:243).
 #pragma once
 #include "xt_common.cuh"
 
@@ -23,15 +27,16 @@
 
 struct K4Args {
   const XtChunk* chunks;
-  const XtWork* tracks;     // one entry per track: (chunk, index in chunk)
   const double* soa;
-  int32_t n_tracks;
+  int32_t n_chunks;
   int32_t cap;              // sequence slots per set
   int32_t n2;               // power of two >= cap (sort network size)
   int32_t Lmax;
   uint32_t* lattice;        // [gridDim.x][Lmax][cap]
+  double* colmax;           // [gridDim.x][cap]: per column, max over the chunk's tracks of the final LP
   double* hist;             // [n_chunks][Lmax][nS], accumulated with atomics
-  int32_t* flags;           // [1]: bit 0 = a final LP exceeded 600 (unsupported rescale), bit 1 = capacity overflow
+  int32_t* flags;           // [0]: bit 0 = some chunk needed the > 600 rescale (informational); [1]: next position in corder
+  const int32_t* corder;    // chunk ids, longest tracks first (CTAs take the next one when they are done)
   double leave_LL[XT_MAX_HEADS];  // log(pBL + (1-e) - pBL(1-e)) per head = newest + nS * previous
   // test seam (P_segment_len outputs) for the tracks of chunk dbg_chunk, or nullptr
   double* dbg_LP;           // [nT][nBf]
@@ -95,10 +100,25 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
   for (int k = 0; k < KS; ++k) l2[k] = P.l2[k];
   const int kmax = P.max_nb_states;
 
-  for (int ti = blockIdx.x; ti < a.n_tracks; ti += gridDim.x) {
-    const XtWork wk = a.tracks[ti];
-    const XtChunk ck = a.chunks[wk.chunk];
-    const int L = ck.L;
+  double* colmax = a.colmax + (size_t)blockIdx.x * cap;
+  __shared__ double s_part[NT / 32], s_max[NT / 32];
+  __shared__ int s_again;
+  __shared__ int s_next;
+  for (;;) {
+   if (tid == 0) s_next = atomicAdd(&a.flags[1], 1);
+   __syncthreads();
+   const int pos = s_next;
+   __syncthreads();
+   if (pos >= a.n_chunks) break;
+   const int ci = a.corder[pos];
+   const XtChunk ck = a.chunks[ci];
+   const int L = ck.L;
+   for (int i = tid; i < (L - 1) * nS; i += NT) shist[i] = 0.0;
+   for (int i = tid; i < cap; i += NT) colmax[i] = -INFINITY;
+   double cmax = -INFINITY;  // this thread's share of the chunk maximum of the final LP
+   for (int pass = 0; pass < 2; ++pass) {
+   for (int tk = 0; tk < ck.nT; ++tk) {
+    struct { int32_t chunk, t0; } wk = {ci, tk};
     const size_t npad = (size_t)ck.nTpad;
     const double* Cs = a.soa + ck.xyz_off + wk.t0;
     auto loc = [&](int i, double (&c)[D]) {
@@ -113,7 +133,6 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
 #define SEG_S(set) ((set) + (size_t)D * cap)
 #define SEG_LP(set) ((set) + (size_t)(D + KS) * cap)
 #define SEG_LL(set) ((set) + (size_t)(D + KS + 1) * cap)
-    for (int i = tid; i < (L - 1) * nS; i += NT) shist[i] = 0.0;
     // ---- first localisation: nS^2 sequences, head = newest + nS * oldest (histograms.py:104-140) ----
     int nB = nS * nS;
     {
@@ -191,22 +210,51 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
         }
       }
       __syncthreads();
-      for (int k = 2; k <= n2; k <<= 1)
-        for (int jj = k >> 1; jj > 0; jj >>= 1) {
-          for (int i = tid; i < n2; i += NT) {
-            const int x = i ^ jj;
-            if (x > i) {
-              const double ka = keys[i], kb = keys[x];
-              const int ia = ord[i], ib = ord[x];
-              const bool up = (i & k) == 0;
-              if (xt_seg_before(kb, ib, ka, ia) == up) {
-                keys[i] = kb; keys[x] = ka;
-                ord[i] = ib; ord[x] = ia;
-              }
+      // bitonic network, n2 >= 4: compare-exchange distances 1 and 2 run in registers on groups of four
+      // consecutive elements (conflict-free 32-byte rows), the longer distances pairwise in shared memory
+      auto ce = [](double& ka, int& ia, double& kb, int& ib, bool up) {
+        if (xt_seg_before(kb, ib, ka, ia) == up) {
+          const double tk = ka; ka = kb; kb = tk;
+          const int ti = ia; ia = ib; ib = ti;
+        }
+      };
+      for (int g = tid; g < (n2 >> 2); g += NT) {  // stages k = 2, 4
+        double k0 = keys[4 * g], k1 = keys[4 * g + 1], k2 = keys[4 * g + 2], k3 = keys[4 * g + 3];
+        int i0 = ord[4 * g], i1 = ord[4 * g + 1], i2 = ord[4 * g + 2], i3 = ord[4 * g + 3];
+        ce(k0, i0, k1, i1, true);
+        ce(k2, i2, k3, i3, false);
+        const bool up = (g & 1) == 0;
+        ce(k0, i0, k2, i2, up); ce(k1, i1, k3, i3, up);
+        ce(k0, i0, k1, i1, up); ce(k2, i2, k3, i3, up);
+        keys[4 * g] = k0; keys[4 * g + 1] = k1; keys[4 * g + 2] = k2; keys[4 * g + 3] = k3;
+        ord[4 * g] = i0; ord[4 * g + 1] = i1; ord[4 * g + 2] = i2; ord[4 * g + 3] = i3;
+      }
+      __syncthreads();
+      for (int k = 8; k <= n2; k <<= 1) {
+        for (int jj = k >> 1; jj >= 4; jj >>= 1) {
+          for (int t = tid; t < (n2 >> 1); t += NT) {
+            const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+            const int x = i + jj;
+            const double ka = keys[i], kb = keys[x];
+            const int ia = ord[i], ib = ord[x];
+            if (xt_seg_before(kb, ib, ka, ia) == ((i & k) == 0)) {
+              keys[i] = kb; keys[x] = ka;
+              ord[i] = ib; ord[x] = ia;
             }
           }
           __syncthreads();
         }
+        for (int g = tid; g < (n2 >> 2); g += NT) {  // distances 2 and 1
+          double k0 = keys[4 * g], k1 = keys[4 * g + 1], k2 = keys[4 * g + 2], k3 = keys[4 * g + 3];
+          int i0 = ord[4 * g], i1 = ord[4 * g + 1], i2 = ord[4 * g + 2], i3 = ord[4 * g + 3];
+          const bool up = ((4 * g) & k) == 0;
+          ce(k0, i0, k2, i2, up); ce(k1, i1, k3, i3, up);
+          ce(k0, i0, k1, i1, up); ce(k2, i2, k3, i3, up);
+          keys[4 * g] = k0; keys[4 * g + 1] = k1; keys[4 * g + 2] = k2; keys[4 * g + 3] = k3;
+          ord[4 * g] = i0; ord[4 * g + 1] = i1; ord[4 * g + 2] = i2; ord[4 * g + 3] = i3;
+        }
+        __syncthreads();
+      }
       for (int j = tid; j < kmax; j += NT) {
         const int src = ord[j];
         const int srcL = ord[nC - kmax + j];  // histograms.py:202: LL keeps the last k ranks
@@ -228,7 +276,13 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
     // per parent: LPf = LP + logdens(last); weights of its nS leave-children (or itself) in keys[], total in sred
     double part = 0.0, lpmax = -INFINITY;
     for (int p = tid; p < nB; p += NT) {
-      const double lpf = __dadd_rn(SEG_LP(par)[p], xt_seg_logdens<D, KS>(Cl, SEG_M(par), SEG_S(par), p, cap, l2));
+      double lpf = __dadd_rn(SEG_LP(par)[p], xt_seg_logdens<D, KS>(Cl, SEG_M(par), SEG_S(par), p, cap, l2));
+      if (pass == 0) {
+        colmax[p] = fmax(colmax[p], lpf);  // (column p of every track of the chunk belongs to this thread)
+        cmax = fmax(cmax, lpf);
+      } else {
+        lpf = __dadd_rn(lpf, -__dadd_rn(colmax[p], -600.0));  // histograms.py:244
+      }
       lpmax = fmax(lpmax, lpf);
       double w = 0.0;
       if (ck.isBL) {
@@ -251,7 +305,6 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
       part += __shfl_down_sync(0xffffffffu, part, off);
       lpmax = fmax(lpmax, __shfl_down_sync(0xffffffffu, lpmax, off));
     }
-    __shared__ double s_part[NT / 32], s_max[NT / 32];
     if ((tid & 31) == 0) {
       s_part[tid >> 5] = part;
       s_max[tid >> 5] = lpmax;
@@ -263,7 +316,7 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
       tot += s_part[k];
       mx = fmax(mx, s_max[k]);
     }
-    if (tid == 0 && mx > 600.0) atomicOr(a.flags, 1);
+    (void)mx;
     // ---- histories by walking the lattice back; run lengths (histograms.py:248-258 restated) ----
     for (int p = tid; p < nB; p += NT) {
       const double w = keys[p] / tot;
@@ -300,8 +353,26 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
       if (last <= L - 1) atomicAdd(&shist[(last - 1) * nS + cur], w);
     }
     __syncthreads();
-    double* gh = a.hist + (size_t)wk.chunk * a.Lmax * nS;
-    for (int i = tid; i < (L - 1) * nS; i += NT) atomicAdd(&gh[i], shist[i]);
-    __syncthreads();
+   }  // tracks of the chunk
+   if (pass == 0) {  // did any final LP of the chunk exceed 600?  then once more with the column shifts
+#pragma unroll
+     for (int off = 16; off > 0; off >>= 1) cmax = fmax(cmax, __shfl_down_sync(0xffffffffu, cmax, off));
+     if ((tid & 31) == 0) s_max[tid >> 5] = cmax;
+     __syncthreads();
+     if (tid == 0) {
+       double m = s_max[0];
+       for (int k = 1; k < NT / 32; ++k) m = fmax(m, s_max[k]);
+       s_again = m > 600.0;
+       if (s_again) atomicOr(a.flags, 1);
+     }
+     __syncthreads();
+     if (!s_again) break;
+     for (int i = tid; i < (L - 1) * nS; i += NT) shist[i] = 0.0;
+     __syncthreads();
+   }
+   }  // passes
+   double* gh = a.hist + (size_t)ci * a.Lmax * nS;
+   for (int i = tid; i < (L - 1) * nS; i += NT) gh[i] = shist[i];  // one CTA per chunk: plain stores, deterministic
+   __syncthreads();
   }
 }

@@ -41,7 +41,7 @@ extern "C" int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* lea
     return XT_ERR_ARG;
   }
   // (max_nb_states itself needs no slots: a step is only cut when it has more children than that)
-  int n2 = 2;
+  int n2 = 4;
   while (n2 < capC && n2 < (1 << 20)) n2 <<= 1;
   const size_t smem = capC <= 65535 ? xt_seg_smem(d, KS, (int)capC, n2, Lmax, nS) : (size_t)-1;
   if (capC > 65535 || smem > (size_t)ctx->smem_optin) {
@@ -50,13 +50,9 @@ extern "C" int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* lea
   }
   if (n_final && dbg_chunk >= 0 && dbg_chunk < nch) *n_final = nBf[dbg_chunk];
   const int cap = (int)capC;
-  // one work item per track
-  std::vector<XtWork> tr;
-  tr.reserve((size_t)ctx->n_tracks);
-  for (int c = 0; c < nch; ++c)
-    for (int t = 0; t < ctx->chunks[c].nT; ++t) tr.push_back(XtWork{c, t});
-  const int grid = (int)std::min<size_t>(tr.size(), (size_t)ctx->n_sm * std::max<size_t>(1, ((size_t)228 * 1024) / (smem + 2048)));
-  XtWork* d_tr = nullptr;
+  // one CTA per chunk (the reference's unit of the > 600 rescale), persistent over the chunk list
+  const int grid = (int)std::min<size_t>((size_t)nch, (size_t)ctx->n_sm * std::max<size_t>(1, ((size_t)228 * 1024) / (smem + 2048)));
+  double* d_colmax = nullptr;
   uint32_t* d_lat = nullptr;
   double* d_hist = nullptr;
   int32_t* d_flags = nullptr;
@@ -67,7 +63,7 @@ extern "C" int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* lea
   const bool dbg = dbg_chunk >= 0 && dbg_chunk < nch && (dbg_LP || dbg_Bs);
   const size_t dn = dbg ? (size_t)ctx->chunks[dbg_chunk].nT * nBf[dbg_chunk] : 0;
   auto cleanup = [&]() {
-    cudaFree(d_tr); cudaFree(d_lat); cudaFree(d_hist); cudaFree(d_flags); cudaFree(d_LP); cudaFree(d_Bs);
+    cudaFree(d_colmax); cudaFree(d_lat); cudaFree(d_hist); cudaFree(d_flags); cudaFree(d_LP); cudaFree(d_Bs);
   };
 #define SEG_OK(call)                                                        \
   do {                                                                      \
@@ -78,26 +74,26 @@ extern "C" int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* lea
       return XT_ERR_CUDA;                                                   \
     }                                                                       \
   } while (0)
-  SEG_OK(cudaMalloc(&d_tr, sizeof(XtWork) * tr.size()));
+  SEG_OK(cudaMalloc(&d_colmax, sizeof(double) * (size_t)grid * cap));
   SEG_OK(cudaMalloc(&d_lat, sizeof(uint32_t) * (size_t)grid * Lmax * cap));
   SEG_OK(cudaMalloc(&d_hist, sizeof(double) * hist_n));
-  SEG_OK(cudaMalloc(&d_flags, sizeof(int32_t)));
+  SEG_OK(cudaMalloc(&d_flags, sizeof(int32_t) * 2));
   if (dbg && dbg_LP) SEG_OK(cudaMalloc(&d_LP, sizeof(double) * dn));
   if (dbg && dbg_Bs) SEG_OK(cudaMalloc(&d_Bs, dn * ctx->chunks[dbg_chunk].L));
-  SEG_OK(cudaMemcpyAsync(d_tr, tr.data(), sizeof(XtWork) * tr.size(), cudaMemcpyHostToDevice, ctx->stream));
   SEG_OK(cudaMemsetAsync(d_hist, 0, sizeof(double) * hist_n, ctx->stream));
-  SEG_OK(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), ctx->stream));
+  SEG_OK(cudaMemsetAsync(d_flags, 0, sizeof(int32_t) * 2, ctx->stream));
   K4Args a{};
   a.chunks = ctx->d_chunks;
-  a.tracks = d_tr;
   a.soa = ctx->d_soa;
-  a.n_tracks = (int)tr.size();
+  a.n_chunks = nch;
+  a.colmax = d_colmax;
   a.cap = cap;
   a.n2 = n2;
   a.Lmax = Lmax;
   a.lattice = d_lat;
   a.hist = d_hist;
   a.flags = d_flags;
+  a.corder = ctx->d_corder;
   for (int h = 0; h < nS * nS; ++h) a.leave_LL[h] = leave_LL ? leave_LL[h] : 0.0;
   a.dbg_LP = d_LP;
   a.dbg_Bs = d_Bs;
@@ -132,11 +128,8 @@ extern "C" int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* lea
   if (e != cudaSuccess) {
     set_error(ctx, std::string("xt_seglen_hist: ") + cudaGetErrorString(e));
     result = XT_ERR_CUDA;
-  } else if (flags & 1) {
-    set_error(ctx, "xt_seglen_hist: a final log-probability exceeds 600; the reference's per-column rescale over the tracks of a "
-                   "chunk (histograms.py:243-244) is not implemented");
-    result = XT_ERR_UNSUPPORTED;
   }
+  ctx->seglen_rescaled = (flags & 1) != 0;
   cleanup();
 #undef SEG_OK
   return result;

@@ -9,9 +9,10 @@ Differences that are documented rather than hidden:
   ``NotImplementedError`` / ``ValueError`` from the engine;
 * equal sort keys in the top-``max_nb_states`` pruning (histograms.py:192-193 uses numpy's unstable
   default ``argsort``, so the reference's order among them is unspecified) are ordered by descending
-  index; keys whose ``exp`` underflows to zero in the reference keep the order of their keys here;
-* a final log-probability above 600 (the reference then rescales ``LP`` per column over the tracks of
-  a chunk, :243-244) raises ``NotImplementedError``.
+  index; keys whose ``exp`` underflows to zero in the reference keep the order of their keys here.
+
+The reference's rescale of final log-probabilities above 600 (per column over the tracks of a chunk,
+:243-244) is reproduced on the device (one CTA per chunk).
 """
 from __future__ import annotations
 

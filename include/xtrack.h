@@ -183,8 +183,8 @@ int xt_get_stats(xt_ctx* ctx, xt_stats* out);
  * chunk of L-localisation tracks stay zero); len_hist = sum over chunks.  Test seam (P_segment_len's
  * other outputs) for the tracks of chunk dbg_chunk >= 0: dbg_LP[nT][nBf] final log-probabilities and
  * dbg_Bs[nT][nBf][L] state histories (column 0 = newest), *n_final = nBf; pass -1 / NULL otherwise.
- * Returns XT_ERR_UNSUPPORTED if a final log-probability exceeds 600 (the reference then rescales per
- * column over the tracks of a chunk, :243-244), XT_ERR_CAPACITY if the live sequences of one track
+ * The rescale of final log-probabilities above 600 (per column over the tracks of a chunk, :243-244) is
+ * applied on the device.  Returns XT_ERR_CAPACITY if the live sequences of one track
  * (max_nb_states * nS) do not fit in shared memory.
  */
 int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* leave_LL, double* hist, int32_t Lmax,

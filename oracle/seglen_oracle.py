@@ -25,9 +25,8 @@ Tie-break of the sort (the reference uses ``argsort()[:, ::-1]`` with numpy's un
 so its order among equal keys is unspecified): descending key, equal keys by descending index — what
 a stable ascending sort followed by the reversal gives.  The reference sorts ``exp(key - shift)``;
 keys that underflow to zero there are in unspecified order, here they keep the order of their keys.
-Not restated (the engine raises for it as well): the ``> 600`` rescale of the final ``LP`` per column
-over the tracks of a chunk (``:243-244``), which needs log-likelihoods above 600 (tracks of hundreds of
-localisations).
+The ``> 600`` rescale of the final ``LP`` (``:243-244``) is per *column* over the tracks of the chunk
+(``np.max(LP, axis=0)``), which changes the relative weights of a track's sequences — reproduced.
 """
 from __future__ import annotations
 
@@ -122,8 +121,8 @@ def segment_len_chunk(C: np.ndarray, model: Model, isBL: int, max_nb_states: int
         lattice.append((np.repeat(par[None], nT, 0), None))   # history of a child = history of its parent
         dropped_newest = True
     LP = LP + _logdens_next(C[:, None, L - 1, :], m, s2, l2)
-    if np.max(LP) > 600:
-        raise NotImplementedError("segment-length oracle: final LP above 600 (column-wise rescale, histograms.py:243-244)")
+    if np.max(LP) > 600:  # histograms.py:243-244: per column, over the tracks of the chunk
+        LP = LP - (np.max(LP, axis=0, keepdims=True) - 600)
     P = np.exp(LP + LL)
     Pn = P / np.sum(P, axis=1, keepdims=True)
 

@@ -42,6 +42,8 @@ CASES = [  # name, nS, L, d, max_nb_states, isBL, LocErr, min_l, nT
     ("seglen_s3_3d_locerr_per_dim", 3, 8, 3, 100, 0, (0.02, 0.03, 0.04), 4, 21),
     ("seglen_s4_L6", 4, 6, 2, 64, 1, (0.02,), 3, 13),
     ("seglen_s2_1d", 2, 10, 1, 32, 1, (0.03,), 2, 17),
+    ("seglen_s2_L260_rescale", 2, 260, 2, 24, 1, (0.02,), 100, 6),   # final LP > 600: per-column rescale (:243-244)
+    ("seglen_s3_3d_L120_rescale", 3, 120, 3, 30, 0, (0.02,), 50, 4),
 ]
 
 
