@@ -54,12 +54,6 @@ __device__ __forceinline__ float xf_sqrt(float x) {
   return r;
 }
 
-// global -> shared staging without registers (the issuing thread waits, the CTA barrier publishes)
-__device__ __forceinline__ void xf_cp_async16(unsigned dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void xf_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // 2^d for -126 <= d <= 0, +0 below
 __device__ __forceinline__ float xf_pow2_le0(int d) { return __int_as_float(max(d + 127, 0) << 23); }
 
@@ -236,7 +230,7 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
   const int nrec = ck.nrec;
   const unsigned B16b = (unsigned)B16 * 16;
   if (w == 0 && nrec > 0) {
-    for (int i = lane; i < B16; i += 32) xf_cp_async16(s_blob + i * 16, gnext + (i - lane));
+    for (int i = lane; i < B16; i += 32) xt_cp_async16(s_blob + i * 16, gnext + (i - lane));
     gnext += bstride;
   }
   for (int h = tid; h < 2 * H; h += NT) {
@@ -289,7 +283,7 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
       csum += cn[dim] * 0.0f;
     }
   }
-  if (w == 0) xf_cp_async_wait();
+  if (w == 0) xt_cp_async_wait();
   __syncthreads();
 
   // ---- steps 3..L-1: merge by the replay record of step-1, update with C[step-1] ----
@@ -308,7 +302,7 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
       cd[dim] = Cs[(size_t)dim * npad];
     }
     if (w == 0 && step < last) {  // record of the next step into the other buffer
-      for (int i = lane; i < B16; i += 32) xf_cp_async16((rb ^ xr) + i * 16, gnext + (i - lane));
+      for (int i = lane; i < B16; i += 32) xt_cp_async16((rb ^ xr) + i * 16, gnext + (i - lane));
       gnext += bstride;
     }
 
@@ -407,7 +401,7 @@ __global__ void __launch_bounds__(128, XT_K2F32_CTAS) k2_replay_f32(const K2FArg
       cn[dim] = (float)(cd[dim] - c0[dim]);
       csum = fmaf(cn[dim], 0.0f, csum);
     }
-    if (w == 0) xf_cp_async_wait();
+    if (w == 0) xt_cp_async_wait();
     __syncthreads();
   }
   const uint8_t* curP = nullptr;

@@ -90,6 +90,12 @@ __device__ __forceinline__ void xt_sts32(unsigned a, int x) {
   asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
 }
 
+// global -> shared staging without registers (the issuing thread waits, the CTA barrier publishes)
+__device__ __forceinline__ void xt_cp_async16(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void xt_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // State memory of the replay kernel: shared memory (32-bit shared-window address `a`) or, in the GST
 // instantiation (live sequences of a tile do not fit in shared memory), a per-CTA block of global
 // memory at `gb` (`a` is then a byte offset).  Plain loads / stores: the CTA barrier between the steps
@@ -374,15 +380,14 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
     gb = a.gstate + ((size_t)smid * 32 + s_slot) * a.gstride;
   }
 
-  // stage the first replay record (steps 3..L-1 use records 0..L-4) and the tables
-  // (up to two 16-byte words per thread: B16 <= 64 * WPC is checked by the host)
+  // stage the first replay record (steps 3..L-1 use records 0..L-4) and the tables; the records are
+  // staged by warp 0 alone with cp.async (no registers, no instructions in the other warps)
   const int bstride = xt_blob_stride16(a.plan.cap);
-  const uint4* gblob = a.plan.blob + (size_t)ck.rec0 * bstride + tid;
+  const uint4* gnext = a.plan.blob + (size_t)ck.rec0 * bstride + lane;
   const int nrec = ck.nrec;
-  uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
-  if (!GST && nrec > 0) {
-    if (tid < B16) pre0 = __ldg(gblob);
-    if (tid + NT < B16) pre1 = __ldg(gblob + NT);
+  if (!GST && w == 0 && nrec > 0) {
+    for (int i = lane; i < B16; i += 32) xt_cp_async16(s_blob + i * 16, gnext + (i - lane));
+    gnext += bstride;
   }
   for (int h = tid; h < 2 * H; h += NT) {
     const int hh = h < H ? h : h - H;
@@ -466,16 +471,9 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
         cn[j][dim] = Cs[(size_t)dim * npad + toff[j]];  // C[2]
       }
   }
-  if (!GST) {
-    if (tid < B16) xt_sts128u(s_blob + tid * 16, pre0);
-    if (tid + NT < B16) xt_sts128u(s_blob + (tid + NT) * 16, pre1);
-  }
+  if (!GST && w == 0) xt_cp_async_wait();
   __syncthreads();
 
-  // loop-invariant parts of the record prefetch / staging
-  const bool st0 = tid < B16, st1 = tid + NT < B16;
-  const unsigned s_stage = s_blob + tid * 16;
-  const uint4* gnext = gblob;
   // ---- steps 3..L-1: merge by the replay record of step-1, update with C[step-1] ----
   unsigned src_v = s_vec, src_e = s_exp, dst_v = s_vec + VB, dst_e = s_exp + EB;
   for (int step = 3; step <= L - 1; ++step) {
@@ -507,12 +505,10 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       const int n16 = (int)(__ldg(gr).y & 0xFFFFu);  // XtBlobHdr::n16
       for (int i = tid; i < n16; i += NT) xt_sts128u(s_blob + i * 16, __ldg(gr + i));
       __syncthreads();
-    } else {
-      gnext += bstride;  // record of the next step (running pointer: no 64-bit multiply per step)
-      if (more) {
-        if (st0) pre0 = __ldg(gnext);
-        if (st1) pre1 = __ldg(gnext + NT);
-      }
+    } else if (w == 0 && more) {  // record of the next step into the other buffer
+      const unsigned nb = s_blob + ((ri + 1) & 1) * (B16 * 16);
+      for (int i = lane; i < B16; i += 32) xt_cp_async16(nb + i * 16, gnext + (i - lane));
+      gnext += bstride;
     }
 
     const unsigned rb = s_blob + (GST ? 0 : (ri & 1) * (B16 * 16));
@@ -632,11 +628,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       unsigned tv = src_v; src_v = dst_v; dst_v = tv;
       unsigned te = src_e; src_e = dst_e; dst_e = te;
     }
-    if (!GST && more) {
-      const unsigned nb = s_stage + ((ri + 1) & 1) * (B16 * 16);
-      if (st0) xt_sts128u(nb, pre0);
-      if (st1) xt_sts128u(nb + NT * 16, pre1);
-    }
+    if (!GST && w == 0) xt_cp_async_wait();
     __syncthreads();
   }
   const uint8_t* curP = nullptr;
