@@ -363,6 +363,8 @@ def main():
                             "bucket with the plan / replay kernels, result read back",
                     "parity_rel_diff_vs_resident": abs(e2e_val - total) / abs(total)},
             "gpu_launches": int(launches),
+            "seq_updates_per_s": float(stats["seq_updates"]) * world * args.steps / (ms * 1e-3),  # sum of nT * nB_in per step
+
             "kernel_ms": {"plan": ms_plan, "replay_and_reduce": replay_ms,
                           "what": "two-phase mode (one plan launch, one replay launch), measured after the timed region"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
