@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
   constexpr int NT = XT_SEG_THREADS;
   const int tid = threadIdx.x;
   const int nS = P.nS, cap = a.cap, n2 = a.n2;
-  extern __shared__ double k4_smem[];
+  extern __shared__ __align__(16) double k4_smem[];
   double* setA = k4_smem;
   double* setB = setA + (size_t)cap * (D + KS + 2);
   double* keys = setB + (size_t)cap * (D + KS + 2);
@@ -219,15 +219,18 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
         }
       };
       for (int g = tid; g < (n2 >> 2); g += NT) {  // stages k = 2, 4
-        double k0 = keys[4 * g], k1 = keys[4 * g + 1], k2 = keys[4 * g + 2], k3 = keys[4 * g + 3];
-        int i0 = ord[4 * g], i1 = ord[4 * g + 1], i2 = ord[4 * g + 2], i3 = ord[4 * g + 3];
+        const double2 ka2 = reinterpret_cast<const double2*>(keys)[2 * g], kb2 = reinterpret_cast<const double2*>(keys)[2 * g + 1];
+        const int4 iv = reinterpret_cast<const int4*>(ord)[g];  // 128-bit rows: 16-byte aligned by construction
+        double k0 = ka2.x, k1 = ka2.y, k2 = kb2.x, k3 = kb2.y;
+        int i0 = iv.x, i1 = iv.y, i2 = iv.z, i3 = iv.w;
         ce(k0, i0, k1, i1, true);
         ce(k2, i2, k3, i3, false);
         const bool up = (g & 1) == 0;
         ce(k0, i0, k2, i2, up); ce(k1, i1, k3, i3, up);
         ce(k0, i0, k1, i1, up); ce(k2, i2, k3, i3, up);
-        keys[4 * g] = k0; keys[4 * g + 1] = k1; keys[4 * g + 2] = k2; keys[4 * g + 3] = k3;
-        ord[4 * g] = i0; ord[4 * g + 1] = i1; ord[4 * g + 2] = i2; ord[4 * g + 3] = i3;
+        reinterpret_cast<double2*>(keys)[2 * g] = make_double2(k0, k1);
+        reinterpret_cast<double2*>(keys)[2 * g + 1] = make_double2(k2, k3);
+        reinterpret_cast<int4*>(ord)[g] = make_int4(i0, i1, i2, i3);
       }
       __syncthreads();
       for (int k = 8; k <= n2; k <<= 1) {
@@ -245,13 +248,16 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
           __syncthreads();
         }
         for (int g = tid; g < (n2 >> 2); g += NT) {  // distances 2 and 1
-          double k0 = keys[4 * g], k1 = keys[4 * g + 1], k2 = keys[4 * g + 2], k3 = keys[4 * g + 3];
-          int i0 = ord[4 * g], i1 = ord[4 * g + 1], i2 = ord[4 * g + 2], i3 = ord[4 * g + 3];
+          const double2 ka2 = reinterpret_cast<const double2*>(keys)[2 * g], kb2 = reinterpret_cast<const double2*>(keys)[2 * g + 1];
+          const int4 iv = reinterpret_cast<const int4*>(ord)[g];
+          double k0 = ka2.x, k1 = ka2.y, k2 = kb2.x, k3 = kb2.y;
+          int i0 = iv.x, i1 = iv.y, i2 = iv.z, i3 = iv.w;
           const bool up = ((4 * g) & k) == 0;
           ce(k0, i0, k2, i2, up); ce(k1, i1, k3, i3, up);
           ce(k0, i0, k1, i1, up); ce(k2, i2, k3, i3, up);
-          keys[4 * g] = k0; keys[4 * g + 1] = k1; keys[4 * g + 2] = k2; keys[4 * g + 3] = k3;
-          ord[4 * g] = i0; ord[4 * g + 1] = i1; ord[4 * g + 2] = i2; ord[4 * g + 3] = i3;
+          reinterpret_cast<double2*>(keys)[2 * g] = make_double2(k0, k1);
+          reinterpret_cast<double2*>(keys)[2 * g + 1] = make_double2(k2, k3);
+          reinterpret_cast<int4*>(ord)[g] = make_int4(i0, i1, i2, i3);
         }
         __syncthreads();
       }
