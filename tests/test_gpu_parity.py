@@ -14,8 +14,9 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f)
+               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f)
 VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
+WINDOW_CASES = sorted(glob.glob(os.path.join(GOLDEN, "window_*.npz")))
 RTOL_LOGL = 1e-9
 
 
@@ -594,3 +595,26 @@ def test_precision_switch_of_the_api_mirror(xt):
     assert v32 != v64 and abs(v32 - v64) <= RTOL_FP32 * abs(v64)
     with pytest.raises(ValueError):
         xt.set_precision("fp16")
+
+
+@pytest.mark.parametrize("path", WINDOW_CASES, ids=[os.path.basename(p)[:-4] for p in WINDOW_CASES])
+def test_window_only_mode_matches_reference_window_function(path, xt, native):
+    """Window-only mode = `P_Cs_inter_bound_stats` (tracking.py:109-318, the function the north star names):
+    the engine at threshold 1e-12 / max_nb_states 10**9 against the unmodified reference function's output
+    (tests/golden/make_golden_window.py; up to nS^(frame_len+nsub) live sequences, dense window fusion)."""
+    z = np.load(path)
+    m = orc.Model(z["loc_err"], z["ds"], z["Fs"], z["TrMat"], float(z["pBL"]), list(z["cell_dims"]), int(z["nsub"]),
+                  int(z["frame_len"]), int(z["min_len"]), 1e-12, 10**9)
+    got = xt.Proba_Cs(z["C"], np.asarray(m.loc_err)[None, None], m.ds, m.Fs, m.TrMat, m.pBL, int(z["isBL"]), m.cell_dims,
+                      m.nb_substeps, m.frame_len, m.min_len, m.threshold, m.max_nb_states)
+    np.testing.assert_allclose(got, z["ref_logp"], rtol=RTOL_LOGL)
+    # the window alone decides: the number of live sequences is the reference's nS^(frame_len + nsub)
+    eng = native.Engine(0)
+    try:
+        eng.upload([z["C"]], [int(z["isBL"])], len(z["C"]))
+        eng.chunk_logp(0, len(z["C"]), engine_params(m, z["C"].shape[2]))
+        # (the reference's final count includes the end-of-track expansion when isBL, the engine's counter does not)
+        K = len(m.ds) ** m.nb_substeps
+        assert eng.stats()["max_nB_in"] == int(z["n_seq"]) // (K if int(z["isBL"]) else 1)
+    finally:
+        eng.close()

@@ -14,8 +14,9 @@ from oracle import ref_loader
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f)
+               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f)
 VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
+WINDOW_CASES = sorted(glob.glob(os.path.join(GOLDEN, "window_*.npz")))
 
 
 def load_case(path):
@@ -172,3 +173,15 @@ def test_oracle_vs_live_reference_tracks_csv_known_answer():
     with contextlib.redirect_stdout(io.StringIO()):
         ref = trk.cum_Proba_Cs(p, st, 0.02, [1], None, 2, 1, 6, 0, 1, 1, 0.2, 120)
     assert abs(got - ref) / abs(ref) < 1e-13
+
+
+@pytest.mark.parametrize("path", WINDOW_CASES, ids=[os.path.basename(p)[:-4] for p in WINDOW_CASES])
+def test_oracle_window_only_mode_matches_reference_window_function(path):
+    """Window-only mode (the north star's `P_Cs_inter_bound_stats`, tracking.py:109-318): golden = the
+    unmodified reference function (tests/golden/make_golden_window.py); the oracle runs the threshold
+    recursion at threshold 1e-12 with no sequence limit, which groups by the sliding window alone."""
+    z = np.load(path)
+    m = orc.Model(z["loc_err"], z["ds"], z["Fs"], z["TrMat"], float(z["pBL"]), list(z["cell_dims"]), int(z["nsub"]),
+                  int(z["frame_len"]), int(z["min_len"]), 1e-12, 10**9)
+    got = orc.chunk_logp(z["C"], m, int(z["isBL"]))
+    np.testing.assert_allclose(got, z["ref_logp"], rtol=1e-12)

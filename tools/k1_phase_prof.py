@@ -21,17 +21,19 @@ tracks = sim_tracks(n, seed=0, device="cuda", max_track_len=30, min_track_len=10
 st, _ = xt._sorted_buckets(tracks)
 model = make_model(nS=2, nsub=1, frame_len=8, min_len=st[0].shape[1], Ds=[1e-5, 0.25], Fs=[0.6, 0.4])
 p = engine_params(model, 2)
-ts = xt.TrackSet(st)
+ts = xt.TrackSet(st, rank=0, world_size=int(os.environ.get("WORLD", "1")))
+for name, val in [kv.split("=") for kv in os.environ.get("XT_OPTS", "").split(",") if kv]:
+    ts.engine.set_option(name, int(val))
 ts.engine.set_option("pipeline", int(os.environ.get("PIPE", "0")))
 for _ in range(3):
     ts.sum_logp(p)
 print(ts.engine.stats())
 lib = _native.load_library()
-nch = len(ts.chunks)
+nch = ts.n_local_chunks
 buf = np.zeros((nch, 12), dtype=np.int64)
 assert lib.xt_debug_k1_prof(buf.ctypes.data_as(C.c_void_p), nch) == 0
 names = ["update+codes", "batch rows", "batch resolve", "copy+zero+barriers", "history (thread 0)", "records (thread 0)", "merge (warp 0)", "end barrier"]
-Ls = np.array([st[b].shape[1] for (b, a, z, _) in ts.chunks])
+Ls = np.array([st[ts.chunks[i][0]].shape[1] for i in ts.my_chunks])
 for L in (10, 20, 30):
     sel = buf[Ls == L]
     if len(sel) == 0:
