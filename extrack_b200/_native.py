@@ -72,6 +72,7 @@ class XtStats(C.Structure):
 
 # every symbol include/xtrack.h declares (tests check the library exports all of them)
 EXPORTS = (
+    "xt_device_count",
     "xt_create",
     "xt_destroy",
     "xt_last_error",
@@ -91,6 +92,18 @@ EXPORTS = (
     "xt_fp64_peak_tflops",
     "xt_host_alloc",
     "xt_host_free",
+    "xt_multi_create",
+    "xt_multi_destroy",
+    "xt_multi_last_error",
+    "xt_multi_n_devices",
+    "xt_multi_upload",
+    "xt_multi_upload_aux",
+    "xt_multi_set_stay_tables",
+    "xt_multi_sum_logp",
+    "xt_multi_chunk_logp",
+    "xt_multi_set_option",
+    "xt_multi_device_load",
+    "xt_multi_get_stats",
 )
 
 _lib = None
@@ -109,6 +122,7 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     P = C.POINTER
+    lib.xt_device_count.argtypes = []
     lib.xt_create.argtypes = [C.c_int, P(vp)]
     lib.xt_destroy.argtypes = [vp]
     lib.xt_destroy.restype = None
@@ -130,8 +144,22 @@ def load_library() -> C.CDLL:
     lib.xt_fp64_peak_tflops.argtypes = [vp, P(dbl)]
     lib.xt_host_alloc.argtypes = [P(vp), C.c_uint64]
     lib.xt_host_free.argtypes = [vp]
+    lib.xt_multi_create.argtypes = [P(i32), i32, P(vp)]
+    lib.xt_multi_destroy.argtypes = [vp]
+    lib.xt_multi_destroy.restype = None
+    lib.xt_multi_last_error.argtypes = [vp]
+    lib.xt_multi_last_error.restype = C.c_char_p
+    lib.xt_multi_n_devices.argtypes = [vp]
+    lib.xt_multi_upload.argtypes = [vp, i32, P(i32), P(i64), P(i32), P(vp), i32, i32]
+    lib.xt_multi_upload_aux.argtypes = [vp, i32, P(i32), P(i64), i32, P(vp), P(vp)]
+    lib.xt_multi_set_stay_tables.argtypes = [vp, i32, i32, P(dbl), P(dbl)]
+    lib.xt_multi_sum_logp.argtypes = [vp, P(XtParams), P(dbl)]
+    lib.xt_multi_chunk_logp.argtypes = [vp, i32, P(XtParams), P(dbl)]
+    lib.xt_multi_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.xt_multi_device_load.argtypes = [vp, i32, P(i32), P(i32), P(i64)]
+    lib.xt_multi_get_stats.argtypes = [vp, P(XtStats)]
     for name in EXPORTS:
-        if name not in ("xt_destroy", "xt_last_error"):
+        if name not in ("xt_destroy", "xt_last_error", "xt_multi_destroy", "xt_multi_last_error"):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
@@ -334,6 +362,125 @@ class Engine:
         out = C.c_double()
         self._check(self._lib.xt_fp64_peak_tflops(self._h, C.byref(out)))
         return out.value
+
+
+def device_count() -> int:
+    """Visible CUDA devices (0 without a driver / GPU)."""
+    return int(load_library().xt_device_count())
+
+
+class MultiEngine:
+    """Several GPUs driven from one Python thread (``xt_multi_*``): the chunk list is dealt to the devices
+    longest-processing-time-first, every device keeps its chunks resident, and the objective is the sum of
+    the per-chunk sums in global chunk order (same bits for any number of devices)."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        devs = [int(d) for d in devices]
+        arr = (C.c_int32 * len(devs))(*devs)
+        rc = self._lib.xt_multi_create(arr, len(devs), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.xt_multi_last_error(None).decode()
+            self._h = None
+            raise EngineError(rc, f"cannot create CUDA contexts on devices {devs}: {msg} (no CPU fallback)")
+        self.devices = devs
+        self.segments = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.xt_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            _raise(rc, self._lib.xt_multi_last_error(self._h).decode())
+
+    def upload(self, segments: Sequence[np.ndarray], isBL: Sequence[int], chunk_size: int):
+        segs = [np.ascontiguousarray(s, dtype=np.float64) for s in segments]
+        if len(segs) == 0:
+            raise ValueError("No track could be detected. The loaded tracks seem empty.")
+        d = segs[0].shape[2]
+        for s in segs:
+            if s.ndim != 3 or s.shape[2] != d:
+                raise ValueError("all track arrays must have shape [n, L, d] with the same d")
+        n = len(segs)
+        self._Ls = (C.c_int32 * n)(*[s.shape[1] for s in segs])
+        self._ns = (C.c_int64 * n)(*[s.shape[0] for s in segs])
+        bl = (C.c_int32 * n)(*[int(b) for b in isBL])
+        ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in segs])
+        self._check(self._lib.xt_multi_upload(self._h, n, self._Ls, self._ns, bl, ptrs, d, int(chunk_size)))
+        self.segments = [(s.shape[1], s.shape[0]) for s in segs]
+        self.chunk_size = int(chunk_size)
+        self.d = d
+
+    def upload_aux(self, sigma: Optional[Sequence[np.ndarray]] = None, dt: Optional[Sequence[np.ndarray]] = None):
+        n = len(self.segments)
+        k = 0
+        sp = dp = None
+        keep = []
+        if sigma is not None:
+            sg = [np.ascontiguousarray(a, dtype=np.float64) for a in sigma]
+            k = sg[0].shape[2] if sg[0].ndim == 3 else -1
+            for a, (L, cnt) in zip(sg, self.segments):
+                if a.ndim != 3 or a.shape != (cnt, L, k):
+                    raise ValueError("Localization error is not specified correctly: input_LocErr arrays must have shape "
+                                     "[n, L, 1] or [n, L, d] matching all_tracks")
+            sp = (C.c_void_p * n)(*[a.ctypes.data for a in sg])
+            keep.append(sg)
+        if dt is not None:
+            ds_ = [np.ascontiguousarray(a, dtype=np.float64) for a in dt]
+            for a, (L, cnt) in zip(ds_, self.segments):
+                if a.shape != (cnt, L):
+                    raise ValueError("dt is not informed properly. It must either be a float number or a dictionary of same "
+                                     "structure than `all_tracks` with each element being an array of dims (nb_tracks, track_len)")
+            dp = (C.c_void_p * n)(*[a.ctypes.data for a in ds_])
+            keep.append(ds_)
+        self._check(self._lib.xt_multi_upload_aux(self._h, n, self._Ls, self._ns, int(k), sp, dp))
+
+    def set_stay_tables(self, per_track: bool, Lp_stay: Optional[np.ndarray], L_leave: Optional[np.ndarray]):
+        if per_track:
+            raise NotImplementedError("per-track field-of-view tables belong to predict_Bs (single-device contexts)")
+        if Lp_stay is None:
+            self._check(self._lib.xt_multi_set_stay_tables(self._h, 0, 0, None, None))
+            return
+        a = np.ascontiguousarray(Lp_stay, dtype=np.float64)
+        b = np.ascontiguousarray(L_leave, dtype=np.float64)
+        pd = C.POINTER(C.c_double)
+        self._check(self._lib.xt_multi_set_stay_tables(self._h, a.shape[1], b.shape[1], a.ctypes.data_as(pd), b.ctypes.data_as(pd)))
+
+    def sum_logp(self, p: XtParams) -> float:
+        out = C.c_double()
+        self._check(self._lib.xt_multi_sum_logp(self._h, C.byref(p), C.byref(out)))
+        return out.value
+
+    def chunk_logp(self, chunk: int, nT: int, p: XtParams) -> np.ndarray:
+        out = np.empty(nT, dtype=np.float64)
+        self._check(self._lib.xt_multi_chunk_logp(self._h, int(chunk), C.byref(p), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.xt_multi_set_option(self._h, name.encode(), int(value)))
+
+    def device_load(self):
+        """[(CUDA ordinal, chunks, track-steps)] per device slot."""
+        out = []
+        for g in range(len(self.devices)):
+            dev, nch, steps = C.c_int32(), C.c_int32(), C.c_int64()
+            self._check(self._lib.xt_multi_device_load(self._h, g, C.byref(dev), C.byref(nch), C.byref(steps)))
+            out.append((dev.value, nch.value, steps.value))
+        return out
+
+    def stats(self) -> dict:
+        st = XtStats()
+        self._check(self._lib.xt_multi_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in XtStats._fields_}
 
 
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "xt_common.cuh"
+#include "xt_launch.h"
 #include "xt_plan.cuh"
 #include "xt_replay.cuh"
 #include "xt_replay_lin.cuh"
@@ -70,6 +71,11 @@ struct xt_ctx {
   double* d_logp = nullptr;
   double* d_partial = nullptr;
   double* d_out = nullptr;
+  // per-chunk sums of log P (fixed order over the chunk's tiles): the objective is their sum in chunk order
+  // on the host, so its bits do not depend on how the chunks are spread over GPUs (xt_multi_*)
+  double* d_csum = nullptr;
+  double* h_csum = nullptr;                 // pinned
+  int32_t* d_cw0[3] = {nullptr, nullptr, nullptr};  // first tile of every position: [0],[1] fused tables (corder), [2] plain table
   XtChunkSummary* d_summ = nullptr;
   std::vector<XtChunkSummary> summ;
   XtChunkSummary* h_summ = nullptr;  // pinned
@@ -186,6 +192,11 @@ static void free_data(xt_ctx* ctx) {
   ctx->d_fstate = nullptr; ctx->d_fslots = nullptr; ctx->fstate_bytes = 0;
   cudaFree(ctx->d_workf[0]); cudaFree(ctx->d_workf[1]); cudaFree(ctx->d_corder);
   ctx->d_corder = nullptr;
+  cudaFree(ctx->d_csum);
+  ctx->d_csum = nullptr;
+  if (ctx->h_csum) cudaFreeHost(ctx->h_csum);
+  ctx->h_csum = nullptr;
+  for (int v = 0; v < 3; ++v) { cudaFree(ctx->d_cw0[v]); ctx->d_cw0[v] = nullptr; }
   ctx->d_workf[0] = ctx->d_workf[1] = nullptr;
   if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
   ctx->d_soa = ctx->d_logp = ctx->d_partial = ctx->d_gstate = nullptr;
@@ -198,21 +209,8 @@ static void free_data(xt_ctx* ctx) {
   free_plan(ctx);
 }
 
-extern "C" int xt_create(int device, xt_ctx** out) {
-  xt_ctx* ctx = nullptr;
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0) {
-    set_error(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e));
-    return XT_ERR_CUDA;
-  }
-  if (device < 0 || device >= ndev) {
-    set_error(nullptr, "device ordinal out of range");
-    return XT_ERR_ARG;
-  }
-  xt_ctx* c = new xt_ctx();
-  c->device = device;
-  ctx = c;
+static int create_resources(xt_ctx* ctx, int device) {
+  xt_ctx* c = ctx;
   XT_CUDA_OK(cudaSetDevice(device));
   XT_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   XT_CUDA_OK(cudaMalloc(&c->d_out, sizeof(double)));
@@ -229,6 +227,30 @@ extern "C" int xt_create(int device, xt_ctx** out) {
   XT_CUDA_OK(cudaMallocHost(&c->h_spec, sizeof(int)));
   XT_CUDA_OK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   XT_CUDA_OK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
+  return XT_OK;
+}
+
+extern "C" void xt_destroy(xt_ctx* ctx);
+
+extern "C" int xt_create(int device, xt_ctx** out) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return XT_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error(nullptr, "device ordinal out of range");
+    return XT_ERR_ARG;
+  }
+  xt_ctx* c = new xt_ctx();
+  c->device = device;
+  const int rc = create_resources(c, device);
+  if (rc) {  // the message goes where xt_last_error(NULL) finds it; nothing of the half-built context is kept
+    g_create_error = c->err;
+    xt_destroy(c);
+    return rc;
+  }
   *out = c;
   return XT_OK;
 }
@@ -236,7 +258,7 @@ extern "C" int xt_create(int device, xt_ctx** out) {
 extern "C" void xt_destroy(xt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_data(ctx);
   for (int b = 0; b < 2; ++b) {
     cudaFree(ctx->stage[b]);
@@ -256,8 +278,18 @@ extern "C" void xt_destroy(xt_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_seg) cudaEventDestroy(e);
   cudaFree(ctx->d_spec);
   if (ctx->h_spec) cudaFreeHost(ctx->h_spec);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
   delete ctx;
+}
+
+extern "C" int xt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
 }
 
 extern "C" const char* xt_last_error(xt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -378,7 +410,17 @@ static int setup_layout(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int6
       ctx->n_workf[v] = (int)wf.size();
       XT_CUDA_OK(cudaMalloc(&ctx->d_workf[v], sizeof(XtWork) * wf.size()));
       XT_CUDA_OK(cudaMemcpy(ctx->d_workf[v], wf.data(), sizeof(XtWork) * wf.size(), cudaMemcpyHostToDevice));
+      XT_CUDA_OK(cudaMalloc(&ctx->d_cw0[v], sizeof(int32_t) * (nch + 1)));
+      XT_CUDA_OK(cudaMemcpy(ctx->d_cw0[v], ctx->chunk_w0[v].data(), sizeof(int32_t) * (nch + 1), cudaMemcpyHostToDevice));
     }
+    {  // plain work table (first-generation / log-domain replay kernels): 32-track tiles in chunk order
+      std::vector<int32_t> w0(nch + 1, 0);
+      for (size_t c = 0; c < nch; ++c) w0[c + 1] = w0[c] + (ctx->chunks[c].nT + 31) / 32;
+      XT_CUDA_OK(cudaMalloc(&ctx->d_cw0[2], sizeof(int32_t) * (nch + 1)));
+      XT_CUDA_OK(cudaMemcpy(ctx->d_cw0[2], w0.data(), sizeof(int32_t) * (nch + 1), cudaMemcpyHostToDevice));
+    }
+    XT_CUDA_OK(cudaMalloc(&ctx->d_csum, sizeof(double) * nch));
+    XT_CUDA_OK(cudaMallocHost(&ctx->h_csum, sizeof(double) * nch));
     while ((int)ctx->ev_seg.size() < n_seg) {
       cudaEvent_t e;
       XT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -609,8 +651,10 @@ static int check_params(xt_ctx* ctx, const xt_params* p, int* bits_out) {
       set_error(ctx, "xt_params: XT_FLAG_VAR_LOC / XT_FLAG_VAR_DT need matching xt_upload_aux data (n_loc = k_sigma)");
       return XT_ERR_STATE;
     }
-    if ((p->flags & XT_FLAG_VAR_DT) && ctx->d_stay[0] &&
-        (ctx->stay_K[0] != ipow(p->nS, p->nsub) || ctx->stay_H[0] != ipow(p->nS, p->nsub + 1))) {
+    bool bad_tables = false;
+    for (int i = 0; i < 2; ++i)  // [0] per chunk (objective), [1] per track (xt_predict)
+      bad_tables = bad_tables || (ctx->d_stay[i] && (ctx->stay_K[i] != ipow(p->nS, p->nsub) || ctx->stay_H[i] != ipow(p->nS, p->nsub + 1)));
+    if ((p->flags & XT_FLAG_VAR_DT) && bad_tables) {
       set_error(ctx, "xt_set_stay_tables: K / H do not match the model");
       return XT_ERR_ARG;
     }
@@ -643,104 +687,6 @@ static int ensure_plan(xt_ctx* ctx, const xt_params* p, int cap) {
   ctx->CO1_alloc = CO1;
   return XT_OK;
 }
-
-template <int D, int KS, bool VAR, int NT>
-static cudaError_t launch_k1_nt(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream) {
-  auto kern = k1_plan<D, KS, VAR, NT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<(unsigned)n_chunks, NT, smem, stream>>>(a, p);
-  return cudaGetLastError();
-}
-template <int D, int KS, bool VAR>
-static cudaError_t launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream, int nthreads) {
-  if (nthreads == 1024) return launch_k1_nt<D, KS, VAR, 1024>(a, p, smem, n_chunks, stream);
-  if (!VAR && a.scapC > 0) {  // scratch in shared memory, known at compile time
-    auto kern = k1_plan<D, KS, false, XT_K1_THREADS, true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<(unsigned)n_chunks, XT_K1_THREADS, smem, stream>>>(a, p);
-    return cudaGetLastError();
-  }
-  return launch_k1_nt<D, KS, VAR, XT_K1_THREADS>(a, p, smem, n_chunks, stream);
-}
-
-template <int D, int KS, int WPC>
-static cudaError_t launch_k2_lin(xt_ctx* ctx, const K2Args& a, const xt_params& p, const K2Lin& lin, size_t smem, int grid) {
-  auto kern = k2_replay_lin<D, KS, WPC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, 32 * WPC, smem, ctx->stream>>>(a, p, lin);
-  return cudaGetLastError();
-}
-
-template <int D, int KS, int WPC, int TPT>
-static cudaError_t launch_k2_fused_w(const K2FArgs& a, const K2Tab& tab, size_t smem, cudaStream_t stream) {
-  auto kern = k2_replay_fused<D, KS, WPC, TPT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<a.n_work, 32 * WPC, smem, stream>>>(a, tab);
-  return cudaGetLastError();
-}
-
-template <int D, int KS>
-static cudaError_t launch_k2_fused(const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt, cudaStream_t stream,
-                                   bool var, bool f32) {
-  if (f32) {  // optional single-precision replay: one configuration (4 warps per tile, one track per thread)
-    auto kern = k2_replay_f32<D, KS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<a.n_work, 128, smem, stream>>>(a, tab);
-    return cudaGetLastError();
-  }
-  if (a.gstate) {  // state in global memory: one configuration (4 warps per tile, one track per thread)
-    auto kern = k2_replay_fused<D, KS, 4, 1, false, true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<a.n_work, 128, smem, stream>>>(a, tab);
-    return cudaGetLastError();
-  }
-  if (var) {  // peak-wise LocErr / per-track dt: one configuration (4 warps per tile, one track per thread)
-    auto kern = k2_replay_fused<D, KS, 4, 1, true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<a.n_work, 128, smem, stream>>>(a, tab);
-    return cudaGetLastError();
-  }
-  if (tpt == 2) {
-    if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 2>(a, tab, smem, stream);
-    if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 2>(a, tab, smem, stream);
-    return launch_k2_fused_w<D, KS, 4, 2>(a, tab, smem, stream);
-  }
-  if (wpc == 8) return launch_k2_fused_w<D, KS, 8, 1>(a, tab, smem, stream);
-  if (wpc == 2) return launch_k2_fused_w<D, KS, 2, 1>(a, tab, smem, stream);
-  return launch_k2_fused_w<D, KS, 4, 1>(a, tab, smem, stream);
-}
-
-template <int D, int KS>
-static cudaError_t launch_k2(xt_ctx* ctx, const K2Args& a, const xt_params& p, const K2Lin& lin, size_t smem,
-                             bool use_smem, int grid, int wpc) {
-  if (is_var(&p)) {  // log-domain kernel, state in global memory
-    k2_replay<D, KS, false, true><<<grid, 32, 0, ctx->stream>>>(a, p);
-    return cudaGetLastError();
-  }
-  if (use_smem) {
-    if (wpc == 8) return launch_k2_lin<D, KS, 8>(ctx, a, p, lin, smem, grid);
-    if (wpc == 2) return launch_k2_lin<D, KS, 2>(ctx, a, p, lin, smem, grid);
-    return launch_k2_lin<D, KS, 4>(ctx, a, p, lin, smem, grid);
-  }
-  k2_replay<D, KS, false><<<grid, 32, 0, ctx->stream>>>(a, p);
-  return cudaGetLastError();
-}
-
-#define XT_DISPATCH(D_, KS_, CALL)                                   \
-  do {                                                               \
-    if (D_ == 1) { CALL(1, 1); }                                     \
-    else if (D_ == 2 && KS_ == 1) { CALL(2, 1); }                    \
-    else if (D_ == 2) { CALL(2, 2); }                                \
-    else if (KS_ == 1) { CALL(3, 1); }                               \
-    else { CALL(3, 3); }                                             \
-  } while (0)
 
 #ifdef XT_K1_PROF
 static long long* g_k1_prof = nullptr;
@@ -802,17 +748,8 @@ static int enqueue_k1(xt_ctx* ctx, const xt_params* p, int bits, int c0, int nc,
   const int varH = var ? ipow(p->nS, p->nsub + 1) : 0;
   const int nt = k1_threads(ctx);
   const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC, varH, nt);
-  cudaError_t e = cudaSuccess;
-  if (var) {
-    a.ax = make_aux(ctx, p, 0);
-#define CALL_K1V(D_, KS_) e = launch_k1<D_, KS_, true>(a, *p, smem, nc, stream, nt)
-    XT_DISPATCH(p->d, p->n_loc, CALL_K1V);
-#undef CALL_K1V
-  } else {
-#define CALL_K1(D_, KS_) e = launch_k1<D_, KS_, false>(a, *p, smem, nc, stream, nt)
-    XT_DISPATCH(p->d, p->n_loc, CALL_K1);
-#undef CALL_K1
-  }
+  if (var) a.ax = make_aux(ctx, p, 0);
+  const cudaError_t e = xt_launch_k1(a, *p, smem, nc, stream, nt);
   XT_CUDA_OK(e);
   ctx->stats.k1_launches++;
   return XT_OK;
@@ -874,11 +811,55 @@ static int run_plan(xt_ctx* ctx, const xt_params* p, int bits) {
   return XT_OK;
 }
 
-static int finish_eval(xt_ctx* ctx, const xt_params* p, int n_work, double* d_out, int64_t su, int64_t sg, int maxC) {
-  k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, n_work, d_out ? d_out : ctx->d_out);
+// Deterministic final reduction of the per-CTA partial sums (second level of tracking.py:1069).
+__global__ void __launch_bounds__(1024) k_reduce(const double* __restrict__ partial, int n, double* out) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += partial[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// per-tile partial sums -> per-chunk sums (one warp per chunk, fixed order) -> device total (fixed tree over the
+// chunk sums).  `table`: 0 / 1 = fused work tables (tiles of 32 / 64 tracks, corder), 2 = plain work table.
+__global__ void k_reduce_chunks(const double* __restrict__ partial, const int32_t* __restrict__ w0,
+                                const int32_t* __restrict__ cid, double* __restrict__ csum) {
+  const int q = blockIdx.x, lane = threadIdx.x;
+  double acc = 0.0;
+  for (int i = w0[q] + lane; i < w0[q + 1]; i += 32) acc += partial[i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if (lane == 0) csum[cid ? cid[q] : q] = acc;
+}
+static int enqueue_reduce(xt_ctx* ctx, int table, double* d_out) {
+  const int nch = (int)ctx->chunks.size();
+  k_reduce_chunks<<<nch, 32, 0, ctx->stream>>>(ctx->d_partial, ctx->d_cw0[table], table < 2 ? ctx->d_corder : nullptr,
+                                               ctx->d_csum);
+  k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_csum, nch, d_out ? d_out : ctx->d_out);
   XT_CUDA_OK(cudaGetLastError());
+  ctx->stats.k2_launches += 2;
+  return XT_OK;
+}
+// objective of this context: the chunk sums added in chunk order on the host (after the evaluation)
+static int read_total(xt_ctx* ctx, double* out) {
+  const size_t nch = ctx->chunks.size();
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_csum, ctx->d_csum, sizeof(double) * nch, cudaMemcpyDeviceToHost, ctx->stream));
+  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  double acc = 0.0;
+  for (size_t c = 0; c < nch; ++c) acc += ctx->h_csum[c];
+  *out = acc;
+  return XT_OK;
+}
+
+static int finish_eval(xt_ctx* ctx, const xt_params* p, int table, double* d_out, int64_t su, int64_t sg, int maxC) {
+  int rcr = enqueue_reduce(ctx, table, d_out);
+  if (rcr) return rcr;
   XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  ctx->stats.k2_launches++;  // the reduction
   ctx->stats.n_tracks = ctx->n_tracks;
   ctx->stats.track_steps = ctx->track_steps;
   ctx->stats.seq_updates = su;
@@ -1046,10 +1027,8 @@ static int enqueue_fused(xt_ctx* ctx, const xt_params* p, const FusedLaunch& fl,
   fa.work0 = w0[c0];
   fa.n_work = w0[c1] - w0[c0];
   if (fa.n_work <= 0) return XT_OK;
-  cudaError_t ef = cudaSuccess;
-#define CALL_K2F(D_, KS_) ef = launch_k2_fused<D_, KS_>(fa, fl.tab, fl.smem, fl.wpc, fl.tpt, stream, fl.var, fl.f32)
-  XT_DISPATCH(p->d, p->n_loc, CALL_K2F);
-#undef CALL_K2F
+  const cudaError_t ef = fl.f32 ? xt_launch_k2_f32(p->d, p->n_loc, fa, fl.tab, fl.smem, stream)
+                                : xt_launch_k2_fused(p->d, p->n_loc, fa, fl.tab, fl.smem, fl.wpc, fl.tpt, stream, fl.var);
   XT_CUDA_OK(ef);
   ctx->stats.k2_launches++;
   ctx->stats.fp32 = fl.f32 ? 1 : 0;
@@ -1138,9 +1117,8 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
     XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
   }
   XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, ctx->n_workf[fl.tpt - 1], d_out ? d_out : ctx->d_out);
-  XT_CUDA_OK(cudaGetLastError());
-  ctx->stats.k2_launches++;  // the reduction
+  rc = enqueue_reduce(ctx, fl.tpt - 1, d_out);
+  if (rc) return rc;
   XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_summ, ctx->d_summ, sizeof(XtChunkSummary) * nch, cudaMemcpyDeviceToHost, ctx->stream));
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1205,7 +1183,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
     rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->stream);
     if (rc) return rc;
     ctx->last_fused = true;
-    return finish_eval(ctx, p, ctx->n_workf[fl.tpt - 1], d_out, su, sg, maxC);
+    return finish_eval(ctx, p, fl.tpt - 1, d_out, su, sg, maxC);
   }
   if (ctx->last_fused || !ctx->plan_has_grec) {  // the plan was written without the records this path reads
     ctx->last_fused = false;
@@ -1254,22 +1232,16 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
     }
     a.gstate = ctx->d_gstate;
   }
-  cudaError_t e = cudaSuccess;
-#define CALL_K2(D_, KS_) e = launch_k2<D_, KS_>(ctx, a, *p, lin, smem, use_smem, grid, wpc)
-  XT_DISPATCH(p->d, p->n_loc, CALL_K2);
-#undef CALL_K2
+  const cudaError_t e = xt_launch_k2_old(a, *p, lin, smem, use_smem, grid, wpc, ctx->stream);
   XT_CUDA_OK(e);
   ctx->stats.k2_launches++;
-  return finish_eval(ctx, p, a.n_work, d_out, su, sg, maxC);
+  return finish_eval(ctx, p, 2, d_out, su, sg, maxC);
 }
 
 extern "C" int xt_sum_logp(xt_ctx* ctx, const xt_params* p, double* out) {
   int rc = evaluate(ctx, p, nullptr, nullptr);
   if (rc) return rc;
-  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  *out = *ctx->h_out;
-  return XT_OK;
+  return read_total(ctx, out);
 }
 
 extern "C" int xt_sum_logp_host(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int64_t* n, const int32_t* isBL,
@@ -1279,10 +1251,7 @@ extern "C" int xt_sum_logp_host(xt_ctx* ctx, int32_t n_seg, const int32_t* L, co
   if (rc) return rc;
   rc = evaluate(ctx, p, nullptr, xyz);
   if (rc) return rc;
-  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  *out = *ctx->h_out;
-  return XT_OK;
+  return read_total(ctx, out);
 }
 
 extern "C" int xt_sum_logp_async(xt_ctx* ctx, const xt_params* p, double* d_out, void* cuda_stream) {
@@ -1498,3 +1467,4 @@ extern "C" int xt_fp64_peak_tflops(xt_ctx* ctx, double* out) {
 
 #include "xt_predict_host.inl"
 #include "xt_seglen_host.inl"
+#include "xt_multi.inl"

@@ -1,0 +1,22 @@
+// Translation unit of the state-annotation kernel (k3_predict).
+#include "xt_launch.h"
+#include "xt_predict.cuh"
+
+template <int D, int KS, bool VAR>
+static cudaError_t launch_k3_v(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
+  auto kern = k3_predict<D, KS, VAR>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32 * nwarps, smem, stream>>>(a, p);
+  return cudaGetLastError();
+}
+
+cudaError_t xt_launch_k3(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+  const bool var = xt_is_var(&p);
+#define CALL_K3(D_, KS_) \
+  e = var ? launch_k3_v<D_, KS_, true>(a, p, grid, nwarps, smem, stream) : launch_k3_v<D_, KS_, false>(a, p, grid, nwarps, smem, stream)
+  XT_DISPATCH(p.d, p.n_loc, CALL_K3);
+#undef CALL_K3
+  return e;
+}

@@ -1,0 +1,39 @@
+// Kernel launchers, one translation unit per kernel family (xt_k1.cu, xt_k2f.cu, ...) so that the
+// engine builds in parallel; the host driver (xt_engine.cu) only sees these non-template entry points.
+#pragma once
+#include "xt_common.cuh"
+
+struct K1Args;
+struct K2Args;
+struct K2Lin;
+struct K2FArgs;
+struct K2Tab;
+struct K3Args;
+struct K4Args;
+
+#define XT_DISPATCH(D_, KS_, CALL)                                   \
+  do {                                                               \
+    if (D_ == 1) { CALL(1, 1); }                                     \
+    else if (D_ == 2 && KS_ == 1) { CALL(2, 1); }                    \
+    else if (D_ == 2) { CALL(2, 2); }                                \
+    else if (KS_ == 1) { CALL(3, 1); }                               \
+    else { CALL(3, 3); }                                             \
+  } while (0)
+
+inline bool xt_is_var(const xt_params* p) { return (p->flags & (XT_FLAG_VAR_LOC | XT_FLAG_VAR_DT)) != 0; }
+
+// plan kernel (xt_plan.cuh); nthreads = 256 or 1024
+cudaError_t xt_launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream, int nthreads);
+// fused replay kernel, FP64 (xt_replay_fused.cuh): shared-memory state, GST or VAR instantiation
+cudaError_t xt_launch_k2_fused(int d, int ks, const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt,
+                               cudaStream_t stream, bool var);
+// optional single-precision replay (xt_replay_f32.cuh)
+cudaError_t xt_launch_k2_f32(int d, int ks, const K2FArgs& a, const K2Tab& tab, size_t smem, cudaStream_t stream);
+// first-generation linear-domain kernel / log-domain fallback (xt_replay_lin.cuh, xt_replay.cuh)
+cudaError_t xt_launch_k2_old(const K2Args& a, const xt_params& p, const K2Lin& lin, size_t smem, bool use_smem, int grid,
+                             int wpc, cudaStream_t stream);
+// state annotation (xt_predict.cuh)
+cudaError_t xt_launch_k3(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
+// segment-length histogram (xt_seglen.cuh)
+cudaError_t xt_launch_k4(const K4Args& a, const xt_params& p, int grid, size_t smem, cudaStream_t stream);
+// final fixed-order sums (xt_replay.cuh: k_reduce) and the FP64 FMA microbenchmark live in xt_engine.cu

@@ -1,17 +1,4 @@
 // Host driver of the state-annotation kernel (included by xt_engine.cu).
-template <int D, int KS, bool VAR>
-static cudaError_t launch_k3_v(xt_ctx* ctx, const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem) {
-  auto kern = k3_predict<D, KS, VAR>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, 32 * nwarps, smem, ctx->stream>>>(a, p);
-  return cudaGetLastError();
-}
-template <int D, int KS>
-static cudaError_t launch_k3(xt_ctx* ctx, const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem) {
-  return is_var(&p) ? launch_k3_v<D, KS, true>(ctx, a, p, grid, nwarps, smem) : launch_k3_v<D, KS, false>(ctx, a, p, grid, nwarps, smem);
-}
-
 extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
   if (!ctx) return XT_ERR_ARG;
   if (ctx->chunks.empty()) {
@@ -31,8 +18,13 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
   double* d_pred = nullptr;
   int32_t* d_err = nullptr;
   double* d_scratch = nullptr;
-  XT_CUDA_OK(cudaMalloc(&d_pred, sizeof(double) * (size_t)ctx->n_locs * nS));
-  XT_CUDA_OK(cudaMalloc(&d_err, sizeof(int32_t) * 2 * (size_t)n_work));
+  if (cudaMalloc(&d_pred, sizeof(double) * (size_t)ctx->n_locs * nS) != cudaSuccess ||
+      cudaMalloc(&d_err, sizeof(int32_t) * 2 * (size_t)n_work) != cudaSuccess) {
+    set_error(ctx, std::string("xt_predict: cannot allocate the output buffers: ") + cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_pred);
+    cudaFree(d_err);
+    return XT_ERR_CUDA;
+  }
   std::vector<int32_t> h_err(2 * (size_t)n_work);
   int cap = std::max(64, nS * nS * nS);
   int result = XT_OK;
@@ -105,9 +97,7 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
     ctx->k3_launches++;
     ctx->k3_cap = cap;
     cudaEventRecord(ctx->ev_k3[0], ctx->stream);
-#define CALL_K3(D_, KS_) e = launch_k3<D_, KS_>(ctx, a, *p, grid, nwarps, smem)
-    XT_DISPATCH(p->d, p->n_loc, CALL_K3);
-#undef CALL_K3
+    e = xt_launch_k3(a, *p, grid, nwarps, smem, ctx->stream);
     cudaEventRecord(ctx->ev_k3[1], ctx->stream);
     if (e != cudaSuccess || cudaMemcpyAsync(h_err.data(), d_err, sizeof(int32_t) * 2 * (size_t)n_work, cudaMemcpyDeviceToHost,
                                             ctx->stream) != cudaSuccess ||

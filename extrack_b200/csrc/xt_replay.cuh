@@ -255,16 +255,3 @@ __global__ void __launch_bounds__(32) k2_replay(const K2Args a, const __grid_con
 #undef DDV
 }
 
-// Deterministic final reduction of the per-CTA partial sums (second level of tracking.py:1069).
-__global__ void __launch_bounds__(1024) k_reduce(const double* __restrict__ partial, int n, double* out) {
-  __shared__ double sh[1024];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024) acc += partial[i];
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s = 512; s > 0; s >>= 1) {
-    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = sh[0];
-}

@@ -104,17 +104,7 @@ extern "C" int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* lea
   SEG_OK(cudaEventCreate(&e0));
   SEG_OK(cudaEventCreate(&e1));
   cudaEventRecord(e0, ctx->stream);
-#define CALL_K4(D_, KS_)                                                                                   \
-  do {                                                                                                     \
-    auto kern = k4_seglen<D_, KS_>;                                                                        \
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
-    if (e == cudaSuccess) {                                                                                \
-      kern<<<grid, XT_SEG_THREADS, smem, ctx->stream>>>(a, *p);                                            \
-      e = cudaGetLastError();                                                                              \
-    }                                                                                                      \
-  } while (0)
-  XT_DISPATCH(p->d, p->n_loc, CALL_K4);
-#undef CALL_K4
+  e = xt_launch_k4(a, *p, grid, smem, ctx->stream);
   cudaEventRecord(e1, ctx->stream);
   int32_t flags = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(hist, d_hist, sizeof(double) * hist_n, cudaMemcpyDeviceToHost, ctx->stream);

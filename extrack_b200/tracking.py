@@ -277,7 +277,7 @@ class TrackSet:
     def __init__(self, sorted_tracks: Sequence[np.ndarray], chunk: int = MAX_TRACKS_PER_CHUNK, device: Optional[int] = None,
                  rank: Optional[int] = None, world_size: Optional[int] = None, reverse: bool = True,
                  input_LocErr: Optional[Sequence[np.ndarray]] = None, dt_list: Optional[Sequence[np.ndarray]] = None,
-                 precision: Optional[str] = None):
+                 precision: Optional[str] = None, devices: Optional[Sequence[int]] = None):
         if len(sorted_tracks) < 1:
             raise ValueError("No track could be detected. The loaded tracks seem empty. Errors often come from wrong input paths.")
         for a in sorted_tracks:
@@ -294,7 +294,10 @@ class TrackSet:
         self.my_chunks = mine
         if device is None:
             device = _default_device()
-        self.engine = _native.Engine(device)
+        # several GPUs driven from this one process (`devices`, see resolve_devices): the engine deals the chunk list
+        # to them; the objective keeps the bits of the one-GPU evaluation.  Not combined with one-process-per-GPU runs.
+        self.devices = [int(x) for x in devices] if (devices is not None and len(devices) > 1 and self.world_size == 1) else None
+        self.engine = _native.MultiEngine(self.devices) if self.devices else _native.Engine(device)
         self.device = device
         self.precision = _check_precision(precision if precision is not None else _PRECISION)
         if self.precision == "fp32":
@@ -353,15 +356,29 @@ class TrackSet:
 
         if self._dist_buf is None:
             dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
-            self._dist_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+            self._dist_buf = torch.zeros(2, dtype=torch.float64, device=dev)  # [sum, error flag]
         buf = self._dist_buf
-        if buf.is_cuda and self.n_local_chunks:
-            # result stays on the device; the all-reduce is chained on torch's current stream
-            self.engine.sum_logp_async(p, buf.data_ptr(), torch.cuda.current_stream(buf.device).cuda_stream)
-        else:
-            buf[0] = self.engine.sum_logp(p) if self.n_local_chunks else 0.0
+        # a rank whose engine fails must still enter the collective (the others would wait for ever): the
+        # second element carries an error flag and every rank raises after the all-reduce
+        err = None
+        buf[1] = 0.0
+        try:
+            if buf.is_cuda and self.n_local_chunks:
+                # result stays on the device; the all-reduce is chained on torch's current stream
+                self.engine.sum_logp_async(p, buf.data_ptr(), torch.cuda.current_stream(buf.device).cuda_stream)
+            else:
+                buf[0] = self.engine.sum_logp(p) if self.n_local_chunks else 0.0
+        except Exception as e:  # noqa: BLE001 - re-raised below on every rank
+            err = e
+            buf[0] = 0.0
+            buf[1] = 1.0
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-        return float(buf.item())
+        total, flag = (float(x) for x in buf.tolist())
+        if err is not None:
+            raise err
+        if flag != 0.0:
+            raise _native.EngineError(_native.XT_ERR_STATE, "the likelihood evaluation failed on another rank")
+        return total
 
     def close(self):
         self.engine.close()
@@ -384,6 +401,31 @@ def _default_device() -> int:
     import os
 
     return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def resolve_devices(workers: int = 1) -> Optional[List[int]]:
+    """GPUs one process drives for a fit, as a list of CUDA ordinals (None = the single default device).
+
+    The reference's ``workers`` is the width of its process pool over chunks (tracking.py:1061-1063); here
+    ``workers = N > 1`` asks for up to N GPUs of this box; ``EXTRACK_B200_GPUS`` (a count or ``all``)
+    overrides it and ``EXTRACK_B200_DEVICES`` (comma-separated ordinals) names the devices explicitly.  Under ``torch.distributed`` (one process per GPU) every process keeps its own device.
+    """
+    import os
+
+    if _dist_info(None, None)[1] > 1:
+        return None
+    explicit = os.environ.get("EXTRACK_B200_DEVICES", "").strip()  # explicit ordinals, e.g. "0,1,2,3" (may repeat: logical shards)
+    if explicit:
+        devs = [int(x) for x in explicit.split(",")]
+        return devs if len(devs) > 1 else None
+    env = os.environ.get("EXTRACK_B200_GPUS", "").strip().lower()
+    want = int(workers) if workers else 1
+    if env:
+        want = 10**6 if env == "all" else int(env)
+    if want <= 1:
+        return None
+    n = min(want, _native.device_count())
+    return list(range(n)) if n > 1 else None
 
 
 # Arithmetic of the replay kernel: "fp64" (reference precision, default) or "fp32" (optional path of the
@@ -417,20 +459,46 @@ def get_precision() -> str:
 _TRACKSET_CACHE: List = []  # [(key, refs, TrackSet)] most recent first
 
 
-def _trackset_for(all_tracks: Sequence[np.ndarray], chunk: int, input_LocErr=None, dt_list=None) -> TrackSet:
-    """Resident data for a list of arrays handed to ``cum_Proba_Cs`` (upload once per fit)."""
-    sig = lambda arrs: tuple((id(a), a.shape, a.__array_interface__["data"][0]) for a in arrs)
-    key = sig(all_tracks) + (chunk,) + (sig(input_LocErr) if input_LocErr is not None else (None,)) + (
+def _fingerprint(a) -> tuple:
+    """Identity + a cheap content sample of one caller array: (id, shape, data pointer, strided-sample sum).  The
+    sample (<= 4096 elements spread over the whole array, O(microseconds)) catches in-place edits of the tracks
+    between objective calls without re-reading the data set."""
+    arr = np.asarray(a)
+    flat = arr.reshape(-1)
+    step = max(1, flat.size // 4096)
+    return (id(a), arr.shape, arr.__array_interface__["data"][0], float(np.sum(flat[::step], dtype=np.float64)))
+
+
+def _trackset_for(all_tracks: Sequence[np.ndarray], chunk: int, input_LocErr=None, dt_list=None, workers: int = 1) -> TrackSet:
+    """Resident data for the arrays handed to ``cum_Proba_Cs`` (upload once per fit, not once per call).
+
+    Contract: the data set of a distinct list of caller arrays stays resident on the GPU(s) and is reused by
+    later calls with the same arrays; it is keyed on the caller's own objects (identity, shape, data pointer)
+    plus a strided content sample, so replacing or editing an array uploads again.  An in-place edit that the
+    sample misses is not seen: call ``invalidate_cache()`` after mutating tracks in place (the reference
+    re-reads its arrays on every call).  At most two data sets are kept; ``invalidate_cache()`` /
+    ``set_precision()`` free them."""
+    sig = lambda arrs: tuple(_fingerprint(a) for a in arrs)
+    devices = resolve_devices(workers)
+    key = sig(all_tracks) + (chunk, tuple(devices or ())) + (sig(input_LocErr) if input_LocErr is not None else (None,)) + (
         sig(dt_list) if dt_list is not None else (None,))
     for k, refs, ts in _TRACKSET_CACHE:
         if k == key:
             return ts
-    ts = TrackSet(all_tracks, chunk, input_LocErr=input_LocErr, dt_list=dt_list)
+    loc = [np.asarray(a, dtype=np.float64) for a in input_LocErr] if input_LocErr is not None else None
+    ts = TrackSet(all_tracks, chunk, input_LocErr=loc, dt_list=dt_list, devices=devices)
     _TRACKSET_CACHE.insert(0, (key, [list(all_tracks), input_LocErr, dt_list], ts))
     while len(_TRACKSET_CACHE) > 2:
         _, _, old = _TRACKSET_CACHE.pop()
         old.close()
     return ts
+
+
+def invalidate_cache() -> None:
+    """Free the data sets ``cum_Proba_Cs`` keeps resident between calls (GPU and pinned host memory)."""
+    for _, _, old in _TRACKSET_CACHE:
+        old.close()
+    del _TRACKSET_CACHE[:]
 
 
 # --------------------------------------------------------------------------------------
@@ -444,14 +512,12 @@ def cum_Proba_Cs(params, all_tracks, dt, cell_dims, input_LocErr, nb_states, nb_
     ``all_tracks`` is the sorted list of ``[n, L, d]`` arrays (as ``param_fitting`` builds it);
     ``input_LocErr`` (optional) the matching list of peak-wise localisation errors ``[n, L, k]`` and
     ``dt`` a float or the matching list of ``[n, L]`` time steps (tracking.py:1024-1044).
-    ``workers`` is accepted and ignored (the GPU replaces the process pool).
+    ``workers`` > 1 asks for that many GPUs of this box (``resolve_devices``); the GPUs replace the process pool.
     """
     loc, Ds, Fs, TrMat, pBL = _extract_scalars(params, nb_substeps, Matrix_type)
     dt_list = dt if type(dt) == list else None
-    if input_LocErr is not None:
-        input_LocErr = [np.asarray(a, dtype=np.float64) for a in input_LocErr] if _trackset is None else input_LocErr
     ts = _trackset if _trackset is not None else _trackset_for(all_tracks, max_number_of_tracks_per_matrix, input_LocErr,
-                                                               dt_list)
+                                                               dt_list, workers)
     quiet = ts.rank != 0
     if dt_list is not None:
         ds = _median_ds(Ds, ts.dt_mid0)[0]  # avg_ds = np.median(ds[0], axis=(0, 1)), tracking.py:1012-1013
@@ -710,7 +776,8 @@ def param_fitting(all_tracks, dt, params=None, nb_states=2, nb_substeps=1, frame
     if type(dt) == dict:
         dt = [np.asarray(dt[k], dtype=np.float64) for k in keys]
     print("cell_dims", cell_dims)
-    ts = TrackSet(sorted_tracks, MAX_TRACKS_PER_CHUNK, input_LocErr=input_LocErr, dt_list=dt if type(dt) == list else None)
+    ts = TrackSet(sorted_tracks, MAX_TRACKS_PER_CHUNK, input_LocErr=input_LocErr, dt_list=dt if type(dt) == list else None,
+                  devices=resolve_devices(workers))
     try:
         fit = minimize(cum_Proba_Cs, params,
                        args=(sorted_tracks, dt, cell_dims, input_LocErr, nb_states, nb_substeps, frame_len, verbose, workers,

@@ -8,8 +8,10 @@
  * success or a negative XT_ERR_* code; xt_last_error() gives the message.
  *
  * Threading: one caller thread per context (the reference objective is called from one
- * Python thread by lmfit, tracking.py:1371).  One context drives one GPU; multi-GPU runs
- * use one process (and one context) per GPU, each holding a subset of the chunks.
+ * Python thread by lmfit, tracking.py:1371).  One context (xt_ctx) drives one GPU.  Multi-GPU:
+ * either one process (and one context) per GPU, each holding a subset of the chunks, or ONE
+ * process driving several GPUs through an xt_multi handle (xt_multi_* below), which is what a
+ * notebook / GUI caller of param_fitting gets.
  */
 #ifndef XTRACK_H
 #define XTRACK_H
@@ -88,6 +90,9 @@ typedef struct xt_stats {
   int32_t k3_cap;        /* sequence capacity of the last xt_predict launch */
   int32_t fp32;          /* 1: the last evaluation's replay ran in the optional FP32 kernel ("fp32_replay") */
 } xt_stats;
+
+/* Number of visible CUDA devices (0 without a driver or GPU; never an error). */
+int xt_device_count(void);
 
 /* Lifetime.  `device` is the CUDA ordinal this context drives. */
 int xt_create(int device, xt_ctx** out);
@@ -208,6 +213,40 @@ int xt_set_option(xt_ctx* ctx, const char* name, int value);
 /* Measured FP64 FMA throughput of this GPU in TFLOP/s (2 flops per DFMA), used as the
  * compute-roofline denominator by bench.py. */
 int xt_fp64_peak_tflops(xt_ctx* ctx, double* out);
+
+/*
+ * In-process multi-GPU objective — stands in for the reference's process pool over chunks
+ * (`Pool(workers).map(pool_star_proba, args_prod)`, tracking.py:1061-1063) behind the single-threaded
+ * objective callback (lmfit.minimize, tracking.py:1371): one handle drives the devices `dev_ids[0..n_dev)`.
+ * xt_multi_upload takes the same segment list as xt_upload (whole length buckets); the chunk list
+ * (numbered in upload order) is dealt to the devices longest-processing-time-first on nT*(L-1) —
+ * chunks are the atomic unit because the grouping plan is per chunk (tracking.py:677-691) — and every
+ * device uploads only its chunks.  xt_multi_sum_logp evaluates all devices concurrently (one host
+ * worker thread per device) and adds the per-chunk sums of log P in global chunk order, so the result
+ * has the same bits for every n_dev (and equals xt_sum_logp of a single context holding all chunks).
+ * SURVEY.md §8(b) proposed `xt_create(dev_ids, n_dev)`; a separate handle type keeps the one-GPU
+ * context the unit that torchrun-style deployments use.
+ */
+typedef struct xt_multi xt_multi;
+int xt_multi_create(const int32_t* dev_ids, int32_t n_dev, xt_multi** out);
+void xt_multi_destroy(xt_multi* m);
+const char* xt_multi_last_error(xt_multi* m); /* m may be NULL: last creation error */
+int xt_multi_n_devices(xt_multi* m);
+int xt_multi_upload(xt_multi* m, int32_t n_segments, const int32_t* L, const int64_t* n, const int32_t* isBL,
+                    const double* const* xyz, int32_t d, int32_t chunk_size);
+/* peak-wise sigma / per-localisation dt of the same segments (see xt_upload_aux) */
+int xt_multi_upload_aux(xt_multi* m, int32_t n_segments, const int32_t* L, const int64_t* n, int32_t k_sigma,
+                        const double* const* sigma, const double* const* dt);
+/* per-chunk field-of-view tables, rows in global chunk order (see xt_set_stay_tables, per_track = 0) */
+int xt_multi_set_stay_tables(xt_multi* m, int32_t K, int32_t H, const double* Lp_stay, const double* L_leave);
+int xt_multi_sum_logp(xt_multi* m, const xt_params* p, double* out);
+/* test seam: log P per track of global chunk `chunk` (see xt_chunk_logp) */
+int xt_multi_chunk_logp(xt_multi* m, int32_t chunk, const xt_params* p, double* out);
+int xt_multi_set_option(xt_multi* m, const char* name, int value);
+/* share of device slot g (0 <= g < n_dev): CUDA ordinal, chunks and track-steps it owns */
+int xt_multi_device_load(xt_multi* m, int32_t g, int32_t* device, int32_t* n_chunks, int64_t* track_steps);
+/* counters of the last evaluation: sums over the devices; times and maxima are the max over the devices */
+int xt_multi_get_stats(xt_multi* m, xt_stats* out);
 
 /* Pinned host memory helpers for end-to-end timing with host buffers. */
 int xt_host_alloc(void** out, uint64_t bytes);

@@ -618,3 +618,78 @@ def test_window_only_mode_matches_reference_window_function(path, xt, native):
         assert eng.stats()["max_nB_in"] == int(z["n_seq"]) // (K if int(z["isBL"]) else 1)
     finally:
         eng.close()
+
+
+# ---- in-process multi-GPU (xt_multi_*): one Python thread drives several device contexts ----
+def _multi_case():
+    rng = np.random.default_rng(31)
+    st = [random_walk_tracks(n, L, 2, rng) for L, n in ((6, 130), (9, 4100), (14, 2500), (21, 700))]
+    return st, make_model(frame_len=6, min_len=6)
+
+
+@pytest.mark.parametrize("devs", [[0], [0, 0], [0, 0, 0, 0, 0]])
+def test_multi_engine_objective_has_the_bits_of_one_context(devs, native, xt):
+    """Chunks dealt to several contexts (logical shards on one GPU when an ordinal repeats): the objective is the sum of
+    the per-chunk sums in global chunk order, so it equals the single-context value bit for bit, and every chunk's
+    per-track values are the same."""
+    st, m = _multi_case()
+    p = engine_params(m, 2)
+    one = xt.TrackSet(st, 2000)
+    want = one.sum_logp(p)
+    many = xt.TrackSet(st, 2000, devices=devs + [devs[0]] if len(devs) == 1 else devs)
+    try:
+        assert isinstance(many.engine, native.MultiEngine)
+        got = many.sum_logp(p)
+        assert got == want
+        assert many.sum_logp(p) == want  # repeatable (pipelined second evaluation)
+        load = many.engine.device_load()
+        assert sum(n for _, n, _ in load) == len(one.chunks)
+        steps = [s for _, _, s in load]
+        assert max(steps) - min(steps) <= max(2000 * 20, 0.2 * max(steps))  # longest-processing-time-first balance
+        for c in (0, 1, len(one.chunks) - 1):
+            b, a, z, _ = one.chunks[c]
+            np.testing.assert_array_equal(many.engine.chunk_logp(c, z - a, p), one.engine.chunk_logp(c, z - a, p))
+        stats = many.engine.stats()
+        assert stats["n_tracks"] == sum(len(a) for a in st) and stats["n_chunks"] == len(one.chunks)
+    finally:
+        one.close()
+        many.close()
+    ref = -orc.neg_log_likelihood(st, m)
+    assert abs(got - ref) <= RTOL_LOGL * abs(ref)
+
+
+def test_multi_engine_two_real_devices(native, xt):
+    if native.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    st, m = _multi_case()
+    p = engine_params(m, 2)
+    one = xt.TrackSet(st, 2000)
+    two = xt.TrackSet(st, 2000, devices=[0, 1])
+    try:
+        assert two.sum_logp(p) == one.sum_logp(p)
+    finally:
+        one.close()
+        two.close()
+
+
+def test_param_fitting_uses_several_devices_from_one_process(xt, monkeypatch):
+    """`param_fitting(..., workers=N)` / EXTRACK_B200_DEVICES: the unchanged API drives several contexts; the fit
+    follows the same path as on one context (identical objective bits => identical iterates)."""
+    rng = np.random.default_rng(5)
+    tracks = {str(L): random_walk_tracks(n, L, 2, rng) for L, n in ((7, 2300), (11, 2100), (16, 600))}
+
+    def fit():
+        params = xt.generate_params(nb_states=2, LocErr_type=1, nb_dims=2, LocErr_bounds=[0.005, 0.1], D_max=3,
+                                    estimated_LocErr=[0.022], estimated_Ds=[1e-4, 0.2], estimated_Fs=[0.5])
+        return xt.param_fitting(tracks, 0.02, params=params, nb_states=2, frame_len=5, verbose=0, workers=3, method="powell")
+
+    monkeypatch.delenv("EXTRACK_B200_DEVICES", raising=False)
+    monkeypatch.setenv("EXTRACK_B200_GPUS", "1")
+    a = fit()
+    monkeypatch.delenv("EXTRACK_B200_GPUS")
+    monkeypatch.setenv("EXTRACK_B200_DEVICES", "0,0,0")
+    assert xt.resolve_devices(1) == [0, 0, 0]
+    b = fit()
+    assert a.residual[0] == b.residual[0]
+    for k in a.params:
+        assert a.params[k].value == b.params[k].value

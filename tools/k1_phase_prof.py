@@ -26,7 +26,7 @@ for name, val in [kv.split("=") for kv in os.environ.get("XT_OPTS", "").split(",
     ts.engine.set_option(name, int(val))
 ts.engine.set_option("pipeline", int(os.environ.get("PIPE", "0")))
 for _ in range(3):
-    ts.sum_logp(p)
+    ts.engine.sum_logp(p)
 print(ts.engine.stats())
 lib = _native.load_library()
 nch = ts.n_local_chunks
