@@ -13,6 +13,12 @@ two-phase mode (one plan launch, one replay launch) after the timed region.  N =
 (weak scaling); ranks evaluate their chunks independently and the partial log-likelihoods are
 summed with one NCCL all-reduce per step.  Prints ONE JSON line (rank 0).
 
+Besides the headline the line carries: `strong` (the SAME 10^6 tracks split over the N ranks by
+`shard_chunks` — the split the north star names — with per-evaluation time, per-rank plan / replay times and the
+efficiency against one GPU), `api` (one evaluation through the Python objective `cum_Proba_Cs` with parameters that
+change every call, as BFGS does) and `secondary` (BASELINE configs 3, 5 and 4 at bounded sizes, sharded over the N
+ranks through the API).
+
 --impl reference times the CPU path instead: the numpy oracle port of the reference algorithm
 (the reference is pure Python and does not travel to the GPU box) on all host cores, on a bounded
 sample of the same workload.
@@ -124,6 +130,199 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def _dist_max(x, local, world):
+    """max over ranks of a scalar (device-timed milliseconds)."""
+    import torch
+
+    t = torch.tensor([float(x)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _time_sharded(ts, p, steps, local, world):
+    """Per-evaluation device time (max over ranks) of a TrackSet sharded over the process group: K evaluations, each
+    followed by the 8-byte all-reduce, bracketed by barrier + synchronize; plus this rank's two-phase kernel times."""
+    import torch
+
+    buf = torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}")
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = ts.engine
+
+    def step():
+        if ts.n_local_chunks:
+            eng.sum_logp_async(p, buf.data_ptr(), stream)
+        else:
+            buf.zero_()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(buf)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = _dist_max(e0.elapsed_time(e1) / steps, local, world)
+    total = float(buf.item())
+    plan = replay = 0.0
+    if ts.n_local_chunks:
+        eng.set_option("pipeline", 0)
+        for i in range(5):
+            eng.sum_logp(p)
+            if i >= 2:
+                s = eng.stats()
+                plan += s["ms_plan"] / 3
+                replay += s["ms_replay"] / 3
+        eng.set_option("pipeline", 1)
+    return ms, total, _dist_max(plan, local, world), _dist_max(replay, local, world)
+
+
+def strong_block(st0, p, steps, local, rank, world, ms_one_gpu):
+    """The SAME data set split over the ranks by `shard_chunks` (whole chunks, longest-processing-time-first on
+    nT*(L-1); reference unit: the chunk list of tracking.py:1030-1044): per-evaluation time and the efficiency
+    against one GPU holding all chunks (`ms_one_gpu`, measured on rank 0 in this run)."""
+    from extrack_b200 import tracking as xt
+
+    ts = xt.TrackSet(st0, device=local)  # rank / world size from the initialised process group
+    ms, total, plan, replay = _time_sharded(ts, p, steps, local, world)
+    chunks = ts.n_local_chunks
+    steps_local = ts.engine.stats()["track_steps"] if chunks else 0
+    ts.close()
+    all_steps = sum((a.shape[1] - 1) * a.shape[0] for a in st0)
+    return {"what": "the same 10^6-track data set (seed 0) split over the N ranks by shard_chunks; one 8-byte all-reduce per evaluation",
+            "n_gpus": world, "tracks": int(sum(len(a) for a in st0)), "track_steps": int(all_steps), "ms_per_eval": ms,
+            "value": all_steps / (ms * 1e-3), "unit": UNIT, "ms_per_eval_one_gpu": ms_one_gpu,
+            "efficiency_vs_one_gpu": ms_one_gpu / (world * ms), "target_efficiency_at_8": 0.85,
+            "rank0": {"chunks": int(chunks), "track_steps": int(steps_local)},
+            "kernel_ms_max_over_ranks": {"plan": plan, "replay_and_reduce": replay}, "sum_logp": total}
+
+
+def api_block(ts, st, n_calls=60):
+    """One evaluation through the Python objective `extrack_b200.tracking.cum_Proba_Cs` (parameter extraction, the
+    field-of-view table with its 1000-point ndtr, the ctypes call, the read-back) on the resident data set, with
+    parameters that change at every call the way BFGS finite differences do."""
+    import contextlib
+    import io
+
+    from extrack_b200 import tracking as xt
+
+    params = eval_params()
+    base = dict(EVAL)
+    names = ["D1", "LocErr", "F0", "p01", "p10", "pBL", "D0"]
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        for i in range(5):
+            xt.cum_Proba_Cs(params, st, DT, CELL, None, 2, 1, FRAME_LEN, 0, 1, 1, THRESHOLD, MAX_NB_STATES, _trackset=ts)
+        t = time.perf_counter()
+        for i in range(n_calls):
+            k = names[i % len(names)]
+            params[k].value = base[k] * (1.0 + 1.5e-8 * (1 + i // len(names)))
+            v = xt.cum_Proba_Cs(params, st, DT, CELL, None, 2, 1, FRAME_LEN, 0, 1, 1, THRESHOLD, MAX_NB_STATES, _trackset=ts)
+            params[k].value = base[k]
+        wall = (time.perf_counter() - t) / n_calls
+    return {"api_eval_ms": wall * 1e3, "calls": n_calls, "neglogl_last": v,
+            "what": "wall time per extrack_b200.tracking.cum_Proba_Cs call on the resident config-2 data set, one parameter "
+                    "perturbed by 1.5e-8 relative per call (finite-difference pattern of BFGS)"}
+
+
+SECONDARY = {
+    "3": dict(name="configs[2]: 3-state 2D, nb_substeps=2, frame_len=6, max_nb_states=500", tracks=200_000,
+              sim=dict(max_track_len=30, min_track_len=10, LocErr=0.02, Ds=[0, 0.04, 0.25], nb_dims=2,
+                       initial_fractions=[0.33, 0.33, 0.34], TrMat=[[0.9, 0.1, 0.0], [0.05, 0.91, 0.04], [0.01, 0.06, 0.93]],
+                       dt=0.02, pBL=0.05, cell_dims=[1, None, None]),
+              ev=dict(nb_substeps=2, frame_len=6, threshold=0.2, max_nb_states=500)),
+    "5": dict(name="configs[4]: 3-state 3D long tracks (100-200), frame_len=10", tracks=20_000,
+              sim=dict(max_track_len=200, min_track_len=100, LocErr=0.02, Ds=[0, 0.05, 0.25], nb_dims=3,
+                       initial_fractions=[0.3, 0.3, 0.4], TrMat=[[0.9, 0.05, 0.05], [0.05, 0.9, 0.05], [0.05, 0.05, 0.9]],
+                       dt=0.02, pBL=0.002, cell_dims=[10, None, None]),
+              ev=dict(nb_substeps=1, frame_len=10, threshold=0.2, max_nb_states=120)),
+}
+
+
+def _params_for(sim):
+    from extrack_b200._lmfit_compat import Parameters
+
+    p = Parameters()
+    p.add("LocErr", value=sim["LocErr"])
+    nS = len(sim["Ds"])
+    for i, D in enumerate(sim["Ds"]):
+        p.add(f"D{i}", value=max(D, 1e-5))
+    for i, F in enumerate(sim["initial_fractions"][:-1]):
+        p.add(f"F{i}", value=F)
+    p.add(f"F{nS-1}", expr="1-" + "-".join(f"F{i}" for i in range(nS - 1)))
+    for i in range(nS):
+        for j in range(nS):
+            if i != j:
+                p.add(f"p{i}{j}", value=max(sim["TrMat"][i][j], 1e-4))
+    p.add("pBL", value=sim["pBL"])
+    return p
+
+
+def secondary_block(local, rank, world, scale=1.0):
+    """BASELINE configs 3, 5 (likelihood) and 4 (predict_Bs) at bounded sizes, sharded over the ranks through the API
+    (TrackSet under the process group / predict_Bs(gather=False)); every rank generates the same data set."""
+    import torch
+
+    from extrack_b200 import tracking as xt
+    from extrack_b200.simulate import sim_tracks
+
+    out = {}
+    for key, cfg in SECONDARY.items():
+        sim, ev = cfg["sim"], cfg["ev"]
+        tracks = sim_tracks(int(cfg["tracks"] * scale), seed=4242, device=f"cuda:{local}", **sim)
+        st, _ = xt._sorted_buckets(tracks)
+        nS = len(sim["Ds"])
+        LocErr, ds, Fs, TrMat, pBL = xt.extract_params(_params_for(sim), sim["dt"], nS, ev["nb_substeps"])
+        p = xt.build_tables(LocErr, ds, Fs, TrMat, pBL, [sim["cell_dims"][0]], ev["nb_substeps"], ev["frame_len"], st[0].shape[1],
+                            ev["threshold"], ev["max_nb_states"], st[0].shape[2])
+        ts = xt.TrackSet(st, device=local)
+        ms, total, plan, replay = _time_sharded(ts, p, 5, local, world)
+        stats = ts.engine.stats() if ts.n_local_chunks else {"max_nB_in": 0}
+        ts.close()
+        steps = sum((a.shape[1] - 1) * a.shape[0] for a in st)
+        out["config_" + key] = {"workload": cfg["name"], "tracks": int(sum(len(a) for a in st)), "track_steps": int(steps),
+                                "n_gpus": world, "ms_per_eval": ms, "track_steps_per_s": steps / (ms * 1e-3),
+                                "kernel_ms_max_over_ranks": {"plan": plan, "replay_and_reduce": replay},
+                                "max_live_sequences_rank0": int(stats["max_nB_in"]), "sum_logp": total}
+        del tracks, st
+        torch.cuda.empty_cache()
+    # config 4: state annotation, every rank annotates its slice of every bucket (no collective on the data path)
+    n4 = int(1_000_000 * scale)
+    tracks = sim_tracks(n4, seed=99, device=f"cuda:{local}", **SIM_KW)
+    params = eval_params()
+    xt.predict_Bs({k: v[:64] for k, v in tracks.items()}, DT, params, cell_dims=CELL, nb_states=2, frame_len=FRAME_LEN, gather=False)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    pred = xt.predict_Bs(tracks, DT, params, cell_dims=CELL, nb_states=2, frame_len=FRAME_LEN, gather=False)
+    torch.cuda.synchronize()
+    wall = _dist_max(time.perf_counter() - t, local, world)
+    locs = sum(int(k) * len(v) for k, v in tracks.items())
+    out["config_4"] = {"workload": "configs[3]: predict_Bs, 2-state, frame_len=8, threshold 0.1, max_nb_states 200, nb_max=1",
+                       "tracks": n4, "localisations": int(locs), "n_gpus": world, "s_per_call_incl_upload_and_readback": wall,
+                       "localisations_per_s": locs / wall,
+                       "rows_annotated_rank0": int(sum(len(v) for v in pred.values()))}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -170,6 +369,7 @@ def main():
     ap.add_argument("--cpu-leg", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the strong / api / secondary blocks (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -314,6 +514,29 @@ def main():
     e2e_value = all_steps / float(te.item())
     e2e_eng.close()
 
+    # ---- strong scaling of the headline data set, API-level evaluation cost, other BASELINE configs ----
+    strong = api = secondary = None
+    if not args.no_secondary:
+        ksteps2 = max(5, min(50, args.steps))
+        # one GPU holding every chunk of the seed-0 data set: that is rank 0's own (weak-scaling) data set
+        ms_one = _time_sharded(ts, p, ksteps2, local, 1)[0] if rank == 0 else 0.0
+        ms_one = _dist_max(ms_one, local, world)
+        if world > 1:
+            st0 = st if rank == 0 else xt._sorted_buckets(sim_tracks(args.tracks, seed=0, device=f"cuda:{local}", **SIM_KW))[0]
+            torch.cuda.empty_cache()
+            strong = strong_block(st0, p, ksteps2, local, rank, world, ms_one)
+            del st0
+        else:
+            strong = {"what": "one GPU: the strong-scaling split is the headline itself", "n_gpus": 1, "tracks": int(stats["n_tracks"]),
+                      "track_steps": int(stats["track_steps"]), "ms_per_eval": ms_one, "value": stats["track_steps"] / (ms_one * 1e-3),
+                      "unit": UNIT, "ms_per_eval_one_gpu": ms_one, "efficiency_vs_one_gpu": 1.0, "target_efficiency_at_8": 0.85,
+                      "kernel_ms_max_over_ranks": {"plan": ms_plan, "replay_and_reduce": ms_replay}}
+        if rank == 0:
+            api = api_block(ts, st)
+            api["resident_ms_per_eval"] = ms_one
+            api["host_tail_ms"] = api["api_eval_ms"] - ms_one
+        secondary = secondary_block(local, rank, world)
+
     if rank == 0:
         peak = eng.fp64_peak_tflops()
         # algorithmic flops of the replay kernel: F = nB_in*(25+9d) + nG*(3+d) per track-step
@@ -380,6 +603,9 @@ def main():
                                   "kernel k2_replay_f32 (not the headline: `value`, `e2e` and `roofline` are FP64)"},
             "cpu_baseline": cpu,
             "parity_rel_err_vs_oracle_on_cpu_sample": parity,
+            "strong": strong,
+            "api": api,
+            "secondary": secondary,
         }
         print(json.dumps(line))
     ts.close()

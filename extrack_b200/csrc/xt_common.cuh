@@ -49,7 +49,7 @@ struct XtRecHdr {
 //   words 0-1 : XtBlobHdr
 //   words 2.. : nG group records (8 bytes each) in *schedule order*: the groups of replay warp w
 //               are entries woff[w] .. woff[w+1]-1 (groups sorted by member count, descending,
-//               dealt round-robin to the warps)
+//               dealt round-robin to the warps; nM of the nG groups have more than one member)
 //   then      : nC member entries (4 bytes each, xt_pack_ent) in CSR order, for groups of > 2 members
 // Group record (fields pre-positioned so that the replay kernel gets byte offsets with one mask
 // each): lo = head0:7 | p0:12 << 7 | g:12 << 19; hi = kind:2 (1 single, 2 pair, 3 list) << 30 and
@@ -58,8 +58,9 @@ struct XtRecHdr {
 struct XtBlobHdr {
   uint16_t nG, nC;
   uint16_t n16;   // 16-byte words of this record
-  uint16_t pad_;
-  uint16_t woff[XT_MAX_WPC + 1];
+  uint16_t nM;    // groups with more than one member: they come first in the schedule order, so replay warp w
+                  // owns ceil((nM - w) / wpc) of them at the head of its list and single-member groups after
+  uint16_t woff[XT_MAX_WPC + 1];  // <= 4 replay warps: woff[5 + w] = multi-member groups at the head of warp w's list
   uint16_t pad2_[3];
 };
 static_assert(sizeof(XtBlobHdr) == 32, "XtBlobHdr must be two 16-byte words");
@@ -122,6 +123,48 @@ __device__ __forceinline__ double xt_dd_exact(const xt_params& P, int head, doub
     prev = cur;
   }
   return nsub == 1 ? sum : __ddiv_rn(sum, (double)nsub);
+}
+
+// ---- shared memory through 32-bit shared-window addresses (no generic-pointer arithmetic) ----
+__device__ __forceinline__ unsigned xt_smem_base(const void* p) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));  // computed once: keeps the base from being rematerialised
+  return a;
+}
+__device__ __forceinline__ void xt_lds128(unsigned a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ double xt_lds64(unsigned a) {
+  double x;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
+  return x;
+}
+__device__ __forceinline__ uint2 xt_lds64u(unsigned a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int xt_lds32(unsigned a) {
+  int x;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(x) : "r"(a));
+  return x;
+}
+__device__ __forceinline__ unsigned xt_lds16(unsigned a) {
+  unsigned x;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(x) : "r"(a));
+  return x;
+}
+__device__ __forceinline__ void xt_sts128(unsigned a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void xt_sts128u(unsigned a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void xt_sts64(unsigned a, double x) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory");
+}
+__device__ __forceinline__ void xt_sts32(unsigned a, int x) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
 }
 
 struct XtWork {  // one replay CTA: 32 tracks of a chunk

@@ -65,6 +65,8 @@ struct xt_ctx {
   int k3_hot_smem = 1;        // state-annotation kernel: forward-pass state of every warp in shared memory
   int k3_ctas_per_sm = 4;     // resident CTAs per SM of the state-annotation kernel (its per-warp scratch should stay in L2)
   int k1_threads = 0;         // plan kernel threads per chunk: 0 = automatic (256, or 1024 for <= n_sm chunks)
+  int k2_lpt = 1;             // replay schedule of the plan records: longest-processing-time-first (0: round-robin)
+  int k2_cost[4] = {4, 7, 6, 2};  // its cost model: single-member group, pair, member list (base, per member)
   int k1_batch = 1;           // plan kernel, > 64 sequences: batched candidate leaders (0: one leader at a time)
   int pipeline = 1;
   int n_groups = 6;
@@ -712,6 +714,8 @@ static K1Args make_k1_args(xt_ctx* ctx, int bits) {
   ctx->plan_has_grec = a.want_grec != 0;
   a.corder = ctx->d_corder;
   a.batch_mode = ctx->k1_batch;
+  a.lpt = ctx->k2_lpt;
+  for (int i = 0; i < 4; ++i) a.cost[i] = ctx->k2_cost[i];
 #ifdef XT_K1_PROF
   if (!g_k1_prof) cudaMalloc(&g_k1_prof, sizeof(long long) * 12 * 65536);
   a.prof = g_k1_prof;
@@ -723,7 +727,10 @@ static K1Args make_k1_args(xt_ctx* ctx, int bits) {
 // threads per chunk of the plan kernel: 1024 when every chunk can have an SM of its own
 static int k1_threads(xt_ctx* ctx) {
   if (ctx->k1_threads) return ctx->k1_threads;
-  return (int)ctx->chunks.size() <= ctx->n_sm ? 1024 : XT_K1_THREADS;
+  if ((int)ctx->chunks.size() > ctx->n_sm) return XT_K1_THREADS;
+  // a chunk per SM: 512 threads (up to 128 registers each) cover the <= 64 live sequences of the matrix-mode grouping,
+  // 1024 threads when the previous evaluation saw more
+  return (ctx->spec_maxC > 0 && ctx->spec_maxC <= 64) ? 512 : 1024;
 }
 
 static void k1_scratch_caps(xt_ctx* ctx, const xt_params* p, bool use_smem, int* scapP, int* scapC) {
@@ -750,7 +757,12 @@ static int enqueue_k1(xt_ctx* ctx, const xt_params* p, int bits, int c0, int nc,
   const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC, varH, nt);
   if (var) a.ax = make_aux(ctx, p, 0);
   const cudaError_t e = xt_launch_k1(a, *p, smem, nc, stream, nt);
-  XT_CUDA_OK(e);
+  if (e != cudaSuccess) {
+    set_error(ctx, std::string("plan kernel launch (") + std::to_string(nc) + " chunks, " + std::to_string(nt) + " threads, " +
+                       std::to_string(smem) + " B shared memory, scratch " + std::to_string(a.scapP) + "/" + std::to_string(a.scapC) +
+                       ", cap " + std::to_string(ctx->cap) + "): " + cudaGetErrorString(e));
+    return XT_ERR_CUDA;
+  }
   ctx->stats.k1_launches++;
   return XT_OK;
 }
@@ -979,11 +991,17 @@ static bool prepare_fused(xt_ctx* ctx, const xt_params* p, int Pmax, FusedLaunch
   }
   K2Tab& tab = fl->tab;
   tab = K2Tab{};
+  // constant folded into the weight factors of the FP64 kernel (K2Tab::lnc): c = prod over dims of sqrt(l2)
+  double cfold = 1.0;
+  if (!fl->var && !fl->f32)
+    for (int dim = 0; dim < p->d; ++dim) cfold *= std::sqrt(p->l2[KS == 1 ? 0 : dim]);
+  if (!(cfold > 1e-30 && cfold < 1e30)) cfold = 1.0;  // (keeps every intermediate product far from the exponent limits)
+  tab.lnc = std::log(cfold);
   for (int h = 0; h < H; ++h) {
-    tab.tau0[h] = std::exp(p->LT[h]);
-    tab.tau1[h] = std::exp(p->LT[h] + p->Lp_stay[h % K]);
+    tab.tau0[h] = std::exp(p->LT[h]) * cfold;
+    tab.tau1[h] = std::exp(p->LT[h] + p->Lp_stay[h % K]) * cfold;
     tab.dd[h] = p->dd[h];
-    tab.winit[h] = std::exp(p->LT[h] + p->LF[h]);
+    tab.winit[h] = std::exp(p->LT[h] + p->LF[h]) * cfold;
   }
   for (int s = 0; s < p->nS; ++s) tab.leave[s] = std::exp(Lsum[s]);
   for (int k = 0; k < KS; ++k) tab.l2[k] = p->l2[k];
@@ -1284,8 +1302,8 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
     return XT_OK;
   }
   if (std::strcmp(name, "k1_threads") == 0) {
-    if (value != 0 && value != 256 && value != 1024) {
-      set_error(ctx, "xt_set_option: k1_threads must be 0 (automatic), 256 or 1024");
+    if (value != 0 && value != 256 && value != 512 && value != 1024) {
+      set_error(ctx, "xt_set_option: k1_threads must be 0 (automatic), 256, 512 or 1024");
       return XT_ERR_ARG;
     }
     ctx->k1_threads = value;
@@ -1325,6 +1343,20 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
       return XT_ERR_ARG;
     }
     ctx->k3_ctas_per_sm = value;
+    return XT_OK;
+  }
+  if (std::strncmp(name, "k2_cost", 7) == 0 && name[7] >= '0' && name[7] <= '3' && name[8] == 0) {
+    if (value < 1 || value > 1000) {
+      set_error(ctx, "xt_set_option: k2_cost0..3 must be in 1..1000");
+      return XT_ERR_ARG;
+    }
+    ctx->k2_cost[name[7] - '0'] = value;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k2_lpt") == 0) {
+    ctx->k2_lpt = value != 0;
+    ctx->have_eval = false;
     return XT_OK;
   }
   if (std::strcmp(name, "k1_batch") == 0) {

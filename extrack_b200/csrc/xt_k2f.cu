@@ -5,7 +5,8 @@
 template <int D, int KS, int WPC, int TPT, bool VAR, bool GST>
 static cudaError_t launch_one(const K2FArgs& a, const K2Tab& tab, size_t smem, cudaStream_t stream) {
   auto kern = k2_replay_fused<D, KS, WPC, TPT, VAR, GST>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static unsigned long long smem_ok = 0;
+  cudaError_t e = xt_allow_smem(kern, smem, &smem_ok);
   if (e != cudaSuccess) return e;
   kern<<<a.n_work, 32 * WPC, smem, stream>>>(a, tab);
   return cudaGetLastError();

@@ -5,7 +5,8 @@
 template <int D, int KS>
 static cudaError_t launch_f32(const K2FArgs& a, const K2Tab& tab, size_t smem, cudaStream_t stream) {
   auto kern = k2_replay_f32<D, KS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static unsigned long long smem_ok = 0;
+  cudaError_t e = xt_allow_smem(kern, smem, &smem_ok);
   if (e != cudaSuccess) return e;
   kern<<<a.n_work, 128, smem, stream>>>(a, tab);
   return cudaGetLastError();

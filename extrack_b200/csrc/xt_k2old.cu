@@ -7,7 +7,8 @@
 template <int D, int KS, int WPC>
 static cudaError_t launch_k2_lin(const K2Args& a, const xt_params& p, const K2Lin& lin, size_t smem, int grid, cudaStream_t stream) {
   auto kern = k2_replay_lin<D, KS, WPC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static unsigned long long smem_ok = 0;
+  cudaError_t e = xt_allow_smem(kern, smem, &smem_ok);
   if (e != cudaSuccess) return e;
   kern<<<grid, 32 * WPC, smem, stream>>>(a, p, lin);
   return cudaGetLastError();

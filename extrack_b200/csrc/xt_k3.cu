@@ -5,7 +5,8 @@
 template <int D, int KS, bool VAR>
 static cudaError_t launch_k3_v(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
   auto kern = k3_predict<D, KS, VAR>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static unsigned long long smem_ok = 0;
+  cudaError_t e = xt_allow_smem(kern, smem, &smem_ok);
   if (e != cudaSuccess) return e;
   kern<<<grid, 32 * nwarps, smem, stream>>>(a, p);
   return cudaGetLastError();

@@ -7,7 +7,7 @@ cudaError_t xt_launch_k4(const K4Args& a, const xt_params& p, int grid, size_t s
 #define CALL_K4(D_, KS_)                                                                    \
   do {                                                                                      \
     auto kern = k4_seglen<D_, KS_>;                                                         \
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    static unsigned long long smem_ok = 0; e = xt_allow_smem(kern, smem, &smem_ok); \
     if (e == cudaSuccess) {                                                                 \
       kern<<<grid, XT_SEG_THREADS, smem, stream>>>(a, p);                                   \
       e = cudaGetLastError();                                                               \

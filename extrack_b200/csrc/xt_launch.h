@@ -20,9 +20,31 @@ struct K4Args;
     else { CALL(3, 3); }                                             \
   } while (0)
 
+// Dynamic shared memory above 48 KB needs an opt-in per kernel.  The attribute belongs to the function (per device),
+// not to a context, so several contexts of one process (xt_multi, one thread each) must never lower it between
+// another thread's opt-in and its launch: it is set once per kernel and device to the most the device allows
+// (opt-in maximum minus the kernel's static shared memory).  `done`: one bit per device ordinal, owned by the call site.
+template <class Kern>
+inline cudaError_t xt_allow_smem(Kern kern, size_t smem, unsigned long long* done) {
+  if (smem <= 32 * 1024) return cudaSuccess;  // (static + dynamic stay below the 48 KB that need no opt-in)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if ((__atomic_load_n(done, __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull) return cudaSuccess;
+  cudaFuncAttributes at;
+  e = cudaFuncGetAttributes(&at, kern);
+  if (e != cudaSuccess) return e;
+  int optin = 0;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)at.sharedSizeBytes);
+  if (e == cudaSuccess) __atomic_or_fetch(done, 1ull << (dev & 63), __ATOMIC_RELEASE);
+  return e;
+}
+
 inline bool xt_is_var(const xt_params* p) { return (p->flags & (XT_FLAG_VAR_LOC | XT_FLAG_VAR_DT)) != 0; }
 
-// plan kernel (xt_plan.cuh); nthreads = 256 or 1024
+// plan kernel (xt_plan.cuh); nthreads = 256, 512 or 1024
 cudaError_t xt_launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream, int nthreads);
 // fused replay kernel, FP64 (xt_replay_fused.cuh): shared-memory state, GST or VAR instantiation
 cudaError_t xt_launch_k2_fused(int d, int ks, const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt,

@@ -42,6 +42,8 @@ struct K1Args {
   int32_t scapP, scapC;
   int32_t want_grec;   // also emit the inline group records of the first-generation replay kernel
   int32_t batch_mode;  // grouping of more than 64 sequences: 1 = batched candidate leaders, 0 = one leader at a time
+  int32_t lpt;         // replay schedule: 1 = longest-processing-time-first (<= 64 groups, <= 4 replay warps), 0 = round-robin
+  int32_t cost[4];     // cost model of the schedule: single-member group, pair, member list (cost[2] + cost[3] * members)
   XtAux ax;            // VAR instantiation only
 };
 
@@ -98,6 +100,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   unsigned char* curP = (unsigned char*)(gcnt + cap + 1);
   __shared__ int s_flag, s_nG, s_left, s_cand[NT / 32];
   __shared__ unsigned long long s_rows[64];  // capture matrix of the matrix-mode grouping
+  __shared__ __align__(4) unsigned char s_js[(NT / 32) * 72];  // matrix mode: per warp, the sequences a row still has to test
   // batch mode: grouped bit mask and one bit row per candidate (= per warp), BW words each
   const int BW = (cap + 63) / 64;
   unsigned long long* s_grp = (unsigned long long*)(k1_smem + ((((size_t)cap * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64) + 15) & ~(size_t)15));
@@ -172,6 +175,13 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   const unsigned long long rowmask = (1ull << bits) - 1ull;
 
 #define ST(buf, slot, comp) (buf)[((size_t)(slot) * CO + (comp)) * 32 + lane]
+  // children state for the predicate rows: 32-bit shared-window addresses when the scratch is known to be in
+  // shared memory (one multiply-add per access instead of 64-bit generic-pointer arithmetic)
+  const unsigned cC32 = SS ? xt_smem_base(bufC) + (unsigned)lane * 8u : 0u;
+  auto ldC = [&](int slot, int comp) -> double {
+    if (SS) return xt_lds64(cC32 + (unsigned)(slot * CO + comp) * 256u);
+    return ST(bufC, slot, comp);
+  };
 
   double l2[KS];
 #pragma unroll
@@ -335,7 +345,8 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     __syncthreads();
     K1_T(0);
 
-    const double th_lo = __dmul_rn(th, 1.0 - 1e-14), th_hi = __dmul_rn(th, 1.0 + 1e-14);
+    double th_lo = __dmul_rn(th, 1.0 - 1e-14), th_hi = __dmul_rn(th, 1.0 + 1e-14);
+    asm volatile("" : "+d"(th_lo), "+d"(th_hi));  // live in registers (otherwise rebuilt from constants at every use)
     // predicate "leader i captures sequence j" (all lanes of the warp must call it together)
     // floating-point half of the predicate (m_mask and s_mask, tracking.py:689-691)
     auto fp_ok = [&](const double (&mi)[D], const double (&si)[KS], int j) -> bool {
@@ -377,12 +388,12 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         as[q] = 0.0;
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) {
-          const double v = fabs(__dsub_rn(ST(bufC, js[q], dim), mi[dim]));
+          const double v = fabs(__dsub_rn(ldC(js[q], dim), mi[dim]));
           am[q] = (dim == 0) ? v : __dadd_rn(am[q], v);
         }
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
-          sj[q][k] = ST(bufC, js[q], D + KS + k);
+          sj[q][k] = ldC(js[q], D + KS + k);
           const double v = fabs(__dsub_rn(sj[q][k], si[k]));
           as[q] = (k == 0) ? v : __dadd_rn(as[q], v);
         }
@@ -454,24 +465,27 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         const unsigned long long win_eq = (unsigned long long)wn_lo | ((unsigned long long)wn_hi << 32);
         unsigned long long row = win_eq & upper;                  // state_mask (:679-681)
         unsigned long long todo = state_eq & ~win_eq & upper;     // need the m/s tests (:689-693)
-        while (todo) {  // four sequences per round
-          int js[4];
-          int nj = 0;
+        // the sequences to test, as a byte list in shared memory (lane l owns bits l and l + 32), padded to a
+        // multiple of four with the first one; then four sequences per round
+        const int ntodo = __popcll(todo);
+        if (ntodo) {
+          unsigned char* myjs = s_js + warp * 72;
+          const unsigned tlo = (unsigned)todo, thi = (unsigned)(todo >> 32);
+          const unsigned below = (1u << lane) - 1u;
+          if ((tlo >> lane) & 1u) myjs[__popc(tlo & below)] = (unsigned char)lane;
+          if ((thi >> lane) & 1u) myjs[__popc(tlo) + __popc(thi & below)] = (unsigned char)(lane + 32);
+          if (lane < 3) myjs[ntodo + lane] = (unsigned char)(__ffsll((long long)todo) - 1);
+          __syncwarp();
+          for (int r0 = 0; r0 < ntodo; r0 += 4) {
+            const unsigned jj = *reinterpret_cast<const unsigned*>(myjs + r0);
+            const int js[4] = {(int)(jj & 0xFFu), (int)((jj >> 8) & 0xFFu), (int)((jj >> 16) & 0xFFu), (int)(jj >> 24)};
+            bool ok[4];
+            fp_ok4(mi, si, js, ok);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (todo) {
-              js[q] = __ffsll((long long)todo) - 1;
-              todo &= todo - 1ull;
-              nj = q + 1;
-            } else {
-              js[q] = js[0];
-            }
+            for (int q = 0; q < 4; ++q)
+              if (r0 + q < ntodo && ok[q]) row |= 1ull << js[q];
           }
-          bool ok[4];
-          fp_ok4(mi, si, js, ok);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q < nj && ok[q]) row |= 1ull << js[q];
+          __syncwarp();  // the next row of this warp reuses the list
         }
         if (lane == 0) s_rows[i] = row;
       }
@@ -857,41 +871,18 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
     }
 
-    {  // replay record of this step (XtBlobHdr, xt_common.cuh).  Schedule: groups sorted by
-       // (members descending, group ascending) are dealt round-robin to the replay warps.
+    {  // replay record of this step (XtBlobHdr, xt_common.cuh).  Schedule: the groups sorted by (members
+       // descending, group ascending) are dealt to the replay warps - up to 64 groups and 4 replay warps:
+       // longest-processing-time-first on a cost model of the replay kernel (the warps of a tile meet at one
+       // barrier per step, so the step lasts as long as its most loaded warp); otherwise round-robin.
       uint4* blob = a.plan.blob + (size_t)rec * xt_blob_stride16(a.plan.cap);
+      XtBlobHdr* h = (XtBlobHdr*)blob;
       const int wpc = a.wpc;
-      if (rtid <= XT_MAX_WPC) {
-        XtBlobHdr* h = (XtBlobHdr*)blob;
-        // groups of warp w: ranks w, w + wpc, ...  => woff[w] = sum_{v<w} ceil((nG - v) / wpc)
-        int o = 0;
-        for (int v = 0; v < rtid && v < wpc; ++v) o += (nG - v + wpc - 1) / wpc;
-        h->woff[rtid] = (uint16_t)o;
-        if (rtid == 0) {
-          h->nG = (uint16_t)nG;
-          h->nC = (uint16_t)nC;
-          h->n16 = (uint16_t)(2 + (nG + 1) / 2 + (nC + 3) / 4);
-        }
-      }
+      const bool lpt = a.lpt && nG <= 64 && wpc <= 4;
       unsigned long long* brec = (unsigned long long*)(blob + 2);
       uint8_t* pcur = a.plan.curG + (size_t)rec * a.plan.cap;
-      for (int g = rtid; g < nG; g += NT) {
-        const int o = gcnt[g], n = gcnt[g + 1] - o;
-        {  // new parent g: newest true state = its first member's (tracking.py:728); curP is not read
-           // again before the barrier that ends the step
-          const uint32_t e = ent[o];
-          const unsigned char cs = (unsigned char)(((int)(e & 0xFFFF) * K + (int)(e >> 24)) % nS);
-          pcur[g] = cs;
-          curP[g] = cs;
-        }
-        int rank = 0;
-        for (int j = 0; j < nG; ++j) {
-          const int nj = gcnt[j + 1] - gcnt[j];
-          rank += (nj > n) || (nj == n && j < g);
-        }
-        const int wq = rank % wpc, pos = rank / wpc;
-        int slot = pos;
-        for (int v = 0; v < wq; ++v) slot += (nG - v + wpc - 1) / wpc;
+      // group record: fields pre-positioned for the replay kernel (xt_common.cuh)
+      auto group_record = [&](int g, int o, int n) -> unsigned long long {
         const uint32_t e0 = ent[o];
         const unsigned lo = ((e0 >> 16) & 0x7Fu) | ((e0 & 0xFFFu) << 7) | ((unsigned)g << 19);
         unsigned hi;
@@ -903,7 +894,113 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         } else {
           hi = (3u << 30) | (unsigned)o | ((unsigned)n << 12);
         }
-        brec[slot] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        return (unsigned long long)lo | ((unsigned long long)hi << 32);
+      };
+      if (rtid == 0) {
+        h->nG = (uint16_t)nG;
+        h->nC = (uint16_t)nC;
+        h->n16 = (uint16_t)(2 + (nG + 1) / 2 + (nC + 3) / 4);
+      }
+      if (lpt) {
+        // one warp (the last of the CTA; its threads have rtid 0..31): lane l owns groups l and l + 32.  The
+        // greedy assignment runs redundantly on every lane (warp-uniform registers), each lane keeps the
+        // (warp, position) of its own groups.
+        if (rtid < 32) {
+          const int l = rtid;
+          int gn[2] = {0, 0}, go[2] = {0, 0};
+          int multi = 0;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int g = l + 32 * hh;
+            if (g < nG) {
+              go[hh] = gcnt[g];
+              gn[hh] = gcnt[g + 1] - go[hh];
+              const uint32_t e = ent[go[hh]];
+              const unsigned char cs = (unsigned char)(((int)(e & 0xFFFF) * K + (int)(e >> 24)) % nS);
+              pcur[g] = cs;  // new parent g: newest true state = its first member's (tracking.py:728); curP is
+              curP[g] = cs;  // not read again before the barrier that ends the step
+              int rank = 0;
+              for (int j = 0; j < nG; ++j) {
+                const int nj = gcnt[j + 1] - gcnt[j];
+                rank += (nj > gn[hh]) || (nj == gn[hh] && j < g);
+                if (hh == 0) multi += nj > 1;
+              }
+              grank[rank] = g;  // (grank is free outside the split-mode grouping)
+            }
+          }
+          __syncwarp();
+          int ld0 = 0, ld1 = 0, ld2 = 0, ld3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+          int myw[2] = {0, 0}, myp[2] = {0, 0};
+          for (int r = 0; r < nG; ++r) {
+            const int g = grank[r];
+            const int n = gcnt[g + 1] - gcnt[g];
+            const int cost = n == 1 ? a.cost[0] : (n == 2 ? a.cost[1] : a.cost[2] + a.cost[3] * n);  // replay cost model
+            int w = 0, best = ld0;
+            if (wpc > 1 && ld1 < best) { w = 1; best = ld1; }
+            if (wpc > 2 && ld2 < best) { w = 2; best = ld2; }
+            if (wpc > 3 && ld3 < best) { w = 3; best = ld3; }
+            const int pos = w == 0 ? c0 : (w == 1 ? c1 : (w == 2 ? c2 : c3));
+            if (g == l) { myw[0] = w; myp[0] = pos; }
+            if (g == l + 32) { myw[1] = w; myp[1] = pos; }
+            const int mm = n > 1;
+            c0 += w == 0; c1 += w == 1; c2 += w == 2; c3 += w == 3;
+            ld0 += w == 0 ? cost : 0; ld1 += w == 1 ? cost : 0; ld2 += w == 2 ? cost : 0; ld3 += w == 3 ? cost : 0;
+            m0 += (w == 0) & mm; m1 += (w == 1) & mm; m2 += (w == 2) & mm; m3 += (w == 3) & mm;
+          }
+          const int o1 = c0, o2 = c0 + c1, o3 = o2 + c2;
+          if (l == 0) {
+            h->nM = (uint16_t)multi;
+            h->woff[0] = 0;
+            h->woff[1] = (uint16_t)o1;
+            h->woff[2] = (uint16_t)(wpc > 1 ? o2 : nG);
+            h->woff[3] = (uint16_t)(wpc > 2 ? o3 : nG);
+            h->woff[4] = (uint16_t)nG;
+            h->woff[5] = (uint16_t)m0;  // multi-member groups at the head of every warp's list (XT_MAX_WPC + 1 - 4 spare entries)
+            h->woff[6] = (uint16_t)m1;
+            h->woff[7] = (uint16_t)m2;
+            h->woff[8] = (uint16_t)m3;
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int g = l + 32 * hh;
+            if (g < nG) {
+              const int base = myw[hh] == 0 ? 0 : (myw[hh] == 1 ? o1 : (myw[hh] == 2 ? o2 : o3));
+              brec[base + myp[hh]] = group_record(g, go[hh], gn[hh]);
+            }
+          }
+        }
+      } else {
+        if (rtid <= XT_MAX_WPC) {
+          // groups of warp w: ranks w, w + wpc, ...  => woff[w] = sum_{v<w} ceil((nG - v) / wpc)
+          int o = 0;
+          for (int v = 0; v < rtid && v < wpc; ++v) o += (nG - v + wpc - 1) / wpc;
+          if (wpc > 4 || rtid <= 4) h->woff[rtid] = (uint16_t)o;
+        }
+        for (int g = rtid; g < nG; g += NT) {
+          const int o = gcnt[g], n = gcnt[g + 1] - o;
+          {  // new parent g: newest true state = its first member's (tracking.py:728); curP is not read
+             // again before the barrier that ends the step
+            const uint32_t e = ent[o];
+            const unsigned char cs = (unsigned char)(((int)(e & 0xFFFF) * K + (int)(e >> 24)) % nS);
+            pcur[g] = cs;
+            curP[g] = cs;
+          }
+          int rank = 0, multi = 0;
+          for (int j = 0; j < nG; ++j) {
+            const int nj = gcnt[j + 1] - gcnt[j];
+            rank += (nj > n) || (nj == n && j < g);
+            multi += nj > 1;
+          }
+          if (rank == nG - 1) {  // one writer: the last group of the schedule
+            h->nM = (uint16_t)multi;
+            if (wpc <= 4)  // multi-member groups at the head of warp w's list: ranks w, w + wpc, ... below `multi`
+              for (int w2 = 0; w2 < 4; ++w2) h->woff[5 + w2] = (uint16_t)(multi > w2 ? (multi - w2 + wpc - 1) / wpc : 0);
+          }
+          const int wq = rank % wpc, pos = rank / wpc;
+          int slot = pos;
+          for (int v = 0; v < wq; ++v) slot += (nG - v + wpc - 1) / wpc;
+          brec[slot] = group_record(g, o, n);
+        }
       }
       uint32_t* bent = (uint32_t*)(blob + 2 + (nG + 1) / 2);
       for (int c = rtid; c < nC; c += NT) bent[c] = ent[c];

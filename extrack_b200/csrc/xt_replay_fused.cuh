@@ -30,6 +30,17 @@
 
 #define XT_ZERO_EXP (-(1 << 30))  // exponent of a sequence with zero weight
 
+// build-time variants (A/B timing on the GPU box: python -m extrack_b200.build -DXT_K2_...=0 --out=...)
+#ifndef XT_K2_SHORT_CHAIN
+#define XT_K2_SHORT_CHAIN 1  // Estrin polynomial + cubic reciprocal step in the update (shorter dependent chains)
+#endif
+#ifndef XT_K2_SINGLES_X2
+#define XT_K2_SINGLES_X2 1  // single-member groups two at a time (one track per thread)
+#endif
+#ifndef XT_K2_SINGLES_IL
+#define XT_K2_SINGLES_IL 1  // ... with the two updates interleaved stage by stage
+#endif
+
 struct K2Tab {  // per-evaluation tables and scalars of the fused replay kernel (built on the host)
   double tau0[XT_MAX_HEADS];      // exp(LT[head])
   double tau1[XT_MAX_HEADS];      // exp(LT[head] + Lp_stay[r])
@@ -44,51 +55,13 @@ struct K2Tab {  // per-evaluation tables and scalars of the fused replay kernel 
   // constants of xt_exp_split: read as constant-bank operands of the FP64 instructions (64-bit
   // immediates would be rebuilt with two moves per use inside the register-bound inner loop)
   double kc[6];
+  // ln of the constant c folded into tau0 / tau1 / winit (c = prod over dims of sqrt(l2), scalar-LocErr models): every
+  // Gaussian-product update multiplies the weight by prod_dim q^-1/2 >= c^-1, so with c folded in a weight never grows by
+  // more than 2x per step and drifts down slowly; the end of the track subtracts (L - 1) * lnc again
+  double lnc;
 };
 #define XT_EXP_CONSTS {23.083120654223414, 6755399441055744.0, -0.04332169878499658, -1.4494042586539372e-18, \
                        4.1666666666666664e-02, 1.6666666666666666e-01}
-
-// ---- shared memory through 32-bit shared-window addresses (no generic-pointer arithmetic) ----
-__device__ __forceinline__ unsigned xt_smem_base(const void* p) {
-  unsigned a = (unsigned)__cvta_generic_to_shared(p);
-  asm volatile("mov.u32 %0, %0;" : "+r"(a));  // computed once: keeps the base from being rematerialised
-  return a;
-}
-__device__ __forceinline__ void xt_lds128(unsigned a, double& x, double& y) {
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
-}
-__device__ __forceinline__ double xt_lds64(unsigned a) {
-  double x;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
-  return x;
-}
-__device__ __forceinline__ uint2 xt_lds64u(unsigned a) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ int xt_lds32(unsigned a) {
-  int x;
-  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(x) : "r"(a));
-  return x;
-}
-__device__ __forceinline__ unsigned xt_lds16(unsigned a) {
-  unsigned x;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(x) : "r"(a));
-  return x;
-}
-__device__ __forceinline__ void xt_sts128(unsigned a, double x, double y) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
-}
-__device__ __forceinline__ void xt_sts128u(unsigned a, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void xt_sts64(unsigned a, double x) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory");
-}
-__device__ __forceinline__ void xt_sts32(unsigned a, int x) {
-  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
-}
 
 // global -> shared staging without registers (the issuing thread waits, the CTA barrier publishes)
 __device__ __forceinline__ void xt_cp_async16(unsigned dst, const void* src) {
@@ -144,6 +117,19 @@ __device__ __forceinline__ double xt_exp_split(double x, unsigned s_e2, int& k, 
   k = n >> 4;
   // the three highest coefficients are truncated to their high word (immediate operands):
   // their terms are below 4e-11, so 21 significant bits keep the error under 2e-17
+#if XT_K2_SHORT_CHAIN
+  // Estrin evaluation: dependency depth 3 instead of 7 (the replay kernel is bound by the latency of its
+  // dependent FP64 chains, not by the instruction count)
+  const double r2 = r * r;
+  const double a0 = r + 1.0;
+  const double a1 = fma(r, T.kc[5], 0.5);
+  const double a2 = fma(r, 0.00833333283662796, T.kc[4]);
+  const double a3 = fma(r, 0.00019841268658638, 0.00138888880610466);
+  const double r4 = r2 * r2;
+  const double b0 = fma(r2, a1, a0);
+  const double b1 = fma(r2, a3, a2);
+  return fma(r4, b1, b0) * tj;
+#else
   double p = 0.00019841268658638;
   p = fma(p, r, 0.00138888880610466);
   p = fma(p, r, 0.00833333283662796);
@@ -153,6 +139,21 @@ __device__ __forceinline__ double xt_exp_split(double x, unsigned s_e2, int& k, 
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   return p * tj;
+#endif
+}
+
+// 1/x for normal positive x: hardware seed (relative error e <= 2^-20) and one cubic step r0 (1 + e + e^2), error e^3:
+// three dependent operations instead of the four of two Newton steps
+__device__ __forceinline__ double xt_rcp_fused(double x) {
+#if XT_K2_SHORT_CHAIN
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
+#else
+  return xt_rcp(x);
+#endif
 }
 
 // v >= 0 (normal or zero) -> mantissa in [1, 2) and exponent base + unbiased exponent of v;
@@ -228,7 +229,7 @@ __device__ __forceinline__ void xt_update(XtSeq<D, KS> (&s)[TPT], const double (
 #pragma unroll
   for (int j = 0; j < TPT; ++j)
 #pragma unroll
-    for (int k = 0; k < KS; ++k) rq[j][k] = xt_rcp(l2[VAR ? j : 0][k] + s[j].u[k]);
+    for (int k = 0; k < KS; ++k) rq[j][k] = xt_rcp_fused(l2[VAR ? j : 0][k] + s[j].u[k]);
 #pragma unroll
   for (int j = 0; j < TPT; ++j) {
     double g[KS];
@@ -261,10 +262,16 @@ __device__ __forceinline__ void xt_update(XtSeq<D, KS> (&s)[TPT], const double (
   int k2[TPT];
 #pragma unroll
   for (int j = 0; j < TPT; ++j) p[j] = xt_exp_split(xt_clamp_neg(e[j]), s_e2, k2[j], T);
+  // The weight stays an ordinary double W * 2^E; it is brought back to a mantissa in [1, 2) only when it leaves
+  // [2^-512, 2^512) (zero, NaN and negative values take the same branch).  With the per-update constant folded into
+  // the tables (K2Tab::lnc) that takes hundreds of steps, so the branch is practically never taken; any member of a
+  // later merge is then at most 2^-1022 / 2^-512 below the member it is aligned to before it is flushed.
 #pragma unroll
   for (int j = 0; j < TPT; ++j) {
     const double wn = (s[j].W * xt_normfac<D, KS>(rq[j])) * p[j];
-    xt_split_exponent(wn, s[j].E + k2[j], s[j].W, s[j].E);
+    s[j].E += k2[j];
+    s[j].W = wn;
+    if ((unsigned)(__double2hiint(wn) - 0x1FF00000) >= 0x40000000u) xt_split_exponent(wn, s[j].E, s[j].W, s[j].E);
   }
 }
 
@@ -520,9 +527,18 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
     // registers (the compiler otherwise rematerialises them from uniform registers every iteration)
     unsigned ga = grec + xt_lds16(rb + 8 + 2 * w) * 8;  // XtBlobHdr::woff
     const unsigned ge = grec + xt_lds16(rb + 8 + 2 * (w + 1)) * 8;
+    // the first groups of this warp's list have several members, the others exactly one
+    int nmw;
+    if (WPC <= 4) {
+      nmw = (int)xt_lds16(rb + 8 + 2 * (5 + w));  // XtBlobHdr::woff[5 + w]
+    } else {
+      const int nM = (int)xt_lds16(rb + 6);  // XtBlobHdr::nM, round-robin schedule
+      nmw = nM > w ? (nM - w + WPC - 1) / WPC : 0;
+    }
+    const unsigned gm = ga + (unsigned)nmw * 8;
     unsigned tabp = tab;
     asm volatile("mov.u32 %0, %0;" : "+r"(tabp));
-    for (; ga < ge; ga += 8) {
+    for (; ga < gm; ga += 8) {
       const uint2 gr = xt_lds64u(ga);
       const unsigned p0o = gr.x & 0x7FF80u;  // p0 * 128
       const unsigned g = gr.x >> 19;
@@ -531,15 +547,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       IO::load(gb, src_v + p0o * (SLOTB / 128), src_e + p0o * (ESLOT / 128), G);
       double tau0, dd0;
       xt_lds128(tabp + (gr.x & 0x7Fu) * 16, tau0, dd0);
-      if (kind == 1u) {
-        // single member: the child itself
-#pragma unroll
-        for (int j = 0; j < TPT; ++j) {
-          G[j].W *= tau0;
-#pragma unroll
-          for (int k = 0; k < KS; ++k) G[j].u[k] += VAR ? dd0 * DTQ(j) : dd0;
-        }
-      } else if (kind == 2u) {
+      if (kind == 2u) {
         const unsigned p1o = gr.y & 0x7FF80u;
         Seq B[TPT];
         IO::load(gb, src_v + p1o * (SLOTB / 128), src_e + p1o * (ESLOT / 128), B);
@@ -551,7 +559,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
           const double w0 = (G[j].W * xt_pow2_le0(G[j].E - Eg)) * tau0;
           const double w1 = (B[j].W * xt_pow2_le0(B[j].E - Eg)) * tau1;
           const double sw = w0 + w1;
-          const double rs = (sw > 1e-280) ? xt_rcp(sw) : 0.0;
+          const double rs = (sw > 1e-300) ? xt_rcp(sw) : 0.0;
           const double lam = w1 * rs;
 #pragma unroll
           for (int dim = 0; dim < D; ++dim) G[j].m[dim] = fma(B[j].m[dim] - G[j].m[dim], lam, G[j].m[dim]);
@@ -609,7 +617,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
         }
 #pragma unroll
         for (int j = 0; j < TPT; ++j) {
-          if (sw[j] > 1e-280) {  // otherwise: zero-weight group, keep the first member's moments
+          if (sw[j] > 1e-300) {  // otherwise: zero-weight group, keep the first member's moments
             const double rs = xt_rcp(sw[j]);
 #pragma unroll
             for (int dim = 0; dim < D; ++dim) G[j].m[dim] = am[j][dim] * rs;
@@ -619,6 +627,64 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
           G[j].W = sw[j];
           G[j].E = Eg[j];
         }
+      }
+      xt_update<D, KS, TPT, VAR>(G, cl, l2, s_e2, T);
+      IO::store(gb, dst_v + g * SLOTB, dst_e + g * ESLOT, G);
+    }
+    // single-member groups (three quarters of the groups of a 2-state model): the child itself, no dispatch; two
+    // at a time when a thread carries one track (two independent dependency chains per instruction stream)
+    if (TPT == 1 && XT_K2_SINGLES_X2) {
+      for (; ga + 8 < ge; ga += 16) {
+        const uint2 gr0 = xt_lds64u(ga), gr1 = xt_lds64u(ga + 8);
+        const unsigned p0o = gr0.x & 0x7FF80u, p1o = gr1.x & 0x7FF80u;
+        Seq G0[TPT], G1[TPT];
+        IO::load(gb, src_v + p0o * (SLOTB / 128), src_e + p0o * (ESLOT / 128), G0);
+        IO::load(gb, src_v + p1o * (SLOTB / 128), src_e + p1o * (ESLOT / 128), G1);
+        double tau0, dd0, tau1, dd1;
+        xt_lds128(tabp + (gr0.x & 0x7Fu) * 16, tau0, dd0);
+        xt_lds128(tabp + (gr1.x & 0x7Fu) * 16, tau1, dd1);
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+          G0[j].W *= tau0;
+          G1[j].W *= tau1;
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            G0[j].u[k] += VAR ? dd0 * DTQ(j) : dd0;
+            G1[j].u[k] += VAR ? dd1 * DTQ(j) : dd1;
+          }
+        }
+        if (XT_K2_SINGLES_IL && !VAR) {  // both updates stage by stage in one instruction stream (two interleaved chains)
+          Seq P2[2] = {G0[0], G1[0]};
+          double cl2[2][D];
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) cl2[0][dim] = cl2[1][dim] = cl[0][dim];
+          double l2s[1][KS];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) l2s[0][k] = l2[0][k];
+          xt_update<D, KS, 2, false>(P2, cl2, l2s, s_e2, T);
+          G0[0] = P2[0];
+          G1[0] = P2[1];
+        } else {
+          xt_update<D, KS, TPT, VAR>(G0, cl, l2, s_e2, T);
+          xt_update<D, KS, TPT, VAR>(G1, cl, l2, s_e2, T);
+        }
+        IO::store(gb, dst_v + (gr0.x >> 19) * SLOTB, dst_e + (gr0.x >> 19) * ESLOT, G0);
+        IO::store(gb, dst_v + (gr1.x >> 19) * SLOTB, dst_e + (gr1.x >> 19) * ESLOT, G1);
+      }
+    }
+    for (; ga < ge; ga += 8) {
+      const uint2 gr = xt_lds64u(ga);
+      const unsigned p0o = gr.x & 0x7FF80u;  // p0 * 128
+      const unsigned g = gr.x >> 19;
+      Seq G[TPT];
+      IO::load(gb, src_v + p0o * (SLOTB / 128), src_e + p0o * (ESLOT / 128), G);
+      double tau0, dd0;
+      xt_lds128(tabp + (gr.x & 0x7Fu) * 16, tau0, dd0);
+#pragma unroll
+      for (int j = 0; j < TPT; ++j) {
+        G[j].W *= tau0;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) G[j].u[k] += VAR ? dd0 * DTQ(j) : dd0;
       }
       xt_update<D, KS, TPT, VAR>(G, cl, l2, s_e2, T);
       IO::store(gb, dst_v + g * SLOTB, dst_e + g * ESLOT, G);
@@ -711,7 +777,7 @@ __global__ void __launch_bounds__(32 * WPC, (TPT == 1 ? XT_K2_WARPS_T1 : 16) / W
       for (int k = 0; k < WPC; ++k)
         tot = fma(xs_ld64<GST>(gb, s_redA + ((k * TPT + j) * 32 + lane) * 8),
                   xt_pow2_le0(xs_ld32<GST>(gb, s_redK + ((k * TPT + j) * 32 + lane) * 4) - Kn), tot);
-      double lp = XT_LN2 * (double)Kn + log(tot) - (double)(L - 1) * (0.5 * (double)D) * XT_LN_2PI;
+      double lp = XT_LN2 * (double)Kn + log(tot) - (double)(L - 1) * ((0.5 * (double)D) * XT_LN_2PI + T.lnc);
       if (!(fabs(csum[j]) <= 1.7976931348623157e308)) lp = __longlong_as_double(0x7ff8000000000000ll);
       if (valid[j]) {
         a.logp[ck.trk_off + wk.t0 + lane + 32 * j] = lp;

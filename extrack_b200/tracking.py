@@ -94,6 +94,9 @@ def extract_params(params, dt, nb_states, nb_substeps, input_LocErr=None, Matrix
     return LocErr, ds, Fs, TrMat, pBL
 
 
+_P_STAY_MEMO: dict = {}
+
+
 def _p_stay(ds, nS, nsub, cell_dims):
     """P(stay in the field of view) per sub-step state tuple (tracking.py:508-523).
 
@@ -105,6 +108,11 @@ def _p_stay(ds, nS, nsub, cell_dims):
 
     ds = np.asarray(ds, dtype=float)
     one = ds.ndim == 1
+    if one:  # memo: most evaluations of a fit perturb a parameter that leaves ds unchanged (LocErr, F, p_ij, pBL)
+        key = (ds.tobytes(), nS, nsub, tuple(float(c) for c in cell_dims))
+        hit = _P_STAY_MEMO.get(key)
+        if hit is not None:
+            return hit.copy()
     ds2 = ds[None] if one else ds
     K = nS**nsub
     tup = np.arange(K)[:, None] // nS ** np.arange(nsub)[None, :] % nS
@@ -120,6 +128,10 @@ def _p_stay(ds, nS, nsub, cell_dims):
             )
             p_stay = p_stay * cur
         out[r0 : r0 + 512] = p_stay
+    if one:
+        if len(_P_STAY_MEMO) > 64:
+            _P_STAY_MEMO.clear()
+        _P_STAY_MEMO[key] = out[0].copy()
     return out[0] if one else out
 
 
@@ -219,10 +231,9 @@ def build_tables(LocErr, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, 
     Lp_stay = np.log(p_stay * (1 - pBL))
     e = p_stay[dig[:, 0]]  # indexed by the newest *state value* (reference quirk, tracking.py:630)
     L_leave = np.log(pBL + (1 - e) - pBL * (1 - e)) + LT
-    for h in range(nH):
-        p.dd[h], p.LT[h], p.LF[h], p.L_leave[h] = dd[h], LT[h], LF[h], L_leave[h]
-    for r in range(K):
-        p.Lp_stay[r] = Lp_stay[r]
+    for field, vals in (("dd", dd), ("LT", LT), ("LF", LF), ("L_leave", L_leave), ("Lp_stay", Lp_stay)):
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        ctypes.memmove(ctypes.addressof(getattr(p, field)), v.ctypes.data, v.nbytes)  # one copy per table, no Python loop
     return p
 
 
