@@ -248,6 +248,9 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
 #endif
+  double cnext[D];
+#pragma unroll
+  for (int dim = 0; dim < D; ++dim) cnext[dim] = Cp[(size_t)(1 * D + dim) * npad];  // step 2 consumes localisation 1
   for (int step = 2; step <= L - 2; ++step) {
     const int nC = nP * K;
     if (nC > cap) {
@@ -276,7 +279,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     //      one warp per parent, its K children share q, the new mean and the log term ----
     double cl[D];
 #pragma unroll
-    for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((step - 1) * D + dim) * npad];
+    for (int dim = 0; dim < D; ++dim) {
+      cl[dim] = cnext[dim];
+      cnext[dim] = Cp[(size_t)(step * D + dim) * npad];  // localisation of the next step (step <= L - 2: it exists),
+    }                                                    // in flight during this step instead of at the head of the next one
     const bool stay = step >= P.min_len;
     if (VAR) {  // (the previous step ended with a barrier: nobody still reads s_dd)
       var_step(step - 1);
@@ -468,6 +474,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         // the sequences to test, as a byte list in shared memory (lane l owns bits l and l + 32), padded to a
         // multiple of four with the first one; then four sequences per round
         const int ntodo = __popcll(todo);
+        unsigned add_lo = 0u, add_hi = 0u;
         if (ntodo) {
           unsigned char* myjs = s_js + warp * 72;
           const unsigned tlo = (unsigned)todo, thi = (unsigned)(todo >> 32);
@@ -482,11 +489,14 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
             bool ok[4];
             fp_ok4(mi, si, js, ok);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (r0 + q < ntodo && ok[q]) row |= 1ull << js[q];
+            for (int q = 0; q < 4; ++q) {
+              const unsigned bit = (r0 + q < ntodo && ok[q]) ? 1u << (js[q] & 31) : 0u;
+              if (js[q] & 32) add_hi |= bit; else add_lo |= bit;
+            }
           }
           __syncwarp();  // the next row of this warp reuses the list
         }
+        row |= (unsigned long long)add_lo | ((unsigned long long)add_hi << 32);
         if (lane == 0) s_rows[i] = row;
       }
       __syncthreads();
@@ -858,7 +868,6 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     __syncthreads();
     if (tid == 0) {
       prof[8] += s_hmax >> 32; prof[9] += s_hslow; prof[10] += s_hmem; prof[11] += nG * rows_out;
-      if (step == 12 && blockIdx.x < 4) printf("chunk %d step %d: slowest history thread %llu cycles n=%llu slow=%llu cycles in slow loops=%llu (nG=%d rows=%d Kh=%d)\n", cid, step, s_hmax >> 32, (s_hmax >> 24) & 0xFF, (s_hmax >> 16) & 0xFF, (s_hmax & 0xFFFF) << 4, nG, rows_out, Kh);
     }
 #endif
     K1_T(4);
@@ -879,6 +888,8 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       XtBlobHdr* h = (XtBlobHdr*)blob;
       const int wpc = a.wpc;
       const bool lpt = a.lpt && nG <= 64 && wpc <= 4;
+      // warp of the schedule: with 16 or more warps one that neither holds history rows (first warps) nor merges (upper half)
+      const int rec_warp = (W >= 16 && (nG << ro_sh) <= NT / 4) ? W / 2 - 1 : W - 1;
       unsigned long long* brec = (unsigned long long*)(blob + 2);
       uint8_t* pcur = a.plan.curG + (size_t)rec * a.plan.cap;
       // group record: fields pre-positioned for the replay kernel (xt_common.cuh)
@@ -905,8 +916,8 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
         // one warp (the last of the CTA; its threads have rtid 0..31): lane l owns groups l and l + 32.  The
         // greedy assignment runs redundantly on every lane (warp-uniform registers), each lane keeps the
         // (warp, position) of its own groups.
-        if (rtid < 32) {
-          const int l = rtid;
+        if (warp == rec_warp) {
+          const int l = lane;
           int gn[2] = {0, 0}, go[2] = {0, 0};
           int multi = 0;
 #pragma unroll

@@ -23,8 +23,13 @@ so = os.path.join(root, "extrack_b200", "libxtrack_b200.so")
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+# one cubin per translation unit: take the one that holds the wanted function
+sass = ""
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    if ".text." + mangled_prefix in txt:
+        sass = txt
+        break
 
 # offset -> (file, line) for the wanted function
 off2line = {}
