@@ -67,6 +67,8 @@ class XtStats(C.Structure):
         ("k3_launches", C.c_int32),
         ("k3_cap", C.c_int32),
         ("fp32", C.c_int32),
+        ("plan_verified", C.c_int32),
+        ("replanned", C.c_int32),
     ]
 
 

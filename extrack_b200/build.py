@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-UNITS = ["xt_engine.cu", "xt_k1.cu", "xt_k1w.cu", "xt_k1x.cu", "xt_k2f.cu", "xt_k2f32.cu", "xt_k2old.cu", "xt_k3.cu", "xt_k4.cu"]
+UNITS = ["xt_engine.cu", "xt_k1.cu", "xt_k1w.cu", "xt_k1x.cu", "xt_k1v.cu", "xt_k2f.cu", "xt_k2f32.cu", "xt_k2old.cu", "xt_k3.cu", "xt_k4.cu"]
 OUT = os.path.join(HERE, "libxtrack_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 

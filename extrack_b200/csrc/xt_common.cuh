@@ -71,6 +71,19 @@ __host__ __device__ inline uint32_t xt_pack_ent(int p, int head, int r) {
   return (uint32_t)p | ((uint32_t)head << 16) | ((uint32_t)r << 24);
 }
 
+// Verification record of one leader of a matrix-mode fusion step (<= 64 sequences): the sequences whose
+// floating-point predicate (m_mask and s_mask, tracking.py:689-691) the greedy loop consulted when it visited this
+// leader - the not yet grouped sequences with the leader's newest state that the window test did not already
+// capture - and the outcome of every one of them.  The plan kernel in verification mode (k1_plan<.., VERIFY>)
+// re-evaluates exactly these predicates with the parameters of a new evaluation: the plan is unchanged if and only if
+// every outcome is.
+struct XtVRec {
+  unsigned long long lead;  // sequence id of the leader
+  unsigned long long cand;  // bit j: the pair (leader, j) was decided by the floating-point predicate
+  unsigned long long exp;   // its outcome (bit j set: captured)
+};
+#define XT_VREC_PER_STEP 64
+
 struct XtPlanPtrs {
   XtRecHdr* hdr;     // [nrec_total]
   uint16_t* goff;    // [nrec_total][cap+1]
@@ -79,6 +92,8 @@ struct XtPlanPtrs {
   uint16_t* gid;     // [nrec_total][cap]   group of each incoming child (dump / tests)
   unsigned long long* grec;  // [nrec_total][cap] per group: p0:16|head0:8|n:8 | (p1:16|head1:8)<<32, n capped at 255
   uint4* blob;       // [nrec_total][xt_blob_stride16(cap)] replay records (see XtBlobHdr)
+  XtVRec* vrec;      // [nrec_total][XT_VREC_PER_STEP] verification records (matrix-mode steps)
+  uint8_t* vok;      // [nrec_total] 1: the step was grouped in matrix mode and vrec describes it completely
   int32_t cap;
 };
 

@@ -70,6 +70,15 @@ struct xt_ctx {
   int k1_batch = 1;           // plan kernel, > 64 sequences: batched candidate leaders (0: one leader at a time)
   int pipeline = 1;
   int n_groups = 6;
+  // plan verification (k1_plan<.., VERIFY>): the resident plan stays valid across evaluations as long as every
+  // floating-point decision behind it is reproduced with the new parameters
+  bool plan_valid = false;      // the resident plan + records describe the resident data for plan_sig
+  xt_params plan_sig{};         // structural fields of the parameters the plan was built with
+  int plan_verify = 1;          // option: 0 = always plan from scratch
+  int32_t* d_vflag = nullptr;   // [n_chunks] verification outcome per chunk
+  int32_t* h_vflag = nullptr;   // pinned
+  int32_t* d_redo = nullptr;    // [n_chunks] chunk ids to plan again
+  std::vector<int> corder_pos;  // position of every chunk in corder
   double* d_logp = nullptr;
   double* d_partial = nullptr;
   double* d_out = nullptr;
@@ -173,6 +182,8 @@ __global__ void k_fp64_peak(double* out, int iters) {
 static void free_plan(xt_ctx* ctx) {
   cudaFree(ctx->plan.hdr); cudaFree(ctx->plan.goff); cudaFree(ctx->plan.ent);
   cudaFree(ctx->plan.curG); cudaFree(ctx->plan.gid); cudaFree(ctx->plan.grec); cudaFree(ctx->plan.blob);
+  cudaFree(ctx->plan.vrec); cudaFree(ctx->plan.vok);
+  ctx->plan_valid = false;
   cudaFree(ctx->d_state1); cudaFree(ctx->d_hist1);
   ctx->plan = XtPlanPtrs{};
   ctx->d_state1 = ctx->d_hist1 = nullptr;
@@ -194,6 +205,11 @@ static void free_data(xt_ctx* ctx) {
   ctx->d_fstate = nullptr; ctx->d_fslots = nullptr; ctx->fstate_bytes = 0;
   cudaFree(ctx->d_workf[0]); cudaFree(ctx->d_workf[1]); cudaFree(ctx->d_corder);
   ctx->d_corder = nullptr;
+  cudaFree(ctx->d_vflag); cudaFree(ctx->d_redo);
+  ctx->d_vflag = ctx->d_redo = nullptr;
+  if (ctx->h_vflag) cudaFreeHost(ctx->h_vflag);
+  ctx->h_vflag = nullptr;
+  ctx->plan_valid = false;
   cudaFree(ctx->d_csum);
   ctx->d_csum = nullptr;
   if (ctx->h_csum) cudaFreeHost(ctx->h_csum);
@@ -423,6 +439,11 @@ static int setup_layout(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int6
     }
     XT_CUDA_OK(cudaMalloc(&ctx->d_csum, sizeof(double) * nch));
     XT_CUDA_OK(cudaMallocHost(&ctx->h_csum, sizeof(double) * nch));
+    XT_CUDA_OK(cudaMalloc(&ctx->d_vflag, sizeof(int32_t) * nch));
+    XT_CUDA_OK(cudaMalloc(&ctx->d_redo, sizeof(int32_t) * nch));
+    XT_CUDA_OK(cudaMallocHost(&ctx->h_vflag, sizeof(int32_t) * nch));
+    ctx->corder_pos.assign(nch, 0);
+    for (size_t q = 0; q < nch; ++q) ctx->corder_pos[ctx->corder[q]] = (int)q;
     while ((int)ctx->ev_seg.size() < n_seg) {
       cudaEvent_t e;
       XT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -431,6 +452,7 @@ static int setup_layout(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int6
     XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   }
   ctx->have_eval = false;
+  ctx->plan_valid = false;  // new coordinates: the resident plan describes the previous data set
   // two staging buffers (AoS as on the host) overlap the copy of one segment with the repack of another
   if ((size_t)max_seg_elems > ctx->stage_elems) {
     for (int b = 0; b < 2; ++b) {
@@ -532,6 +554,7 @@ extern "C" int xt_upload_aux(xt_ctx* ctx, int32_t k_sigma, const double* const* 
   ctx->aux_ka = k_sigma;
   ctx->aux_has_dt = dt ? 1 : 0;
   ctx->have_eval = false;
+  ctx->plan_valid = false;
   const int chunk_size = (int)ctx->upload_sig[2];
   int slot = 0;
   for (int pass = 0; pass < 2; ++pass) {
@@ -567,6 +590,7 @@ extern "C" int xt_set_stay_tables(xt_ctx* ctx, int32_t per_track, int32_t K, int
   ctx->d_stay[i] = ctx->d_leave[i] = nullptr;
   ctx->stay_K[i] = ctx->stay_H[i] = 0;
   ctx->have_eval = false;
+  ctx->plan_valid = false;
   if (!Lp_stay || !L_leave) return XT_OK;
   if (ctx->chunks.empty() || K < 1 || H < K || H % K != 0) {
     set_error(ctx, "xt_set_stay_tables: upload the tracks first; need K >= 1 and H a multiple of K");
@@ -680,6 +704,9 @@ static int ensure_plan(xt_ctx* ctx, const xt_params* p, int cap) {
   XT_CUDA_OK(cudaMalloc(&ctx->plan.gid, sizeof(uint16_t) * nrec * cap));
   XT_CUDA_OK(cudaMalloc(&ctx->plan.grec, sizeof(unsigned long long) * nrec * cap));
   XT_CUDA_OK(cudaMalloc(&ctx->plan.blob, sizeof(uint4) * nrec * xt_blob_stride16(cap)));
+  XT_CUDA_OK(cudaMalloc(&ctx->plan.vrec, sizeof(XtVRec) * nrec * XT_VREC_PER_STEP));
+  XT_CUDA_OK(cudaMalloc(&ctx->plan.vok, nrec));
+  XT_CUDA_OK(cudaMemset(ctx->plan.vok, 0, nrec));
   ctx->plan.cap = cap;
   XT_CUDA_OK(cudaMalloc(&ctx->d_state1, sizeof(double) * nch * 2 * cap * CO1 * 32));
   XT_CUDA_OK(cudaMalloc(&ctx->d_hist1, sizeof(double) * nch * 2 * cap * RH * p->nS));
@@ -1053,6 +1080,15 @@ static int enqueue_fused(xt_ctx* ctx, const xt_params* p, const FusedLaunch& fl,
   return XT_OK;
 }
 
+// shape of the model: a resident plan can only be verified for parameters of the same shape
+static bool same_structure(const xt_params& a, const xt_params& b) {
+  return a.nS == b.nS && a.nsub == b.nsub && a.d == b.d && a.n_loc == b.n_loc && a.frame_len == b.frame_len && a.flags == b.flags;
+}
+static void mark_plan_valid(xt_ctx* ctx, const xt_params* p) {
+  ctx->plan_valid = true;
+  ctx->plan_sig = *p;
+}
+
 #define XT_RETRY 1        // internal: the speculative single-pass evaluation has to be redone in two phases
 #define XT_RETRY_EARLY 2  // same, and nothing was enqueued yet (host buffers not copied)
 
@@ -1159,6 +1195,110 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
   ctx->stats.n_chunks = nch;
   ctx->last_p = *p;
   ctx->have_eval = true;
+  ctx->last_fused = true;
+  mark_plan_valid(ctx, p);
+  return XT_OK;
+}
+
+// Evaluation along the RESIDENT plan: the replay kernel runs on the resident records while the plan kernel, in
+// verification mode, re-evaluates every floating-point decision those records rest on with the new parameters (both
+// only read the plan, so they run concurrently).  Chunks with a changed decision are planned again from scratch and
+// replayed again before the sums are formed; everything else of the result is already final.  Returns XT_RETRY when
+// the evaluation has to take the construction path instead.
+static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* d_out) {
+  const int nch = (int)ctx->chunks.size();
+  FusedLaunch fl;
+  if (is_var(p) || ctx->spec_maxC <= 0 || ctx->spec_maxC > 64 || !prepare_fused(ctx, p, ctx->spec_Pmax, &fl)) return XT_RETRY_EARLY;
+  int nt = k1_threads(ctx);
+  if (nt == 1024) nt = 512;
+  K1Args a = make_k1_args(ctx, bits);
+  a.chunk0 = 0;
+  a.vflag = ctx->d_vflag;
+  k1_scratch_caps(ctx, p, true, &a.scapP, &a.scapC);
+  if (a.scapC <= 0) return XT_RETRY_EARLY;
+  const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC, 0, nt);
+  XT_CUDA_OK(cudaMemsetAsync(ctx->d_spec, 0, sizeof(int), ctx->stream));
+  XT_CUDA_OK(cudaMemsetAsync(ctx->d_vflag, 0, sizeof(int32_t) * nch, ctx->stream));
+  XT_CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  XT_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamWaitEvent(ctx->cs[i], ctx->ev_fork, 0));
+  {
+    const cudaError_t e = xt_launch_k1_verify(a, *p, smem, nch, ctx->cs[0], nt);
+    if (e != cudaSuccess) {
+      set_error(ctx, std::string("plan verification launch: ") + cudaGetErrorString(e));
+      return XT_ERR_CUDA;
+    }
+    ctx->stats.k1_launches++;
+  }
+  int rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->cs[1]);
+  if (rc) return rc;
+  for (int i = 0; i < 2; ++i) {
+    XT_CUDA_OK(cudaEventRecord(ctx->ev_join[i], ctx->cs[i]));
+    XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+  }
+  XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  rc = enqueue_reduce(ctx, fl.tpt - 1, d_out);
+  if (rc) return rc;
+  XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_vflag, ctx->d_vflag, sizeof(int32_t) * nch, cudaMemcpyDeviceToHost, ctx->stream));
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (*ctx->h_spec) return XT_RETRY;
+  std::vector<int32_t> redo;
+  for (int c = 0; c < nch; ++c)
+    if (ctx->h_vflag[c]) redo.push_back(c);
+  ctx->stats.plan_verified = 1;
+  ctx->stats.replanned = (int)redo.size();
+  if (!redo.empty()) {
+    // a decision changed in some chunks: new plans for those (construction mode), their tiles replayed again
+    if ((int)redo.size() > 64 || (int)redo.size() * 4 > nch + 3) return XT_RETRY;
+    std::stable_sort(redo.begin(), redo.end(), [&](int x, int y) { return ctx->chunks[x].L > ctx->chunks[y].L; });
+    XT_CUDA_OK(cudaMemcpyAsync(ctx->d_redo, redo.data(), sizeof(int32_t) * redo.size(), cudaMemcpyHostToDevice, ctx->stream));
+    K1Args b = make_k1_args(ctx, bits);
+    b.chunk0 = 0;
+    b.corder = ctx->d_redo;
+    k1_scratch_caps(ctx, p, true, &b.scapP, &b.scapC);
+    const int ntc = k1_threads(ctx);
+    const size_t smem_c = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, b.scapP, b.scapC, 0, ntc);
+    const cudaError_t e = xt_launch_k1(b, *p, smem_c, (int)redo.size(), ctx->stream, ntc);
+    if (e != cudaSuccess) {
+      set_error(ctx, std::string("plan kernel launch (changed chunks): ") + cudaGetErrorString(e));
+      return XT_ERR_CUDA;
+    }
+    ctx->stats.k1_launches++;
+    XT_CUDA_OK(cudaMemcpyAsync(ctx->h_summ, ctx->d_summ, sizeof(XtChunkSummary) * nch, cudaMemcpyDeviceToHost, ctx->stream));
+    XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (int c : redo) {  // anything but a plain new plan within the sizes of this launch: full construction path
+      const XtChunkSummary& sm = ctx->h_summ[c];
+      if (sm.err != 0 || sm.max_nP > ctx->spec_Pmax) return XT_RETRY;
+    }
+    for (int c : redo) {
+      rc = enqueue_fused(ctx, p, fl, ctx->corder_pos[c], ctx->corder_pos[c] + 1, ctx->stream);
+      if (rc) return rc;
+    }
+    XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = enqueue_reduce(ctx, fl.tpt - 1, d_out);
+    if (rc) return rc;
+    XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_spec) return XT_RETRY;
+    for (int c : redo) ctx->summ[c] = ctx->h_summ[c];
+  }
+  int Pmax, maxC;
+  int64_t su, sg;
+  work_counters(ctx, p, &Pmax, &maxC, &su, &sg);
+  ctx->spec_Pmax = std::max(ctx->spec_Pmax, Pmax);
+  ctx->stats.pipelined = 1;
+  ctx->stats.n_tracks = ctx->n_tracks;
+  ctx->stats.track_steps = ctx->track_steps;
+  ctx->stats.seq_updates = su;
+  ctx->stats.seq_groups = sg;
+  ctx->stats.max_nB_in = maxC;
+  ctx->stats.n_chunks = nch;
+  ctx->last_p = *p;
+  ctx->have_eval = true;
+  mark_plan_valid(ctx, p);
   return XT_OK;
 }
 
@@ -1173,6 +1313,12 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
   if (rc) return rc;
   XT_CUDA_OK(cudaSetDevice(ctx->device));
   ctx->stats = xt_stats{};
+  if (!xyz && ctx->pipeline && ctx->plan_verify && ctx->plan_valid && ctx->last_fused && same_structure(*p, ctx->plan_sig)) {
+    rc = evaluate_verified(ctx, p, bits, d_out);
+    if (rc != XT_RETRY && rc != XT_RETRY_EARLY) return rc;
+    ctx->stats = xt_stats{};
+    ctx->plan_valid = false;
+  }
   if (ctx->pipeline && ctx->spec_Pmax > 0) {
     rc = evaluate_pipelined(ctx, p, bits, d_out, xyz);
     if (rc != XT_RETRY && rc != XT_RETRY_EARLY) return rc;
@@ -1201,7 +1347,9 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
     rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->stream);
     if (rc) return rc;
     ctx->last_fused = true;
-    return finish_eval(ctx, p, fl.tpt - 1, d_out, su, sg, maxC);
+    rc = finish_eval(ctx, p, fl.tpt - 1, d_out, su, sg, maxC);
+    if (rc == XT_OK) mark_plan_valid(ctx, p);
+    return rc;
   }
   if (ctx->last_fused || !ctx->plan_has_grec) {  // the plan was written without the records this path reads
     ctx->last_fused = false;
@@ -1287,6 +1435,11 @@ extern "C" int xt_sum_logp_async(xt_ctx* ctx, const xt_params* p, double* d_out,
 
 extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return XT_ERR_ARG;
+  ctx->plan_valid = false;  // (records and schedules depend on the options: the next evaluation plans from scratch)
+  if (std::strcmp(name, "plan_verify") == 0) {
+    ctx->plan_verify = value != 0;
+    return XT_OK;
+  }
   if (std::strcmp(name, "force_global_replay") == 0) {
     ctx->force_global = value != 0;
     ctx->have_eval = false;

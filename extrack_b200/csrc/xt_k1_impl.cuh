@@ -4,9 +4,9 @@
 #include "xt_launch.h"
 #include "xt_plan.cuh"
 
-template <int D, int KS, bool VAR, int NT, bool SS>
+template <int D, int KS, bool VAR, int NT, bool SS, bool VERIFY = false>
 static cudaError_t launch_k1_one(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream) {
-  auto kern = k1_plan<D, KS, VAR, NT, SS>;
+  auto kern = k1_plan<D, KS, VAR, NT, SS, VERIFY>;
   static unsigned long long smem_ok = 0;
   cudaError_t e = xt_allow_smem(kern, smem, &smem_ok);
   if (e != cudaSuccess) return e;
@@ -30,5 +30,15 @@ static cudaError_t launch_k1_nt(const K1Args& a, const xt_params& p, size_t smem
     XT_DISPATCH(p.d, p.n_loc, CALL_K1);
 #undef CALL_K1
   }
+  return e;
+}
+
+// verification mode (scalar models, scratch in shared memory)
+template <int NT>
+static cudaError_t launch_k1_verify_nt(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+#define CALL_K1Y(D_, KS_) e = launch_k1_one<D_, KS_, false, NT, true, true>(a, p, smem, n_chunks, stream)
+  XT_DISPATCH(p.d, p.n_loc, CALL_K1Y);
+#undef CALL_K1Y
   return e;
 }

@@ -46,6 +46,8 @@ inline bool xt_is_var(const xt_params* p) { return (p->flags & (XT_FLAG_VAR_LOC 
 
 // plan kernel (xt_plan.cuh); nthreads = 256, 512 or 1024
 cudaError_t xt_launch_k1(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream, int nthreads);
+// ... in verification mode (k1_plan<.., VERIFY>): scalar models, scratch in shared memory, nthreads = 256 or 512
+cudaError_t xt_launch_k1_verify(const K1Args& a, const xt_params& p, size_t smem, int n_chunks, cudaStream_t stream, int nthreads);
 // fused replay kernel, FP64 (xt_replay_fused.cuh): shared-memory state, GST or VAR instantiation
 cudaError_t xt_launch_k2_fused(int d, int ks, const K2FArgs& a, const K2Tab& tab, size_t smem, int wpc, int tpt,
                                cudaStream_t stream, bool var);

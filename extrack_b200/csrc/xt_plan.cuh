@@ -42,6 +42,8 @@ struct K1Args {
   int32_t scapP, scapC;
   int32_t want_grec;   // also emit the inline group records of the first-generation replay kernel
   int32_t batch_mode;  // grouping of more than 64 sequences: 1 = batched candidate leaders, 0 = one leader at a time
+  int32_t* vflag;      // VERIFY instantiation: [n_chunks] 0 = every decision of the resident plan was reproduced, else the step
+                       // (>= 2) at which one changed (or 1: the plan has no verification records for this chunk)
   int32_t lpt;         // replay schedule: 1 = longest-processing-time-first (<= 64 groups, <= 4 replay warps), 0 = round-robin
   int32_t cost[4];     // cost model of the schedule: single-member group, pair, member list (cost[2] + cost[3] * members)
   XtAux ax;            // VAR instantiation only
@@ -76,9 +78,16 @@ __device__ __forceinline__ int xt_label(int x, int nS, bool wrap) {
 // the GPU has SMs (long tracks: the per-step phases then run in a quarter of the rounds)
 // SS: the scratch is known at compile time to be in shared memory (scapC > 0): the accesses then compile
 // to shared-memory instructions with 32-bit addresses instead of generic loads / stores.
-template <int D, int KS, bool VAR, int NT, bool SS = false>
+// VERIFY: plan verification instead of plan construction (scalar models, matrix-mode plans).  The leader tracks are
+// advanced with the same arithmetic (update, merge) along the RESIDENT plan, and every floating-point decision that plan
+// rests on (XtVRec) is re-evaluated with the parameters of this evaluation; codes, histories, member lists and replay
+// records are pure functions of the decisions, so they stay valid exactly as long as every decision is reproduced.  The
+// replay kernel can therefore run concurrently on the resident records; a chunk whose verification fails is planned
+// again from scratch (and replayed again) before the result is used.
+template <int D, int KS, bool VAR, int NT, bool SS = false, bool VERIFY = false>
 __global__ void __launch_bounds__(NT, NT == XT_K1_THREADS ? XT_K1_MIN_CTAS : 1)
 k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
+  static_assert(!VERIFY || (!VAR && SS), "verification mode: scalar models with the scratch in shared memory");
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
   constexpr int W = NT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
@@ -100,6 +109,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   unsigned char* curP = (unsigned char*)(gcnt + cap + 1);
   __shared__ int s_flag, s_nG, s_left, s_cand[NT / 32];
   __shared__ unsigned long long s_rows[64];  // capture matrix of the matrix-mode grouping
+  __shared__ unsigned long long s_todo[64];  // ... and, per row, the sequences its floating-point predicate was evaluated for
   __shared__ __align__(4) unsigned char s_js[(NT / 32) * 72];  // matrix mode: per warp, the sequences a row still has to test
   // batch mode: grouped bit mask and one bit row per candidate (= per warp), BW words each
   const int BW = (cap + 63) / 64;
@@ -108,7 +118,11 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 
   XtChunkSummary* sm = &a.summ[cid];
   const int nP0 = K * nS;
-  if (tid == 0) {
+  if (VERIFY) {
+    if (tid == 0) s_flag = 0;
+    if (ck.L < 4) return;  // no fusion step, nothing to verify
+  }
+  if (!VERIFY && tid == 0) {
     sm->err = 0;
     sm->need_cap = 0;
     sm->max_nP = nP0;
@@ -168,7 +182,9 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     }
   }
   if (scapC > 0 && nP0 > scapP) {
-    if (tid == 0) sm->err = 3;
+    if (tid == 0) {
+      if (VERIFY) a.vflag[cid] = 1; else sm->err = 3;
+    }
     return;
   }
   const int bits = a.bits;
@@ -226,6 +242,9 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     ST(bufP, c, D + 2 * KS) = __dadd_rn(P.LT[c], P.LF[c]);
   }
   int LhP = nsub + 1;
+  if (VERIFY) {
+    for (int c = tid; c < nP; c += NT) curP[c] = (unsigned char)(c % nS);
+  } else
   for (int c = tid; c < nP; c += NT) {
     curP[c] = (unsigned char)(c % nS);
     unsigned long long code = 0;
@@ -253,6 +272,13 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   for (int dim = 0; dim < D; ++dim) cnext[dim] = Cp[(size_t)(1 * D + dim) * npad];  // step 2 consumes localisation 1
   for (int step = 2; step <= L - 2; ++step) {
     const int nC = nP * K;
+    if (VERIFY) {  // the resident plan must describe this very step in matrix mode (uniform: same words for every thread)
+      const int rec_v = ck.rec0 + (step - 2);
+      if (nC > cap || nC > scapC || nC > 64 || a.plan.hdr[rec_v].nC != nC || !a.plan.vok[rec_v] || a.plan.hdr[rec_v].nG > scapP) {
+        if (tid == 0) a.vflag[cid] = 1;
+        return;
+      }
+    } else {
     if (nC > cap) {
       if (tid == 0) {
         sm->err = 2;
@@ -263,6 +289,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     if (scapC > 0 && nC > scapC) {  // more children than the shared-memory scratch was sized for
       if (tid == 0) sm->err = 3;
       return;
+    }
     }
     sum_nC += nC;
     max_nC = nC > max_nC ? nC : max_nC;
@@ -336,6 +363,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
     }
     // window codes of the children: nsub new labels in front of the parent's rows
+    if (!VERIFY)
     for (int c = tid; c < nC; c += NT) {
       const int p = c / K;
       unsigned long long code = codeP[p] << (bits * nsub);
@@ -439,7 +467,56 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     };
 
     int nG = 0;
-    if (nC <= 64) {
+    if (VERIFY) {
+      // ---- verification: the member lists of the resident plan, and every floating-point decision behind them ----
+      nG = a.plan.hdr[rec].nG;
+      for (int c = tid; c < nC; c += NT) ent[c] = gent[c];
+      for (int g = tid; g <= nG; g += NT) gcnt[g] = (int)goff[g];
+      const XtVRec* vr = a.plan.vrec + (size_t)rec * XT_VREC_PER_STEP;
+      for (int g = warp; g < nG; g += W) {
+        const XtVRec v = vr[g];
+        const int i = (int)v.lead;
+        double mi[D], si[KS];
+#pragma unroll
+        for (int dim = 0; dim < D; ++dim) mi[dim] = ldC(i, dim);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) si[k] = ldC(i, D + KS + k);
+        const unsigned long long todo = v.cand;
+        const int ntodo = __popcll(todo);
+        unsigned add_lo = 0u, add_hi = 0u;
+        if (ntodo) {
+          unsigned char* myjs = s_js + warp * 72;
+          const unsigned tlo = (unsigned)todo, thi = (unsigned)(todo >> 32);
+          const unsigned below = (1u << lane) - 1u;
+          if ((tlo >> lane) & 1u) myjs[__popc(tlo & below)] = (unsigned char)lane;
+          if ((thi >> lane) & 1u) myjs[__popc(tlo) + __popc(thi & below)] = (unsigned char)(lane + 32);
+          if (lane < 3) myjs[ntodo + lane] = (unsigned char)(__ffsll((long long)todo) - 1);
+          __syncwarp();
+          for (int r0 = 0; r0 < ntodo; r0 += 4) {
+            const unsigned jj = *reinterpret_cast<const unsigned*>(myjs + r0);
+            const int js[4] = {(int)(jj & 0xFFu), (int)((jj >> 8) & 0xFFu), (int)((jj >> 16) & 0xFFu), (int)(jj >> 24)};
+            bool ok[4];
+            fp_ok4(mi, si, js, ok);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const unsigned bit = (r0 + q < ntodo && ok[q]) ? 1u << (js[q] & 31) : 0u;
+              if (js[q] & 32) add_hi |= bit; else add_lo |= bit;
+            }
+          }
+          __syncwarp();
+        }
+        const unsigned long long got = (unsigned long long)add_lo | ((unsigned long long)add_hi << 32);
+        if (got != v.exp && lane == 0) s_flag = 1;  // a decision changed: this chunk needs a new plan
+      }
+      __syncthreads();
+      if (s_flag) {
+        if (tid == 0) a.vflag[cid] = step;
+        return;
+      }
+      // newest true state of the groups (next step's parents): curP is not read again before the end-of-step barrier
+      const uint8_t* pcur_v = a.plan.curG + (size_t)rec * a.plan.cap;
+      for (int g = tid; g < nG; g += NT) curP[g] = pcur_v[g];
+    } else if (nC <= 64) {
       // ---- matrix mode ----
       // Phase 1 (parallel, no dependency between leaders): row i of the capture matrix for every
       // sequence i, restricted to j >= i.  The greedy loop of the reference visits leaders in
@@ -497,7 +574,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
           __syncwarp();  // the next row of this warp reuses the list
         }
         row |= (unsigned long long)add_lo | ((unsigned long long)add_hi << 32);
-        if (lane == 0) s_rows[i] = row;
+        if (lane == 0) {
+          s_rows[i] = row;
+          s_todo[i] = todo;
+        }
       }
       __syncthreads();
       K1_T(1);
@@ -530,7 +610,15 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
           }
           if (mem & bit0) { myg[0] = ng; myoff[0] = off; mymem[0] = mem; }
           if (mem & bit1) { myg[1] = ng; myoff[1] = off; mymem[1] = mem; }
-          if (lane == 0) gcnt[ng] = off;
+          if (lane == 0) {
+            gcnt[ng] = off;
+            // verification record: the floating-point decisions this leader's capture rests on
+            const unsigned long long cand = s_todo[i] & ~grouped;
+            XtVRec* vw = a.plan.vrec + (size_t)rec * XT_VREC_PER_STEP + ng;
+            vw->lead = (unsigned long long)i;
+            vw->cand = cand;
+            vw->exp = mem & cand;
+          }
           off += __popcll(mem);
           grouped |= mem;
           rem &= ~mem;
@@ -742,6 +830,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       }
       __syncthreads();  // ent visible to the CTA
     }
+    const int rows_out = rows_cmp;  // history rows kept: truncated to frame_len
+    int ro_sh = 0;  // rows padded to a power of two: (group, row) of a thread by shifts
+    while ((1 << ro_sh) < rows_out) ++ro_sh;
+    if (!VERIFY) {
     if (scapC > 0 && nG > scapP) {  // more groups than parent slots in shared memory
       if (tid == 0) sm->err = 3;
       return;
@@ -759,10 +851,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       a.plan.hdr[rec].nC = nC;
       a.plan.hdr[rec].nG = nG;
       a.plan.hdr[rec].th = th;
+      a.plan.vok[rec] = (uint8_t)(nC <= 64);  // matrix mode: the verification records describe the step completely
     }
     // ---- history rows of the groups (fit mode: mean one-hot over members and leader tracks,
     //      tracking.py:714-715,735-737), accumulated in numpy's (member, track) order ----
-    const int rows_out = rows_cmp;  // truncated to frame_len
     const int Kh = hist_dim0_is_nT ? Kt : 1;
     // one thread per (group, row): the nS values of the row, then their argmax (ties -> lowest
     // state) goes straight into the group's window code.  The sums run in numpy's order for the
@@ -775,8 +867,6 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     const long long h_t0 = clock64();
     unsigned h_slow = 0, h_mem = 0, h_slowcyc = 0;
 #endif
-    int ro_sh = 0;  // rows padded to a power of two: (group, row) of a thread by shifts
-    while ((1 << ro_sh) < rows_out) ++ro_sh;
     for (int idx = tid; (idx >> ro_sh) < nG; idx += NT) {
       const int row = idx & ((1 << ro_sh) - 1), g = idx >> ro_sh;
       if (row >= rows_out) continue;
@@ -1016,6 +1106,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
       uint32_t* bent = (uint32_t*)(blob + 2 + (nG + 1) / 2);
       for (int c = rtid; c < nC; c += NT) bent[c] = ent[c];
     }
+    }  // !VERIFY
 
     K1_T(5);
     // ---- merge on the leader tracks (tracking.py:723-741) ----
@@ -1023,7 +1114,7 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
     // members runs sequentially in ascending member order (checked against numpy 2.3).
     // (warps whose threads hold history rows merge fewer groups: with <= 128 rows the merge runs
     // on the upper half of the CTA)
-    const int mw0 = ((nG << ro_sh) <= NT / 2) ? W / 2 : 0, mW = W - mw0;
+    const int mw0 = (!VERIFY && (nG << ro_sh) <= NT / 2) ? W / 2 : 0, mW = W - mw0;
     for (int g = warp - mw0; g >= 0 && g < nG; g += mW) {
       const int o = gcnt[g], n = gcnt[g + 1] - o;
       if (n == 1) {
@@ -1088,6 +1179,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
 #ifdef XT_K1_PROF
   if (tid == 0 && a.prof) for (int i = 0; i < 12; ++i) a.prof[(size_t)cid * 12 + i] = prof[i];
 #endif
+  if (VERIFY) {
+    if (tid == 0) a.vflag[cid] = 0;
+    return;
+  }
   if (tid == 0) {
     // last step (no fusion) and the optional end-of-track expansion, for the work counters
     const int nC = nP * K;

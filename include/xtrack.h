@@ -89,6 +89,8 @@ typedef struct xt_stats {
   int32_t k3_launches;   /* kernel launches of the last xt_predict call (> 1: the sequence capacity had to grow) */
   int32_t k3_cap;        /* sequence capacity of the last xt_predict launch */
   int32_t fp32;          /* 1: the last evaluation's replay ran in the optional FP32 kernel ("fp32_replay") */
+  int32_t plan_verified; /* 1: the evaluation ran along the resident plan, every decision of it re-evaluated (verification mode) */
+  int32_t replanned;     /* ... and this many chunks had a changed decision and were planned (and replayed) again */
 } xt_stats;
 
 /* Number of visible CUDA devices (0 without a driver or GPU; never an error). */

@@ -693,3 +693,52 @@ def test_param_fitting_uses_several_devices_from_one_process(xt, monkeypatch):
     assert a.residual[0] == b.residual[0]
     for k in a.params:
         assert a.params[k].value == b.params[k].value
+
+
+# ---- plan verification: evaluations along the resident plan, every decision re-evaluated ----
+def test_plan_verification_reproduces_planning_from_scratch(native, xt):
+    """After one evaluation the plan stays resident; the next evaluations re-evaluate every floating-point decision
+    behind it (k1_plan<.., VERIFY>) while the replay runs on the resident records.  Same bits as an engine that plans
+    from scratch: for BFGS-like perturbations (nothing changes), for a moderate move (some chunks are planned again)
+    and for a jump / another frame_len (construction path)."""
+    rng = np.random.default_rng(77)
+    st = [random_walk_tracks(n, L, 2, rng) for L, n in ((8, 4100), (13, 2500), (19, 2100), (27, 700))]
+    a, b = xt.TrackSet(st, 2000), xt.TrackSet(st, 2000)
+    b.engine.set_option("plan_verify", 0)
+    try:
+        def both(model):
+            p = engine_params(model, 2)
+            va, vb = a.sum_logp(p), b.sum_logp(p)
+            assert va == vb
+            assert b.engine.stats()["plan_verified"] == 0
+            return a.engine.stats()
+
+        base = dict(frame_len=7, min_len=8, Ds=[1e-4, 0.22], Fs=[0.55, 0.45], loc_err=(0.021,), rates=0.12, pBL=0.07)
+        s = both(make_model(**base))
+        assert s["plan_verified"] == 0                      # first evaluation: nothing resident yet
+        for k in range(6):                                  # finite-difference pattern: one parameter, 1.5e-8 relative
+            kw = dict(base)
+            kw["loc_err"] = (0.021 * (1 + 1.5e-8 * (k + 1)),)
+            kw["Ds"] = [1e-4, 0.22 * (1 + 1.5e-8 * k)]
+            s = both(make_model(**kw))
+            assert s["plan_verified"] == 1 and s["replanned"] == 0
+        kw = dict(base, Ds=[1e-4, 0.2215], loc_err=(0.0212,))  # a small line-search move: decisions change somewhere
+        s = both(make_model(**kw))
+        moved = (s["plan_verified"], s["replanned"])
+        s = both(make_model(**kw))                          # and the (partly) new plan is verified again
+        assert s["plan_verified"] == 1 and s["replanned"] == 0
+        s = both(make_model(**dict(base, Ds=[1e-3, 0.9], loc_err=(0.04,), rates=0.3)))  # jump
+        s = both(make_model(**dict(base, frame_len=5)))     # other model shape: construction path
+        assert s["plan_verified"] == 0
+        s = both(make_model(**dict(base, frame_len=5, pBL=0.0700001)))
+        assert s["plan_verified"] == 1
+        print("line-search move served as (verified, chunks planned again):", moved)
+        # per-track values too
+        p = engine_params(make_model(**dict(base, frame_len=5, pBL=0.0700002)), 2)
+        for c in (0, len(a.chunks) - 1):
+            bb, aa, zz, _ = a.chunks[c]
+            np.testing.assert_array_equal(a.engine.chunk_logp(c, zz - aa, p), b.engine.chunk_logp(c, zz - aa, p))
+        assert a.engine.stats()["plan_verified"] == 1
+    finally:
+        a.close()
+        b.close()

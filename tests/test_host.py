@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_params_struct_layout_matches_header():
     assert ctypes.sizeof(_native.XtParams) == 8 * 4 + 8 + 8 * 3 + 5 * 8 * _native.XT_MAX_HEADS + 8 * _native.XT_MAX_STATES + 2 * 8
-    assert ctypes.sizeof(_native.XtStats) == 4 * 8 + 4 * 4 + 2 * 4 + 2 * 4 + 2 * 4 + 4 + 4  # (+ fp32, + tail padding)
+    assert ctypes.sizeof(_native.XtStats) == 4 * 8 + 4 * 4 + 2 * 4 + 2 * 4 + 2 * 4 + 4 + 4 + 2 * 4  # (+ fp32, tail padding, plan_verified, replanned)
 
 
 def test_engine_fails_loudly_without_gpu(gpu_available):
