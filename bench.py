@@ -55,6 +55,24 @@ def eval_params():
     return p
 
 
+def param_variants(min_len, n=8):
+    """Parameter tables of consecutive objective calls the way BFGS makes them: the base point, then one parameter at a
+    time moved by 1.5e-8 relative (scipy's finite-difference step).  Every timed step uses the next table, so no two
+    consecutive evaluations see the same numbers."""
+    from extrack_b200 import tracking as xt
+
+    out = []
+    names = [None, "D1", "LocErr", "F0", "p01", "p10", "pBL", "D0"]
+    for i in range(n):
+        params = eval_params()
+        k = names[i % len(names)]
+        if k is not None:
+            params[k].value = EVAL[k] * (1.0 + 1.5e-8 * (1 + i // len(names)))
+        LocErr, ds, Fs, TrMat, pBL = xt.extract_params(params, DT, 2, 1)
+        out.append(xt.build_tables(LocErr, ds, Fs, TrMat, pBL, CELL, 1, FRAME_LEN, min_len, THRESHOLD, MAX_NB_STATES, 2))
+    return out
+
+
 def oracle_model(min_len):
     import numpy as np
 
@@ -151,9 +169,14 @@ def _time_sharded(ts, p, steps, local, world):
     stream = torch.cuda.current_stream().cuda_stream
     eng = ts.engine
 
+    plist = p if isinstance(p, (list, tuple)) else [p]
+    p = plist[0]
+    count = [0]
+
     def step():
         if ts.n_local_chunks:
-            eng.sum_logp_async(p, buf.data_ptr(), stream)
+            eng.sum_logp_async(plist[count[0] % len(plist)], buf.data_ptr(), stream)
+            count[0] += 1
         else:
             buf.zero_()
         if world > 1:
@@ -411,8 +434,13 @@ def main():
     buf = torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}")
     stream = torch.cuda.current_stream().cuda_stream
 
+    pvar = param_variants(st[0].shape[1])  # pvar[0] = p; the others differ by one BFGS finite-difference step each
+    nstep = [0]
+    served = {"verified": 0, "chunks_planned_again": 0, "planned_from_scratch": 0}
+
     def step():
-        eng.sum_logp_async(p, buf.data_ptr(), stream)
+        eng.sum_logp_async(pvar[nstep[0] % len(pvar)], buf.data_ptr(), stream)
+        nstep[0] += 1
         if world > 1:
             dist.all_reduce(buf)
 
@@ -435,9 +463,15 @@ def main():
         step()
         s = eng.stats()
         launches += s["k1_launches"] + s["k2_launches"]
+        served["verified" if s["plan_verified"] else "planned_from_scratch"] += 1
+        served["chunks_planned_again"] += s["replanned"]
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    eng.sum_logp_async(p, buf.data_ptr(), stream)  # (untimed) the base parameters again: `sum_logp` of the line
+    if world > 1:
+        dist.all_reduce(buf)
+    torch.cuda.synchronize()
     total = float(buf.item())
     stats = eng.stats()
     total_local = eng.sum_logp(p)  # this rank's own sum (== total on one GPU)
@@ -519,12 +553,12 @@ def main():
     if not args.no_secondary:
         ksteps2 = max(5, min(50, args.steps))
         # one GPU holding every chunk of the seed-0 data set: that is rank 0's own (weak-scaling) data set
-        ms_one = _time_sharded(ts, p, ksteps2, local, 1)[0] if rank == 0 else 0.0
+        ms_one = _time_sharded(ts, pvar, ksteps2, local, 1)[0] if rank == 0 else 0.0
         ms_one = _dist_max(ms_one, local, world)
         if world > 1:
             st0 = st if rank == 0 else xt._sorted_buckets(sim_tracks(args.tracks, seed=0, device=f"cuda:{local}", **SIM_KW))[0]
             torch.cuda.empty_cache()
-            strong = strong_block(st0, p, ksteps2, local, rank, world, ms_one)
+            strong = strong_block(st0, pvar, ksteps2, local, rank, world, ms_one)
             del st0
         else:
             strong = {"what": "one GPU: the strong-scaling split is the headline itself", "n_gpus": 1, "tracks": int(stats["n_tracks"]),
@@ -586,6 +620,13 @@ def main():
                             "bucket with the plan / replay kernels, result read back",
                     "parity_rel_diff_vs_resident": abs(e2e_val - total) / abs(total)},
             "gpu_launches": int(launches),
+            "plan": {"steps_verified": served["verified"], "steps_planned_from_scratch": served["planned_from_scratch"],
+                     "chunks_planned_again": served["chunks_planned_again"],
+                     "what": "every timed step evaluates other parameters than the step before (one parameter moved by 1.5e-8 relative, "
+                             "the finite-difference pattern of BFGS).  `verified`: the evaluation ran along the resident plan while the "
+                             "plan kernel re-evaluated every floating-point decision behind it (k1_plan<VERIFY>, concurrent with the "
+                             "replay); a chunk with a changed decision is planned and replayed again inside the step.  "
+                             "kernel_ms / roofline are the construction-mode kernels (one plan launch, one replay launch)"},
             "seq_updates_per_s": float(stats["seq_updates"]) * world * args.steps / (ms * 1e-3),  # sum of nT * nB_in per step
 
             "kernel_ms": {"plan": ms_plan, "replay_and_reduce": replay_ms,

@@ -86,6 +86,7 @@ struct xt_ctx {
   // on the host, so its bits do not depend on how the chunks are spread over GPUs (xt_multi_*)
   double* d_csum = nullptr;
   double* h_csum = nullptr;                 // pinned
+  bool csum_fetched = false;                // h_csum already holds the chunk sums of the last evaluation
   int32_t* d_cw0[3] = {nullptr, nullptr, nullptr};  // first tile of every position: [0],[1] fused tables (corder), [2] plain table
   XtChunkSummary* d_summ = nullptr;
   std::vector<XtChunkSummary> summ;
@@ -887,8 +888,10 @@ static int enqueue_reduce(xt_ctx* ctx, int table, double* d_out) {
 // objective of this context: the chunk sums added in chunk order on the host (after the evaluation)
 static int read_total(xt_ctx* ctx, double* out) {
   const size_t nch = ctx->chunks.size();
-  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_csum, ctx->d_csum, sizeof(double) * nch, cudaMemcpyDeviceToHost, ctx->stream));
-  XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->csum_fetched) {
+    XT_CUDA_OK(cudaMemcpyAsync(ctx->h_csum, ctx->d_csum, sizeof(double) * nch, cudaMemcpyDeviceToHost, ctx->stream));
+    XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
   double acc = 0.0;
   for (size_t c = 0; c < nch; ++c) acc += ctx->h_csum[c];
   *out = acc;
@@ -1242,14 +1245,17 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
   XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_vflag, ctx->d_vflag, sizeof(int32_t) * nch, cudaMemcpyDeviceToHost, ctx->stream));
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_csum, ctx->d_csum, sizeof(double) * nch, cudaMemcpyDeviceToHost, ctx->stream));  // one round trip
   XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   if (*ctx->h_spec) return XT_RETRY;
+  ctx->csum_fetched = true;
   std::vector<int32_t> redo;
   for (int c = 0; c < nch; ++c)
     if (ctx->h_vflag[c]) redo.push_back(c);
   ctx->stats.plan_verified = 1;
   ctx->stats.replanned = (int)redo.size();
   if (!redo.empty()) {
+    ctx->csum_fetched = false;
     // a decision changed in some chunks: new plans for those (construction mode), their tiles replayed again
     if ((int)redo.size() > 64 || (int)redo.size() * 4 > nch + 3) return XT_RETRY;
     std::stable_sort(redo.begin(), redo.end(), [&](int x, int y) { return ctx->chunks[x].L > ctx->chunks[y].L; });
@@ -1313,6 +1319,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
   if (rc) return rc;
   XT_CUDA_OK(cudaSetDevice(ctx->device));
   ctx->stats = xt_stats{};
+  ctx->csum_fetched = false;
   if (!xyz && ctx->pipeline && ctx->plan_verify && ctx->plan_valid && ctx->last_fused && same_structure(*p, ctx->plan_sig)) {
     rc = evaluate_verified(ctx, p, bits, d_out);
     if (rc != XT_RETRY && rc != XT_RETRY_EARLY) return rc;

@@ -260,6 +260,7 @@ extern "C" int xt_multi_sum_logp(xt_multi* m, const xt_params* p, double* out) {
     if (m->gchunks[g].empty()) return XT_OK;
     int r = evaluate(c, p, nullptr, nullptr);
     if (r) return r;
+    if (c->csum_fetched) return XT_OK;  // (the verified evaluation already fetched the chunk sums)
     if (cudaMemcpyAsync(c->h_csum, c->d_csum, sizeof(double) * c->chunks.size(), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
         cudaStreamSynchronize(c->stream) != cudaSuccess) {
       c->err = "xt_multi_sum_logp: read-back of the chunk sums failed";
