@@ -235,6 +235,44 @@ def strong_block(st0, p, steps, local, rank, world, ms_one_gpu):
             "kernel_ms_max_over_ranks": {"plan": plan, "replay_and_reduce": replay}, "sum_logp": total}
 
 
+def in_process_block(st0, pvar, steps, rank, world, ms_one_gpu):
+    """Strong scaling of the same data set with ONE Python process driving the N GPUs through TrackSet(devices=...)
+    (xt_multi_*: per-device worker threads, per-chunk sums added in global chunk order, no collective)."""
+    import torch.distributed as dist
+
+    from extrack_b200 import _native
+    from extrack_b200 import tracking as xt
+
+    store = dist.distributed_c10d._get_default_store()
+    out = None
+    if rank == 0:
+        try:
+            if _native.device_count() < world:
+                raise RuntimeError("fewer visible devices than ranks")
+            ts = xt.TrackSet(st0, devices=list(range(world)), rank=0, world_size=1)
+            for p in pvar * 2:
+                ts.sum_logp(p)
+            n = max(steps, len(pvar))
+            t = time.perf_counter()
+            for i in range(n):
+                v = ts.sum_logp(pvar[i % len(pvar)])
+            ms = (time.perf_counter() - t) / n * 1e3
+            st_ = ts.engine.stats()
+            load = ts.engine.device_load()
+            all_steps = sum((a.shape[1] - 1) * a.shape[0] for a in st0)
+            out = {"what": "one process, N GPUs: TrackSet(devices=range(N)).sum_logp, wall clock per call incl. the read-back",
+                   "n_gpus": world, "ms_per_eval": ms, "value": all_steps / (ms * 1e-3), "unit": UNIT,
+                   "efficiency_vs_one_gpu": ms_one_gpu / (world * ms), "chunks_per_device": [c for _, c, _ in load],
+                   "plan_verified": int(st_["plan_verified"]), "sum_logp_last": v}
+            ts.close()
+        except Exception as e:  # noqa: BLE001 - reported in the line, the other ranks must be released
+            out = {"error": repr(e)}
+        store.set("xt_in_process_done", "1")
+    else:
+        store.wait(["xt_in_process_done"])
+    return out
+
+
 def api_block(ts, st, n_calls=60):
     """One evaluation through the Python objective `extrack_b200.tracking.cum_Proba_Cs` (parameter extraction, the
     field-of-view table with its 1000-point ndtr, the ctypes call, the read-back) on the resident data set, with
@@ -559,6 +597,9 @@ def main():
             st0 = st if rank == 0 else xt._sorted_buckets(sim_tracks(args.tracks, seed=0, device=f"cuda:{local}", **SIM_KW))[0]
             torch.cuda.empty_cache()
             strong = strong_block(st0, pvar, ksteps2, local, rank, world, ms_one)
+            # the same split driven by ONE process (xt_multi_*: what a notebook / GUI caller of param_fitting gets with
+            # workers = N): rank 0 drives all N GPUs while the other ranks wait on the store (no GPU work, no collective)
+            strong["in_process"] = in_process_block(st0, pvar, ksteps2, rank, world, ms_one)
             del st0
         else:
             strong = {"what": "one GPU: the strong-scaling split is the headline itself", "n_gpus": 1, "tracks": int(stats["n_tracks"]),

@@ -38,6 +38,8 @@ if not HAVE_LMFIT:
     }
     _SAFE_FUNCS.update({"abs": abs, "min": min, "max": max})
 
+    _EXPR_CODE = {}
+
     class Parameter:
         """One named fit parameter (subset of ``lmfit.Parameter``)."""
 
@@ -111,7 +113,9 @@ if not HAVE_LMFIT:
                 if p.expr is None:
                     names[k] = p._val
             # resolve nested expressions on demand
-            code = compile(expr, "<expr>", "eval")
+            code = _EXPR_CODE.get(expr)
+            if code is None:
+                code = _EXPR_CODE[expr] = compile(expr, "<expr>", "eval")  # (constraint expressions are evaluated at every objective call)
             for n in code.co_names:
                 if n not in names and n in self:
                     names[n] = self._eval(OrderedDict.__getitem__(self, n).expr, _depth + 1)

@@ -1,6 +1,7 @@
 // Translation unit of the state-annotation kernel (k3_predict).
 #include "xt_launch.h"
 #include "xt_predict.cuh"
+#include "xt_predict_shared.cuh"
 
 template <int D, int KS, bool VAR>
 static cudaError_t launch_k3_v(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
@@ -19,5 +20,35 @@ cudaError_t xt_launch_k3(const K3Args& a, const xt_params& p, int grid, int nwar
   e = var ? launch_k3_v<D_, KS_, true>(a, p, grid, nwarps, smem, stream) : launch_k3_v<D_, KS_, false>(a, p, grid, nwarps, smem, stream)
   XT_DISPATCH(p.d, p.n_loc, CALL_K3);
 #undef CALL_K3
+  return e;
+}
+
+// predict_Bs with nb_max > 1: the plans shared by the tracks of a chunk, then the annotation that follows them
+template <int D, int KS>
+static cudaError_t launch_k3s(const K3SArgs& a, const xt_params& p, int grid, cudaStream_t stream) {
+  k3_shared_plan<D, KS><<<grid, 256, 0, stream>>>(a, p);
+  return cudaGetLastError();
+}
+cudaError_t xt_launch_k3_shared_plan(const K3SArgs& a, const xt_params& p, int grid, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+#define CALL_K3S(D_, KS_) e = launch_k3s<D_, KS_>(a, p, grid, stream)
+  XT_DISPATCH(p.d, p.n_loc, CALL_K3S);
+#undef CALL_K3S
+  return e;
+}
+template <int D, int KS>
+static cudaError_t launch_k3f(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
+  auto kern = k3_predict<D, KS, false, true>;
+  static unsigned long long smem_ok = 0;
+  cudaError_t e = xt_allow_smem(kern, smem, &smem_ok);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32 * nwarps, smem, stream>>>(a, p);
+  return cudaGetLastError();
+}
+cudaError_t xt_launch_k3_follow(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+#define CALL_K3F(D_, KS_) e = launch_k3f<D_, KS_>(a, p, grid, nwarps, smem, stream)
+  XT_DISPATCH(p.d, p.n_loc, CALL_K3F);
+#undef CALL_K3F
   return e;
 }

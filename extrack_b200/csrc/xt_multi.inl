@@ -308,6 +308,7 @@ extern "C" int xt_multi_device_load(xt_multi* m, int32_t g, int32_t* device, int
 extern "C" int xt_multi_get_stats(xt_multi* m, xt_stats* out) {
   if (!m || !out) return XT_ERR_ARG;
   xt_stats acc{};
+  bool first = true;
   for (size_t g = 0; g < m->ctx.size(); ++g) {
     if (m->gchunks.empty() || m->gchunks[g].empty()) continue;
     xt_stats s{};
@@ -328,6 +329,9 @@ extern "C" int xt_multi_get_stats(xt_multi* m, xt_stats* out) {
     acc.ms_replay = std::max(acc.ms_replay, s.ms_replay);
     acc.pipelined = s.pipelined;
     acc.fp32 = s.fp32;
+    acc.plan_verified = (first || acc.plan_verified) && s.plan_verified;  // 1: every device ran along its resident plan
+    first = false;
+    acc.replanned += s.replanned;
   }
   *out = acc;
   return XT_OK;

@@ -35,6 +35,10 @@ struct K3Args {
   size_t warp_scratch; // 8-byte units per warp in `scratch`: cold part (+ hot part unless hot_smem)
   int32_t hot_smem;    // 1: the hot part of every warp is in dynamic shared memory
   XtAux ax;            // VAR instantiation only; stay = [n_tracks][K] Lp_stay, leave = [n_tracks][nS] log-sums
+  // FOLLOW instantiation (predict_Bs with nb_max > 1): the groups of every fusion step come from the chunk's shared
+  // plan (k3_shared_plan, xt_predict_shared.cuh) instead of this track's own decisions
+  const int32_t* splan;  // [n_chunks][splan_stride]: nC[maxL], nG[maxL], then per step goff[cap + 1], order[cap]
+  size_t splan_stride;
 };
 
 // per-warp scratch layout, in 8-byte units: the *hot* part (state of the forward pass, touched at
@@ -71,8 +75,9 @@ __host__ __device__ inline K3Layout k3_layout(int cap, int CO, int fl, int nS, i
   return l;
 }
 
-template <int D, int KS, bool VAR = false>
+template <int D, int KS, bool VAR = false, bool FOLLOW = false>
 __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, const __grid_constant__ xt_params P) {
+  static_assert(!(VAR && FOLLOW), "shared plans are built for scalar LocErr / dt models");
   extern __shared__ double k3_smem[];
   const int nwarps = blockDim.x >> 5;  // <= XT_K3_WARPS (fewer when the hot scratch of 8 warps exceeds shared memory)
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
@@ -226,6 +231,18 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         // ---- greedy grouping from this track alone (tracking.py:667-698 with one leader track) ----
         const double th_lo = __dmul_rn(th, 1.0 - 1e-14), th_hi = __dmul_rn(th, 1.0 + 1e-14);
         int nG = 0, off = 0;
+        if (FOLLOW) {  // the chunk's shared plan: member lists of this step
+          const int32_t* plan = a.splan + (size_t)wk.chunk * a.splan_stride;
+          const int32_t* pl = plan + 2 * a.maxL + (size_t)step * (2 * cap + 1);
+          nG = plan[a.maxL + step];
+          if (plan[step] != nC || nG < 1 || nG > nC) errc = 1;  // (cannot happen: same expansion, same groups)
+          else {
+            for (int g = lane; g <= nG; g += 32) goff[g] = pl[g];
+            for (int c = lane; c < nC; c += 32) order[c] = pl[cap + 1 + c];
+            off = nC;
+          }
+          __syncwarp();
+        } else
         for (int i = 0; i < nC; ++i) {
           if (gid[i] >= 0) continue;  // warp-uniform (memory made visible by __syncwarp)
           double mi[D], si[KS];
@@ -282,9 +299,11 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
           ++nG;
           __syncwarp();
         }
-        if (lane == 0) goff[nG] = off;
-        for (int c = lane; c < nC; c += 32)
-          if (gid[c] < 0) errc = 1;  // tracking.py:700-701
+        if (!FOLLOW) {
+          if (lane == 0) goff[nG] = off;
+          for (int c = lane; c < nC; c += 32)
+            if (gid[c] < 0) errc = 1;  // tracking.py:700-701
+        }
         if (errc == 0 && nG * K > cap) {  // the next expansion would not fit (history rows are sized for it)
           errc = 2;
           if (lane == 0) atomicMax(&a.err_need[wi], nG * K);
@@ -304,6 +323,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
             for (int q = 0; q < CO; ++q) BP(g, q) = BC(c0, q);
             recW[(size_t)step * cap + c0] = 1.0;
             recGid[(size_t)step * cap + c0] = (uint16_t)g;
+            if (!FOLLOW)  // (history window and codes only serve this track's own decisions)
             for (int row = 0; row < rows_out; ++row)
               for (int s = 0; s < nS; ++s)
                 histN[((size_t)g * fl + row) * nS + s] =
@@ -340,6 +360,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
               recW[(size_t)step * cap + c] = __ddiv_rn(recW[(size_t)step * cap + c], sw);
             }
             // weighted mean of the members' window rows (tracking.py:733), member order
+            if (!FOLLOW)
             for (int row = 0; row < rows_out; ++row)
               for (int s = 0; s < nS; ++s) {
                 double acc = 0.0;
@@ -355,6 +376,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
           }
           // window code of the merged history (argmax per row, ties -> lowest state)
           unsigned long long code = 0;
+          if (!FOLLOW)
           for (int row = 0; row < rows_out; ++row) {
             int best = 0;
             double bv = histN[((size_t)g * fl + row) * nS];

@@ -29,6 +29,18 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
   int cap = std::max(64, nS * nS * nS);
   int result = XT_OK;
   ctx->k3_launches = 0;
+  // nb_max > 1 (the upload's chunk size): one plan per chunk, decided from its first 30 tracks (xt_predict_shared.cuh)
+  const bool shared = ctx->k3_shared && (int)ctx->upload_sig[2] > 1;  // option "predict_shared_plans"
+  const int nch = (int)ctx->chunks.size();
+  int32_t* d_splan = nullptr;
+  double* d_sscratch = nullptr;
+  int32_t* d_serr = nullptr;
+  if (shared && is_var(p)) {
+    set_error(ctx, "predict_Bs with nb_max > 1 is implemented for scalar LocErr / dt (per-localisation inputs: use nb_max = 1)");
+    cudaFree(d_pred);
+    cudaFree(d_err);
+    return XT_ERR_UNSUPPORTED;
+  }
   for (;;) {
     if (cap > XT_HARD_CAP) {
       set_error(ctx, "more than " + std::to_string(XT_HARD_CAP) + " live state sequences; lower frame_len or raise threshold");
@@ -97,6 +109,65 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
     ctx->k3_launches++;
     ctx->k3_cap = cap;
     cudaEventRecord(ctx->ev_k3[0], ctx->stream);
+    if (shared) {
+      if (cap > 1024) {
+        set_error(ctx, "predict_Bs with nb_max > 1: more than 1024 live state sequences; lower frame_len or raise threshold");
+        result = XT_ERR_CAPACITY;
+        break;
+      }
+      const K3SLayout sl = k3s_layout(cap, CO, p->frame_len, nS);
+      const int sgrid = std::max(1, std::min((nch + 7) / 8, ctx->n_sm * 2));
+      K3SArgs sa{};
+      sa.chunks = ctx->d_chunks;
+      sa.soa = ctx->d_soa;
+      sa.warp_scratch = sl.total;
+      sa.splan_stride = k3s_splan_stride(cap, a.maxL);
+      sa.n_chunks = nch;
+      sa.cap = cap;
+      sa.maxL = a.maxL;
+      sa.bits = bits;
+      cudaFree(d_splan); cudaFree(d_sscratch); cudaFree(d_serr);
+      d_splan = nullptr; d_sscratch = nullptr; d_serr = nullptr;
+      if (cudaMalloc(&d_splan, sizeof(int32_t) * sa.splan_stride * nch) != cudaSuccess ||
+          cudaMalloc(&d_sscratch, sizeof(double) * sl.total * (size_t)sgrid * 8) != cudaSuccess ||
+          cudaMalloc(&d_serr, sizeof(int32_t) * 2 * (size_t)nch) != cudaSuccess) {
+        set_error(ctx, "xt_predict: cannot allocate the shared-plan buffers");
+        result = XT_ERR_CUDA;
+        break;
+      }
+      cudaMemsetAsync(d_serr, 0, sizeof(int32_t) * 2 * (size_t)nch, ctx->stream);
+      sa.scratch = d_sscratch;
+      sa.splan = d_splan;
+      sa.err = d_serr;
+      sa.err_need = d_serr + nch;
+      e = xt_launch_k3_shared_plan(sa, *p, sgrid, ctx->stream);
+      std::vector<int32_t> h_serr(2 * (size_t)nch);
+      if (e != cudaSuccess || cudaMemcpyAsync(h_serr.data(), d_serr, sizeof(int32_t) * 2 * (size_t)nch, cudaMemcpyDeviceToHost,
+                                              ctx->stream) != cudaSuccess ||
+          cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        set_error(ctx, std::string("xt_predict (shared plans): ") + cudaGetErrorString(cudaGetLastError()));
+        result = XT_ERR_CUDA;
+        break;
+      }
+      int sneed = 0;
+      bool sgrouping = false;
+      for (int i = 0; i < nch; ++i) {
+        if (h_serr[i] == 1) sgrouping = true;
+        sneed = std::max(sneed, h_serr[nch + i]);
+      }
+      if (sgrouping) {
+        set_error(ctx, "problem with grouping: a state sequence ended ungrouped (threshold must be > 0 and the model finite)");
+        result = XT_ERR_GROUPING;
+        break;
+      }
+      if (sneed) {
+        while (cap < sneed) cap *= 2;
+        continue;
+      }
+      a.splan = d_splan;
+      a.splan_stride = sa.splan_stride;
+      e = xt_launch_k3_follow(a, *p, grid, nwarps, smem, ctx->stream);
+    } else
     e = xt_launch_k3(a, *p, grid, nwarps, smem, ctx->stream);
     cudaEventRecord(ctx->ev_k3[1], ctx->stream);
     if (e != cudaSuccess || cudaMemcpyAsync(h_err.data(), d_err, sizeof(int32_t) * 2 * (size_t)n_work, cudaMemcpyDeviceToHost,
@@ -142,5 +213,8 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
   cudaFree(d_pred);
   cudaFree(d_err);
   cudaFree(d_scratch);
+  cudaFree(d_splan);
+  cudaFree(d_sscratch);
+  cudaFree(d_serr);
   return result;
 }

@@ -30,18 +30,29 @@ MAX_TRACKS_PER_CHUNK = 2000  # tracking.py:991 max_number_of_tracks_per_matrix
 # --------------------------------------------------------------------------------------
 def _extract_scalars(params, nb_substeps, Matrix_type=1):
     """lmfit ``Parameters`` -> ``(LocErr values, Ds, Fs, TrMat, pBL)`` (tracking.py:918-975)."""
-    names = sorted(params.keys())
-    loc = [params[n].value for n in names if n.startswith("LocErr")]
-    Ds = np.array([params[n].value for n in names if n.startswith("D") and len(n) < 3], dtype=float)
-    Fs = np.array([params[n].value for n in names if n.startswith("F")], dtype=float)
+    # one pass over the sorted names (every `.value` of a constrained parameter evaluates its expression)
+    loc, Dv, Fv, rates, pBL = [], [], [], [], None
+    for n in sorted(params.keys()):
+        c = n[0]
+        if c == "L":
+            if n.startswith("LocErr"):
+                loc.append(params[n].value)
+        elif c == "D":
+            if len(n) < 3:
+                Dv.append(params[n].value)
+        elif c == "F":
+            Fv.append(params[n].value)
+        elif c == "p":
+            if n == "pBL":
+                pBL = params[n].value
+            else:
+                rates.append((int(n[1]), int(n[2]), params[n].value))
+    Ds = np.array(Dv, dtype=float)
+    Fs = np.array(Fv, dtype=float)
     nS = len(Ds)
     TrMat = np.zeros((nS, nS))
-    pBL = None
-    for n in params:
-        if n == "pBL":
-            pBL = params[n].value
-        elif n.startswith("p"):
-            TrMat[int(n[1]), int(n[2])] = params[n].value
+    for i, j, v in rates:
+        TrMat[i, j] = v
     TrMat = TrMat / nb_substeps
     diag = np.arange(nS)
     if Matrix_type == 0:
@@ -95,6 +106,7 @@ def extract_params(params, dt, nb_states, nb_substeps, input_LocErr=None, Matrix
 
 
 _P_STAY_MEMO: dict = {}
+_FOV_GRID: dict = {}
 
 
 def _p_stay(ds, nS, nsub, cell_dims):
@@ -120,12 +132,13 @@ def _p_stay(ds, nS, nsub, cell_dims):
     for r0 in range(0, len(ds2), 512):
         sub_ds = np.mean(ds2[r0 : r0 + 512][:, tup] ** 2, axis=2) ** 0.5  # [rows, K]
         p_stay = np.ones(sub_ds.shape)
+        den = sub_ds + 1e-200
         for cell_len in cell_dims:
-            xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
-            cur = np.mean(
-                ndtr((cell_len - xs[:, None, None]) / (sub_ds + 1e-200)) - ndtr(-xs[:, None, None] / (sub_ds + 1e-200)),
-                0,
-            )
+            grid = _FOV_GRID.get(cell_len)
+            if grid is None:  # (cell_len - x) and -x on the 1000-point grid: the same arrays at every evaluation
+                xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
+                grid = _FOV_GRID[cell_len] = ((cell_len - xs[:, None, None]), -xs[:, None, None])
+            cur = np.mean(ndtr(grid[0] / den) - ndtr(grid[1] / den), 0)
             p_stay = p_stay * cur
         out[r0 : r0 + 512] = p_stay
     if one:
@@ -581,7 +594,7 @@ def Proba_Cs(Cs, LocErr, ds, Fs, TrMat, pBL, isBL, cell_dims, nb_substeps, frame
 # --------------------------------------------------------------------------------------
 # state annotation (tracking.py:792-906)
 # --------------------------------------------------------------------------------------
-def _gather_predictions(preds_local, sorted_tracks, world, nb_states):
+def _gather_predictions(preds_local, sorted_tracks, world, nb_states, nb_max=1):
     """All ranks' slices of every bucket -> full arrays in input order (rank r holds rows predict_shard(n, r, world))."""
     import torch
     import torch.distributed as dist
@@ -590,7 +603,7 @@ def _gather_predictions(preds_local, sorted_tracks, world, nb_states):
     out = []
     for a, mine in zip(sorted_tracks, preds_local):
         n, L = a.shape[0], a.shape[1]
-        rows = [predict_shard(n, r, world) for r in range(world)]
+        rows = [predict_shard(n, r, world, nb_max) for r in range(world)]
         pad = max(hi - lo for lo, hi in rows)
         buf = torch.zeros((pad, L, nb_states), dtype=torch.float64, device=dev)
         buf[: len(mine)] = torch.from_numpy(np.ascontiguousarray(mine)).to(dev)
@@ -600,18 +613,21 @@ def _gather_predictions(preds_local, sorted_tracks, world, nb_states):
     return out
 
 
-def predict_shard(n: int, rank: int, world_size: int):
-    """Rows ``[lo, hi)`` of an ``n``-track bucket annotated by ``rank`` (contiguous, balanced)."""
-    return n * rank // world_size, n * (rank + 1) // world_size
+def predict_shard(n: int, rank: int, world_size: int, nb_max: int = 1):
+    """Rows ``[lo, hi)`` of an ``n``-track bucket annotated by ``rank``: contiguous, balanced, and cut at multiples of
+    ``nb_max`` so that every rank holds whole chunks of the reference's chunk list (tracking.py:866-867)."""
+    nch = -(-n // nb_max)
+    return min(n, (nch * rank // world_size) * nb_max), min(n, (nch * (rank + 1) // world_size) * nb_max)
 
 
 def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, max_nb_states=200, threshold=0.1,
                workers=1, input_LocErr=None, verbose=0, nb_max=1, gather=True):
     """Per-localisation state posteriors, ``{str(L): float64[n, L, nb_states]}`` (forward time).
 
-    Implements the reference default ``nb_max = 1``: every track gets its own grouping plan
-    (tracking.py:803,866-867).  ``nb_max > 1`` (plan shared by ``nb_max`` tracks, "might affect the
-    predictions quality") is not provided by the CUDA engine and raises ``NotImplementedError``.
+    ``nb_max`` tracks share one grouping plan, decided from the first 30 tracks of their chunk exactly as the
+    reference does (tracking.py:803,866-867; "higher numbers ... might affect the predictions quality"); with the
+    default ``nb_max = 1`` every track gets its own plan.  ``nb_max > 1`` is implemented for scalar ``LocErr`` /
+    ``dt`` (``NotImplementedError`` with peak-wise ``input_LocErr`` or a ``dt`` dictionary).
     ``workers`` is accepted and ignored.
 
     With ``torch.distributed`` initialised (one process per GPU) every rank annotates a contiguous
@@ -626,8 +642,12 @@ def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, 
     nb_substeps = 1  # substeps should not impact the step labelling (tracking.py:839)
     if not isinstance(params, Parameters):
         raise TypeError("params must be either of the class 'lmfit.parameter.Parameters' or a dictionary of the relevant parameters")
-    if nb_max != 1:
-        raise NotImplementedError("predict_Bs on the CUDA engine implements nb_max = 1 (the reference default) only")
+    nb_max = int(nb_max)
+    if nb_max < 1:
+        raise ValueError("nb_max must be a positive integer")
+    if nb_max > 1 and (input_LocErr is not None or type(dt) == dict):
+        raise NotImplementedError("predict_Bs with nb_max > 1 is implemented for scalar LocErr / dt; use nb_max = 1 with "
+                                  "peak-wise localisation errors or per-track time steps")
     loc, Ds, Fs, TrMat, pBL = _extract_scalars(params, nb_substeps)
     if len(Ds) != nb_states:
         raise ValueError("nb_states (%d) must equal the number of D parameters (%d)" % (nb_states, len(Ds)))
@@ -654,16 +674,18 @@ def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, 
     p = build_tables(loc, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, min_len, threshold, max_nb_states,
                      sorted_tracks[0].shape[2], var_loc_k=loc_k, var_dt=sorted_dt is not None, Ds=Ds, slope_offset=slope)
     rank, world = _dist_info(None, None)
-    cuts = [predict_shard(len(a), rank, world) for a in sorted_tracks]
+    cuts = [predict_shard(len(a), rank, world, nb_max) for a in sorted_tracks]
     mine = [b for b, (lo, hi) in enumerate(cuts) if hi > lo]
     loc = lambda arrs: [arrs[b][cuts[b][0]:cuts[b][1]] for b in mine] if arrs is not None else None
     preds_local = [np.empty((0, a.shape[1], nb_states)) for a in sorted_tracks]
     if mine:
         eng = _native.Engine(_default_device())
         try:
-            # chunk size only shapes the device layout here; plans are per track
+            # nb_max = 1: plans are per track and the chunk size only shapes the device layout; nb_max > 1: the chunks
+            # of nb_max tracks are the reference's (tracking.py:866-867) and share one plan each
             eng.upload(loc(sorted_tracks), [0 if sorted_tracks[b].shape[1] == max_len else 1 for b in mine],
-                       MAX_TRACKS_PER_CHUNK)
+                       MAX_TRACKS_PER_CHUNK if nb_max == 1 else nb_max)
+            eng.set_option("predict_shared_plans", int(nb_max > 1))
             if sorted_LocErrs is not None or sorted_dt is not None:
                 eng.upload_aux(loc(sorted_LocErrs), loc(sorted_dt))
             if sorted_dt is not None:
@@ -673,7 +695,7 @@ def predict_Bs(all_tracks, dt, params, cell_dims=[1], nb_states=4, frame_len=5, 
                 preds_local[b] = pr
         finally:
             eng.close()
-    preds = preds_local if (world == 1 or not gather) else _gather_predictions(preds_local, sorted_tracks, world, nb_states)
+    preds = preds_local if (world == 1 or not gather) else _gather_predictions(preds_local, sorted_tracks, world, nb_states, nb_max)
     for a, pr in zip(sorted_tracks, preds):
         out[str(a.shape[1])] = pr
     return out

@@ -171,7 +171,10 @@ int xt_plan_dump(xt_ctx* ctx, int32_t chunk, int32_t step, int32_t* nB_in, int32
 
 /*
  * State annotation — replaces the chunk loop of predict_Bs (tracking.py:860-896) for the
- * uploaded tracks (upload them with the caller's nb_max as chunk_size; default 1 track).
+ * uploaded tracks.  Default (reference default nb_max = 1): every track gets its own grouping plan, whatever the
+ * upload's chunk size.  With xt_set_option("predict_shared_plans", 1) the chunks of the upload (chunk_size = the
+ * caller's nb_max, tracking.py:866-867) share one plan each, decided from the chunk's first 30 tracks with per-track
+ * weighted histories (fuse_tracks_th with do_preds = 1); scalar LocErr / dt models (else XT_ERR_UNSUPPORTED).
  * out[s] receives double[n[s]][L[s]][nS] posteriors of segment s in forward time
  * (tracking.py:641-649).
  */

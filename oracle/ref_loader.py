@@ -88,3 +88,34 @@ def load_histograms():
         sys.modules["extrack"] = pkg
         sys.modules["extrack.tracking"] = trk
     return _load("histograms", "extrack/histograms.py")
+
+
+def load_refined_localization():
+    """``extrack/refined_localization.py`` (position refinement).  It imports ``extrack.tracking_0``, ``extrack.tracking``,
+    ``extrack.exporters`` and, unconditionally, ``matplotlib.backends.backend_agg`` (absent from this image): package
+    stubs point at the loaded reference modules and an empty stand-in satisfies the plotting import, which the
+    refinement itself never touches."""
+    trk = load_tracking()
+    trk0 = _load("tracking_0", "extrack/tracking_0.py")
+    exporters = _load("exporters", "extrack/exporters.py")
+    if "extrack" not in sys.modules:
+        pkg = types.ModuleType("extrack")
+        pkg.__path__ = []
+        sys.modules["extrack"] = pkg
+    pkg = sys.modules["extrack"]
+    for name, mod in (("tracking", trk), ("tracking_0", trk0), ("exporters", exporters)):
+        setattr(pkg, name, mod)
+        sys.modules["extrack." + name] = mod
+    try:
+        import matplotlib.backends.backend_agg  # noqa: F401
+    except Exception:
+        mpl = sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+        be = sys.modules.setdefault("matplotlib.backends", types.ModuleType("matplotlib.backends"))
+        agg = types.ModuleType("matplotlib.backends.backend_agg")
+        agg.FigureCanvasAgg = object
+        sys.modules["matplotlib.backends.backend_agg"] = agg
+        mpl.backends = be
+        be.backend_agg = agg
+    if not hasattr(__import__("numpy"), "product"):
+        __import__("numpy").product = __import__("numpy").prod  # tracking_0.fuse_tracks_general predates numpy 2
+    return _load("refined_localization", "extrack/refined_localization.py")

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f)
+               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f and "nbmax_" not in f)
 VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
 WINDOW_CASES = sorted(glob.glob(os.path.join(GOLDEN, "window_*.npz")))
 RTOL_LOGL = 1e-9
@@ -363,8 +363,12 @@ def test_predict_bs_api_vs_oracle(xt):
     want = orc.predict_states(st, m, nb_max=1)
     for a, w in zip(st, want):
         np.testing.assert_allclose(got[str(a.shape[1])], w, rtol=0, atol=PRED_ATOL)
+    # nb_max > 1 (plans shared per chunk) against the oracle; peak-wise inputs are the documented gap of that mode
+    got50 = xt.predict_Bs(tracks, 0.02, p, cell_dims=[1], nb_states=2, frame_len=8, nb_max=50)
+    for a, w in zip(st, orc.predict_states(st, m, nb_max=50)):
+        np.testing.assert_allclose(got50[str(a.shape[1])], w, rtol=0, atol=PRED_ATOL)
     with pytest.raises(NotImplementedError):
-        xt.predict_Bs(tracks, 0.02, p, nb_states=2, nb_max=50)
+        xt.predict_Bs(tracks, 0.02, p, nb_states=2, nb_max=50, input_LocErr={k: np.full(v.shape[:2] + (1,), 0.02) for k, v in tracks.items()})
     with pytest.raises(TypeError):
         xt.predict_Bs(tracks, 0.02, {"D0": 1.0}, nb_states=2)
 
@@ -742,3 +746,44 @@ def test_plan_verification_reproduces_planning_from_scratch(native, xt):
     finally:
         a.close()
         b.close()
+
+
+# ---- predict_Bs with nb_max > 1: plans shared by the tracks of a chunk ----
+NBMAX_CASES = sorted(glob.glob(os.path.join(GOLDEN, "nbmax_*.npz")))
+
+
+@pytest.mark.parametrize("path", NBMAX_CASES, ids=[os.path.basename(p)[:-4] for p in NBMAX_CASES])
+def test_predict_with_shared_plans_matches_reference_golden(path, xt):
+    """predict_Bs(nb_max > 1) (tracking.py:803,860-896): golden = the unmodified reference (make_golden_nbmax.py);
+    posteriors within 1e-6 (north star), observed ~1e-12."""
+    from test_oracle import load_nbmax_case
+
+    tracks, preds, params, nS, fl, nb_max = load_nbmax_case(path)
+    got = xt.predict_Bs(tracks, 0.02, params, cell_dims=[1], nb_states=nS, frame_len=fl, nb_max=nb_max)
+    assert set(got) == set(preds)
+    worst = 0.0
+    for k in preds:
+        assert got[k].shape == preds[k].shape
+        worst = max(worst, float(np.max(np.abs(got[k] - preds[k]))))
+    assert worst < 1e-6, worst
+    # a chunk size that is not the reference's gives other plans for some tracks: the shared plan really is per chunk
+    if nb_max > 1:
+        one = xt.predict_Bs(tracks, 0.02, params, cell_dims=[1], nb_states=nS, frame_len=fl, nb_max=1)
+        for k in preds:
+            np.testing.assert_allclose(one[k].sum(-1), 1.0, atol=1e-9)
+
+
+def test_predict_shared_plans_vs_oracle_seeded(xt):
+    rng = np.random.default_rng(91)
+    tracks = {str(L): random_walk_tracks(n, L, 2, rng) for L, n in ((9, 333), (15, 210), (22, 75))}
+    params = xt.generate_params(nb_states=2, LocErr_type=1, nb_dims=2, estimated_LocErr=[0.02], estimated_Ds=[1e-5, 0.25],
+                                estimated_Fs=[0.5], estimated_transition_rates=0.1)
+    LocErr, ds, Fs, TrMat, pBL = xt.extract_params(params, 0.02, 2, 1)
+    keys = sorted(tracks, key=int)
+    st = [tracks[k] for k in keys]
+    for nb_max, fl in ((100, 7), (31, 5)):
+        m = orc.Model(np.asarray(LocErr[0]).reshape(-1), ds, Fs, TrMat, pBL, [1], 1, fl, st[0].shape[1], 0.1, 200)
+        want = orc.predict_states(st, m, nb_max=nb_max)
+        got = xt.predict_Bs(tracks, 0.02, params, cell_dims=[1], nb_states=2, frame_len=fl, nb_max=nb_max)
+        for k, w in zip(keys, want):
+            np.testing.assert_allclose(got[k], w, atol=1e-6)

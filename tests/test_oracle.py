@@ -14,7 +14,7 @@ from oracle import ref_loader
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f)
+               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f and "nbmax_" not in f)
 VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
 WINDOW_CASES = sorted(glob.glob(os.path.join(GOLDEN, "window_*.npz")))
 
@@ -185,3 +185,34 @@ def test_oracle_window_only_mode_matches_reference_window_function(path):
                   int(z["frame_len"]), int(z["min_len"]), 1e-12, 10**9)
     got = orc.chunk_logp(z["C"], m, int(z["isBL"]))
     np.testing.assert_allclose(got, z["ref_logp"], rtol=1e-12)
+
+
+NBMAX_CASES = sorted(glob.glob(os.path.join(GOLDEN, "nbmax_*.npz")))
+
+
+def load_nbmax_case(path):
+    from extrack_b200._lmfit_compat import Parameters
+
+    z = np.load(path, allow_pickle=False)
+    keys = [str(k) for k in z["keys"]]
+    tracks = {k: z["C" + k] for k in keys}
+    preds = {k: z["P" + k] for k in keys}
+    params = Parameters()
+    for k, v in zip(z["param_names"], z["param_values"]):
+        params.add(str(k), value=float(v))
+    return tracks, preds, params, int(z["nS"]), int(z["fl"]), int(z["nb_max"])
+
+
+@pytest.mark.parametrize("path", NBMAX_CASES, ids=[os.path.basename(p)[:-4] for p in NBMAX_CASES])
+def test_oracle_predict_with_shared_plans_matches_reference(path):
+    """predict_Bs(nb_max > 1): golden = the unmodified reference (tests/golden/make_golden_nbmax.py)."""
+    from extrack_b200 import tracking as xt
+
+    tracks, preds, params, nS, fl, nb_max = load_nbmax_case(path)
+    LocErr, ds, Fs, TrMat, pBL = xt.extract_params(params, 0.02, nS, 1)
+    keys = sorted(tracks, key=int)
+    st = [tracks[k] for k in keys]
+    m = orc.Model(np.asarray(LocErr[0]).reshape(-1), ds, Fs, TrMat, pBL, [1], 1, fl, st[0].shape[1], 0.1, 200)
+    got = orc.predict_states(st, m, nb_max=nb_max)
+    for k, g in zip(keys, got):
+        np.testing.assert_allclose(g, preds[k], atol=1e-10)
