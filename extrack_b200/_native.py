@@ -87,6 +87,7 @@ EXPORTS = (
     "xt_chunk_logp",
     "xt_plan_dump",
     "xt_predict",
+    "xt_refine_positions",
     "xt_get_stats",
     "xt_seglen_hist",
     "xt_seglen_last_ms",
@@ -139,6 +140,7 @@ def load_library() -> C.CDLL:
     lib.xt_chunk_logp.argtypes = [vp, i32, P(XtParams), P(dbl)]
     lib.xt_plan_dump.argtypes = [vp, i32, i32, P(i32), P(i32), P(i32), i32, P(dbl)]
     lib.xt_predict.argtypes = [vp, P(XtParams), P(vp)]
+    lib.xt_refine_positions.argtypes = [vp, P(XtParams), P(XtParams), P(vp), P(vp)]
     lib.xt_get_stats.argtypes = [vp, P(XtStats)]
     lib.xt_seglen_hist.argtypes = [vp, P(XtParams), P(dbl), P(dbl), i32, i32, vp, vp, P(i32)]
     lib.xt_seglen_last_ms.argtypes = [vp, P(C.c_float)]
@@ -324,6 +326,16 @@ class Engine:
         ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
         self._check(self._lib.xt_predict(self._h, C.byref(p), ptrs))
         return outs
+
+    def refine_positions(self, p_rev: XtParams, p_fwd: XtParams):
+        """Refined positions [n, L, d] and their standard deviations [n, L] per uploaded segment (every segment
+        uploaded as one chunk); see ``xt_refine_positions``."""
+        mus = [np.empty((n, L, self.d), dtype=np.float64) for (L, n) in self.segments]
+        sigmas = [np.empty((n, L), dtype=np.float64) for (L, n) in self.segments]
+        pm = (C.c_void_p * len(mus))(*[o.ctypes.data for o in mus])
+        ps = (C.c_void_p * len(sigmas))(*[o.ctypes.data for o in sigmas])
+        self._check(self._lib.xt_refine_positions(self._h, C.byref(p_rev), C.byref(p_fwd), pm, ps))
+        return mus, sigmas
 
     def seglen_hist(self, p: XtParams, leave_LL: np.ndarray, Lmax: int, nS: int, n_chunks: int, dbg_chunk: int = -1,
                     dbg_shape=None):

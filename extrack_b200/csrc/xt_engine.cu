@@ -17,6 +17,7 @@
 #include "xt_seglen.cuh"
 #include "xt_predict.cuh"
 #include "xt_predict_shared.cuh"
+#include "xt_refine.cuh"
 
 struct xt_ctx {
   int device = 0;
@@ -1664,5 +1665,6 @@ extern "C" int xt_fp64_peak_tflops(xt_ctx* ctx, double* out) {
 }
 
 #include "xt_predict_host.inl"
+#include "xt_refine_host.inl"
 #include "xt_seglen_host.inl"
 #include "xt_multi.inl"

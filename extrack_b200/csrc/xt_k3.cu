@@ -2,6 +2,7 @@
 #include "xt_launch.h"
 #include "xt_predict.cuh"
 #include "xt_predict_shared.cuh"
+#include "xt_refine.cuh"
 
 template <int D, int KS, bool VAR>
 static cudaError_t launch_k3_v(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
@@ -51,4 +52,28 @@ cudaError_t xt_launch_k3_follow(const K3Args& a, const xt_params& p, int grid, i
   XT_DISPATCH(p.d, p.n_loc, CALL_K3F);
 #undef CALL_K3F
   return e;
+}
+
+// position refinement: the recursion along the buckets' plans that stores every step, and the combination of its two passes
+template <int D, int KS>
+static cudaError_t launch_k3r(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
+  auto kern = k3_predict<D, KS, false, true, true>;
+  static unsigned long long smem_ok = 0;
+  cudaError_t e = xt_allow_smem(kern, smem, &smem_ok);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32 * nwarps, smem, stream>>>(a, p);
+  return cudaGetLastError();
+}
+cudaError_t xt_launch_k3_refine(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+#define CALL_K3R(D_, KS_) e = launch_k3r<D_, KS_>(a, p, grid, nwarps, smem, stream)
+  XT_DISPATCH(p.d, p.n_loc, CALL_K3R);
+#undef CALL_K3R
+  return e;
+}
+cudaError_t xt_launch_refine_combine(int d, int ks, const KRArgs& a, unsigned grid, cudaStream_t stream) {
+#define CALL_KR(D_, KS_) k_refine_combine<D_, KS_><<<grid, 256, 0, stream>>>(a)
+  XT_DISPATCH(d, ks, CALL_KR);
+#undef CALL_KR
+  return cudaGetLastError();
 }

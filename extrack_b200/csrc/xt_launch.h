@@ -10,6 +10,7 @@ struct K2FArgs;
 struct K2Tab;
 struct K3Args;
 struct K3SArgs;
+struct KRArgs;
 struct K4Args;
 
 #define XT_DISPATCH(D_, KS_, CALL)                                   \
@@ -62,6 +63,9 @@ cudaError_t xt_launch_k3(const K3Args& a, const xt_params& p, int grid, int nwar
 // ... with plans shared by the nb_max tracks of a chunk (xt_predict_shared.cuh): the plans, then the annotation along them
 cudaError_t xt_launch_k3_shared_plan(const K3SArgs& a, const xt_params& p, int grid, cudaStream_t stream);
 cudaError_t xt_launch_k3_follow(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
+// position refinement (xt_refine.cuh): recursion that stores every step, combination of its two passes
+cudaError_t xt_launch_k3_refine(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
+cudaError_t xt_launch_refine_combine(int d, int ks, const KRArgs& a, unsigned grid, cudaStream_t stream);
 // segment-length histogram (xt_seglen.cuh)
 cudaError_t xt_launch_k4(const K4Args& a, const xt_params& p, int grid, size_t smem, cudaStream_t stream);
 // final fixed-order sums (xt_replay.cuh: k_reduce) and the FP64 FMA microbenchmark live in xt_engine.cu

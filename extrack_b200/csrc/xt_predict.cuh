@@ -39,6 +39,15 @@ struct K3Args {
   // plan (k3_shared_plan, xt_predict_shared.cuh) instead of this track's own decisions
   const int32_t* splan;  // [n_chunks][splan_stride]: nC[maxL], nG[maxL], then per step goff[cap + 1], order[cap]
   size_t splan_stride;
+  // REFINE instantiation (position refinement, refined_localization.py:48-204 get_LC_Km_Ks): the recursion without
+  // field-of-view / bleaching terms, initial fractions added at the end; instead of posteriors it stores, for every
+  // step, (mean[d], std[KS], log-weight, newest state) of every surviving sequence of every track
+  int32_t rev;           // 1: consume the localisations from the last to the first (get_LC_Km_Ks' own order)
+  double* dump;          // [n_tracks][L - 1 entries][capD][d + KS + 2] doubles, per chunk at dump_off[chunk]
+  const int64_t* dump_off;
+  int32_t* ent_n;        // [n_chunks][maxL]: sequences per entry (written by the chunk's first track)
+  int32_t capD;
+  double LF[XT_MAX_STATES];  // log initial fractions by state (REFINE: added at the end, refined_localization.py:190)
 };
 
 // per-warp scratch layout, in 8-byte units: the *hot* part (state of the forward pass, touched at
@@ -75,9 +84,10 @@ __host__ __device__ inline K3Layout k3_layout(int cap, int CO, int fl, int nS, i
   return l;
 }
 
-template <int D, int KS, bool VAR = false, bool FOLLOW = false>
+template <int D, int KS, bool VAR = false, bool FOLLOW = false, bool REFINE = false>
 __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, const __grid_constant__ xt_params P) {
   static_assert(!(VAR && FOLLOW), "shared plans are built for scalar LocErr / dt models");
+  static_assert(!REFINE || FOLLOW, "the refinement recursion follows the bucket's shared plan");
   extern __shared__ double k3_smem[];
   const int nwarps = blockDim.x >> 5;  // <= XT_K3_WARPS (fewer when the hot scratch of 8 warps exceeds shared memory)
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
@@ -126,6 +136,12 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
       const size_t npad = (size_t)ck.nTpad;
       double* out = a.pred + ((size_t)ck.loc_off + (size_t)t * L) * nS;
       int errc = 0;
+      const bool rev = REFINE && a.rev;
+#define LROW(j) (rev ? (L - 1 - (j)) : (j))  // localisation consumed j-th
+      // REFINE: this track's entries [L - 1][capD][d + KS + 2]
+      constexpr int COD = D + KS + 2;
+      double* dmp = REFINE ? a.dump + a.dump_off[wk.chunk] + (size_t)t * (L - 1) * a.capD * COD : nullptr;
+      int32_t* entn = (REFINE && t == 0) ? a.ent_n + (size_t)wk.chunk * a.maxL : nullptr;
       // VAR: row j of the aux block = (sigma components, time-reversed dt) of localisation j
       const double* Ap = VAR ? a.ax.aux + (size_t)(ck.xyz_off / D) * a.ax.R + t : nullptr;
       const double* Lps = (VAR && a.ax.stay) ? a.ax.stay + (size_t)(ck.trk_off + t) * K : P.Lp_stay;
@@ -145,10 +161,19 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
       int nP = nS * nS;
       for (int c = lane; c < nP; c += 32) {
 #pragma unroll
-        for (int dim = 0; dim < D; ++dim) BP(c, dim) = Cp[(size_t)dim * npad];
+        for (int dim = 0; dim < D; ++dim) BP(c, dim) = Cp[(size_t)(LROW(0) * D + dim) * npad];
 #pragma unroll
         for (int k = 0; k < KS; ++k) BP(c, D + k) = __dadd_rn(l2[k], DDX(c));
-        BP(c, D + 2 * KS) = __dadd_rn(P.LT[c], P.LF[c]);
+        BP(c, D + 2 * KS) = REFINE ? P.LT[c] : __dadd_rn(P.LT[c], P.LF[c]);
+        if (REFINE && L > 2) {  // entry 0 (for L == 2 the only entry is written at the end, with the final weights)
+          double* e0 = dmp + (size_t)c * COD;
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) e0[dim] = BP(c, dim);
+#pragma unroll
+          for (int k = 0; k < KS; ++k) e0[D + k] = __dsqrt_rn(BP(c, D + k));
+          e0[D + KS] = BP(c, D + 2 * KS);
+          e0[D + KS + 1] = (double)(c % nS);
+        }
         curP[c] = c % nS;
         const int d0 = c % nS, d1 = c / nS;
         codeP[c] = (unsigned long long)d0 | ((unsigned long long)d1 << bits);
@@ -159,6 +184,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
       }
       int LhP = 2;       // full history length (never truncated in predict mode)
       double th = P.threshold;
+      if (entn && lane == 0) entn[0] = nP;
       __syncwarp();
 
       for (int step = 2; step <= L - 1; ++step) {
@@ -174,8 +200,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         const unsigned long long cmask = (bits * rows_cmp >= 64) ? ~0ull : ((1ull << (bits * rows_cmp)) - 1ull);
         double cl[D];
 #pragma unroll
-        for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((step - 1) * D + dim) * npad];
-        const bool stay = step >= P.min_len;
+        for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)(LROW(step - 1) * D + dim) * npad];
+        const bool stay = !REFINE && step >= P.min_len;
         if (VAR) var_row(step - 1);
         // ---- expansion + Gaussian update (tracking.py:540-570, :87-98), lane = child ----
         for (int c = lane; c < nC; c += 32) {
@@ -393,7 +419,17 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         for (int g = lane; g < nG; g += 32) {
           codeP[g] = codeC[g];
           curP[g] = gid[g];
+          if (REFINE) {  // entry step - 1: the merged sequences (refined_localization.py:183-186)
+            double* e1 = dmp + ((size_t)(step - 1) * a.capD + g) * COD;
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) e1[dim] = BP(g, dim);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) e1[D + k] = __dsqrt_rn(BP(g, D + k));
+            e1[D + KS] = BP(g, D + 2 * KS);
+            e1[D + KS + 1] = (double)gid[g];
+          }
         }
+        if (entn && lane == 0) entn[step - 1] = nG;
         {
           double* tmp = histP;
           histP = histN;
@@ -414,7 +450,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
       const int fbs = have_children ? cap : capP;  // slot pitch of that buffer
       double clast[D];
 #pragma unroll
-      for (int dim = 0; dim < D; ++dim) clast[dim] = Cp[(size_t)((L - 1) * D + dim) * npad];
+      for (int dim = 0; dim < D; ++dim) clast[dim] = Cp[(size_t)(LROW(L - 1) * D + dim) * npad];
       if (VAR) var_row(L - 1);
       double vmax = -INFINITY;
       for (int c = lane; c < nP; c += 32) {
@@ -428,9 +464,27 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
           term = (dim == 0) ? tt : __dadd_rn(term, tt);
         }
         double v = FB[(size_t)(D + 2 * KS) * fbs + c] + term;
+        if (REFINE) {
+          // last entry: the unfused sequences of the last step with the end-of-track term and the initial fraction of
+          // their newest state (refined_localization.py:188-194: the last stored LP is the array updated in place)
+          v = __dadd_rn(FB[(size_t)(D + 2 * KS) * fbs + c], __dadd_rn(term, a.LF[c % nS]));
+          double* e2 = dmp + ((size_t)(L - 2) * a.capD + c) * COD;
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) e2[dim] = FB[(size_t)dim * fbs + c];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) e2[D + k] = have_children ? FB[(size_t)(D + KS + k) * fbs + c] : __dsqrt_rn(FB[(size_t)(D + k) * fbs + c]);
+          e2[D + KS] = v;
+          e2[D + KS + 1] = (double)(c % nS);
+          continue;
+        }
         if (ck.isBL) v += Lsm[c % nS];
         aC[c] = v;
         vmax = fmax(vmax, v);
+      }
+      if (REFINE) {
+        if (entn && lane == 0) entn[L - 2] = nP;
+        __syncwarp();
+        continue;  // no posteriors in this mode
       }
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o2));
@@ -491,4 +545,5 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
 #undef BP
 #undef BC
 #undef DDX
+#undef LROW
 }

@@ -23,6 +23,9 @@ struct K3SArgs {
   size_t splan_stride;  // int32 units per chunk
   int32_t n_chunks;
   int32_t cap, maxL, bits;
+  int32_t refine;       // 1: the recursion of the position refinement (get_LC_Km_Ks, refined_localization.py:48-204): no
+                        // field-of-view / bleaching term, no initial fraction at the start
+  int32_t rev;          // 1: consume the localisations from the last to the first
 };
 
 __host__ __device__ inline size_t k3s_splan_stride(int cap, int maxL) { return (size_t)2 * maxL + (size_t)maxL * (2 * cap + 1); }
@@ -96,6 +99,8 @@ __global__ void __launch_bounds__(256) k3_shared_plan(const K3SArgs a, const __g
     }
     int errc = 0;
     int hsel = 0;  // which history buffer holds the parents' rows
+    const bool rev = a.rev != 0;
+#define LROW(j) (rev ? (L - 1 - (j)) : (j))  // localisation consumed j-th
     // ---- first localisation (tracking.py:478-529) ----
     int nP = nS * nS;
     for (int t = 0; t < Kt; ++t) {
@@ -104,10 +109,10 @@ __global__ void __launch_bounds__(256) k3_shared_plan(const K3SArgs a, const __g
       double* hP = HP(T, hsel);
       for (int c = lane; c < nP; c += 32) {
 #pragma unroll
-        for (int dim = 0; dim < D; ++dim) BP(T, c, dim) = Cp[(size_t)dim * npad];
+        for (int dim = 0; dim < D; ++dim) BP(T, c, dim) = Cp[(size_t)(LROW(0) * D + dim) * npad];
 #pragma unroll
         for (int k = 0; k < KS; ++k) BP(T, c, D + k) = __dadd_rn(l2[k], P.dd[c]);
-        BP(T, c, D + 2 * KS) = __dadd_rn(P.LT[c], P.LF[c]);
+        BP(T, c, D + 2 * KS) = a.refine ? P.LT[c] : __dadd_rn(P.LT[c], P.LF[c]);
         const int d0 = c % nS, d1 = c / nS;
         CODEP(T)[c] = (unsigned long long)d0 | ((unsigned long long)d1 << bits);
         for (int s = 0; s < nS; ++s) {
@@ -132,14 +137,14 @@ __global__ void __launch_bounds__(256) k3_shared_plan(const K3SArgs a, const __g
       const int rows_cmp = LhC < fl ? LhC : fl;
       const bool use_window = LhC > fl;
       const unsigned long long cmask = (bits * rows_cmp >= 64) ? ~0ull : ((1ull << (bits * rows_cmp)) - 1ull);
-      const bool stay = step >= P.min_len;
+      const bool stay = !a.refine && step >= P.min_len;
       // ---- expansion + Gaussian update of every leader track (tracking.py:540-570, :87-98), lane = child ----
       for (int t = 0; t < Kt; ++t) {
         double* T = TRK(t);
         const double* Cp = a.soa + ck.xyz_off + t;
         double cl[D];
 #pragma unroll
-        for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)((step - 1) * D + dim) * npad];
+        for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)(LROW(step - 1) * D + dim) * npad];
         for (int c = lane; c < nC; c += 32) {
           const int p = c / K, r = c - p * K;
           const int head = r + K * curP[p];
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(256) k3_shared_plan(const K3SArgs a, const __g
     }
     if (errc && lane == 0) atomicMax(&a.err[ci], errc);
   }
+#undef LROW
 #undef TRK
 #undef BP
 #undef BC

@@ -180,6 +180,19 @@ int xt_plan_dump(xt_ctx* ctx, int32_t chunk, int32_t step, int32_t* nB_in, int32
  */
 int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out);
 
+/*
+ * Position refinement — replaces extrack/refined_localization.py:207-338 (get_pos_PDF + the weighted means of
+ * position_refinement) for the uploaded tracks.  Upload every length bucket as ONE chunk (chunk_size >= its track
+ * count): the reference hands whole buckets to get_LC_Km_Ks (:48-204), whose grouping plan comes from the bucket's first
+ * 30 tracks.  p_rev holds the tables of the pass that consumes a track from its last to its first localisation
+ * (get_pos_PDF's first call: ds, Fs, TrMat), p_fwd those of the pass in forward time (second call: neutral fractions,
+ * transposed transition matrix); both with nb_substeps = 1 and scalar or per-dimension LocErr; threshold, frame_len and
+ * max_nb_states as in the reference call.  mu_out[s] receives double[n[s]][L[s]][d] refined positions, sigma_out[s]
+ * double[n[s]][L[s]] their standard deviations (:329-337).
+ */
+int xt_refine_positions(xt_ctx* ctx, const xt_params* p_rev, const xt_params* p_fwd, double* const* mu_out,
+                        double* const* sigma_out);
+
 int xt_get_stats(xt_ctx* ctx, xt_stats* out);
 
 /*

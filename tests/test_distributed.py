@@ -49,6 +49,9 @@ def _worker(rank, world, port, q):
             pm = make_model(frame_len=5, min_len=6, threshold=0.1, max_nb_states=200)
             return [np.concatenate([orc.chunk_recursion(s[i : i + 1], pm, b, 1)[2] for i in range(len(s))]) for s, b in self.segs]
 
+        def set_option(self, name, value):
+            assert name == "predict_shared_plans" and value == 0  # nb_max = 1 here: per-track plans
+
         def close(self):
             pass
 

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f and "nbmax_" not in f)
+               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f and "nbmax_" not in f and "refine_" not in f)
 VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
 WINDOW_CASES = sorted(glob.glob(os.path.join(GOLDEN, "window_*.npz")))
 RTOL_LOGL = 1e-9
@@ -787,3 +787,40 @@ def test_predict_shared_plans_vs_oracle_seeded(xt):
         got = xt.predict_Bs(tracks, 0.02, params, cell_dims=[1], nb_states=2, frame_len=fl, nb_max=nb_max)
         for k, w in zip(keys, want):
             np.testing.assert_allclose(got[k], w, atol=1e-6)
+
+
+# ---- position refinement ----
+REFINE_CASES = sorted(glob.glob(os.path.join(GOLDEN, "refine_*.npz")))
+
+
+@pytest.mark.parametrize("path", REFINE_CASES, ids=[os.path.basename(p)[:-4] for p in REFINE_CASES])
+def test_position_refinement_matches_reference_golden(path):
+    """extrack_b200.refined_localization.position_refinement against the unmodified reference
+    (refined_localization.py:304-338; golden: make_golden_refine.py).  Tolerance 1e-8 um on positions and standard
+    deviations (FP64 throughout; observed ~1e-13)."""
+    from extrack_b200 import refined_localization as rl
+    from test_oracle import load_refine_case
+
+    tracks, mus, sigmas, kw = load_refine_case(path)
+    got_mu, got_sig = rl.position_refinement(tracks, kw["LocErr"], kw["ds"], kw["Fs"], kw["TrMat"], frame_len=kw["frame_len"],
+                                             threshold=kw["threshold"], max_nb_states=kw["max_nb_states"])
+    assert set(got_mu) == set(mus)
+    for k in tracks:
+        np.testing.assert_allclose(got_mu[k], mus[k], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(got_sig[k], sigmas[k], rtol=0, atol=1e-8)
+
+
+def test_position_refinement_vs_oracle_larger_bucket():
+    from extrack_b200 import refined_localization as rl
+    from oracle import refine_oracle
+
+    rng = np.random.default_rng(8)
+    m = make_model(nS=2, frame_len=6)
+    tracks = {"12": random_walk_tracks(700, 12, 2, rng), "20": random_walk_tracks(150, 20, 2, rng)}
+    got_mu, got_sig = rl.position_refinement(tracks, 0.02, m.ds, m.Fs, m.TrMat, frame_len=6, threshold=0.1, max_nb_states=1000)
+    want_mu, want_sig = refine_oracle.position_refinement(tracks, 0.02, m.ds, m.Fs, m.TrMat, 6, 0.1, 1000)
+    for k in tracks:
+        np.testing.assert_allclose(got_mu[k], want_mu[k], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(got_sig[k], want_sig[k], rtol=0, atol=1e-8)
+    with pytest.raises(NotImplementedError):
+        rl.position_refinement(tracks, {k: np.full(v.shape[:2] + (1,), 0.02) for k, v in tracks.items()}, m.ds, m.Fs, m.TrMat)

@@ -14,7 +14,7 @@ from oracle import ref_loader
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f and "nbmax_" not in f)
+               if "objective" not in f and "var_" not in f and "fit_" not in f and "seglen_" not in f and "window_" not in f and "nbmax_" not in f and "refine_" not in f)
 VAR_CASES = sorted(glob.glob(os.path.join(GOLDEN, "var_*.npz")))
 WINDOW_CASES = sorted(glob.glob(os.path.join(GOLDEN, "window_*.npz")))
 
@@ -216,3 +216,46 @@ def test_oracle_predict_with_shared_plans_matches_reference(path):
     got = orc.predict_states(st, m, nb_max=nb_max)
     for k, g in zip(keys, got):
         np.testing.assert_allclose(g, preds[k], atol=1e-10)
+
+
+REFINE_CASES = sorted(glob.glob(os.path.join(GOLDEN, "refine_*.npz")))
+
+
+def load_refine_case(path):
+    z = np.load(path, allow_pickle=False)
+    keys = [str(k) for k in z["keys"]]
+    return ({k: z["C" + k] for k in keys}, {k: z["M" + k] for k in keys}, {k: z["S" + k] for k in keys},
+            dict(LocErr=float(z["loc_err"]), ds=z["ds"], Fs=z["Fs"], TrMat=z["TrMat"], frame_len=int(z["frame_len"]),
+                 threshold=float(z["threshold"]), max_nb_states=int(z["max_nb_states"])))
+
+
+@pytest.mark.parametrize("path", REFINE_CASES, ids=[os.path.basename(p)[:-4] for p in REFINE_CASES])
+def test_refinement_oracle_matches_reference_golden(path):
+    """Position refinement (refined_localization.py:304-338): golden = the unmodified reference (make_golden_refine.py)."""
+    from oracle import refine_oracle
+
+    tracks, mus, sigmas, kw = load_refine_case(path)
+    got_mu, got_sig = refine_oracle.position_refinement(tracks, kw["LocErr"], kw["ds"], kw["Fs"], kw["TrMat"], kw["frame_len"],
+                                                        kw["threshold"], kw["max_nb_states"])
+    for k in tracks:
+        np.testing.assert_allclose(got_mu[k], mus[k], atol=1e-12)
+        np.testing.assert_allclose(got_sig[k], sigmas[k], atol=1e-12)
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not present")
+def test_refinement_oracle_vs_live_reference():
+    import contextlib
+    import io
+
+    from oracle import refine_oracle
+
+    rl = ref_loader.load_refined_localization()
+    rng = np.random.default_rng(12)
+    m = make_model(nS=2, frame_len=5)
+    tracks = {"7": random_walk_tracks(33, 7, 2, rng), "10": random_walk_tracks(31, 10, 2, rng)}
+    with contextlib.redirect_stdout(io.StringIO()):
+        mus, sig = rl.position_refinement(tracks, 0.02, m.ds, m.Fs, m.TrMat, frame_len=5, threshold=0.15, max_nb_states=1000)
+    omus, osig = refine_oracle.position_refinement(tracks, 0.02, m.ds, m.Fs, m.TrMat, 5, 0.15, 1000)
+    for k in tracks:
+        np.testing.assert_allclose(omus[k], mus[k], atol=1e-12)
+        np.testing.assert_allclose(osig[k], sig[k], atol=1e-12)
