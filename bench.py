@@ -411,7 +411,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: sim_FOV synthetic 2-state 2D, tracks length 10-30, frame_len=8 (bounded sample)",
+        "config": {"workload": "configs[1]: sim_FOV synthetic 2-state 2D, 10^6 tracks length 10-30, frame_len=8, one -logL evaluation",
+                   "sample": f"{n} tracks of the same generator per step (the metric is throughput-normalised: the CPU path needs "
+                             f"~{1e6 / n * 1e-3 * (1e3 * dt / args.steps):.0f} s per evaluation of the full 10^6 tracks)",
                    "tracks_per_step": n, "neglogl": val},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
   const int capP = cap / nS + 1;  // parent / group slots
 #define BP(slot, comp) bufP[(size_t)(comp) * capP + (slot)]
 #define BC(slot, comp) bufC[(size_t)(comp) * cap + (slot)]
+  // history window [row][state][slot]: consecutive lanes (slots) hit consecutive shared-memory banks
+#define HIX(slot, row, st) (((size_t)(row) * nS + (st)) * capP + (slot))
 
   double l2[KS];
 #pragma unroll
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         const int d0 = c % nS, d1 = c / nS;
         codeP[c] = (unsigned long long)d0 | ((unsigned long long)d1 << bits);
         for (int s = 0; s < nS; ++s) {
-          histP[((size_t)c * fl + 0) * nS + s] = (d0 == s) ? 1.0 : 0.0;
-          if (fl > 1) histP[((size_t)c * fl + 1) * nS + s] = (d1 == s) ? 1.0 : 0.0;
+          histP[HIX(c, 0, s)] = (d0 == s) ? 1.0 : 0.0;
+          if (fl > 1) histP[HIX(c, 1, s)] = (d1 == s) ? 1.0 : 0.0;
         }
       }
       int LhP = 2;       // full history length (never truncated in predict mode)
@@ -352,8 +354,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
             if (!FOLLOW)  // (history window and codes only serve this track's own decisions)
             for (int row = 0; row < rows_out; ++row)
               for (int s = 0; s < nS; ++s)
-                histN[((size_t)g * fl + row) * nS + s] =
-                    (row == 0) ? ((xt_label(c0, nS, wrap) == s) ? 1.0 : 0.0) : histP[((size_t)(c0 / K) * fl + row - 1) * nS + s];
+                histN[HIX(g, row, s)] =
+                    (row == 0) ? ((xt_label(c0, nS, wrap) == s) ? 1.0 : 0.0) : histP[HIX((c0 / K), row - 1, s)];
           } else {
             double mx = BC(c0, D + 2 * KS);
             for (int k = 1; k < n; ++k) mx = fmax(mx, BC(order[o + k], D + 2 * KS));
@@ -385,35 +387,60 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
               const int c = order[o + k];
               recW[(size_t)step * cap + c] = __ddiv_rn(recW[(size_t)step * cap + c], sw);
             }
-            // weighted mean of the members' window rows (tracking.py:733), member order
-            if (!FOLLOW)
-            for (int row = 0; row < rows_out; ++row)
-              for (int s = 0; s < nS; ++s) {
-                double acc = 0.0;
-                for (int k = 0; k < n; ++k) {
-                  const int c = order[o + k];
-                  const double hv = (row == 0) ? ((xt_label(c, nS, wrap) == s) ? 1.0 : 0.0)
-                                               : histP[((size_t)(c / K) * fl + row - 1) * nS + s];
-                  const double v = __dmul_rn(aC[c], hv);  // aC[c] = exp(LP_c - max) of this fusion (set above)
-                  acc = (k == 0) ? v : __dadd_rn(acc, v);
-                }
-                histN[((size_t)g * fl + row) * nS + s] = __ddiv_rn(acc, sw);
-              }
+            aP[g] = sw;  // (aP, like aC, is only used after the forward pass) for the history rows below
           }
-          // window code of the merged history (argmax per row, ties -> lowest state)
+          // window code of the merged history (argmax per row, ties -> lowest state); groups of several members: below
           unsigned long long code = 0;
-          if (!FOLLOW)
+          if (!FOLLOW && n == 1)
           for (int row = 0; row < rows_out; ++row) {
             int best = 0;
-            double bv = histN[((size_t)g * fl + row) * nS];
+            double bv = histN[HIX(g, row, 0)];
             for (int s = 1; s < nS; ++s) {
-              const double v = histN[((size_t)g * fl + row) * nS + s];
+              const double v = histN[HIX(g, row, s)];
               if (v > bv) { bv = v; best = s; }
             }
             code |= (unsigned long long)best << (bits * row);
           }
           codeC[g] = code;                 // staged: codeP/curP are still read by other lanes' merges? (no: only codeC/BC/histP)
           gid[g] = c0 % nS;                // staged newest true state (gid is dead after the CSR build)
+        }
+        if (!FOLLOW) {
+          // Groups of several members: weighted mean of the members' window rows (tracking.py:733, member order) with the
+          // whole warp, lane = (row, state) - a lane per group would leave most of the warp idle in the longest loop of
+          // the step - then their window codes, lane = group again.
+          __syncwarp();
+          const int items = rows_out * nS;
+          for (int g = 0; g < nG; ++g) {  // warp-uniform
+            const int o = goff[g], n = goff[g + 1] - o;
+            if (n == 1) continue;
+            const double sw = aP[g];
+            for (int idx = lane; idx < items; idx += 32) {
+              const int row = idx / nS, st = idx - row * nS;
+              double acc = 0.0;
+              for (int k = 0; k < n; ++k) {
+                const int c = order[o + k];
+                const double hv = (row == 0) ? ((xt_label(c, nS, wrap) == st) ? 1.0 : 0.0) : histP[HIX((c / K), row - 1, st)];
+                const double v = __dmul_rn(aC[c], hv);  // aC[c] = exp(LP_c - max) of this fusion
+                acc = (k == 0) ? v : __dadd_rn(acc, v);
+              }
+              histN[HIX(g, row, st)] = __ddiv_rn(acc, sw);
+            }
+          }
+          __syncwarp();
+          for (int g = lane; g < nG; g += 32) {
+            if (goff[g + 1] - goff[g] == 1) continue;
+            unsigned long long code = 0;
+            for (int row = 0; row < rows_out; ++row) {
+              int best = 0;
+              double bv = histN[HIX(g, row, 0)];
+              for (int st = 1; st < nS; ++st) {
+                const double v = histN[HIX(g, row, st)];
+                if (v > bv) { bv = v; best = st; }
+              }
+              code |= (unsigned long long)best << (bits * row);
+            }
+            codeC[g] = code;
+          }
         }
         __syncwarp();
         for (int g = lane; g < nG; g += 32) {
@@ -544,6 +571,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
   }
 #undef BP
 #undef BC
+#undef HIX
 #undef DDX
 #undef LROW
 }

@@ -824,3 +824,24 @@ def test_position_refinement_vs_oracle_larger_bucket():
         np.testing.assert_allclose(got_sig[k], want_sig[k], rtol=0, atol=1e-8)
     with pytest.raises(NotImplementedError):
         rl.position_refinement(tracks, {k: np.full(v.shape[:2] + (1,), 0.02) for k, v in tracks.items()}, m.ds, m.Fs, m.TrMat)
+
+
+def test_live_sequence_cap_is_reported_not_silently_exceeded(native):
+    """The engine holds at most XT_HARD_CAP = 4096 live state sequences after an expansion (the reference has no such
+    limit: it merely gets slow).  A model that needs more - 4 states, frame_len 6, a threshold that never fuses:
+    4^7 = 16384 - must fail with the documented message, on the fit path and on the annotation path."""
+    m = make_model(nS=4, frame_len=6, threshold=1e-9, max_nb_states=10**9)
+    C = random_walk_tracks(40, 12, 2, np.random.default_rng(2), Ds=m.ds**2 / 0.04)
+    eng = native.Engine(0)
+    try:
+        eng.upload([C], [1], len(C))
+        with pytest.raises(ValueError, match="live state sequences"):
+            eng.chunk_logp(0, len(C), engine_params(m, 2))
+        with pytest.raises(ValueError, match="live state sequences"):
+            eng.predict(engine_params(m, 2), 4)
+        # within the cap the same model works (frame_len 4: 4^5 = 1024 sequences)
+        m2 = make_model(nS=4, frame_len=4, threshold=1e-9, max_nb_states=10**9)
+        got = eng.chunk_logp(0, len(C), engine_params(m2, 2))
+    finally:
+        eng.close()
+    np.testing.assert_allclose(got, orc.chunk_logp(C, m2, 1), rtol=RTOL_LOGL)
