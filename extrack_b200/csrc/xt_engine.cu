@@ -70,6 +70,7 @@ struct xt_ctx {
   int k1_threads = 0;         // plan kernel threads per chunk: 0 = automatic (256, or 1024 for <= n_sm chunks)
   int k2_lpt = 1;             // replay schedule of the plan records: longest-processing-time-first (0: round-robin)
   int k2_cost[4] = {4, 7, 6, 2};  // its cost model: single-member group, pair, member list (base, per member)
+  int k2_cost_w0 = 0;         // per-step extra work of replay warp 0 (record staging), same units
   int k1_batch = 1;           // plan kernel, > 64 sequences: batched candidate leaders (0: one leader at a time)
   int pipeline = 1;
   int n_groups = 6;
@@ -90,6 +91,7 @@ struct xt_ctx {
   double* d_csum = nullptr;
   double* h_csum = nullptr;                 // pinned
   bool csum_fetched = false;                // h_csum already holds the chunk sums of the last evaluation
+  bool spec_dirty = true;                   // d_spec may be non-zero (set by a replay launch, or never cleared yet)
   int32_t* d_cw0[3] = {nullptr, nullptr, nullptr};  // first tile of every position: [0],[1] fused tables (corder), [2] plain table
   XtChunkSummary* d_summ = nullptr;
   std::vector<XtChunkSummary> summ;
@@ -747,6 +749,7 @@ static K1Args make_k1_args(xt_ctx* ctx, int bits) {
   a.batch_mode = ctx->k1_batch;
   a.lpt = ctx->k2_lpt;
   for (int i = 0; i < 4; ++i) a.cost[i] = ctx->k2_cost[i];
+  a.cost_w0 = ctx->k2_cost_w0;
 #ifdef XT_K1_PROF
   if (!g_k1_prof) cudaMalloc(&g_k1_prof, sizeof(long long) * 12 * 65536);
   a.prof = g_k1_prof;
@@ -883,9 +886,12 @@ static int enqueue_reduce(xt_ctx* ctx, int table, double* d_out) {
   const int nch = (int)ctx->chunks.size();
   k_reduce_chunks<<<nch, 32, 0, ctx->stream>>>(ctx->d_partial, ctx->d_cw0[table], table < 2 ? ctx->d_corder : nullptr,
                                                ctx->d_csum);
-  k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_csum, nch, d_out ? d_out : ctx->d_out);
+  ctx->stats.k2_launches += 1;
+  if (d_out) {  // device-resident total (xt_sum_logp_async); the synchronous entry points add the chunk sums on the host
+    k_reduce<<<1, 1024, 0, ctx->stream>>>(ctx->d_csum, nch, d_out);
+    ctx->stats.k2_launches += 1;
+  }
   XT_CUDA_OK(cudaGetLastError());
-  ctx->stats.k2_launches += 2;
   return XT_OK;
 }
 // objective of this context: the chunk sums added in chunk order on the host (after the evaluation)
@@ -1223,8 +1229,11 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
   k1_scratch_caps(ctx, p, true, &a.scapP, &a.scapC);
   if (a.scapC <= 0) return XT_RETRY_EARLY;
   const size_t smem = xt_k1_smem(ctx->cap, p->d + 2 * p->n_loc + 1, ctx->RH, p->nS, a.scapP, a.scapC, 0, nt);
-  XT_CUDA_OK(cudaMemsetAsync(ctx->d_spec, 0, sizeof(int), ctx->stream));
-  XT_CUDA_OK(cudaMemsetAsync(ctx->d_vflag, 0, sizeof(int32_t) * nch, ctx->stream));
+  if (ctx->spec_dirty) {  // (the replay kernel only ever sets the flag: it is cleared here after it was seen set)
+    XT_CUDA_OK(cudaMemsetAsync(ctx->d_spec, 0, sizeof(int), ctx->stream));
+    ctx->spec_dirty = false;
+  }
+  // (every CTA of the verification launch writes its chunk's flag, 0 included: no clearing pass)
   XT_CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
   XT_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
   for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamWaitEvent(ctx->cs[i], ctx->ev_fork, 0));
@@ -1250,7 +1259,10 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_csum, ctx->d_csum, sizeof(double) * nch, cudaMemcpyDeviceToHost, ctx->stream));  // one round trip
   XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  if (*ctx->h_spec) return XT_RETRY;
+  if (*ctx->h_spec) {
+    ctx->spec_dirty = true;
+    return XT_RETRY;
+  }
   ctx->csum_fetched = true;
   std::vector<int32_t> redo;
   for (int c = 0; c < nch; ++c)
@@ -1291,7 +1303,10 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
     XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
     XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    if (*ctx->h_spec) return XT_RETRY;
+    if (*ctx->h_spec) {
+      ctx->spec_dirty = true;
+      return XT_RETRY;
+    }
     for (int c : redo) ctx->summ[c] = ctx->h_summ[c];
   }
   int Pmax, maxC;
@@ -1329,6 +1344,7 @@ static int evaluate(xt_ctx* ctx, const xt_params* p, double* d_out, const double
     ctx->stats = xt_stats{};
     ctx->plan_valid = false;
   }
+  ctx->spec_dirty = true;  // (the construction paths clear the flag themselves and may leave it set)
   if (ctx->pipeline && ctx->spec_Pmax > 0) {
     rc = evaluate_pipelined(ctx, p, bits, d_out, xyz);
     if (rc != XT_RETRY && rc != XT_RETRY_EARLY) return rc;
@@ -1518,6 +1534,11 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
       return XT_ERR_ARG;
     }
     ctx->k2_cost[name[7] - '0'] = value;
+    ctx->have_eval = false;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k2_cost_w0") == 0) {
+    ctx->k2_cost_w0 = value < 0 ? 0 : value;
     ctx->have_eval = false;
     return XT_OK;
   }

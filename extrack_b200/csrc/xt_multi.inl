@@ -11,6 +11,8 @@
 // any number of devices (BFGS finite differences rely on reproducibility, and a fit does not change with
 // the GPU count).  No collective is needed in process: the 8-byte-per-chunk read-back replaces the
 // all-reduce of the one-process-per-GPU mode.
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -32,6 +34,9 @@ struct xt_multi {
   uint64_t gen = 0;
   int pending = 0;
   bool quit = false;
+  std::atomic<uint64_t> gen_atomic{0};  // mirrors of gen / pending / quit for the short spin phases
+  std::atomic<int> pending_atomic{0};
+  std::atomic<bool> quit_atomic{false};
   std::function<int(int)> job;
   std::vector<int> rc;
 };
@@ -43,6 +48,12 @@ static void xt_multi_worker(xt_multi* m, int g) {
   for (;;) {
     std::function<int(int)> job;
     {
+      // objective calls of a fit follow each other within ~0.1 ms: look at the generation counter for that long before
+      // going to sleep on the condition variable (a futex wake-up costs about as much as the GPU work of a small shard)
+      const auto t0 = std::chrono::steady_clock::now();
+      while (m->gen_atomic.load(std::memory_order_acquire) == seen && !m->quit_atomic.load(std::memory_order_acquire) &&
+             std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200)) {
+      }
       std::unique_lock<std::mutex> lk(m->mu);
       m->cv_go.wait(lk, [&] { return m->quit || m->gen != seen; });
       if (m->quit) return;
@@ -54,6 +65,7 @@ static void xt_multi_worker(xt_multi* m, int g) {
       std::lock_guard<std::mutex> lk(m->mu);
       m->rc[g] = r;
       if (--m->pending == 0) m->cv_done.notify_one();
+      m->pending_atomic.store(m->pending, std::memory_order_release);
     }
   }
 }
@@ -65,11 +77,17 @@ static int xt_multi_run(xt_multi* m, const std::function<int(int)>& job) {
     std::lock_guard<std::mutex> lk(m->mu);
     m->job = job;
     m->pending = n - 1;
+    m->pending_atomic.store(n - 1, std::memory_order_release);
     ++m->gen;
+    m->gen_atomic.store(m->gen, std::memory_order_release);
   }
   if (n > 1) m->cv_go.notify_all();
   m->rc[0] = job(0);
   if (n > 1) {
+    const auto t0 = std::chrono::steady_clock::now();  // the other devices finish within microseconds of this one
+    while (m->pending_atomic.load(std::memory_order_acquire) != 0 &&
+           std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200)) {
+    }
     std::unique_lock<std::mutex> lk(m->mu);
     m->cv_done.wait(lk, [&] { return m->pending == 0; });
   }
@@ -111,6 +129,7 @@ extern "C" void xt_multi_destroy(xt_multi* m) {
   {
     std::lock_guard<std::mutex> lk(m->mu);
     m->quit = true;
+    m->quit_atomic.store(true, std::memory_order_release);
   }
   m->cv_go.notify_all();
   for (std::thread& t : m->th) t.join();

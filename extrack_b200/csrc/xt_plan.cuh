@@ -46,6 +46,7 @@ struct K1Args {
                        // (>= 2) at which one changed (or 1: the plan has no verification records for this chunk)
   int32_t lpt;         // replay schedule: 1 = longest-processing-time-first (<= 64 groups, <= 4 replay warps), 0 = round-robin
   int32_t cost[4];     // cost model of the schedule: single-member group, pair, member list (cost[2] + cost[3] * members)
+  int32_t cost_w0;     // ... and the per-step extra work of replay warp 0 in the same units
   XtAux ax;            // VAR instantiation only
 };
 
@@ -120,7 +121,10 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
   const int nP0 = K * nS;
   if (VERIFY) {
     if (tid == 0) s_flag = 0;
-    if (ck.L < 4) return;  // no fusion step, nothing to verify
+    if (ck.L < 4) {  // no fusion step, nothing to verify
+      if (tid == 0) a.vflag[cid] = 0;
+      return;
+    }
   }
   if (!VERIFY && tid == 0) {
     sm->err = 0;
@@ -1030,7 +1034,8 @@ k1_plan(const K1Args a, const __grid_constant__ xt_params P) {
             }
           }
           __syncwarp();
-          int ld0 = 0, ld1 = 0, ld2 = 0, ld3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+          // (replay warp 0 also stages the next record and the next localisation's prefetch bookkeeping: a head start for the others)
+          int ld0 = a.cost_w0, ld1 = 0, ld2 = 0, ld3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
           int myw[2] = {0, 0}, myp[2] = {0, 0};
           for (int r = 0; r < nG; ++r) {
             const int g = grank[r];
