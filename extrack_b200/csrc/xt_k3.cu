@@ -4,24 +4,45 @@
 #include "xt_predict_shared.cuh"
 #include "xt_refine.cuh"
 
-template <int D, int KS, bool VAR>
-static cudaError_t launch_k3_v(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
-  auto kern = k3_predict<D, KS, VAR>;
+// The own-plan annotation kernel of a model: scalar models with 2 or 3 states and the hot scratch in shared memory get
+// the instantiation with the number of states fixed at compile time (NSC), everything else the generic one.
+using K3Kern = void (*)(const K3Args, const xt_params);
+struct K3Pick {
+  K3Kern kern;
+  unsigned long long* smem_ok;
+};
+template <int D, int KS, bool VAR, int NSC>
+static K3Pick k3_one() {
   static unsigned long long smem_ok = 0;
-  cudaError_t e = xt_allow_smem(kern, smem, &smem_ok);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, 32 * nwarps, smem, stream>>>(a, p);
-  return cudaGetLastError();
+  return K3Pick{k3_predict<D, KS, VAR, false, false, NSC>, &smem_ok};
+}
+static K3Pick k3_pick(const xt_params& p, int hot_smem) {
+  K3Pick k{nullptr, nullptr};
+  const bool var = xt_is_var(&p);
+  const int nsc = (!var && hot_smem && (p.nS == 2 || p.nS == 3)) ? p.nS : 0;
+#define PICK_K3(D_, KS_)                                      \
+  k = var ? k3_one<D_, KS_, true, 0>()                        \
+          : (nsc == 2 ? k3_one<D_, KS_, false, 2>() : (nsc == 3 ? k3_one<D_, KS_, false, 3>() : k3_one<D_, KS_, false, 0>()))
+  XT_DISPATCH(p.d, p.n_loc, PICK_K3);
+#undef PICK_K3
+  return k;
+}
+
+int xt_k3_regs(const xt_params& p, int hot_smem) {
+  cudaFuncAttributes at;
+  if (cudaFuncGetAttributes(&at, k3_pick(p, hot_smem).kern) != cudaSuccess) {
+    cudaGetLastError();
+    return 128;
+  }
+  return at.numRegs;
 }
 
 cudaError_t xt_launch_k3(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaSuccess;
-  const bool var = xt_is_var(&p);
-#define CALL_K3(D_, KS_) \
-  e = var ? launch_k3_v<D_, KS_, true>(a, p, grid, nwarps, smem, stream) : launch_k3_v<D_, KS_, false>(a, p, grid, nwarps, smem, stream)
-  XT_DISPATCH(p.d, p.n_loc, CALL_K3);
-#undef CALL_K3
-  return e;
+  const K3Pick k = k3_pick(p, a.hot_smem);
+  cudaError_t e = xt_allow_smem(k.kern, smem, k.smem_ok);
+  if (e != cudaSuccess) return e;
+  k.kern<<<grid, 32 * nwarps, smem, stream>>>(a, p);
+  return cudaGetLastError();
 }
 
 // predict_Bs with nb_max > 1: the plans shared by the tracks of a chunk, then the annotation that follows them

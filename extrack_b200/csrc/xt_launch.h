@@ -60,6 +60,7 @@ cudaError_t xt_launch_k2_old(const K2Args& a, const xt_params& p, const K2Lin& l
                              int wpc, cudaStream_t stream);
 // state annotation (xt_predict.cuh)
 cudaError_t xt_launch_k3(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
+int xt_k3_regs(const xt_params& p, int hot_smem);  // registers per thread of the kernel xt_launch_k3 would launch
 // ... with plans shared by the nb_max tracks of a chunk (xt_predict_shared.cuh): the plans, then the annotation along them
 cudaError_t xt_launch_k3_shared_plan(const K3SArgs& a, const xt_params& p, int grid, cudaStream_t stream);
 cudaError_t xt_launch_k3_follow(const K3Args& a, const xt_params& p, int grid, int nwarps, size_t smem, cudaStream_t stream);

@@ -18,6 +18,9 @@
 #include "xt_plan.cuh"
 
 #define XT_K3_WARPS 8
+#ifndef XT_K3_MIN_CTAS
+#define XT_K3_MIN_CTAS 2  // resident CTAs of 8 warps the register allocation leaves room for (2: 128 registers)
+#endif
 
 struct K3Args {
   const XtChunk* chunks;
@@ -75,52 +78,65 @@ __host__ __device__ inline K3Layout k3_layout(int cap, int CO, int fl, int nS, i
   l.order = o;  o += (cap + 1) / 2;
   l.goff = o;   o += (cap + 2) / 2;        // int32[cap+1]
   l.curP = o;   o += (cap + 1) / 2;
+  l.recN = o;   o += (maxL + 2) / 2;       // int32[maxL+1]: children per fused step (read again by the backward sweep)
   l.hot_total = (o + 1) & ~(size_t)1;
   o = 0;
   l.recW = o;   o += (size_t)maxL * cap;
-  l.recN = o;   o += (maxL + 2) / 2;       // int32[maxL+1]
   l.recGid = o; o += ((size_t)maxL * cap + 3) / 4;  // uint16[maxL][cap]
   l.cold_total = o + 4;
   return l;
 }
 
-template <int D, int KS, bool VAR = false, bool FOLLOW = false, bool REFINE = false>
-__global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, const __grid_constant__ xt_params P) {
+template <int D, int KS, bool VAR = false, bool FOLLOW = false, bool REFINE = false, int NSC = 0>
+__global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(const K3Args a, const __grid_constant__ xt_params P) {
   static_assert(!(VAR && FOLLOW), "shared plans are built for scalar LocErr / dt models");
   static_assert(!REFINE || FOLLOW, "the refinement recursion follows the bucket's shared plan");
+  // NSC > 0: the number of states is the compile-time constant NSC and the hot scratch is known to be in shared memory
+  // (32-bit shared-memory addressing, shifts / multiply-shifts instead of integer divisions); NSC == 0: both at run time
+  constexpr bool HOT = NSC > 0;
   extern __shared__ double k3_smem[];
   const int nwarps = blockDim.x >> 5;  // <= XT_K3_WARPS (fewer when the hot scratch of 8 warps exceeds shared memory)
   constexpr int CO = D + 2 * KS + 1;  // m[D], s2[KS], s[KS], LP
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nS = P.nS, K = P.nS, cap = a.cap, fl = P.frame_len, bits = a.bits;
+  const int nS = NSC ? NSC : P.nS, K = nS, cap = a.cap, fl = P.frame_len, bits = a.bits;
   const bool wrap = (P.flags & XT_FLAG_INT8_WRAP) != 0;
   const unsigned long long rowmask = (1ull << bits) - 1ull;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // history label of child c (tracking.py:543: the int8 wrap); 256 is a multiple of a power-of-two nS, so there the
+  // wrap leaves the residue alone
+  auto label = [&](int c) -> int {
+    if constexpr (NSC == 2 || NSC == 4) return c & (NSC - 1);
+    else return xt_label(c, nS, wrap);
+  };
 
   // ---- per-warp scratch carve-up ----
   const K3Layout lay = k3_layout(cap, CO, fl, nS, a.maxL);
   double* cold = a.scratch + (size_t)(blockIdx.x * nwarps + warp) * a.warp_scratch;
-  double* base = a.hot_smem ? k3_smem + (size_t)warp * lay.hot_total : cold + lay.cold_total;
-  double* bufP = base + lay.bufP;            // [CO][cap]
-  double* bufC = base + lay.bufC;
-  double* histP = base + lay.histP;          // [cap][fl][nS]
-  double* histN = base + lay.histN;
-  unsigned long long* codeP = (unsigned long long*)(base + lay.codeP);
-  unsigned long long* codeC = (unsigned long long*)(base + lay.codeC);
-  double* aC = base + lay.aC;
-  double* aP = base + lay.aP;
-  int* gid = (int*)(base + lay.gid);
-  int* order = (int*)(base + lay.order);
-  int* goff = (int*)(base + lay.goff);       // [cap+1]
-  int* curP = (int*)(base + lay.curP);
-  double* recW = cold + lay.recW;            // [maxL][cap]
-  int* recN = (int*)(cold + lay.recN);       // children per fused step
+  double* base;
+  if constexpr (HOT) base = k3_smem + warp * (int)lay.hot_total;
+  else base = a.hot_smem ? k3_smem + (size_t)warp * lay.hot_total : cold + lay.cold_total;
+  double* bufP = base + (int)lay.bufP;            // [CO][capP]
+  double* bufC = base + (int)lay.bufC;            // [CO][cap]
+  int hP = (int)lay.histP, hN = (int)lay.histN;   // history windows [fl][nS][capP] (offsets: the two swap every step)
+  unsigned long long* codeP = (unsigned long long*)(base + (int)lay.codeP);
+  unsigned long long* codeC = (unsigned long long*)(base + (int)lay.codeC);
+  double* aC = base + (int)lay.aC;
+  double* aP = base + (int)lay.aP;
+  int* gid = (int*)(base + (int)lay.gid);
+  int* order = (int*)(base + (int)lay.order);
+  int* goff = (int*)(base + (int)lay.goff);       // [cap+1]
+  int* curP = (int*)(base + (int)lay.curP);
+  int* recN = (int*)(base + (int)lay.recN);       // children per fused step
+  double* recW = cold + lay.recW;                 // [maxL][cap]
   uint16_t* recGid = (uint16_t*)(cold + lay.recGid);
 
   const int capP = cap / nS + 1;  // parent / group slots
-#define BP(slot, comp) bufP[(size_t)(comp) * capP + (slot)]
-#define BC(slot, comp) bufC[(size_t)(comp) * cap + (slot)]
+#define BP(slot, comp) bufP[(comp) * capP + (slot)]
+#define BC(slot, comp) bufC[(comp) * cap + (slot)]
   // history window [row][state][slot]: consecutive lanes (slots) hit consecutive shared-memory banks
-#define HIX(slot, row, st) (((size_t)(row) * nS + (st)) * capP + (slot))
+#define HIX(slot, row, st) (((row) * nS + (st)) * capP + (slot))
+#define HISTP(slot, row, st) base[hP + HIX(slot, row, st)]
+#define HISTN(slot, row, st) base[hN + HIX(slot, row, st)]
 
   double l2[KS];
 #pragma unroll
@@ -180,8 +196,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         const int d0 = c % nS, d1 = c / nS;
         codeP[c] = (unsigned long long)d0 | ((unsigned long long)d1 << bits);
         for (int s = 0; s < nS; ++s) {
-          histP[HIX(c, 0, s)] = (d0 == s) ? 1.0 : 0.0;
-          if (fl > 1) histP[HIX(c, 1, s)] = (d1 == s) ? 1.0 : 0.0;
+          HISTP(c, 0, s) = (d0 == s) ? 1.0 : 0.0;
+          if (fl > 1) HISTP(c, 1, s) = (d1 == s) ? 1.0 : 0.0;
         }
       }
       int LhP = 2;       // full history length (never truncated in predict mode)
@@ -200,6 +216,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         const int rows_cmp = LhC < fl ? LhC : fl;    // rows stored / compared for the children
         const bool use_window = LhC > fl;
         const unsigned long long cmask = (bits * rows_cmp >= 64) ? ~0ull : ((1ull << (bits * rows_cmp)) - 1ull);
+        // the own-plan grouping keeps the candidates of up to 64 children in registers (two per lane)
+        const bool reg_grouping = !FOLLOW && nC <= 64;
         double cl[D];
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) cl[dim] = Cp[(size_t)(LROW(step - 1) * D + dim) * npad];
@@ -245,8 +263,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
           double add = __dadd_rn(P.LT[head], __dsub_rn(logs, quad));
           if (stay) add = __dadd_rn(add, Lps[r]);
           BC(c, D + 2 * KS) = __dadd_rn(BP(p, D + 2 * KS), add);
-          codeC[c] = ((codeP[p] << bits) | (unsigned long long)xt_label(c, nS, wrap)) & cmask;
-          gid[c] = -1;
+          codeC[c] = ((codeP[p] << bits) | (unsigned long long)label(c)) & cmask;
+          if (!FOLLOW && !reg_grouping) gid[c] = -1;
         }
         if (nC > P.max_nb_states) th = __dmul_rn(th, 1.2);
         __syncwarp();
@@ -258,6 +276,37 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
 
         // ---- greedy grouping from this track alone (tracking.py:667-698 with one leader track) ----
         const double th_lo = __dmul_rn(th, 1.0 - 1e-14), th_hi = __dmul_rn(th, 1.0 + 1e-14);
+        // does the leader (ci, mi, si) capture the candidate (cj, mj, sj)?
+        auto captures = [&](unsigned long long ci, const double* mi, const double* si, unsigned long long cj, const double* mj,
+                            const double* sj) -> bool {
+          if (use_window && cj == ci) return true;
+          if ((cj & rowmask) != (ci & rowmask)) return false;
+          double am = 0.0, as = 0.0;
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) {
+            const double v = fabs(__dsub_rn(mj[dim], mi[dim]));
+            am = (dim == 0) ? v : __dadd_rn(am, v);
+          }
+          am = (D == 2) ? __dmul_rn(am, 0.5) : ((D == 1) ? am : __ddiv_rn(am, (double)D));
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            const double v = fabs(__dsub_rn(sj[k], si[k]));
+            as = (k == 0) ? v : __dadd_rn(as, v);
+          }
+          as = (KS == 2) ? __dmul_rn(as, 0.5) : ((KS == 1) ? as : __ddiv_rn(as, (double)KS));
+          // one leader track: mean(bool over KS comps) > 0.8  <=>  every component passes
+          // fl(x / s) < th decided without a division unless x is within 1e-14 (relative) of th*s
+          bool ok = true;
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            const double lo = __dmul_rn(th_lo, sj[k]), hi = __dmul_rn(th_hi, sj[k]);
+            bool pm = am < lo, ps = as < lo;
+            if (!pm && !(am > hi)) pm = __ddiv_rn(am, sj[k]) < th;
+            if (!ps && !(as > hi)) ps = __ddiv_rn(as, sj[k]) < th;
+            ok = ok && pm && ps;
+          }
+          return ok;
+        };
         int nG = 0, off = 0;
         if (FOLLOW) {  // the chunk's shared plan: member lists of this step
           const int32_t* plan = a.splan + (size_t)wk.chunk * a.splan_stride;
@@ -270,64 +319,87 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
             off = nC;
           }
           __syncwarp();
-        } else
-        for (int i = 0; i < nC; ++i) {
-          if (gid[i] >= 0) continue;  // warp-uniform (memory made visible by __syncwarp)
-          double mi[D], si[KS];
+        } else if (reg_grouping) {
+          // lane holds the children lane and lane + 32; the next leader is the first child nobody captured yet
+          double mj0[D], sj0[KS], mj1[D], sj1[KS];
+          unsigned long long cj0 = 0, cj1 = 0;
+          const bool has0 = lane < nC, has1 = lane + 32 < nC;
 #pragma unroll
-          for (int dim = 0; dim < D; ++dim) mi[dim] = BC(i, dim);
-#pragma unroll
-          for (int k = 0; k < KS; ++k) si[k] = BC(i, D + KS + k);
-          const unsigned long long ci = codeC[i];
-          goff[nG] = off;
-          for (int j0 = 0; j0 < nC; j0 += 32) {
-            const int j = j0 + lane;
-            bool ok = false;
-            if (j < nC && gid[j] < 0) {
-              const unsigned long long cj = codeC[j];
-              if (use_window && cj == ci) {
-                ok = true;
-              } else if ((cj & rowmask) == (ci & rowmask)) {
-                double am = 0.0, as = 0.0;
-#pragma unroll
-                for (int dim = 0; dim < D; ++dim) {
-                  const double v = fabs(__dsub_rn(BC(j, dim), mi[dim]));
-                  am = (dim == 0) ? v : __dadd_rn(am, v);
-                }
-                am = (D == 2) ? __dmul_rn(am, 0.5) : ((D == 1) ? am : __ddiv_rn(am, (double)D));
-                double sj[KS];
-#pragma unroll
-                for (int k = 0; k < KS; ++k) {
-                  sj[k] = BC(j, D + KS + k);
-                  const double v = fabs(__dsub_rn(sj[k], si[k]));
-                  as = (k == 0) ? v : __dadd_rn(as, v);
-                }
-                as = (KS == 2) ? __dmul_rn(as, 0.5) : ((KS == 1) ? as : __ddiv_rn(as, (double)KS));
-                // one leader track: mean(bool over KS comps) > 0.8  <=>  every component passes
-                // fl(x / s) < th decided without a division unless x is within 1e-14 (relative) of th*s
-                ok = true;
-#pragma unroll
-                for (int k = 0; k < KS; ++k) {
-                  const double lo = __dmul_rn(th_lo, sj[k]), hi = __dmul_rn(th_hi, sj[k]);
-                  bool pm = am < lo, ps = as < lo;
-                  if (!pm && !(am > hi)) pm = __ddiv_rn(am, sj[k]) < th;
-                  if (!ps && !(as > hi)) ps = __ddiv_rn(as, sj[k]) < th;
-                  ok = ok && pm && ps;
-                }
-              }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-              gid[j] = nG;
-              order[off + __popc(m & ((1u << lane) - 1u))] = j;
-            }
-            off += __popc(m);
+          for (int dim = 0; dim < D; ++dim) {
+            mj0[dim] = has0 ? BC(lane, dim) : 0.0;
+            mj1[dim] = has1 ? BC(lane + 32, dim) : 0.0;
           }
-          if (off == goff[nG]) errc = 1;  // leader failed its own test and captured nobody (:725)
-          ++nG;
-          __syncwarp();
-        }
-        if (!FOLLOW) {
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            sj0[k] = has0 ? BC(lane, D + KS + k) : 1.0;
+            sj1[k] = has1 ? BC(lane + 32, D + KS + k) : 1.0;
+          }
+          if (has0) cj0 = codeC[lane];
+          if (has1) cj1 = codeC[lane + 32];
+          unsigned u0 = __ballot_sync(0xffffffffu, has0), u1 = __ballot_sync(0xffffffffu, has1);
+          while (u0 | u1) {
+            const int i = u0 ? (__ffs(u0) - 1) : (31 + __ffs(u1));
+            double mi[D], si[KS];
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) mi[dim] = BC(i, dim);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) si[k] = BC(i, D + KS + k);
+            const unsigned long long ci = codeC[i];
+            if (lane == 0) goff[nG] = off;
+            const int off_in = off;
+            if (u0) {
+              const bool ok = ((u0 >> lane) & 1u) && captures(ci, mi, si, cj0, mj0, sj0);
+              const unsigned m = __ballot_sync(0xffffffffu, ok);
+              if (ok) order[off + __popc(m & lt_mask)] = lane;
+              off += __popc(m);
+              u0 &= ~m;
+            }
+            if (u1) {
+              const bool ok = ((u1 >> lane) & 1u) && captures(ci, mi, si, cj1, mj1, sj1);
+              const unsigned m = __ballot_sync(0xffffffffu, ok);
+              if (ok) order[off + __popc(m & lt_mask)] = lane + 32;
+              off += __popc(m);
+              u1 &= ~m;
+            }
+            if (off == off_in) {  // leader failed its own test and captured nobody (:725, :700-701)
+              errc = 1;
+              break;
+            }
+            ++nG;
+          }
+          if (lane == 0) goff[nG] = off;
+        } else {
+          for (int i = 0; i < nC; ++i) {
+            if (gid[i] >= 0) continue;  // warp-uniform (memory made visible by __syncwarp)
+            double mi[D], si[KS];
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) mi[dim] = BC(i, dim);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) si[k] = BC(i, D + KS + k);
+            const unsigned long long ci = codeC[i];
+            goff[nG] = off;
+            for (int j0 = 0; j0 < nC; j0 += 32) {
+              const int j = j0 + lane;
+              bool ok = false;
+              if (j < nC && gid[j] < 0) {
+                double mj[D], sj[KS];
+#pragma unroll
+                for (int dim = 0; dim < D; ++dim) mj[dim] = BC(j, dim);
+#pragma unroll
+                for (int k = 0; k < KS; ++k) sj[k] = BC(j, D + KS + k);
+                ok = captures(ci, mi, si, codeC[j], mj, sj);
+              }
+              const unsigned m = __ballot_sync(0xffffffffu, ok);
+              if (ok) {
+                gid[j] = nG;
+                order[off + __popc(m & lt_mask)] = j;
+              }
+              off += __popc(m);
+            }
+            if (off == goff[nG]) errc = 1;  // leader failed its own test and captured nobody (:725)
+            ++nG;
+            __syncwarp();
+          }
           if (lane == 0) goff[nG] = off;
           for (int c = lane; c < nC; c += 32)
             if (gid[c] < 0) errc = 1;  // tracking.py:700-701
@@ -343,124 +415,122 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         // ---- merge, lane = group (tracking.py:723-741); record normalised weights ----
         if (lane == 0) recN[step] = nC;
         const int rows_out = rows_cmp;  // window rows kept (older rows never influence a decision)
-        for (int g = lane; g < nG; g += 32) {
-          const int o = goff[g], n = goff[g + 1] - o;
-          const int c0 = order[o];
-          if (n == 1) {
-#pragma unroll
-            for (int q = 0; q < CO; ++q) BP(g, q) = BC(c0, q);
-            recW[(size_t)step * cap + c0] = 1.0;
-            recGid[(size_t)step * cap + c0] = (uint16_t)g;
-            if (!FOLLOW)  // (history window and codes only serve this track's own decisions)
-            for (int row = 0; row < rows_out; ++row)
-              for (int s = 0; s < nS; ++s)
-                histN[HIX(g, row, s)] =
-                    (row == 0) ? ((xt_label(c0, nS, wrap) == s) ? 1.0 : 0.0) : histP[HIX((c0 / K), row - 1, s)];
-          } else {
-            double mx = BC(c0, D + 2 * KS);
-            for (int k = 1; k < n; ++k) mx = fmax(mx, BC(order[o + k], D + 2 * KS));
-            double sw = 0.0, am[D], as2[KS];
-            for (int k = 0; k < n; ++k) {
-              const int c = order[o + k];
-              const double w = exp(__dsub_rn(BC(c, D + 2 * KS), mx));
-              recW[(size_t)step * cap + c] = w;
-              aC[c] = w;  // (aC is only used after the forward pass: free scratch here)
-              recGid[(size_t)step * cap + c] = (uint16_t)g;
-              sw = (k == 0) ? w : __dadd_rn(sw, w);
-#pragma unroll
-              for (int dim = 0; dim < D; ++dim) {
-                const double v = __dmul_rn(w, BC(c, dim));
-                am[dim] = (k == 0) ? v : __dadd_rn(am[dim], v);
-              }
-#pragma unroll
-              for (int k2 = 0; k2 < KS; ++k2) {
-                const double v = __dmul_rn(w, BC(c, D + k2));
-                as2[k2] = (k == 0) ? v : __dadd_rn(as2[k2], v);
-              }
-            }
-#pragma unroll
-            for (int dim = 0; dim < D; ++dim) BP(g, dim) = __ddiv_rn(am[dim], sw);
-#pragma unroll
-            for (int k2 = 0; k2 < KS; ++k2) BP(g, D + k2) = __ddiv_rn(as2[k2], sw);
-            BP(g, D + 2 * KS) = __dadd_rn(log(sw), mx);
-            for (int k = 0; k < n; ++k) {  // normalise the recorded weights
-              const int c = order[o + k];
-              recW[(size_t)step * cap + c] = __ddiv_rn(recW[(size_t)step * cap + c], sw);
-            }
-            aP[g] = sw;  // (aP, like aC, is only used after the forward pass) for the history rows below
-          }
-          // window code of the merged history (argmax per row, ties -> lowest state); groups of several members: below
-          unsigned long long code = 0;
-          if (!FOLLOW && n == 1)
-          for (int row = 0; row < rows_out; ++row) {
-            int best = 0;
-            double bv = histN[HIX(g, row, 0)];
-            for (int s = 1; s < nS; ++s) {
-              const double v = histN[HIX(g, row, s)];
-              if (v > bv) { bv = v; best = s; }
-            }
-            code |= (unsigned long long)best << (bits * row);
-          }
-          codeC[g] = code;                 // staged: codeP/curP are still read by other lanes' merges? (no: only codeC/BC/histP)
-          gid[g] = c0 % nS;                // staged newest true state (gid is dead after the CSR build)
-        }
-        if (!FOLLOW) {
-          // Groups of several members: weighted mean of the members' window rows (tracking.py:733, member order) with the
-          // whole warp, lane = (row, state) - a lane per group would leave most of the warp idle in the longest loop of
-          // the step - then their window codes, lane = group again.
-          __syncwarp();
-          const int items = rows_out * nS;
-          for (int g = 0; g < nG; ++g) {  // warp-uniform
+        double* rw = recW + (size_t)step * cap;
+        uint16_t* rg = recGid + (size_t)step * cap;
+        int nM = 0;  // groups of several members, listed in gid[] (free after the grouping)
+        for (int g0 = 0; g0 < nG; g0 += 32) {
+          const int g = g0 + lane;
+          bool multi = false;
+          if (g < nG) {
             const int o = goff[g], n = goff[g + 1] - o;
-            if (n == 1) continue;
-            const double sw = aP[g];
-            for (int idx = lane; idx < items; idx += 32) {
-              const int row = idx / nS, st = idx - row * nS;
-              double acc = 0.0;
+            const int c0 = order[o];
+            if (n == 1) {
+#pragma unroll
+              for (int q = 0; q < CO; ++q) BP(g, q) = BC(c0, q);
+              rw[c0] = 1.0;
+              rg[c0] = (uint16_t)g;
+              if (!FOLLOW) {  // (history window and codes only serve this track's own decisions)
+                const int lab = label(c0), p0 = c0 / K;
+                for (int s = 0; s < nS; ++s) HISTN(g, 0, s) = (lab == s) ? 1.0 : 0.0;
+                for (int it = nS; it < rows_out * nS; ++it) base[hN + it * capP + g] = base[hP + (it - nS) * capP + p0];
+                // the window code of an unmerged sequence is its own (codes are the per-row argmax of the window)
+                codeP[g] = codeC[c0];
+              }
+            } else {
+              multi = true;
+              double mx = BC(c0, D + 2 * KS);
+              for (int k = 1; k < n; ++k) mx = fmax(mx, BC(order[o + k], D + 2 * KS));
+              double sw = 0.0, am[D], as2[KS];
               for (int k = 0; k < n; ++k) {
                 const int c = order[o + k];
-                const double hv = (row == 0) ? ((xt_label(c, nS, wrap) == st) ? 1.0 : 0.0) : histP[HIX((c / K), row - 1, st)];
-                const double v = __dmul_rn(aC[c], hv);  // aC[c] = exp(LP_c - max) of this fusion
-                acc = (k == 0) ? v : __dadd_rn(acc, v);
+                const double w = exp(__dsub_rn(BC(c, D + 2 * KS), mx));
+                aC[c] = w;  // (aC is only used after the forward pass: free scratch here)
+                rg[c] = (uint16_t)g;
+                sw = (k == 0) ? w : __dadd_rn(sw, w);
+#pragma unroll
+                for (int dim = 0; dim < D; ++dim) {
+                  const double v = __dmul_rn(w, BC(c, dim));
+                  am[dim] = (k == 0) ? v : __dadd_rn(am[dim], v);
+                }
+#pragma unroll
+                for (int k2 = 0; k2 < KS; ++k2) {
+                  const double v = __dmul_rn(w, BC(c, D + k2));
+                  as2[k2] = (k == 0) ? v : __dadd_rn(as2[k2], v);
+                }
               }
-              histN[HIX(g, row, st)] = __ddiv_rn(acc, sw);
+#pragma unroll
+              for (int dim = 0; dim < D; ++dim) BP(g, dim) = __ddiv_rn(am[dim], sw);
+#pragma unroll
+              for (int k2 = 0; k2 < KS; ++k2) BP(g, D + k2) = __ddiv_rn(as2[k2], sw);
+              BP(g, D + 2 * KS) = __dadd_rn(log(sw), mx);
+              for (int k = 0; k < n; ++k) {  // the recorded weights, normalised
+                const int c = order[o + k];
+                rw[c] = __ddiv_rn(aC[c], sw);
+              }
+              aP[g] = sw;  // (aP, like aC, is only used after the forward pass) for the history rows below
             }
+            curP[g] = c0 % nS;  // newest true state (curP / codeP are only read by the expansion)
+          }
+          if (!FOLLOW) {
+            const unsigned mm = __ballot_sync(0xffffffffu, multi);
+            if (multi) gid[nM + __popc(mm & lt_mask)] = g;
+            nM += __popc(mm);
+          }
+        }
+        if (!FOLLOW && nM > 0) {
+          // Groups of several members: weighted mean of the members' window rows (tracking.py:733, member order), one lane
+          // per (group, row, state) over all of them at once, then their window codes (argmax per row, ties -> lowest
+          // state), lane = group again.
+          __syncwarp();
+          const int items = rows_out * nS, tot = nM * items;
+          const float inv_items = 1.0f / (float)items;
+          for (int idx = lane; idx < tot; idx += 32) {
+            const int gm = (int)(((float)idx + 0.5f) * inv_items), it = idx - gm * items;
+            const int row = it / nS, st = it - row * nS;
+            const int g = gid[gm];
+            const int o = goff[g], n = goff[g + 1] - o;
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) {
+              const int c = order[o + k];
+              const double hv = (row == 0) ? ((label(c) == st) ? 1.0 : 0.0) : base[hP + (it - nS) * capP + c / K];
+              const double v = __dmul_rn(aC[c], hv);  // aC[c] = exp(LP_c - max) of this fusion
+              acc = (k == 0) ? v : __dadd_rn(acc, v);
+            }
+            base[hN + it * capP + g] = __ddiv_rn(acc, aP[g]);
           }
           __syncwarp();
-          for (int g = lane; g < nG; g += 32) {
-            if (goff[g + 1] - goff[g] == 1) continue;
+          for (int gm = lane; gm < nM; gm += 32) {
+            const int g = gid[gm];
             unsigned long long code = 0;
             for (int row = 0; row < rows_out; ++row) {
               int best = 0;
-              double bv = histN[HIX(g, row, 0)];
+              double bv = HISTN(g, row, 0);
               for (int st = 1; st < nS; ++st) {
-                const double v = histN[HIX(g, row, st)];
+                const double v = HISTN(g, row, st);
                 if (v > bv) { bv = v; best = st; }
               }
               code |= (unsigned long long)best << (bits * row);
             }
-            codeC[g] = code;
+            codeP[g] = code;
           }
         }
         __syncwarp();
-        for (int g = lane; g < nG; g += 32) {
-          codeP[g] = codeC[g];
-          curP[g] = gid[g];
-          if (REFINE) {  // entry step - 1: the merged sequences (refined_localization.py:183-186)
+        if (REFINE) {  // entry step - 1: the merged sequences (refined_localization.py:183-186)
+          for (int g = lane; g < nG; g += 32) {
             double* e1 = dmp + ((size_t)(step - 1) * a.capD + g) * COD;
 #pragma unroll
             for (int dim = 0; dim < D; ++dim) e1[dim] = BP(g, dim);
 #pragma unroll
             for (int k = 0; k < KS; ++k) e1[D + k] = __dsqrt_rn(BP(g, D + k));
             e1[D + KS] = BP(g, D + 2 * KS);
-            e1[D + KS + 1] = (double)gid[g];
+            e1[D + KS + 1] = (double)curP[g];
           }
         }
         if (entn && lane == 0) entn[step - 1] = nG;
         {
-          double* tmp = histP;
-          histP = histN;
-          histN = tmp;
+          const int tmp = hP;
+          hP = hN;
+          hN = tmp;
         }
         nP = nG;
         LhP = LhC;
@@ -485,21 +555,21 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) {
           const int k = (KS == 1) ? 0 : dim;
-          const double q = __dadd_rn(FB[(size_t)(D + k) * fbs + c], l2[k]);
-          const double df = __dsub_rn(clast[dim], FB[(size_t)dim * fbs + c]);
+          const double q = __dadd_rn(FB[(D + k) * fbs + c], l2[k]);
+          const double df = __dsub_rn(clast[dim], FB[dim * fbs + c]);
           const double tt = __dsub_rn(__dmul_rn(-0.5, log(__dmul_rn(XT_TWO_PI, q))), __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, q)));
           term = (dim == 0) ? tt : __dadd_rn(term, tt);
         }
-        double v = FB[(size_t)(D + 2 * KS) * fbs + c] + term;
+        double v = FB[(D + 2 * KS) * fbs + c] + term;
         if (REFINE) {
           // last entry: the unfused sequences of the last step with the end-of-track term and the initial fraction of
           // their newest state (refined_localization.py:188-194: the last stored LP is the array updated in place)
-          v = __dadd_rn(FB[(size_t)(D + 2 * KS) * fbs + c], __dadd_rn(term, a.LF[c % nS]));
+          v = __dadd_rn(FB[(D + 2 * KS) * fbs + c], __dadd_rn(term, a.LF[c % nS]));
           double* e2 = dmp + ((size_t)(L - 2) * a.capD + c) * COD;
 #pragma unroll
-          for (int dim = 0; dim < D; ++dim) e2[dim] = FB[(size_t)dim * fbs + c];
+          for (int dim = 0; dim < D; ++dim) e2[dim] = FB[dim * fbs + c];
 #pragma unroll
-          for (int k = 0; k < KS; ++k) e2[D + k] = have_children ? FB[(size_t)(D + KS + k) * fbs + c] : __dsqrt_rn(FB[(size_t)(D + k) * fbs + c]);
+          for (int k = 0; k < KS; ++k) e2[D + k] = have_children ? FB[(D + KS + k) * fbs + c] : __dsqrt_rn(FB[(D + k) * fbs + c]);
           e2[D + KS] = v;
           e2[D + KS + 1] = (double)(c % nS);
           continue;
@@ -531,20 +601,40 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
       // aC holds the posterior of the sequences *after* the expansion of `step`.
       auto emit_row = [&](int row, const double* av, int n, int mode) {
         // mode 0: label = int8-wrapped child index; 1: j % nS; 2: j / nS
+        if ((NSC == 2 || NSC == 4) && mode != 2) {
+          // the label of a child is the residue of its lane: one strided sum, reduced across the lanes of a residue
+          double acc = 0.0;
+          for (int c = lane; c < n; c += 32) acc += av[c];
+#pragma unroll
+          for (int o2 = 16; o2 >= (NSC ? NSC : 1); o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+          if (lane < nS) out[row * nS + lane] = acc;
+          return;
+        }
         for (int s = 0; s < nS; ++s) {
           double acc = 0.0;
           for (int c = lane; c < n; c += 32) {
-            const int lab = (mode == 0) ? xt_label(c, nS, wrap) : ((mode == 1) ? (c % nS) : (c / nS));
+            const int lab = (mode == 0) ? label(c) : ((mode == 1) ? (c % nS) : (c / nS));
             if (lab == s) acc += av[c];
           }
 #pragma unroll
           for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
-          if (lane == 0) out[(size_t)row * nS + s] = acc;
+          if (lane == 0) out[row * nS + s] = acc;
         }
       };
       int nC = nP;
       const double* init_src = aC;  // L == 2: the final sequences are the initial ones
       for (int step = L - 1; step >= 2; --step) {
+        // the fusion records of the step before (global memory) are fetched under this level's reductions
+        const int nCprev = step > 2 ? recN[step - 1] : 0;
+        const bool pre = step > 2 && nCprev <= 64;
+        const double* rwp = recW + (size_t)(step - 1) * cap;
+        const uint16_t* rgp = recGid + (size_t)(step - 1) * cap;
+        double w0 = 0.0, w1 = 0.0;
+        int q0 = 0, q1 = 0;
+        if (pre) {
+          if (lane < nCprev) { w0 = rwp[lane]; q0 = rgp[lane]; }
+          if (lane + 32 < nCprev) { w1 = rwp[lane + 32]; q1 = rgp[lane + 32]; }
+        }
         emit_row(step, aC, nC, 0);  // newest row of this level: forward-time index = step
         const int nPar = nC / K;
         for (int p = lane; p < nPar; p += 32) {
@@ -554,9 +644,12 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
         }
         __syncwarp();
         if (step > 2) {  // the parents of `step` are the groups of step-1
-          const int nCprev = recN[step - 1];
-          for (int c = lane; c < nCprev; c += 32)
-            aC[c] = aP[recGid[(size_t)(step - 1) * cap + c]] * recW[(size_t)(step - 1) * cap + c];
+          if (pre) {
+            if (lane < nCprev) aC[lane] = aP[q0] * w0;
+            if (lane + 32 < nCprev) aC[lane + 32] = aP[q1] * w1;
+          } else {
+            for (int c = lane; c < nCprev; c += 32) aC[c] = aP[rgp[c]] * rwp[c];
+          }
           nC = nCprev;
         } else {
           init_src = aP;
@@ -572,6 +665,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS) k3_predict(const K3Args a, c
 #undef BP
 #undef BC
 #undef HIX
+#undef HISTP
+#undef HISTN
 #undef DDX
 #undef LROW
 }

@@ -26,11 +26,19 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
     return XT_ERR_CUDA;
   }
   std::vector<int32_t> h_err(2 * (size_t)n_work);
-  int cap = std::max(64, nS * nS * nS);
+  int cap = std::max(ctx->k3_cap0, nS * nS * nS);
+  cap += cap & 1;
   int result = XT_OK;
   ctx->k3_launches = 0;
   // nb_max > 1 (the upload's chunk size): one plan per chunk, decided from its first 30 tracks (xt_predict_shared.cuh)
   const bool shared = ctx->k3_shared && (int)ctx->upload_sig[2] > 1;  // option "predict_shared_plans"
+  // work items of the current launch: all of them first, then only those whose tracks outgrew the capacity (own-plan
+  // mode; the outputs of a track depend on nothing but the track, so the others keep theirs)
+  const XtWork* d_work_cur = ctx->d_work;
+  XtWork* d_retry = nullptr;
+  std::vector<XtWork> retry;
+  int n_cur = n_work;
+  float ms_total = 0.f;
   const int nch = (int)ctx->chunks.size();
   int32_t* d_splan = nullptr;
   double* d_sscratch = nullptr;
@@ -57,7 +65,7 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       // warps per CTA (<= 8) that maximise the resident warps per SM under the shared-memory and
       // register limits (the kernel is latency-bound: more resident warps = more throughput)
       hot_smem = 1;
-      const int regs = 128;  // __launch_bounds__(256) lets the compiler use up to 128 registers per thread
+      const int regs = shared ? 128 : xt_k3_regs(*p, 1);  // registers per thread of the kernel that will run
       int best = 0;
       for (int nw = XT_K3_WARPS; nw >= 1; --nw) {
         if (hot_bytes * nw > smem_cap) continue;
@@ -72,7 +80,7 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       }
     }
     const size_t smem = hot_smem ? hot_bytes * nwarps : 0;
-    const int grid = std::min(n_work, ctx->n_sm * ctas_per_sm);
+    const int grid = std::min(n_cur, ctx->n_sm * ctas_per_sm);
     const size_t warp_units = lay.cold_total + (hot_smem ? 0 : lay.hot_total);
     const size_t bytes = sizeof(double) * warp_units * (size_t)grid * nwarps;
     cudaFree(d_scratch);
@@ -85,13 +93,13 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
     cudaMemsetAsync(d_err, 0, sizeof(int32_t) * 2 * (size_t)n_work, ctx->stream);
     K3Args a{};
     a.chunks = ctx->d_chunks;
-    a.work = ctx->d_work;
+    a.work = d_work_cur;
     a.soa = ctx->d_soa;
     a.scratch = d_scratch;
     a.pred = d_pred;
     a.err = d_err;
     a.err_need = d_err + n_work;
-    a.n_work = n_work;
+    a.n_work = n_cur;
     a.cap = cap;
     a.maxL = ctx->maxL + 1;
     a.bits = bits;
@@ -179,9 +187,16 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
     }
     int need = 0;
     bool grouping = false;
-    for (int i = 0; i < n_work; ++i) {
+    std::vector<XtWork> again;
+    for (int i = 0; i < n_cur; ++i) {
       if (h_err[i] == 1) grouping = true;
       need = std::max(need, h_err[n_work + i]);
+      if (h_err[i] == 2 && !shared) again.push_back(retry.empty() ? ctx->work[i] : retry[i]);
+    }
+    {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev_k3[0], ctx->ev_k3[1]);
+      ms_total += ms;
     }
     if (grouping) {
       set_error(ctx, "problem with grouping: a state sequence ended ungrouped (threshold must be > 0 and the model finite)");
@@ -189,10 +204,23 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       break;
     }
     if (!need) {
-      cudaEventElapsedTime(&ctx->ms_predict, ctx->ev_k3[0], ctx->ev_k3[1]);
+      ctx->ms_predict = ms_total;
       break;
     }
     while (cap < need) cap *= 2;
+    if (!shared) {  // only the work items that overflowed run again
+      retry.swap(again);
+      n_cur = (int)retry.size();
+      cudaFree(d_retry);
+      d_retry = nullptr;
+      if (cudaMalloc(&d_retry, sizeof(XtWork) * retry.size()) != cudaSuccess ||
+          cudaMemcpyAsync(d_retry, retry.data(), sizeof(XtWork) * retry.size(), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        set_error(ctx, "xt_predict: cannot stage the work items to run again");
+        result = XT_ERR_CUDA;
+        break;
+      }
+      d_work_cur = d_retry;
+    }
   }
   if (result == XT_OK) {
     for (size_t s = 0; s < ctx->seg_n.size(); ++s) {
@@ -213,6 +241,7 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
   cudaFree(d_pred);
   cudaFree(d_err);
   cudaFree(d_scratch);
+  cudaFree(d_retry);
   cudaFree(d_splan);
   cudaFree(d_sscratch);
   cudaFree(d_serr);

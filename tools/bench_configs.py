@@ -96,6 +96,9 @@ def predict_config(n_tracks, reps=3):
     eng = _native.Engine(0)
     eng.upload(st, [0 if a.shape[1] == st[-1].shape[1] else 1 for a in st], xt.MAX_TRACKS_PER_CHUNK)
     locs = sum(a.shape[0] * a.shape[1] for a in st)
+    for kv in filter(None, os.environ.get("XT_OPTS", "").split(",")):
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     eng.predict(p, 2)
     if os.environ.get("K3_SWEEP"):  # kernel time vs resident CTAs per SM (per-warp scratch vs L2 capacity)
         for c in (1, 2, 3, 4, 6, 8):
