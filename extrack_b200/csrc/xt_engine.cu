@@ -66,6 +66,7 @@ struct xt_ctx {
   int k2_global_ctas = 32;    // one-warp CTAs per SM of the global-memory replay kernel (latency-bound: as many as fit)
   int k3_shared = 0;          // state annotation: 1 = the tracks of an uploaded chunk share one plan (predict_Bs with nb_max > 1)
   int k3_cap0 = 48;           // state annotation: sequence capacity of the first launch (tracks that outgrow it run again with more)
+  int k3_pieces = 8;          // state annotation of a large data set: launches of the first round (read-back of a piece under the next)
   int k3_hot_smem = 1;        // state-annotation kernel: forward-pass state of every warp in shared memory
   int k3_ctas_per_sm = 4;     // resident CTAs per SM of the state-annotation kernel (its per-warp scratch should stay in L2)
   int k1_threads = 0;         // plan kernel threads per chunk: 0 = automatic (256, or 1024 for <= n_sm chunks)
@@ -1523,6 +1524,10 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
       return XT_ERR_ARG;
     }
     ctx->k3_cap0 = value;
+    return XT_OK;
+  }
+  if (std::strcmp(name, "k3_pieces") == 0) {
+    ctx->k3_pieces = value < 1 ? 1 : (value > 64 ? 64 : value);
     return XT_OK;
   }
   if (std::strcmp(name, "k3_hot_smem") == 0) {

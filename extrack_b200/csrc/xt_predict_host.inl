@@ -39,6 +39,41 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
   std::vector<XtWork> retry;
   int n_cur = n_work;
   float ms_total = 0.f;
+  // Own-plan mode on a large data set: the first round is launched in a few pieces of consecutive length buckets, and
+  // the read-back of a piece (into the caller's pageable arrays: the host thread does the staging and takes the page
+  // faults) runs while the kernel works on the next pieces.
+  std::vector<int> piece_w0, piece_s0;  // first work item / first segment of every piece (+ one past the end)
+  bool copied = false, ran_again = false;
+  cudaStream_t s_copy = nullptr;
+  std::vector<cudaEvent_t> ev_piece;
+  if (!shared && ctx->k3_pieces > 1 && n_work >= 64 * ctx->n_sm) {
+    const int n_seg = (int)ctx->seg_n.size();
+    std::vector<int> seg_w0(n_seg + 1, n_work);
+    for (int i = n_work - 1; i >= 0; --i) seg_w0[ctx->chunks[ctx->work[i].chunk].seg] = i;
+    for (int sg = n_seg - 1; sg >= 0; --sg) seg_w0[sg] = std::min(seg_w0[sg], seg_w0[sg + 1]);  // (empty segments)
+    double total = 0, acc = 0;
+    for (int sg = 0; sg < n_seg; ++sg) total += (double)ctx->seg_n[sg] * ctx->seg_L[sg];
+    const int want = std::min(ctx->k3_pieces, n_seg);
+    piece_w0.push_back(0);
+    piece_s0.push_back(0);
+    for (int sg = 0; sg < n_seg; ++sg) {
+      acc += (double)ctx->seg_n[sg] * ctx->seg_L[sg];
+      if (sg + 1 < n_seg && acc >= total * (double)piece_w0.size() / want && seg_w0[sg + 1] > piece_w0.back()) {
+        piece_w0.push_back(seg_w0[sg + 1]);
+        piece_s0.push_back(sg + 1);
+      }
+    }
+    piece_w0.push_back(n_work);
+    piece_s0.push_back(n_seg);
+    if (piece_w0.size() < 3 || cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      piece_w0.clear();
+      s_copy = nullptr;
+    } else {
+      ev_piece.resize(piece_w0.size() - 1, nullptr);
+      for (auto& ev : ev_piece) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    }
+  }
   const int nch = (int)ctx->chunks.size();
   int32_t* d_splan = nullptr;
   double* d_sscratch = nullptr;
@@ -175,9 +210,34 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       a.splan = d_splan;
       a.splan_stride = sa.splan_stride;
       e = xt_launch_k3_follow(a, *p, grid, nwarps, smem, ctx->stream);
-    } else
-    e = xt_launch_k3(a, *p, grid, nwarps, smem, ctx->stream);
-    cudaEventRecord(ctx->ev_k3[1], ctx->stream);
+    } else if (!piece_w0.empty() && !copied) {
+      const int np = (int)piece_w0.size() - 1;
+      for (int g = 0; g < np && e == cudaSuccess; ++g) {
+        K3Args ag = a;
+        ag.work = ctx->d_work + piece_w0[g];
+        ag.n_work = piece_w0[g + 1] - piece_w0[g];
+        ag.err = d_err + piece_w0[g];
+        ag.err_need = d_err + n_work + piece_w0[g];
+        e = xt_launch_k3(ag, *p, std::min(ag.n_work, grid), nwarps, smem, ctx->stream);
+        cudaEventRecord(ev_piece[g], ctx->stream);
+      }
+      ctx->k3_launches += np - 1;
+      cudaEventRecord(ctx->ev_k3[1], ctx->stream);
+      for (int g = 0; g < np && e == cudaSuccess; ++g) {
+        cudaStreamWaitEvent(s_copy, ev_piece[g], 0);
+        for (int sg = piece_s0[g]; sg < piece_s0[g + 1] && e == cudaSuccess; ++sg) {
+          const XtChunk& c0 = ctx->chunks[ctx->seg_chunk0[sg]];
+          const size_t cnt = (size_t)ctx->seg_n[sg] * ctx->seg_L[sg] * nS;
+          if (cnt) e = cudaMemcpyAsync(out[sg], d_pred + (size_t)c0.loc_off * nS, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s_copy);
+        }
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s_copy);
+      copied = true;
+    } else {
+      e = xt_launch_k3(a, *p, grid, nwarps, smem, ctx->stream);
+      cudaEventRecord(ctx->ev_k3[1], ctx->stream);
+    }
+    if (shared) cudaEventRecord(ctx->ev_k3[1], ctx->stream);
     if (e != cudaSuccess || cudaMemcpyAsync(h_err.data(), d_err, sizeof(int32_t) * 2 * (size_t)n_work, cudaMemcpyDeviceToHost,
                                             ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -208,6 +268,7 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       break;
     }
     while (cap < need) cap *= 2;
+    ran_again = true;
     if (!shared) {  // only the work items that overflowed run again
       retry.swap(again);
       n_cur = (int)retry.size();
@@ -222,7 +283,7 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       d_work_cur = d_retry;
     }
   }
-  if (result == XT_OK) {
+  if (result == XT_OK && (!copied || ran_again)) {
     for (size_t s = 0; s < ctx->seg_n.size(); ++s) {
       const XtChunk& c0 = ctx->chunks[ctx->seg_chunk0[s]];
       const size_t cnt = (size_t)ctx->seg_n[s] * ctx->seg_L[s] * nS;
@@ -238,6 +299,9 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       result = XT_ERR_CUDA;
     }
   }
+  for (auto ev : ev_piece)
+    if (ev) cudaEventDestroy(ev);
+  if (s_copy) cudaStreamDestroy(s_copy);
   cudaFree(d_pred);
   cudaFree(d_err);
   cudaFree(d_scratch);
