@@ -59,6 +59,13 @@ struct xt_ctx {
   std::vector<cudaEvent_t> ev_seg;
   int* d_spec = nullptr;
   int* h_spec = nullptr;  // pinned
+  int* d_spec_own = nullptr;  // the word of a context without data; after an upload d_spec / h_spec point into the tail block
+  int* h_spec_own = nullptr;
+  // one device block [chunk sums f64[n] | verification flags i32[n] | speculation word i32] and its pinned mirror: what
+  // the host reads after a verified evaluation comes back in one copy
+  unsigned char* d_tail = nullptr;
+  unsigned char* h_tail = nullptr;
+  size_t tail_bytes = 0;
   int spec_Pmax = 0;      // 0: unknown (first evaluation of a data set runs the two-phase path)
   int spec_maxP = 0, spec_maxC = 0;  // most parents / children of the previous evaluation: sizes the plan kernel's
                                      // shared-memory scratch (0: global-memory scratch)
@@ -213,15 +220,18 @@ static void free_data(xt_ctx* ctx) {
   ctx->d_fstate = nullptr; ctx->d_fslots = nullptr; ctx->fstate_bytes = 0;
   cudaFree(ctx->d_workf[0]); cudaFree(ctx->d_workf[1]); cudaFree(ctx->d_corder);
   ctx->d_corder = nullptr;
-  cudaFree(ctx->d_vflag); cudaFree(ctx->d_redo);
-  ctx->d_vflag = ctx->d_redo = nullptr;
-  if (ctx->h_vflag) cudaFreeHost(ctx->h_vflag);
-  ctx->h_vflag = nullptr;
+  cudaFree(ctx->d_redo);
+  ctx->d_redo = nullptr;
   ctx->plan_valid = false;
-  cudaFree(ctx->d_csum);
-  ctx->d_csum = nullptr;
-  if (ctx->h_csum) cudaFreeHost(ctx->h_csum);
-  ctx->h_csum = nullptr;
+  cudaFree(ctx->d_tail);
+  if (ctx->h_tail) cudaFreeHost(ctx->h_tail);
+  ctx->d_tail = ctx->h_tail = nullptr;
+  ctx->tail_bytes = 0;
+  ctx->d_vflag = ctx->h_vflag = nullptr;
+  ctx->d_csum = ctx->h_csum = nullptr;
+  ctx->d_spec = ctx->d_spec_own;
+  ctx->h_spec = ctx->h_spec_own;
+  ctx->spec_dirty = true;
   for (int v = 0; v < 3; ++v) { cudaFree(ctx->d_cw0[v]); ctx->d_cw0[v] = nullptr; }
   ctx->d_workf[0] = ctx->d_workf[1] = nullptr;
   if (ctx->h_summ) cudaFreeHost(ctx->h_summ);
@@ -249,8 +259,10 @@ static int create_resources(xt_ctx* ctx, int device) {
   }
   XT_CUDA_OK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
   XT_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  XT_CUDA_OK(cudaMalloc(&c->d_spec, sizeof(int)));
-  XT_CUDA_OK(cudaMallocHost(&c->h_spec, sizeof(int)));
+  XT_CUDA_OK(cudaMalloc(&c->d_spec_own, sizeof(int)));
+  XT_CUDA_OK(cudaMallocHost(&c->h_spec_own, sizeof(int)));
+  c->d_spec = c->d_spec_own;
+  c->h_spec = c->h_spec_own;
   XT_CUDA_OK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   XT_CUDA_OK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
   return XT_OK;
@@ -302,8 +314,8 @@ extern "C" void xt_destroy(xt_ctx* ctx) {
   if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (cudaEvent_t e : ctx->ev_seg) cudaEventDestroy(e);
-  cudaFree(ctx->d_spec);
-  if (ctx->h_spec) cudaFreeHost(ctx->h_spec);
+  cudaFree(ctx->d_spec_own);
+  if (ctx->h_spec_own) cudaFreeHost(ctx->h_spec_own);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
   delete ctx;
@@ -445,11 +457,19 @@ static int setup_layout(xt_ctx* ctx, int32_t n_seg, const int32_t* L, const int6
       XT_CUDA_OK(cudaMalloc(&ctx->d_cw0[2], sizeof(int32_t) * (nch + 1)));
       XT_CUDA_OK(cudaMemcpy(ctx->d_cw0[2], w0.data(), sizeof(int32_t) * (nch + 1), cudaMemcpyHostToDevice));
     }
-    XT_CUDA_OK(cudaMalloc(&ctx->d_csum, sizeof(double) * nch));
-    XT_CUDA_OK(cudaMallocHost(&ctx->h_csum, sizeof(double) * nch));
-    XT_CUDA_OK(cudaMalloc(&ctx->d_vflag, sizeof(int32_t) * nch));
+    ctx->tail_bytes = sizeof(double) * nch + sizeof(int32_t) * (nch + 1);
+    XT_CUDA_OK(cudaMalloc(&ctx->d_tail, ctx->tail_bytes));
+    XT_CUDA_OK(cudaMallocHost(&ctx->h_tail, ctx->tail_bytes));
+    XT_CUDA_OK(cudaMemsetAsync(ctx->d_tail, 0, ctx->tail_bytes, ctx->stream));
+    std::memset(ctx->h_tail, 0, ctx->tail_bytes);
+    ctx->d_csum = (double*)ctx->d_tail;
+    ctx->h_csum = (double*)ctx->h_tail;
+    ctx->d_vflag = (int32_t*)(ctx->d_tail + sizeof(double) * nch);
+    ctx->h_vflag = (int32_t*)(ctx->h_tail + sizeof(double) * nch);
+    ctx->d_spec = (int*)(ctx->d_vflag + nch);
+    ctx->h_spec = (int*)(ctx->h_vflag + nch);
+    ctx->spec_dirty = true;
     XT_CUDA_OK(cudaMalloc(&ctx->d_redo, sizeof(int32_t) * nch));
-    XT_CUDA_OK(cudaMallocHost(&ctx->h_vflag, sizeof(int32_t) * nch));
     ctx->corder_pos.assign(nch, 0);
     for (size_t q = 0; q < nch; ++q) ctx->corder_pos[ctx->corder[q]] = (int)q;
     while ((int)ctx->ev_seg.size() < n_seg) {
@@ -1236,9 +1256,10 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
     ctx->spec_dirty = false;
   }
   // (every CTA of the verification launch writes its chunk's flag, 0 included: no clearing pass)
+  // the replay stays on the main stream; only the verification kernel forks off (and joins before the reduction)
   XT_CUDA_OK(cudaEventRecord(ctx->ev[0], ctx->stream));
   XT_CUDA_OK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-  for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamWaitEvent(ctx->cs[i], ctx->ev_fork, 0));
+  XT_CUDA_OK(cudaStreamWaitEvent(ctx->cs[0], ctx->ev_fork, 0));
   {
     const cudaError_t e = xt_launch_k1_verify(a, *p, smem, nch, ctx->cs[0], nt);
     if (e != cudaSuccess) {
@@ -1247,19 +1268,16 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
     }
     ctx->stats.k1_launches++;
   }
-  int rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->cs[1]);
+  int rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->stream);
   if (rc) return rc;
-  for (int i = 0; i < 2; ++i) {
-    XT_CUDA_OK(cudaEventRecord(ctx->ev_join[i], ctx->cs[i]));
-    XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
-  }
+  XT_CUDA_OK(cudaEventRecord(ctx->ev_join[0], ctx->cs[0]));
   XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
   rc = enqueue_reduce(ctx, fl.tpt - 1, d_out);
   if (rc) return rc;
   XT_CUDA_OK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_vflag, ctx->d_vflag, sizeof(int32_t) * nch, cudaMemcpyDeviceToHost, ctx->stream));
-  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_spec, ctx->d_spec, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_csum, ctx->d_csum, sizeof(double) * nch, cudaMemcpyDeviceToHost, ctx->stream));  // one round trip
+  XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));  // (the flags of the verification kernel)
+  // chunk sums, verification flags and the speculation word in one copy (one round trip)
+  XT_CUDA_OK(cudaMemcpyAsync(ctx->h_tail, ctx->d_tail, ctx->tail_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   if (*ctx->h_spec) {
     ctx->spec_dirty = true;
