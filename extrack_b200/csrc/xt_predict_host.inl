@@ -223,14 +223,45 @@ extern "C" int xt_predict(xt_ctx* ctx, const xt_params* p, double* const* out) {
       }
       ctx->k3_launches += np - 1;
       cudaEventRecord(ctx->ev_k3[1], ctx->stream);
+      // The caller's arrays are usually fresh allocations: every 4 KB page faults at its first write, which bounds a
+      // pageable read-back to ~2 GB/s when the copy takes the faults.  A few host threads touch the pages, segment by
+      // segment, while the kernels run; the copy of a segment starts once its pages are resident.
+      const int n_seg_all = (int)ctx->seg_n.size();
+      std::atomic<int> touched{0};
+      std::thread toucher([&] {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nthr = (int)std::max(1u, std::min(8u, hw / 2));
+        for (int sg = 0; sg < n_seg_all; ++sg) {
+          char* base = (char*)out[sg];
+          const size_t bytes = sizeof(double) * (size_t)ctx->seg_n[sg] * ctx->seg_L[sg] * nS;
+          auto touch = [base](size_t b0, size_t b1) {
+            for (size_t o = b0; o < b1; o += 4096) *(volatile char*)(base + o) = 0;
+            if (b1 > b0) *(volatile char*)(base + b1 - 1) = 0;
+          };
+          if (bytes >= ((size_t)8 << 20) && nthr > 1) {
+            std::vector<std::thread> th;
+            const size_t per = ((bytes / nthr) + 4095) & ~(size_t)4095;
+            for (int t = 0; t < nthr; ++t) {
+              const size_t b0 = std::min(bytes, per * t), b1 = std::min(bytes, per * (t + 1));
+              if (b1 > b0) th.emplace_back(touch, b0, b1);
+            }
+            for (auto& x : th) x.join();
+          } else if (bytes) {
+            touch(0, bytes);
+          }
+          touched.store(sg + 1, std::memory_order_release);
+        }
+      });
       for (int g = 0; g < np && e == cudaSuccess; ++g) {
         cudaStreamWaitEvent(s_copy, ev_piece[g], 0);
         for (int sg = piece_s0[g]; sg < piece_s0[g + 1] && e == cudaSuccess; ++sg) {
           const XtChunk& c0 = ctx->chunks[ctx->seg_chunk0[sg]];
           const size_t cnt = (size_t)ctx->seg_n[sg] * ctx->seg_L[sg] * nS;
+          while (touched.load(std::memory_order_acquire) <= sg) std::this_thread::yield();
           if (cnt) e = cudaMemcpyAsync(out[sg], d_pred + (size_t)c0.loc_off * nS, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s_copy);
         }
       }
+      toucher.join();
       if (e == cudaSuccess) e = cudaStreamSynchronize(s_copy);
       copied = true;
     } else {
