@@ -87,6 +87,26 @@ __host__ __device__ inline K3Layout k3_layout(int cap, int CO, int fl, int nS, i
   return l;
 }
 
+// The annotation kernel is sensitive to instruction fetch (ncu: 32 % of the stall samples were "no instruction" with
+// 4 k SASS instructions and 16 warps per SM in different phases): its run-time loops are kept rolled (`#pragma unroll 1`:
+// 4096 -> 3472 instructions, 116 -> 87.5 ms per 10^6 tracks).  Going further - log / exp / the rarely taken exact division
+// of the grouping predicate as shared out-of-line subroutines, one predicate copy for both register halves - was measured
+// and is slower (the macros below keep the experiment reproducible).
+#ifndef XT_K3_NOINLINE
+#define XT_K3_NOINLINE 0  // (measured: out-of-line log / exp / exact-division helpers cost more in calls than they save in fetch: 92 vs 87.5 ms)
+#endif
+#if XT_K3_NOINLINE
+#define K3_NI __noinline__
+#else
+#define K3_NI __forceinline__
+#endif
+#ifndef XT_K3_HLOOP
+#define XT_K3_HLOOP 0     // (measured: one predicate copy with operand selects 90.5 vs 87.5 ms with the two inline copies)
+#endif
+static __device__ K3_NI double k3_log(double x) { return log(x); }
+static __device__ K3_NI double k3_exp(double x) { return exp(x); }
+static __device__ K3_NI bool k3_div_lt(double a, double s, double th) { return __ddiv_rn(a, s) < th; }
+
 template <int D, int KS, bool VAR = false, bool FOLLOW = false, bool REFINE = false, int NSC = 0>
 __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(const K3Args a, const __grid_constant__ xt_params P) {
   static_assert(!(VAR && FOLLOW), "shared plans are built for scalar LocErr / dt models");
@@ -177,6 +197,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
 
       // ---- first localisation (tracking.py:478-529) ----
       int nP = nS * nS;
+      #pragma unroll 1
       for (int c = lane; c < nP; c += 32) {
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) BP(c, dim) = Cp[(size_t)(LROW(0) * D + dim) * npad];
@@ -245,11 +266,11 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
             BC(c, dim) = __ddiv_rn(__dadd_rn(__dmul_rn(mm, l2[k]), __dmul_rn(cl[dim], s2[k])), __dadd_rn(l2[k], s2[k]));
           }
           if (KS == 1) {
-            logs = __dmul_rn((double)D * -0.5, log(__dmul_rn(XT_TWO_PI, q[0])));
+            logs = __dmul_rn((double)D * -0.5, k3_log(__dmul_rn(XT_TWO_PI, q[0])));
           } else {
 #pragma unroll
             for (int k = 0; k < KS; ++k) {
-              const double lg = __dmul_rn(-0.5, log(__dmul_rn(XT_TWO_PI, q[k])));
+              const double lg = __dmul_rn(-0.5, k3_log(__dmul_rn(XT_TWO_PI, q[k])));
               logs = (k == 0) ? lg : __dadd_rn(logs, lg);
             }
           }
@@ -301,8 +322,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
           for (int k = 0; k < KS; ++k) {
             const double lo = __dmul_rn(th_lo, sj[k]), hi = __dmul_rn(th_hi, sj[k]);
             bool pm = am < lo, ps = as < lo;
-            if (!pm && !(am > hi)) pm = __ddiv_rn(am, sj[k]) < th;
-            if (!ps && !(as > hi)) ps = __ddiv_rn(as, sj[k]) < th;
+            if (!pm && !(am > hi)) pm = k3_div_lt(am, sj[k], th);
+            if (!ps && !(as > hi)) ps = k3_div_lt(as, sj[k], th);
             ok = ok && pm && ps;
           }
           return ok;
@@ -347,6 +368,23 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
             const unsigned long long ci = codeC[i];
             if (lane == 0) goff[nG] = off;
             const int off_in = off;
+#if XT_K3_HLOOP
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {  // (one copy of the predicate: the two halves select their operands)
+              const unsigned uh = h ? u1 : u0;
+              if (!uh) continue;
+              double mj[D], sj[KS];
+#pragma unroll
+              for (int dim = 0; dim < D; ++dim) mj[dim] = h ? mj1[dim] : mj0[dim];
+#pragma unroll
+              for (int k = 0; k < KS; ++k) sj[k] = h ? sj1[k] : sj0[k];
+              const bool ok = ((uh >> lane) & 1u) && captures(ci, mi, si, h ? cj1 : cj0, mj, sj);
+              const unsigned m = __ballot_sync(0xffffffffu, ok);
+              if (ok) order[off + __popc(m & lt_mask)] = lane + 32 * h;
+              off += __popc(m);
+              if (h) u1 &= ~m; else u0 &= ~m;
+            }
+#else
             if (u0) {
               const bool ok = ((u0 >> lane) & 1u) && captures(ci, mi, si, cj0, mj0, sj0);
               const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -361,6 +399,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
               off += __popc(m);
               u1 &= ~m;
             }
+#endif
             if (off == off_in) {  // leader failed its own test and captured nobody (:725, :700-701)
               errc = 1;
               break;
@@ -432,6 +471,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
               if (!FOLLOW) {  // (history window and codes only serve this track's own decisions)
                 const int lab = label(c0), p0 = c0 / K;
                 for (int s = 0; s < nS; ++s) HISTN(g, 0, s) = (lab == s) ? 1.0 : 0.0;
+                #pragma unroll 1
                 for (int it = nS; it < rows_out * nS; ++it) base[hN + it * capP + g] = base[hP + (it - nS) * capP + p0];
                 // the window code of an unmerged sequence is its own (codes are the per-row argmax of the window)
                 codeP[g] = codeC[c0];
@@ -439,11 +479,13 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
             } else {
               multi = true;
               double mx = BC(c0, D + 2 * KS);
+              #pragma unroll 1
               for (int k = 1; k < n; ++k) mx = fmax(mx, BC(order[o + k], D + 2 * KS));
               double sw = 0.0, am[D], as2[KS];
+              #pragma unroll 1
               for (int k = 0; k < n; ++k) {
                 const int c = order[o + k];
-                const double w = exp(__dsub_rn(BC(c, D + 2 * KS), mx));
+                const double w = k3_exp(__dsub_rn(BC(c, D + 2 * KS), mx));
                 aC[c] = w;  // (aC is only used after the forward pass: free scratch here)
                 rg[c] = (uint16_t)g;
                 sw = (k == 0) ? w : __dadd_rn(sw, w);
@@ -462,7 +504,8 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
               for (int dim = 0; dim < D; ++dim) BP(g, dim) = __ddiv_rn(am[dim], sw);
 #pragma unroll
               for (int k2 = 0; k2 < KS; ++k2) BP(g, D + k2) = __ddiv_rn(as2[k2], sw);
-              BP(g, D + 2 * KS) = __dadd_rn(log(sw), mx);
+              BP(g, D + 2 * KS) = __dadd_rn(k3_log(sw), mx);
+              #pragma unroll 1
               for (int k = 0; k < n; ++k) {  // the recorded weights, normalised
                 const int c = order[o + k];
                 rw[c] = __ddiv_rn(aC[c], sw);
@@ -490,6 +533,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
             const int g = gid[gm];
             const int o = goff[g], n = goff[g + 1] - o;
             double acc = 0.0;
+            #pragma unroll 1
             for (int k = 0; k < n; ++k) {
               const int c = order[o + k];
               const double hv = (row == 0) ? ((label(c) == st) ? 1.0 : 0.0) : base[hP + (it - nS) * capP + c / K];
@@ -502,6 +546,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
           for (int gm = lane; gm < nM; gm += 32) {
             const int g = gid[gm];
             unsigned long long code = 0;
+            #pragma unroll 1
             for (int row = 0; row < rows_out; ++row) {
               int best = 0;
               double bv = HISTN(g, row, 0);
@@ -550,6 +595,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
       for (int dim = 0; dim < D; ++dim) clast[dim] = Cp[(size_t)(LROW(L - 1) * D + dim) * npad];
       if (VAR) var_row(L - 1);
       double vmax = -INFINITY;
+      #pragma unroll 1
       for (int c = lane; c < nP; c += 32) {
         double term = 0.0;
 #pragma unroll
@@ -557,7 +603,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
           const int k = (KS == 1) ? 0 : dim;
           const double q = __dadd_rn(FB[(D + k) * fbs + c], l2[k]);
           const double df = __dsub_rn(clast[dim], FB[dim * fbs + c]);
-          const double tt = __dsub_rn(__dmul_rn(-0.5, log(__dmul_rn(XT_TWO_PI, q))), __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, q)));
+          const double tt = __dsub_rn(__dmul_rn(-0.5, k3_log(__dmul_rn(XT_TWO_PI, q))), __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, q)));
           term = (dim == 0) ? tt : __dadd_rn(term, tt);
         }
         double v = FB[(D + 2 * KS) * fbs + c] + term;
@@ -586,14 +632,16 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o2));
       double ssum = 0.0;
+      #pragma unroll 1
       for (int c = lane; c < nP; c += 32) {
-        const double e = exp(aC[c] - vmax);
+        const double e = k3_exp(aC[c] - vmax);
         aC[c] = e;
         ssum += e;
       }
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o2);
       const double inv = 1.0 / ssum;
+      #pragma unroll 1
       for (int c = lane; c < nP; c += 32) aC[c] *= inv;
       __syncwarp();
 
@@ -604,6 +652,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
         if ((NSC == 2 || NSC == 4) && mode != 2) {
           // the label of a child is the residue of its lane: one strided sum, reduced across the lanes of a residue
           double acc = 0.0;
+          #pragma unroll 1
           for (int c = lane; c < n; c += 32) acc += av[c];
 #pragma unroll
           for (int o2 = 16; o2 >= (NSC ? NSC : 1); o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
@@ -612,6 +661,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
         }
         for (int s = 0; s < nS; ++s) {
           double acc = 0.0;
+          #pragma unroll 1
           for (int c = lane; c < n; c += 32) {
             const int lab = (mode == 0) ? label(c) : ((mode == 1) ? (c % nS) : (c / nS));
             if (lab == s) acc += av[c];
@@ -639,6 +689,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
         const int nPar = nC / K;
         for (int p = lane; p < nPar; p += 32) {
           double sacc = 0.0;
+          #pragma unroll 1
           for (int r = 0; r < K; ++r) sacc += aC[p * K + r];
           aP[p] = sacc;
         }
@@ -648,6 +699,7 @@ __global__ void __launch_bounds__(32 * XT_K3_WARPS, XT_K3_MIN_CTAS) k3_predict(c
             if (lane < nCprev) aC[lane] = aP[q0] * w0;
             if (lane + 32 < nCprev) aC[lane + 32] = aP[q1] * w1;
           } else {
+            #pragma unroll 1
             for (int c = lane; c < nCprev; c += 32) aC[c] = aP[rgp[c]] * rwp[c];
           }
           nC = nCprev;
