@@ -225,7 +225,15 @@ int xt_seglen_last_ms(xt_ctx* ctx, float* ms); /* CUDA-event time of the last xt
  *      within 1e-4 relative of the FP64 result).  The plan stays FP64 (same fusion decisions as the
  *      reference); the per-sequence moments and weight mantissas are FP32 with the same 32-bit extended
  *      exponent.  Applies to scalar LocErr / dt models whose state fits in shared memory and whose
- *      tables are representable in FP32; otherwise the FP64 kernel runs (xt_stats::fp32 tells which). */
+ *      tables are representable in FP32; otherwise the FP64 kernel runs (xt_stats::fp32 tells which);
+ *  "plan_verify" = 0: plan every evaluation from scratch instead of verifying the resident plan (same bits);
+ *  "k2_lpt" = 0, "k2_cost0".."k2_cost3", "k2_cost_w0": schedule of the groups of a step over the replay warps
+ *      (longest-processing-time-first on a cost model; 0 = round-robin); "k1_threads" (256|512|1024): threads per chunk
+ *      of the plan kernel (0 = by the number of chunks);
+ *  "predict_shared_plans" = 1: see xt_predict; "k3_cap0": sequence capacity of the first launch of xt_predict (tracks
+ *      that outgrow it run again with twice as much); "k3_pieces": launches the first round of xt_predict is cut into on
+ *      a large data set (the read-back of a piece runs under the kernels of the next); "k3_hot_smem", "k3_ctas_per_sm":
+ *      placement of the per-warp scratch of the annotation kernel. */
 int xt_set_option(xt_ctx* ctx, const char* name, int value);
 
 /* Measured FP64 FMA throughput of this GPU in TFLOP/s (2 flops per DFMA), used as the
