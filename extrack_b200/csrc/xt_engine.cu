@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <atomic>
 #include <string>
@@ -1241,8 +1243,17 @@ static int evaluate_pipelined(xt_ctx* ctx, const xt_params* p, int bits, double*
 // only read the plan, so they run concurrently).  Chunks with a changed decision are planned again from scratch and
 // replayed again before the sums are formed; everything else of the result is already final.  Returns XT_RETRY when
 // the evaluation has to take the construction path instead.
+static double xt_now_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
 static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* d_out) {
   const int nch = (int)ctx->chunks.size();
+  static const bool trace = std::getenv("XT_TRACE") != nullptr;  // host-side timeline of the call (diagnostic)
+  const double t_in = trace ? xt_now_us() : 0.0;
+  double t_k1 = 0, t_k2 = 0, t_enq = 0;
   FusedLaunch fl;
   if (is_var(p) || ctx->spec_maxC <= 0 || ctx->spec_maxC > 64 || !prepare_fused(ctx, p, ctx->spec_Pmax, &fl)) return XT_RETRY_EARLY;
   int nt = k1_threads(ctx);
@@ -1270,8 +1281,10 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
     }
     ctx->stats.k1_launches++;
   }
+  if (trace) t_k1 = xt_now_us();
   int rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->stream);
   if (rc) return rc;
+  if (trace) t_k2 = xt_now_us();
   XT_CUDA_OK(cudaEventRecord(ctx->ev_join[0], ctx->cs[0]));
   XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
   rc = enqueue_reduce(ctx, fl.tpt - 1, d_out);
@@ -1280,7 +1293,17 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
   XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));  // (the flags of the verification kernel)
   // chunk sums, verification flags and the speculation word in one copy (one round trip)
   XT_CUDA_OK(cudaMemcpyAsync(ctx->h_tail, ctx->d_tail, ctx->tail_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (trace) t_enq = xt_now_us();
   XT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (trace) {
+    const double t_sync = xt_now_us();
+    float g01 = 0.f, g12 = 0.f;
+    cudaEventElapsedTime(&g01, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&g12, ctx->ev[1], ctx->ev[2]);
+    std::fprintf(stderr, "xt trace: host us: prepare+fork+K1v launch %.1f, K2 launch %.1f, join+reduce+copy enqueue %.1f, wait %.1f, total %.1f"
+                         " | device us: replay %.1f, reduce %.1f\n",
+                 t_k1 - t_in, t_k2 - t_k1, t_enq - t_k2, t_sync - t_enq, t_sync - t_in, g01 * 1e3, g12 * 1e3);
+  }
   if (*ctx->h_spec) {
     ctx->spec_dirty = true;
     return XT_RETRY;
