@@ -139,3 +139,82 @@ def read_table(paths, lengths=np.arange(5, 40), dist_th=np.inf, frames_boundarie
             for m in opt_colnames:
                 opt_metrics[m][str(l)] = np.concatenate(per_len_opt[m][l]) if per_len_opt[m][l] else np.array([])
     return tracks, frames, opt_metrics
+
+
+def read_trackmate_xml(paths, lengths=np.arange(5, 40), dist_th=0.5, frames_boundaries=[-np.inf, np.inf], remove_no_disp=True,
+                       opt_metrics_names=["t", "x"], opt_metrics_types=[int, "float64"]
+                       ) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray], Dict[str, Dict[str, np.ndarray]]]:
+    """TrackMate "export tracks to XML" files -> ``(tracks, frames, opt_metrics)`` with the rules of
+    ``extrack.readers.read_trackmate_xml`` (``readers.py:5-98``; the reference parses with ``xmltodict``, absent from this
+    image: ``xml.etree`` here).
+
+    Per ``<particle>`` (in file order): the ``x`` / ``y`` / ``t`` attributes of its ``<detection>`` elements (``:53``);
+    ``remove_no_disp`` drops the track if any x-displacement or any y-displacement is exactly zero (``:60-63``: the
+    product of the minimal squared displacements); it is kept if its first frame lies inside ``frames_boundaries`` and
+    every step is shorter than ``dist_th`` (``:65-66``); length in ``lengths`` -> that bucket, longer than
+    ``max(lengths)`` -> truncated into the largest bucket (``:68-79``), other lengths are dropped.  ``frames`` holds
+    the frame numbers as floats (they pass through the reference's float track array), ``opt_metrics[name][str(l)]``
+    the detection attribute ``name`` cast to ``opt_metrics_types`` (``:84-93``).  Empty buckets are removed.  A particle
+    the reference cannot walk (fewer than two detections) raises the same ``ValueError`` (``:80-81``)."""
+    import xml.etree.ElementTree as ET
+
+    if isinstance(paths, (str, np.str_)):
+        paths = [paths]
+    lengths = np.asarray(lengths)
+    names = list(opt_metrics_names)
+    types = ["float64"] * len(names) if opt_metrics_types is None else list(opt_metrics_types)
+    keys = [str(l) for l in lengths]
+    traces: Dict[str, list] = {k: [] for k in keys}
+    frames: Dict[str, list] = {k: [] for k in keys}
+    opt: Dict[str, Dict[str, list]] = {m: {k: [] for k in keys} for m in names}
+    lmax = int(np.max(lengths))
+    for path in paths:
+        root = ET.parse(path).getroot()
+        framerate = float(root.attrib["frameInterval"]) / 1000.0  # (kept for parity of the failure modes: the attribute must exist)
+        del framerate
+        for particle in root.iter("particle"):
+            dets = particle.findall("detection")
+            try:
+                if len(dets) < 2:
+                    raise ValueError("a particle needs at least two detections")
+                xy = np.array([(float(d.attrib["x"]), float(d.attrib["y"])) for d in dets])
+                fr = np.array([float(int(d.attrib["t"])) for d in dets])
+                met = np.empty((int(particle.attrib["nSpots"]), len(names)), dtype=object)
+                for k, d in enumerate(dets):
+                    for j, m in enumerate(names):
+                        met[k, j] = d.attrib[m]
+            except Exception:
+                raise ValueError("problem with data on path: " + path)
+            step = xy[1:] - xy[:-1]
+            if remove_no_disp and np.min(step[:, 0] ** 2) * np.min(step[:, 1] ** 2) == 0:
+                continue
+            dists = np.sum(step**2, axis=1) ** 0.5
+            if not (fr[0] >= frames_boundaries[0] and fr[0] <= frames_boundaries[1] and np.all(dists < dist_th)):
+                continue
+            l = len(xy)
+            if np.any(lengths == l):
+                key, cut = str(l), l
+            elif l > lmax:
+                key, cut = str(lmax), lmax
+            else:
+                continue
+            traces[key].append(xy[:cut])
+            frames[key].append(fr[:cut])
+            for j, m in enumerate(names):
+                opt[m][key].append(met[:cut, j])
+    for k in keys:
+        if len(traces[k]) > 0:
+            traces[k] = np.array(traces[k])
+            frames[k] = np.array(frames[k])
+            for j, m in enumerate(names):
+                cur = np.array(opt[m][k])
+                try:
+                    cur = cur.astype(types[j])
+                except Exception:
+                    print("Error of type with the optional metric:", m)
+                opt[m][k] = cur
+        else:
+            del traces[k], frames[k]
+            for m in names:
+                del opt[m][k]
+    return traces, frames, opt

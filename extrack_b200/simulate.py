@@ -27,9 +27,12 @@ def sim_FOV(nb_tracks=10000, max_track_len=40, min_track_len=2, LocErr=0.02, Ds=
             initial_fractions=(0.6, 0.4), TrMat=((0.9, 0.1), (0.1, 0.9)), LocErr_std=0, dt=0.02, pBL=0.1,
             cell_dims=(0.5, None, None), seed: Optional[int] = 0, device: str = "cpu", nb_sub_steps: int = 20,
             return_states: bool = False) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]:
-    """Returns ``(all_tracks, all_states)`` keyed by ``str(length)``: ``float64[n, L, nb_dims]`` / ``int[n, L]``."""
-    if LocErr_std != 0:
-        raise NotImplementedError("LocErr_std != 0 (per-peak localisation error) is not generated here")
+    """Returns ``(all_tracks, all_states)`` keyed by ``str(length)``: ``float64[n, L, nb_dims]`` / ``int[n, L]``.
+
+    ``LocErr_std != 0`` (simulate_tracks.py:131,207-209): every localisation gets its own error standard deviation
+    ``sigma = LocErr * chi2(k) / k`` with ``k = 2 / LocErr_std**2`` (mean ``LocErr``, relative spread ``LocErr_std``),
+    the noise is drawn with it, and a third dictionary ``{str(length): float64[n, L, nb_dims]}`` of these sigmas is
+    returned (what the reference returns as its third value and ``param_fitting(input_LocErr=...)`` consumes)."""
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
     if seed is not None:
@@ -102,8 +105,9 @@ def sim_FOV(nb_tracks=10000, max_track_len=40, min_track_len=2, LocErr=0.02, Ds=
 
     all_tracks: Dict[str, np.ndarray] = {}
     all_states: Dict[str, np.ndarray] = {}
+    all_sigmas: Dict[str, np.ndarray] = {}
     if not rec_traj:
-        return all_tracks, all_states
+        return (all_tracks, all_states, all_sigmas) if LocErr_std != 0 else (all_tracks, all_states)
     traj = torch.cat(rec_traj)
     st = torch.cat(rec_start)
     ln = torch.cat(rec_len)
@@ -116,10 +120,22 @@ def sim_FOV(nb_tracks=10000, max_track_len=40, min_track_len=2, LocErr=0.02, Ds=
             continue
         idx = st[sel][:, None] + torch.arange(Lk, device=dev)[None, :]
         p = pos[traj[sel][:, None], idx]  # [n, L, 3]
-        p = p + LocErr * torch.randn(p.shape, generator=gen, device=dev, dtype=f64)
+        if LocErr_std != 0:
+            kk = 2.0 / (float(LocErr_std) ** 2 + 1e-20)  # chi2(k) / k: mean 1, standard deviation LocErr_std
+            loc = torch.as_tensor(np.asarray(LocErr, dtype=float).reshape(-1), dtype=f64, device=dev)  # scalar or per dimension
+            if loc.numel() not in (1, 3):
+                loc = torch.cat([loc, loc[-1:].expand(3 - loc.numel())])
+            gam = torch._standard_gamma(torch.full(p.shape, kk / 2.0, dtype=f64, device=dev), generator=gen)
+            sig = (2.0 * gam / kk) * loc
+            p = p + sig * torch.randn(p.shape, generator=gen, device=dev, dtype=f64)
+            all_sigmas[str(Lk)] = sig[:, :, :nb_dims].contiguous().cpu().numpy()
+        else:
+            p = p + LocErr * torch.randn(p.shape, generator=gen, device=dev, dtype=f64)
         all_tracks[str(Lk)] = p[:, :, :nb_dims].contiguous().cpu().numpy()
         if return_states:
             all_states[str(Lk)] = frame_state[traj[sel][:, None], idx].cpu().numpy()
+    if LocErr_std != 0:
+        return all_tracks, all_states, all_sigmas
     return all_tracks, all_states
 
 

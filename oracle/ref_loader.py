@@ -69,12 +69,40 @@ def load_simulate():
 
 
 def load_readers():
-    # readers.py imports xmltodict at module import; only the csv reader is used here
+    # readers.py imports xmltodict at module import (absent from this image): a stand-in with xmltodict's documented
+    # mapping for attribute-only documents (attributes -> '@name' keys, repeated child elements -> a list, a single child
+    # -> a dict), which is all read_trackmate_xml touches
     if "xmltodict" not in sys.modules:
         try:
             import xmltodict  # noqa: F401
         except Exception:
-            sys.modules["xmltodict"] = types.ModuleType("xmltodict")
+            stub = types.ModuleType("xmltodict")
+
+            def parse(text, encoding="utf-8", **_kw):
+                import xml.etree.ElementTree as ET
+
+                def conv(el):
+                    d = {"@" + k: v for k, v in el.attrib.items()}
+                    for ch in el:
+                        v = conv(ch)
+                        if ch.tag in d:
+                            if not isinstance(d[ch.tag], list):
+                                d[ch.tag] = [d[ch.tag]]
+                            d[ch.tag].append(v)
+                        else:
+                            d[ch.tag] = v
+                    if el.text and el.text.strip():
+                        if d:
+                            d["#text"] = el.text.strip()
+                        else:
+                            return el.text.strip()
+                    return d if d else None
+
+                root = ET.fromstring(text.encode(encoding) if isinstance(text, str) else text)
+                return {root.tag: conv(root)}
+
+            stub.parse = parse
+            sys.modules["xmltodict"] = stub
     return _load("readers", "extrack/readers.py")
 
 

@@ -315,3 +315,108 @@ def test_read_table_matches_reference_reader(tmp_path):
             np.testing.assert_array_equal(t1[k], t2[k])
             np.testing.assert_array_equal(f1[k], f2[k])
     assert sum(len(v) for v in t2.values()) > 0
+
+
+# ---- TrackMate xml reader (readers.py:5-98) and per-peak localisation errors of the generator ----
+def _synthetic_trackmate_xml(tmp_path, rng, n_tracks=120, name="tracks.xml"):
+    """A TrackMate "export tracks" file: <Tracks frameInterval=..><particle nSpots=..><detection t= x= y= z=/>..."""
+    lines = ['<?xml version="1.0" encoding="UTF-8"?>',
+             '<Tracks nTracks="%d" spaceUnits="um" frameInterval="20.0" timeUnits="ms" from="TrackMate v4.0.1">' % n_tracks]
+    spec = []
+    for tid in range(n_tracks):
+        L = int(rng.integers(2, 30))
+        pos = np.cumsum(rng.normal(size=(L, 2)) * 0.05, 0) + 10.0
+        if tid % 11 == 0 and L > 3:
+            pos[3, 0] = pos[2, 0]     # one zero x-displacement: removed by remove_no_disp
+        if tid % 13 == 0 and L > 4:
+            pos[4:] += 5.0            # one long step: removed by dist_th
+        f0 = int(rng.integers(0, 60))
+        lines.append('  <particle nSpots="%d">' % L)
+        for k in range(L):
+            lines.append('    <detection t="%d" x="%r" y="%r" z="0.0" />' % (f0 + k, float(pos[k, 0]), float(pos[k, 1])))
+        lines.append("  </particle>")
+        spec.append((pos, f0))
+    lines.append("</Tracks>")
+    path = str(tmp_path / name)
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines))
+    return path, spec
+
+
+def test_read_trackmate_xml_rules(tmp_path):
+    """Own expectation (loop restating readers.py:51-79) on a synthetic file."""
+    from extrack_b200 import readers
+
+    path, spec = _synthetic_trackmate_xml(tmp_path, np.random.default_rng(3))
+    lengths = np.array([4, 5, 6, 9, 12])
+    tracks, frames, opt = readers.read_trackmate_xml(path, lengths=lengths, dist_th=1.0, frames_boundaries=[5, 50])
+    want, want_f = {}, {}
+    for pos, f0 in spec:
+        st = pos[1:] - pos[:-1]
+        if np.min(st[:, 0] ** 2) * np.min(st[:, 1] ** 2) == 0 or not (5 <= f0 <= 50) or not np.all(np.sum(st**2, 1) ** 0.5 < 1.0):
+            continue
+        L = len(pos)
+        key = L if L in lengths else (12 if L > 12 else None)
+        if key is None:
+            continue
+        want.setdefault(key, []).append(pos[:key])
+        want_f.setdefault(key, []).append(np.arange(f0, f0 + key, dtype=float))
+    assert sorted(int(k) for k in tracks) == sorted(want) and len(want) >= 3
+    for k, arr in tracks.items():
+        np.testing.assert_array_equal(arr, np.array(want[int(k)]))
+        np.testing.assert_array_equal(frames[k], np.array(want_f[int(k)]))
+        assert opt["t"][k].dtype.kind == "i" and np.array_equal(opt["t"][k], frames[k].astype(int))
+        np.testing.assert_array_equal(opt["x"][k], arr[:, :, 0])
+    # a particle with a single detection is the reference's error path (:80-81)
+    bad = str(tmp_path / "bad.xml")
+    with open(bad, "w") as fh:
+        fh.write('<Tracks nTracks="1" frameInterval="20.0"><particle nSpots="1"><detection t="1" x="0.5" y="0.5" z="0"/></particle></Tracks>')
+    with pytest.raises(ValueError, match="problem with data"):
+        readers.read_trackmate_xml(bad)
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not present on this box")
+def test_read_trackmate_xml_matches_reference_reader(tmp_path):
+    """Against the unmodified reference reader (its xmltodict import served by the ElementTree stand-in of
+    oracle.ref_loader) on the tutorial file and a synthetic one: same buckets, same arrays, same dtypes."""
+    from extrack_b200 import readers
+
+    rd = ref_loader.load_readers()
+    syn, _ = _synthetic_trackmate_xml(tmp_path, np.random.default_rng(4))
+    tut = os.path.join(ref_loader.REFERENCE_ROOT, "Tutorials", "example_tracks.xml")
+    cases = [(tut, dict()),
+             (tut, dict(lengths=np.arange(3, 12), dist_th=0.3, frames_boundaries=[0, 40], remove_no_disp=False,
+                        opt_metrics_names=["t", "x", "z"], opt_metrics_types=[int, "float64", "float64"])),
+             ([tut, syn], dict(lengths=np.array([4, 7, 10]), dist_th=np.inf, opt_metrics_names=[], opt_metrics_types=None)),
+             (syn, dict(lengths=np.arange(2, 15), dist_th=1.0, frames_boundaries=[5, 50]))]
+    n = 0
+    for path, kw in cases:
+        t1, f1, m1 = rd.read_trackmate_xml(path, **kw)
+        t2, f2, m2 = readers.read_trackmate_xml(path, **kw)
+        assert list(t1) == list(t2) and list(m1) == list(m2)
+        for k in t1:
+            np.testing.assert_array_equal(t1[k], t2[k])
+            np.testing.assert_array_equal(f1[k], f2[k])
+            assert t1[k].dtype == t2[k].dtype and f1[k].dtype == f2[k].dtype
+            for m in m1:
+                np.testing.assert_array_equal(m1[m][k], m2[m][k])
+                assert m1[m][k].dtype == m2[m][k].dtype
+            n += len(t1[k])
+    assert n > 100
+
+
+def test_sim_FOV_per_peak_localisation_errors():
+    """LocErr_std != 0 (simulate_tracks.py:207-209): sigma = LocErr * chi2(k) / k with k = 2 / LocErr_std^2, i.e. mean
+    LocErr and relative spread LocErr_std; the noise added to a localisation has that localisation's sigma."""
+    from extrack_b200.simulate import sim_FOV
+
+    kw = dict(nb_tracks=4000, max_track_len=20, min_track_len=5, LocErr=0.03, Ds=[0.0, 0.0], nb_dims=2, pBL=0.02, seed=11)
+    tr, _, sg = sim_FOV(LocErr_std=0.25, **kw)
+    assert list(tr) == list(sg) and all(tr[k].shape == sg[k].shape for k in tr)
+    s = np.concatenate([v.reshape(-1) for v in sg.values()])
+    assert abs(s.mean() / 0.03 - 1) < 0.01 and abs(s.std() / s.mean() / 0.25 - 1) < 0.03 and s.min() > 0
+    # immobile particles (D = 0): a track's scatter around its mean is the localisation noise itself
+    z = np.concatenate([((tr[k] - tr[k].mean(1, keepdims=True)) / sg[k]).reshape(-1) for k in tr if int(k) >= 10])
+    assert 0.85 < z.std() < 1.05
+    tr0 = sim_FOV(**kw)[0]  # LocErr_std = 0 keeps the two-value return and the same selection of runs
+    assert {k: v.shape for k, v in tr0.items()} == {k: v.shape for k, v in tr.items()}
