@@ -31,22 +31,36 @@ MAX_TRACKS_PER_CHUNK = 2000  # tracking.py:991 max_number_of_tracks_per_matrix
 def _extract_scalars(params, nb_substeps, Matrix_type=1):
     """lmfit ``Parameters`` -> ``(LocErr values, Ds, Fs, TrMat, pBL)`` (tracking.py:918-975)."""
     # one pass over the sorted names (every `.value` of a constrained parameter evaluates its expression)
+    names = tuple(params.keys())
+    plan = _NAME_PLAN.get(names)
+    if plan is None:  # classification of the (sorted) names: the same at every evaluation of a fit
+        plan = []
+        for n in sorted(names):
+            c = n[0]
+            if c == "L" and n.startswith("LocErr"):
+                plan.append((n, 0, 0, 0))
+            elif c == "D" and len(n) < 3:
+                plan.append((n, 1, 0, 0))
+            elif c == "F":
+                plan.append((n, 2, 0, 0))
+            elif c == "p":
+                plan.append((n, 4, 0, 0) if n == "pBL" else (n, 3, int(n[1]), int(n[2])))
+        if len(_NAME_PLAN) > 32:
+            _NAME_PLAN.clear()
+        _NAME_PLAN[names] = plan
     loc, Dv, Fv, rates, pBL = [], [], [], [], None
-    for n in sorted(params.keys()):
-        c = n[0]
-        if c == "L":
-            if n.startswith("LocErr"):
-                loc.append(params[n].value)
-        elif c == "D":
-            if len(n) < 3:
-                Dv.append(params[n].value)
-        elif c == "F":
-            Fv.append(params[n].value)
-        elif c == "p":
-            if n == "pBL":
-                pBL = params[n].value
-            else:
-                rates.append((int(n[1]), int(n[2]), params[n].value))
+    for n, kind, i, j in plan:
+        v = params[n].value
+        if kind == 0:
+            loc.append(v)
+        elif kind == 1:
+            Dv.append(v)
+        elif kind == 2:
+            Fv.append(v)
+        elif kind == 3:
+            rates.append((i, j, v))
+        else:
+            pBL = v
     Ds = np.array(Dv, dtype=float)
     Fs = np.array(Fv, dtype=float)
     nS = len(Ds)
@@ -107,6 +121,8 @@ def extract_params(params, dt, nb_states, nb_substeps, input_LocErr=None, Matrix
 
 _P_STAY_MEMO: dict = {}
 _FOV_GRID: dict = {}
+_DIGITS: dict = {}
+_NAME_PLAN: dict = {}
 
 
 def _p_stay(ds, nS, nsub, cell_dims):
@@ -151,8 +167,11 @@ def _p_stay(ds, nS, nsub, cell_dims):
 def _head_tables(ds, Fs, TrMat, nS, nsub):
     """digits, dd, LT, LF per head (tracking.py:487-488,549-555,759-767); head h: digit k (base nS) =
     state k sub-steps ago, digit nsub = newest state of the parent."""
-    nH = nS ** (nsub + 1)
-    dig = np.arange(nH)[:, None] // nS ** np.arange(nsub + 1)[None, :] % nS
+    dig = _DIGITS.get((nS, nsub))
+    if dig is None:  # (the same small index table at every evaluation of a fit)
+        nH0 = nS ** (nsub + 1)
+        dig = _DIGITS[(nS, nsub)] = np.arange(nH0)[:, None] // nS ** np.arange(nsub + 1)[None, :] % nS
+    nH = len(dig)
     d2 = ds[dig] ** 2
     dd = np.mean((d2[:, 1:] + d2[:, :-1]) / 2, axis=1)
     Tt = TrMat.T
