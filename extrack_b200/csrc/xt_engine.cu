@@ -800,9 +800,11 @@ static void k1_scratch_caps(xt_ctx* ctx, const xt_params* p, bool use_smem, int*
   const int nt = k1_threads(ctx);
   const size_t b = xt_k1_smem(ctx->cap, CO1, ctx->RH, p->nS, ctx->spec_maxP, ctx->spec_maxC,
                               is_var(p) ? ipow(p->nS, p->nsub + 1) : 0, nt);
-  // (2 KB: static shared memory of the kernel + the per-CTA reservation)
+  // static shared memory of the kernel (bit rows, byte lists: 1.6 / 2.2 / 3.4 KB at 256 / 512 / 1024 threads; it counts
+  // against the opt-in maximum of a block together with the dynamic part) and the 1 KB the system reserves per CTA
+  const size_t stat = nt >= 1024 ? 3584 : (nt >= 512 ? 2304 : 1792);
   const int ctas = nt == XT_K1_THREADS ? XT_K1_MIN_CTAS : 1;
-  if (b + 2048 > (size_t)(228 * 1024) / ctas || b > (size_t)ctx->smem_optin) return;
+  if (b + stat + 1024 > (size_t)(228 * 1024) / ctas || b + stat > (size_t)ctx->smem_optin) return;
   *scapP = ctx->spec_maxP;
   *scapC = ctx->spec_maxC;
 }

@@ -37,6 +37,9 @@
 #ifndef XT_K2_SINGLES_X2
 #define XT_K2_SINGLES_X2 1  // single-member groups two at a time (one track per thread)
 #endif
+#ifndef XT_K2_EXP_DEG
+#define XT_K2_EXP_DEG 7  // degree of the exp polynomial of the short-chain evaluation (6 | 7)
+#endif
 #ifndef XT_K2_SINGLES_IL
 #define XT_K2_SINGLES_IL 1  // ... with the two updates interleaved stage by stage
 #endif
@@ -124,10 +127,16 @@ __device__ __forceinline__ double xt_exp_split(double x, unsigned s_e2, int& k, 
   const double a0 = r + 1.0;
   const double a1 = fma(r, T.kc[5], 0.5);
   const double a2 = fma(r, 0.00833333283662796, T.kc[4]);
-  const double a3 = fma(r, 0.00019841268658638, 0.00138888880610466);
   const double r4 = r2 * r2;
   const double b0 = fma(r2, a1, a0);
+#if XT_K2_EXP_DEG == 6
+  // degree 6: |r| <= ln2/32, so the dropped r^7/5040 is below 4.4e-16 relative at the ends of the interval (5e-17 rms),
+  // and the leaf with two constants (two moves to build the second one in registers at every use) disappears
+  const double b1 = fma(r2, 0.00138888880610466, a2);
+#else
+  const double a3 = fma(r, 0.00019841268658638, 0.00138888880610466);
   const double b1 = fma(r2, a3, a2);
+#endif
   return fma(r4, b1, b0) * tj;
 #else
   double p = 0.00019841268658638;

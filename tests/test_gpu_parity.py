@@ -845,3 +845,24 @@ def test_live_sequence_cap_is_reported_not_silently_exceeded(native):
     finally:
         eng.close()
     np.testing.assert_allclose(got, orc.chunk_logp(C, m2, 1), rtol=RTOL_LOGL)
+
+
+def test_plan_scratch_leaves_room_for_static_shared_memory(native):
+    """Regression (found by tools/fuzz_parity.py, seed 5): 3 states, frame_len 10, threshold 0.05 - the plan kernel's
+    shared-memory scratch of the second evaluation came within 3 KB of the opt-in maximum of a block, and the static
+    shared memory of the 1024-thread instantiation no longer fitted next to it (launch: invalid argument)."""
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "fixtures", "k1_smem_boundary_case.npz"))
+    C, Ds = z["C"], z["Ds"]
+    m = make_model(nS=int(z["nS"]), nsub=int(z["nsub"]), loc_err=tuple(z["loc"]), frame_len=int(z["fl"]), min_len=int(z["min_len"]),
+                   threshold=float(z["th"]), max_nb_states=int(z["mx"]), pBL=float(z["pBL"]), Ds=Ds, rates=float(z["rates"]))
+    ref = orc.chunk_logp(C, m, int(z["isBL"]))
+    p = engine_params(m, C.shape[2])
+    eng = native.Engine(0)
+    try:
+        eng.upload([C], [int(z["isBL"])], len(C))
+        for _ in range(3):  # the first evaluation sizes the scratch of the following ones
+            eng.sum_logp(p)
+            got = eng.chunk_logp(0, len(C), p)
+            np.testing.assert_allclose(got, ref, rtol=RTOL_LOGL)
+    finally:
+        eng.close()
