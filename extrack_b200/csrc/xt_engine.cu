@@ -268,6 +268,7 @@ static int create_resources(xt_ctx* ctx, int device) {
   c->d_spec = c->d_spec_own;
   c->h_spec = c->h_spec_own;
   XT_CUDA_OK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  c->smem_optin -= 256;  // the kernels' static shared memory counts against the same limit (<= 144 B; the plan kernel: k1_scratch_caps)
   XT_CUDA_OK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
   return XT_OK;
 }
