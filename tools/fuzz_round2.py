@@ -24,13 +24,14 @@ from helpers import engine_params, make_model, random_walk_tracks  # noqa: E402
 from oracle import extrack_oracle as orc  # noqa: E402
 from oracle import refine_oracle  # noqa: E402
 
+KINDS = tuple(os.environ.get("FUZZ_KINDS", "predict,refine,verify,seglen,multi").split(","))
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 240.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 t_end = time.time() + budget
-n = {"predict": 0, "refine": 0, "verify": 0}
+n = {"predict": 0, "refine": 0, "verify": 0, "seglen": 0, "multi": 0}
 bad = 0
 limit_hits = 0
-worst = {"predict": 0.0, "refine": 0.0}
+worst = {"predict": 0.0, "refine": 0.0, "seglen": 0.0}
 served = {"verified": 0, "replanned_chunks": 0, "scratch": 0}
 
 
@@ -41,7 +42,7 @@ def finding(kind, desc, what):
 
 
 while time.time() < t_end:
-    kind = ("predict", "refine", "verify")[int(rng.integers(0, 3))]
+    kind = KINDS[int(rng.integers(0, len(KINDS)))]
     nS = int(rng.choice([2, 2, 3]))
     d = int(rng.choice([1, 2, 2, 3]))
     fl = int(rng.integers(3, 9))
@@ -89,6 +90,50 @@ while time.time() < t_end:
             worst["refine"] = max(worst["refine"], err)
             if not err < 1e-8:
                 finding(kind, desc, err)
+        elif kind == "seglen":
+            from extrack_b200 import histograms as xh
+            from oracle import seglen_oracle as so
+
+            L, nT, mx = int(rng.integers(2, 31)), int(rng.integers(1, 51)), int(rng.choice([12, 40, 200, 500]))
+            isBL, min_l = int(rng.integers(0, 2)), int(rng.integers(2, 8))
+            per_dim = d > 1 and rng.integers(0, 3) == 0
+            loc = tuple(0.02 + 0.01 * rng.random(d)) if per_dim else (0.02,)
+            desc = f"nS={nS} d={d} L={L} nT={nT} mx={mx} isBL={isBL} min_l={min_l} loc={loc}"
+            m = make_model(nS=nS, loc_err=loc, Ds=Ds, rates=float(rng.random() * 0.3 + 0.02), pBL=float(rng.random() * 0.2 + 0.01))
+            C = random_walk_tracks(nT, L, d, rng, Ds=Ds)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                LP0, h0 = so.segment_len_chunk(C, m, isBL, mx, min_l)
+            LP, Bs, hist = xh.P_segment_len(C, np.asarray(m.loc_err)[None, None], m.ds, m.Fs, m.TrMat, min_l=min_l, pBL=m.pBL, isBL=isBL,
+                                            cell_dims=[1.0], nb_substeps=1, max_nb_states=mx)
+            fin = np.isfinite(LP0)
+            e1 = float(np.max(np.abs(LP[fin] - LP0[fin]) / np.maximum(np.abs(LP0[fin]), 1e-300))) if fin.any() else 0.0
+            e2 = float(np.max(np.abs(hist - h0))) if h0.size else 0.0
+            worst["seglen"] = max(worst["seglen"], e2)
+            if not (e1 < 1e-9 and e2 < 1e-6 and LP.shape == LP0.shape):
+                finding(kind, desc, (e1, e2))
+        elif kind == "multi":
+            st = [random_walk_tracks(int(rng.integers(1, 4200)), L, d, rng, Ds=Ds)
+                  for L in sorted(set(int(x) for x in rng.integers(3, 30, size=int(rng.integers(1, 6)))))]
+            nd = int(rng.integers(2, 6))
+            desc = f"nS={nS} d={d} fl={fl} th={th} logical devices={nd} buckets={[a.shape[:2] for a in st]}"
+            a, b = xt.TrackSet(st, 2000, devices=[0] * nd), xt.TrackSet(st, 2000)
+            try:
+                cur = dict(nS=nS, frame_len=fl, threshold=th, min_len=st[0].shape[1], Ds=Ds, loc_err=(0.02,),
+                           rates=float(rng.random() * 0.3 + 0.02), pBL=float(rng.random() * 0.2 + 0.01))
+                for step in range(int(rng.integers(3, 8))):
+                    scale = float(rng.choice([1.5e-8, 1e-4, 3e-3, 0.2]))
+                    cur = dict(cur)
+                    cur["Ds"] = np.sort(np.asarray(cur["Ds"]) * (1 + scale * rng.standard_normal(nS)))
+                    cur["loc_err"] = (cur["loc_err"][0] * (1 + scale * float(rng.standard_normal())),)
+                    p = engine_params(make_model(**cur), d)
+                    va, vb = a.sum_logp(p), b.sum_logp(p)
+                    if not (va == vb or (np.isnan(va) and np.isnan(vb))):
+                        finding(kind, desc, f"step {step} scale {scale}: {va!r} != {vb!r}")
+                        break
+            finally:
+                a.close()
+                b.close()
         else:
             st = [random_walk_tracks(int(rng.integers(1, 2600)), L, d, rng, Ds=Ds)
                   for L in sorted(set(int(x) for x in rng.integers(3, 30, size=int(rng.integers(1, 5)))))]
@@ -130,5 +175,5 @@ while time.time() < t_end:
     except Exception as e:  # engine errors are findings too
         finding(kind, "?", repr(e)[:300])
 print(f"fuzz round 2: cases {n}, {bad} findings, worst |posterior error| {worst['predict']:.2e}, worst |refined position / sigma error| "
-      f"{worst['refine']:.2e} um, verification steps served {served}; cases that hit the documented sequence-capacity limit: {limit_hits}")
+      f"{worst['refine']:.2e} um, worst |segment-length histogram error| {worst['seglen']:.2e}, verification steps served {served}; cases that hit the documented sequence-capacity limit: {limit_hits}")
 sys.exit(1 if bad else 0)
