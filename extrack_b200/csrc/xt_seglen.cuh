@@ -80,7 +80,101 @@ __device__ __forceinline__ double xt_seg_logdens(const double (&Cn)[D], const do
   return acc;
 }
 
-template <int D, int KS>
+// Bitonic sort of the n2 (key, index) pairs in keys[] / ord[] into the pruning order (xt_seg_before), with the elements
+// in registers: thread t holds the EPT consecutive elements EPT*t .. EPT*t + EPT - 1 for the whole network.
+// Compare-exchange distances below EPT run inside the thread, distances up to 16 * EPT between the lanes of a warp with
+// shuffles, and only the longer ones (thread distance >= 32) go through shared memory: for 1024 pairs on 256 threads that
+// is 6 of the 55 stages (the first version passed 36 stages through shared memory with a CTA barrier each).
+// All XT_SEG_THREADS threads call it; n2 is a power of two, 4 <= n2 <= EPT * XT_SEG_THREADS.  The total order (keys,
+// then indices, all indices distinct) makes the result independent of the network.
+template <int EPT>
+__device__ __forceinline__ void xt_seg_sort(double* keys, int* ord, int n2, int tid) {
+  static_assert(EPT == 4 || EPT == 8 || EPT == 16, "elements per thread");
+  double kk[EPT];
+  int ii[EPT];
+  const int base = EPT * tid;
+  const bool live = base < n2;  // (n2 is a multiple of EPT: a thread is live with all of its elements or none)
+  if (live) {
+#pragma unroll
+    for (int e = 0; e < EPT; e += 2) {
+      const double2 v = reinterpret_cast<const double2*>(keys)[(base + e) >> 1];
+      kk[e] = v.x;
+      kk[e + 1] = v.y;
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; e += 4) {
+      const int4 v = reinterpret_cast<const int4*>(ord)[(base + e) >> 2];
+      ii[e] = v.x; ii[e + 1] = v.y; ii[e + 2] = v.z; ii[e + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      kk[e] = -INFINITY;
+      ii[e] = -1 - (base + e);
+    }
+  }
+  for (int k = 2; k <= n2; k <<= 1) {
+    int jj = k >> 1;
+    for (; jj >= 32 * EPT; jj >>= 1) {
+      // partner in another warp: through shared memory (own elements out, barrier, partner's elements in, barrier)
+      if (live) {
+#pragma unroll
+        for (int e = 0; e < EPT; e += 2) reinterpret_cast<double2*>(keys)[(base + e) >> 1] = make_double2(kk[e], kk[e + 1]);
+#pragma unroll
+        for (int e = 0; e < EPT; e += 4) reinterpret_cast<int4*>(ord)[(base + e) >> 2] = make_int4(ii[e], ii[e + 1], ii[e + 2], ii[e + 3]);
+      }
+      __syncthreads();
+      if (live) {
+        const int pb = base ^ jj;  // (jj is a multiple of EPT: the partner thread's elements, slot by slot)
+        const bool keep_first = ((base & jj) == 0) == ((base & k) == 0);
+#pragma unroll
+        for (int e = 0; e < EPT; e += 2) {
+          const double2 v = reinterpret_cast<const double2*>(keys)[(pb + e) >> 1];
+          const int2 w = reinterpret_cast<const int2*>(ord)[(pb + e) >> 1];
+          const bool f0 = xt_seg_before(kk[e], ii[e], v.x, w.x), f1 = xt_seg_before(kk[e + 1], ii[e + 1], v.y, w.y);
+          if (f0 != keep_first) { kk[e] = v.x; ii[e] = w.x; }
+          if (f1 != keep_first) { kk[e + 1] = v.y; ii[e + 1] = w.y; }
+        }
+      }
+      __syncthreads();
+    }
+    for (; jj >= EPT; jj >>= 1) {
+      // partner in the same warp
+      const int lm = jj / EPT;
+      const bool keep_first = ((base & jj) == 0) == ((base & k) == 0);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const double ok = __shfl_xor_sync(0xffffffffu, kk[e], lm);
+        const int oi = __shfl_xor_sync(0xffffffffu, ii[e], lm);
+        if (xt_seg_before(kk[e], ii[e], ok, oi) != keep_first) { kk[e] = ok; ii[e] = oi; }
+      }
+    }
+    // both elements in this thread: the remaining distances, with compile-time register indices
+#pragma unroll
+    for (int j2 = EPT / 2; j2 >= 1; j2 >>= 1) {
+      if (j2 <= jj) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          if ((e & j2) == 0) {
+            const int x = e | j2;
+            const bool up = (((base + e) & k) == 0);
+            if (xt_seg_before(kk[x], ii[x], kk[e], ii[e]) == up) {
+              const double tk = kk[e]; kk[e] = kk[x]; kk[x] = tk;
+              const int ti = ii[e]; ii[e] = ii[x]; ii[x] = ti;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (live) {  // (only the order is read afterwards)
+#pragma unroll
+    for (int e = 0; e < EPT; e += 4) reinterpret_cast<int4*>(ord)[(base + e) >> 2] = make_int4(ii[e], ii[e + 1], ii[e + 2], ii[e + 3]);
+  }
+  __syncthreads();
+}
+
+template <int D, int KS, int EPT = 4>
 __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, const xt_params P) {
   constexpr int NT = XT_SEG_THREADS;
   const int tid = threadIdx.x;
@@ -210,57 +304,7 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
         }
       }
       __syncthreads();
-      // bitonic network, n2 >= 4: compare-exchange distances 1 and 2 run in registers on groups of four
-      // consecutive elements (conflict-free 32-byte rows), the longer distances pairwise in shared memory
-      auto ce = [](double& ka, int& ia, double& kb, int& ib, bool up) {
-        if (xt_seg_before(kb, ib, ka, ia) == up) {
-          const double tk = ka; ka = kb; kb = tk;
-          const int ti = ia; ia = ib; ib = ti;
-        }
-      };
-      for (int g = tid; g < (n2 >> 2); g += NT) {  // stages k = 2, 4
-        const double2 ka2 = reinterpret_cast<const double2*>(keys)[2 * g], kb2 = reinterpret_cast<const double2*>(keys)[2 * g + 1];
-        const int4 iv = reinterpret_cast<const int4*>(ord)[g];  // 128-bit rows: 16-byte aligned by construction
-        double k0 = ka2.x, k1 = ka2.y, k2 = kb2.x, k3 = kb2.y;
-        int i0 = iv.x, i1 = iv.y, i2 = iv.z, i3 = iv.w;
-        ce(k0, i0, k1, i1, true);
-        ce(k2, i2, k3, i3, false);
-        const bool up = (g & 1) == 0;
-        ce(k0, i0, k2, i2, up); ce(k1, i1, k3, i3, up);
-        ce(k0, i0, k1, i1, up); ce(k2, i2, k3, i3, up);
-        reinterpret_cast<double2*>(keys)[2 * g] = make_double2(k0, k1);
-        reinterpret_cast<double2*>(keys)[2 * g + 1] = make_double2(k2, k3);
-        reinterpret_cast<int4*>(ord)[g] = make_int4(i0, i1, i2, i3);
-      }
-      __syncthreads();
-      for (int k = 8; k <= n2; k <<= 1) {
-        for (int jj = k >> 1; jj >= 4; jj >>= 1) {
-          for (int t = tid; t < (n2 >> 1); t += NT) {
-            const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
-            const int x = i + jj;
-            const double ka = keys[i], kb = keys[x];
-            const int ia = ord[i], ib = ord[x];
-            if (xt_seg_before(kb, ib, ka, ia) == ((i & k) == 0)) {
-              keys[i] = kb; keys[x] = ka;
-              ord[i] = ib; ord[x] = ia;
-            }
-          }
-          __syncthreads();
-        }
-        for (int g = tid; g < (n2 >> 2); g += NT) {  // distances 2 and 1
-          const double2 ka2 = reinterpret_cast<const double2*>(keys)[2 * g], kb2 = reinterpret_cast<const double2*>(keys)[2 * g + 1];
-          const int4 iv = reinterpret_cast<const int4*>(ord)[g];
-          double k0 = ka2.x, k1 = ka2.y, k2 = kb2.x, k3 = kb2.y;
-          int i0 = iv.x, i1 = iv.y, i2 = iv.z, i3 = iv.w;
-          const bool up = ((4 * g) & k) == 0;
-          ce(k0, i0, k2, i2, up); ce(k1, i1, k3, i3, up);
-          ce(k0, i0, k1, i1, up); ce(k2, i2, k3, i3, up);
-          reinterpret_cast<double2*>(keys)[2 * g] = make_double2(k0, k1);
-          reinterpret_cast<double2*>(keys)[2 * g + 1] = make_double2(k2, k3);
-          reinterpret_cast<int4*>(ord)[g] = make_int4(i0, i1, i2, i3);
-        }
-        __syncthreads();
-      }
+      xt_seg_sort<EPT>(keys, ord, n2, tid);
       for (int j = tid; j < kmax; j += NT) {
         const int src = ord[j];
         const int srcL = ord[nC - kmax + j];  // histograms.py:202: LL keeps the last k ranks

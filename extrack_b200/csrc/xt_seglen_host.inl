@@ -44,7 +44,7 @@ extern "C" int xt_seglen_hist(xt_ctx* ctx, const xt_params* p, const double* lea
   int n2 = 4;
   while (n2 < capC && n2 < (1 << 20)) n2 <<= 1;
   const size_t smem = capC <= 65535 ? xt_seg_smem(d, KS, (int)capC, n2, Lmax, nS) : (size_t)-1;
-  if (capC > 65535 || smem > (size_t)ctx->smem_optin) {
+  if (capC > 65535 || n2 > 16 * XT_SEG_THREADS || smem > (size_t)ctx->smem_optin) {
     set_error(ctx, "xt_seglen_hist: " + std::to_string(capC) + " live state sequences per track do not fit in shared memory; lower max_nb_states");
     return XT_ERR_CAPACITY;
   }
