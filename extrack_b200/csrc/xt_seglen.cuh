@@ -175,7 +175,7 @@ __device__ __forceinline__ void xt_seg_sort(double* keys, int* ord, int n2, int 
 }
 
 template <int D, int KS, int EPT = 4>
-__global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, const xt_params P) {
+__global__ void __launch_bounds__(XT_SEG_THREADS, EPT == 4 ? 2 : 1) k4_seglen(const K4Args a, const xt_params P) {
   constexpr int NT = XT_SEG_THREADS;
   const int tid = threadIdx.x;
   const int nS = P.nS, cap = a.cap, n2 = a.n2;
@@ -251,22 +251,23 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
       loc(step - 1, Ci);
       loc(step, Cn);  // step <= L-1
       const bool prune = step < L - 1 && nC > kmax;
-      for (int j = tid; j < nC; j += NT) {
-        const int p = j / nS, s = j - p * nS;
-        const int h = s + nS * (int)stp[p];
-        double q[KS], sp[KS];
+      // One thread per parent: the new mean, the quadratic term and the log term of the update depend on the parent only
+      // (every child of a parent consumes the same localisation from the same moments; only the diffusion length of
+      // the step, hence s2, differs between the children), so they are computed once per parent instead of once per
+      // child; the children then get their own s2, weights, lattice record and - in a pruning step - their sort key.
+      for (int p = tid; p < nB; p += NT) {
+        double q[KS], sp[KS], mc[D];
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
           sp[k] = SEG_S(par)[k * cap + p];
           q[k] = __dadd_rn(l2[k], sp[k]);
         }
-        const double dd = P.dd[h];
         double quad = 0.0, lgs = 0.0;
 #pragma unroll
         for (int dim = 0; dim < D; ++dim) {
           const int k = KS == 1 ? 0 : dim;
           const double mp = SEG_M(par)[dim * cap + p];
-          SEG_M(chi)[dim * cap + j] = __ddiv_rn(__dadd_rn(__dmul_rn(mp, l2[k]), __dmul_rn(Ci[dim], sp[k])), q[k]);
+          mc[dim] = __ddiv_rn(__dadd_rn(__dmul_rn(mp, l2[k]), __dmul_rn(Ci[dim], sp[k])), q[k]);
           const double df = __dadd_rn(Ci[dim], -mp);
           const double t = __ddiv_rn(__dmul_rn(df, df), __dmul_rn(2.0, q[k]));
           quad = dim == 0 ? t : __dadd_rn(quad, t);
@@ -276,15 +277,61 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
           }
         }
         if (KS == 1) lgs = __dmul_rn((double)D * -0.5, log(__dmul_rn(XT_TWO_PI, q[0])));
-#pragma unroll
-        for (int k = 0; k < KS; ++k)
-          SEG_S(chi)[k * cap + j] =
-              __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(dd, l2[k]), __dmul_rn(dd, sp[k])), __dmul_rn(l2[k], sp[k])), q[k]);
         const double LC = __dadd_rn(lgs, -quad);
-        SEG_LP(chi)[j] = __dadd_rn(SEG_LP(par)[p], __dadd_rn(P.LT[h], LC));
-        SEG_LL(chi)[j] = (step >= P.min_len) ? __dadd_rn(SEG_LL(par)[p], P.Lp_stay[s]) : SEG_LL(par)[p];
-        stc[j] = (uint8_t)s;
-        if (!prune) lat[(size_t)(step - 1) * cap + j] = (uint32_t)p | ((uint32_t)s << 16);
+        const double LPp = SEG_LP(par)[p], LLp = SEG_LL(par)[p];
+        const int hb = nS * (int)stp[p];
+        double dn[D];  // next localisation minus the children's common mean (sort key)
+        if (prune) {
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) dn[dim] = __dadd_rn(Cn[dim], -mc[dim]);
+        }
+        for (int s = 0; s < nS; ++s) {
+          const int j = p * nS + s, h = s + hb;
+          const double dd = P.dd[h];
+          double sc[KS];
+#pragma unroll
+          for (int dim = 0; dim < D; ++dim) SEG_M(chi)[dim * cap + j] = mc[dim];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            sc[k] = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(dd, l2[k]), __dmul_rn(dd, sp[k])), __dmul_rn(l2[k], sp[k])), q[k]);
+            SEG_S(chi)[k * cap + j] = sc[k];
+          }
+          const double lpc = __dadd_rn(LPp, __dadd_rn(P.LT[h], LC));
+          SEG_LP(chi)[j] = lpc;
+          SEG_LL(chi)[j] = (step >= P.min_len) ? __dadd_rn(LLp, P.Lp_stay[s]) : LLp;
+          stc[j] = (uint8_t)s;
+          if (!prune) {
+            lat[(size_t)(step - 1) * cap + j] = (uint32_t)p | ((uint32_t)s << 16);
+          } else {
+            // key = LP + log-density of the next localisation (histograms.py:186-196; same operations as xt_seg_logdens)
+            double acc = 0.0, lg0 = 0.0, n0 = 0.0;
+            if (KS == 1) {
+              n0 = __dadd_rn(sc[0], l2[0]);
+              lg0 = __dmul_rn(-0.5, log(__dmul_rn(XT_TWO_PI, n0)));
+            }
+#pragma unroll
+            for (int dim = 0; dim < D; ++dim) {
+              double ns, lg;
+              if (KS == 1) {
+                ns = n0;
+                lg = lg0;
+              } else {
+                ns = __dadd_rn(sc[dim], l2[dim]);
+                lg = __dmul_rn(-0.5, log(__dmul_rn(XT_TWO_PI, ns)));
+              }
+              const double t = __dadd_rn(lg, -__ddiv_rn(__dmul_rn(dn[dim], dn[dim]), __dmul_rn(2.0, ns)));
+              acc = dim == 0 ? t : __dadd_rn(acc, t);
+            }
+            keys[j] = __dadd_rn(lpc, acc);
+            ord[j] = j;
+          }
+        }
+      }
+      if (prune) {
+        for (int j = nC + tid; j < n2; j += NT) {
+          keys[j] = -INFINITY;
+          ord[j] = -1 - j;
+        }
       }
       __syncthreads();
       if (!prune) {
@@ -293,17 +340,6 @@ __global__ void __launch_bounds__(XT_SEG_THREADS, 1) k4_seglen(const K4Args a, c
         nB = nC;
         continue;
       }
-      // literal top-k: key = LP + log-density of the next localisation (histograms.py:186-196)
-      for (int j = tid; j < n2; j += NT) {
-        if (j < nC) {
-          keys[j] = __dadd_rn(SEG_LP(chi)[j], xt_seg_logdens<D, KS>(Cn, SEG_M(chi), SEG_S(chi), j, cap, l2));
-          ord[j] = j;
-        } else {
-          keys[j] = -INFINITY;
-          ord[j] = -1 - j;
-        }
-      }
-      __syncthreads();
       xt_seg_sort<EPT>(keys, ord, n2, tid);
       for (int j = tid; j < kmax; j += NT) {
         const int src = ord[j];
