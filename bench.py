@@ -503,30 +503,21 @@ def main():
     nstep = [0]
     served = {"verified": 0, "chunks_planned_again": 0, "planned_from_scratch": 0}
 
-    # N > 1: one 8-byte all-reduce per step, asynchronous on NCCL's own stream with two alternating result buffers, so
-    # that the evaluation of the next step does not queue behind the collective of this one (at N = 1 the value stays
-    # on the device per step as well); every collective completes inside the timed region (`drain`)
-    bufs = [buf, torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}")]
-    pending = [None, None]
-
+    # N > 1: one 8-byte all-reduce per step on torch's current stream, right behind the evaluation that produced the
+    # partial sum (the engine orders its streams after that stream, so step i + 1 starts when the collective of step i
+    # is done).  An asynchronous variant (collective on NCCL's own stream, two alternating result buffers) was measured:
+    # 0.97 of N x one GPU at N = 2, but at N = 8 the collective's kernels compete with the next replay for SM slots on
+    # all eight ranks and the step time rose from 1.76 to 2.17 ms (profiles/r12/bench_n8_async_allreduce.json).
     def step():
-        i = nstep[0] % 2
-        if pending[i] is not None:
-            pending[i].wait()  # (stream-level) the collective that last read this buffer
-            pending[i] = None
-        eng.sum_logp_async(pvar[nstep[0] % len(pvar)], bufs[i].data_ptr(), stream)
+        eng.sum_logp_async(pvar[nstep[0] % len(pvar)], buf.data_ptr(), stream)
         nstep[0] += 1
         if world > 1:
-            pending[i] = dist.all_reduce(bufs[i], async_op=True)
+            dist.all_reduce(buf)
 
     def drain():
-        for i in range(2):
-            if pending[i] is not None:
-                pending[i].wait()
-                pending[i] = None
+        pass
 
     def barrier():
-        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -704,8 +695,7 @@ def main():
                        "l2_policy": f"inputs larger than L2 ({alg_bytes/1e6:.0f} MB of localisations per GPU vs 126 MB L2)",
                        "sum_logp": total, "generator_seconds": round(gen_s, 1),
                        "collective": ("none (one GPU)" if world == 1 else
-                                      "one 8-byte NCCL all-reduce of the partial sums per step, asynchronous (two alternating "
-                                      "result buffers), all completed inside the timed region")},
+                                      "one 8-byte NCCL all-reduce of the partial sums per step on the evaluation's stream")},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "what": "xt_sum_logp_host per step: pinned host buffers -> device + repack, overlapped per length "
