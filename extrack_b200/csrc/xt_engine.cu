@@ -78,6 +78,7 @@ struct xt_ctx {
   int k3_shared = 0;          // state annotation: 1 = the tracks of an uploaded chunk share one plan (predict_Bs with nb_max > 1)
   int k3_cap0 = 48;           // state annotation: sequence capacity of the first launch (tracks that outgrow it run again with more)
   int k3_pieces = 8;          // state annotation of a large data set: launches of the first round (read-back of a piece under the next)
+  int verify_fork_k2 = 0;     // verified evaluation: 1 = the replay on a stream of its own (0: on the context's main stream)
   int k3_hot_smem = 1;        // state-annotation kernel: forward-pass state of every warp in shared memory
   int k3_ctas_per_sm = 4;     // resident CTAs per SM of the state-annotation kernel (its per-warp scratch should stay in L2)
   int k1_threads = 0;         // plan kernel threads per chunk: 0 = automatic (256, or 1024 for <= n_sm chunks)
@@ -1285,8 +1286,17 @@ static int evaluate_verified(xt_ctx* ctx, const xt_params* p, int bits, double* 
     ctx->stats.k1_launches++;
   }
   if (trace) t_k1 = xt_now_us();
-  int rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->stream);
-  if (rc) return rc;
+  int rc;
+  if (ctx->verify_fork_k2) {  // (option "verify_fork_k2": the replay on a stream of its own, joined before the reduction)
+    XT_CUDA_OK(cudaStreamWaitEvent(ctx->cs[1], ctx->ev_fork, 0));
+    rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->cs[1]);
+    if (rc) return rc;
+    XT_CUDA_OK(cudaEventRecord(ctx->ev_join[1], ctx->cs[1]));
+    XT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
+  } else {
+    rc = enqueue_fused(ctx, p, fl, 0, nch, ctx->stream);
+    if (rc) return rc;
+  }
   if (trace) t_k2 = xt_now_us();
   XT_CUDA_OK(cudaEventRecord(ctx->ev_join[0], ctx->cs[0]));
   XT_CUDA_OK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -1574,6 +1584,10 @@ extern "C" int xt_set_option(xt_ctx* ctx, const char* name, int value) {
   }
   if (std::strcmp(name, "k3_pieces") == 0) {
     ctx->k3_pieces = value < 1 ? 1 : (value > 64 ? 64 : value);
+    return XT_OK;
+  }
+  if (std::strcmp(name, "verify_fork_k2") == 0) {
+    ctx->verify_fork_k2 = value != 0;
     return XT_OK;
   }
   if (std::strcmp(name, "k3_hot_smem") == 0) {
