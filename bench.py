@@ -118,21 +118,59 @@ def cpu_baseline(st):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of this rank's GPU, sampled during the timed region.  Through NVML in-process (one
+    handle, a few microseconds per sample); spawning `nvidia-smi` every 100 ms - the fallback when NVML cannot be loaded -
+    initialises the driver's management layer for all GPUs of the box at every call and was seen to stretch the timed
+    steps of an 8-GPU run by tenths of a millisecond."""
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, False, []
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(index)
+            bdf = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode())
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = self.handle = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = float("nan")
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda bit: "Active" if (r & bit) else "Not Active"  # noqa: E731
+        return [str(sm), str(mx), f"{pw:.1f}", flag(n.nvmlClocksEventReasonHwSlowdown), flag(n.nvmlClocksEventReasonHwThermalSlowdown),
+                flag(n.nvmlClocksEventReasonSwThermalSlowdown), flag(n.nvmlClocksEventReasonSwPowerCap)]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                    time.sleep(0.02)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
-                pass
+                if self.nvml is not None:  # NVML query failed: fall back to the command-line tool
+                    self.nvml = None
             time.sleep(0.1)
 
     def summary(self):
@@ -145,7 +183,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "via": "nvml" if self.handle is not None and self.nvml is not None else "nvidia-smi"}
 
 
 def _bind_to_gpu_numa_node(local):
