@@ -121,6 +121,8 @@ def extract_params(params, dt, nb_states, nb_substeps, input_LocErr=None, Matrix
 
 _P_STAY_MEMO: dict = {}
 _FOV_GRID: dict = {}
+_FOV_COLS: dict = {}
+_FOV_LIN: dict = {}
 _DIGITS: dict = {}
 _NAME_PLAN: dict = {}
 
@@ -141,9 +143,41 @@ def _p_stay(ds, nS, nsub, cell_dims):
         hit = _P_STAY_MEMO.get(key)
         if hit is not None:
             return hit.copy()
-    ds2 = ds[None] if one else ds
     K = nS**nsub
-    tup = np.arange(K)[:, None] // nS ** np.arange(nsub)[None, :] % nS
+    tup = _DIGITS.get((nS, nsub, "tuples"))
+    if tup is None:
+        tup = _DIGITS[(nS, nsub, "tuples")] = np.arange(K)[:, None] // nS ** np.arange(nsub)[None, :] % nS
+    if one:
+        # One column per distinct diffusion length, memoised: a finite-difference step of a fit moves one D, so one
+        # column is new.  np.mean(.., 0) of the reference's [1000, 1, K] array accumulates every column sequentially
+        # over the grid points (the reduction runs over the outer axis), which np.cumsum reproduces bit for bit
+        # (tests/test_host.py::test_p_stay_columns_reproduce_the_array_formula); a plain 1-D sum would be pairwise.
+        sub_ds = np.mean(ds[tup] ** 2, axis=1) ** 0.5  # [K]
+        out1 = np.ones(K)
+        for cell_len in cell_dims:
+            grid = _FOV_GRID.get(cell_len)
+            if grid is None:
+                xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
+                grid = _FOV_GRID[cell_len] = ((cell_len - xs[:, None, None]), -xs[:, None, None])
+            cols = _FOV_COLS.setdefault(cell_len, {})
+            for k in range(K):
+                sk = float(sub_ds[k])
+                cur = cols.get(sk)
+                if cur is None:
+                    lin = _FOV_LIN.get(cell_len)
+                    if lin is None:
+                        lin = _FOV_LIN[cell_len] = (np.ascontiguousarray(grid[0][:, 0, 0]), np.ascontiguousarray(grid[1][:, 0, 0]))
+                    den1 = sub_ds[k] + 1e-200
+                    cur = np.cumsum(ndtr(lin[0] / den1) - ndtr(lin[1] / den1))[-1] / 1000
+                    if len(cols) > 256:
+                        cols.clear()
+                    cols[sk] = cur
+                out1[k] = out1[k] * cur
+        if len(_P_STAY_MEMO) > 64:
+            _P_STAY_MEMO.clear()
+        _P_STAY_MEMO[key] = out1.copy()
+        return out1
+    ds2 = ds
     out = np.ones((len(ds2), K))
     for r0 in range(0, len(ds2), 512):
         sub_ds = np.mean(ds2[r0 : r0 + 512][:, tup] ** 2, axis=2) ** 0.5  # [rows, K]
@@ -157,11 +191,7 @@ def _p_stay(ds, nS, nsub, cell_dims):
             cur = np.mean(ndtr(grid[0] / den) - ndtr(grid[1] / den), 0)
             p_stay = p_stay * cur
         out[r0 : r0 + 512] = p_stay
-    if one:
-        if len(_P_STAY_MEMO) > 64:
-            _P_STAY_MEMO.clear()
-        _P_STAY_MEMO[key] = out[0].copy()
-    return out[0] if one else out
+    return out
 
 
 def _head_tables(ds, Fs, TrMat, nS, nsub):

@@ -420,3 +420,37 @@ def test_sim_FOV_per_peak_localisation_errors():
     assert 0.85 < z.std() < 1.05
     tr0 = sim_FOV(**kw)[0]  # LocErr_std = 0 keeps the two-value return and the same selection of runs
     assert {k: v.shape for k, v in tr0.items()} == {k: v.shape for k, v in tr.items()}
+
+
+def test_p_stay_columns_reproduce_the_array_formula():
+    """tracking._p_stay memoises one column per distinct diffusion length (sequential sum over the 1000 grid points) - it
+    must have the bits of the reference's array formula (tracking.py:515-523: np.mean over axis 0 of a [1000, 1, K] array)."""
+    from scipy.special import ndtr
+
+    from extrack_b200 import tracking as xt
+
+    rng = np.random.default_rng(5)
+    for it in range(120):
+        nS = int(rng.choice([2, 3, 4]))
+        nsub = int(rng.choice([1, 2])) if nS < 4 else 1
+        cells = [float(c) for c in rng.choice([0.5, 1.0, 3.0, 10.0], size=int(rng.integers(1, 3)), replace=False)]
+        ds = np.sort(rng.random(nS) * 0.2 * 10.0 ** float(rng.integers(-2, 1)) + 1e-4)
+        K = nS**nsub
+        tup = np.arange(K)[:, None] // nS ** np.arange(nsub)[None, :] % nS
+        sub_ds = np.mean(ds[tup][None] ** 2, axis=2) ** 0.5
+        want = np.ones(sub_ds.shape[-1])
+        for cell_len in cells:
+            xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
+            cur = np.mean(ndtr((cell_len - xs[:, None, None]) / (sub_ds + 1e-200)) - ndtr(-xs[:, None, None] / (sub_ds + 1e-200)), 0)
+            want = want * cur
+        got = xt._p_stay(ds, nS, nsub, cells)
+        np.testing.assert_array_equal(got, want[0])
+        ds2 = ds.copy()
+        ds2[int(rng.integers(0, nS))] *= 1 + 1.5e-8   # a finite-difference step: the other columns come from the memo
+        ds2 = np.sort(ds2)
+        sub2 = np.mean(ds2[tup][None] ** 2, axis=2) ** 0.5
+        want2 = np.ones(K)
+        for cell_len in cells:
+            xs = np.linspace(0 + cell_len / 2000, cell_len - cell_len / 2000, 1000)
+            want2 = want2 * np.mean(ndtr((cell_len - xs[:, None, None]) / (sub2 + 1e-200)) - ndtr(-xs[:, None, None] / (sub2 + 1e-200)), 0)[0]
+        np.testing.assert_array_equal(xt._p_stay(ds2, nS, nsub, cells), want2)
