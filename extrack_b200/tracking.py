@@ -596,7 +596,9 @@ def cum_Proba_Cs(params, all_tracks, dt, cell_dims, input_LocErr, nb_states, nb_
         ds = _median_ds(Ds, ts.dt_mid0)[0]  # avg_ds = np.median(ds[0], axis=(0, 1)), tracking.py:1012-1013
     else:
         ds = np.sqrt(2 * Ds * dt)
-    if np.all(TrMat > 0) and np.all(Fs > 0) and np.all(ds[1:] - ds[:-1] >= 0):
+    # validity guard of the reference (tracking.py:1017: all transition probabilities and fractions positive, diffusion
+    # lengths ascending); minima instead of three np.all passes - NaN fails either way
+    if TrMat.min() > 0 and Fs.min() > 0 and (len(ds) < 2 or (ds[1:] - ds[:-1]).min() >= 0):
         slope = (params["slope_LocErr"].value, params["offset_LocErr"].value) if (ts.loc_k and _has_slope(params)) else None
         p = build_tables(loc, ds, Fs, TrMat, pBL, cell_dims, nb_substeps, frame_len, ts.min_len, threshold,
                          max_nb_states, ts.nb_dims, var_loc_k=ts.loc_k, var_dt=ts.has_dt, Ds=Ds, slope_offset=slope)
